@@ -1,0 +1,200 @@
+/*
+ * signal_b200.h -- C ABI of libsignal_b200.so, the sm_100a implementation of the
+ * Signal fusion head (SIM + GAM + LAM), forward and backward.
+ *
+ * The reference (maxingan2412/Signal) is pure PyTorch: it has no FFI for this
+ * path.  The functions below are what a binding for the path would call; each
+ * one names the reference Python function it replaces.  INTEGRATION.md shows
+ * the ctypes stub and the nn.Module shims that sit on top.
+ *
+ * Conventions (all entry points)
+ *   - extern "C", returns int: 0 = work enqueued; <0 = argument rejected
+ *     (nothing launched), see sig_error_string; >0 = cudaError_t of a launch.
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the
+ *     library allocates nothing, frees nothing and keeps no pointer after the
+ *     call returns.  No host synchronisation, no default-stream use: all work
+ *     is enqueued on `stream` (a cudaStream_t) of device ordinal `device`.
+ *     Calls are re-entrant and CUDA-graph capturable.
+ *   - token maps are given as strided views (element strides, channel stride
+ *     must be 1): patches x[:,1:] and CLS x[:,0] of a [B,1+L,d] map
+ *     (modeling/meta_arch.py:108-109) are consumed without a copy.
+ *   - parameters are fp32 masters with the reference's state_dict layouts.
+ *   - `ctx` is an opaque caller-owned buffer of sig_ctx_bytes(...) bytes that
+ *     carries saved activations from a *_fwd call to the matching *_bwd call.
+ */
+#ifndef SIGNAL_B200_H
+#define SIGNAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIG_ABI_VERSION 1
+
+enum sig_dtype { SIG_F32 = 0, SIG_BF16 = 1 };
+
+enum sig_error {
+  SIG_OK = 0,
+  SIG_ERR_NULL = -1,       /* a required pointer is NULL */
+  SIG_ERR_SHAPE = -2,      /* unsupported B / L / d / grid / k */
+  SIG_ERR_DTYPE = -3,      /* unknown dtype enum */
+  SIG_ERR_ALIGN = -4,      /* pointer or stride not 16-byte aligned */
+  SIG_ERR_WORKSPACE = -5,  /* ctx buffer too small */
+  SIG_ERR_ARCH = -6        /* device is not sm_100 (tcgen05 path requested) */
+};
+
+enum sig_ctx_kind { SIG_CTX_SIM = 0, SIG_CTX_ALIGN = 1, SIG_CTX_SELECT = 2, SIG_CTX_DAS = 3 };
+
+/* sig_flags bits (argument `flags` of the fwd/bwd entry points) */
+#define SIG_FLAG_FORCE_SIMT 1u /* bf16 inputs: use the fp32 SIMT kernels instead of tcgen05 (cross-check) */
+
+/* Three modality token maps, order RGB, NI, TI.
+ * patch[m] -> element (b=0,l=0,c=0) of the [B,L,d] patch view, cls[m] -> (b=0,c=0)
+ * of the [B,d] CLS view.  Strides in ELEMENTS. */
+typedef struct sig_tokens {
+  const void* patch[3];
+  const void* cls[3];            /* may be NULL for the AlignM entry points */
+  int64_t patch_stride_b[3];
+  int64_t patch_stride_l[3];
+  int64_t cls_stride_b[3];
+  int32_t dtype;                 /* enum sig_dtype */
+  int32_t B, L, d;
+} sig_tokens;
+
+/* Gradient destinations with the same geometry (dtype = tokens' dtype).
+ * accumulate = 0: every addressed element is overwritten (rows of unselected
+ * tokens get zeros); 1: the gradient is added to what is there. */
+typedef struct sig_token_grads {
+  void* dpatch[3];
+  void* dcls[3];                 /* may be NULL (AlignM has no CLS input) */
+  int64_t patch_stride_b[3];
+  int64_t patch_stride_l[3];
+  int64_t cls_stride_b[3];
+  int32_t accumulate;
+  int32_t zero_cls;              /* AlignM: also write zeros to dcls rows when dcls != NULL */
+} sig_token_grads;
+
+/* Select_Interactive_Module parameters (modeling/AddModule/useA.py:33-48,340-361).
+ * token_selection.W_v is never used by the reference forward (useA.py:48) and is absent. */
+typedef struct sig_sim_params {
+  const float* sel_wq;   const float* sel_bq;     /* token_selection.W_q  [d,d],[d] */
+  const float* sel_wk;   const float* sel_bk;     /* token_selection.W_k  [d,d],[d] */
+  const float* in_proj_w;  const float* in_proj_b;  /* cross_attn.in_proj_*  [3d,d],[3d] */
+  const float* out_proj_w; const float* out_proj_b; /* cross_attn.out_proj.* [d,d],[d] */
+  const float* ffn0_w; const float* ffn0_b;       /* ffn.0 [2d,d],[2d] */
+  const float* ffn2_w; const float* ffn2_b;       /* ffn.2 [d,2d],[d] */
+  const float* ln1_w; const float* ln1_b;         /* norm1 [d] */
+  const float* ln2_w; const float* ln2_b;         /* norm2 [d] */
+} sig_sim_params;
+
+/* Gradients of the trainable SIM parameters (token_selection.* never receive
+ * gradients: selection is not differentiable, useA.py:79-93).  Overwritten. */
+typedef struct sig_sim_param_grads {
+  float* in_proj_w;  float* in_proj_b;
+  float* out_proj_w; float* out_proj_b;
+  float* ffn0_w; float* ffn0_b;
+  float* ffn2_w; float* ffn2_b;
+  float* ln1_w; float* ln1_b;
+  float* ln2_w; float* ln2_b;
+} sig_sim_param_grads;
+
+/* AlignmentM parameters (modeling/AddModule/useB.py:44-74, DAS.py:30-72), index = modality r,n,t */
+typedef struct sig_align_params {
+  const float* contra_temp;                      /* [] */
+  const float* proj_q_w[3]; const float* proj_q_b[3];   /* DAS_*.proj_q         [d,d,1,1],[d] */
+  const float* off0_w[3];   const float* off0_b[3];     /* DAS_*.conv_offset.0  [d,d,1,1],[d] */
+  const float* off2_w[3];   const float* off2_b[3];     /* DAS_*.conv_offset.2  [d,1,4,4],[d] */
+  const float* off4_w[3];                                /* DAS_*.conv_offset.4  [1,d,1,1]     */
+} sig_align_params;
+
+typedef struct sig_align_param_grads {           /* overwritten */
+  float* contra_temp;
+  float* proj_q_w[3]; float* proj_q_b[3];
+  float* off0_w[3];   float* off0_b[3];
+  float* off2_w[3];   float* off2_b[3];
+  float* off4_w[3];
+} sig_align_param_grads;
+
+/* ---- library info ------------------------------------------------------ */
+int sig_version(void);                       /* SIG_ABI_VERSION */
+const char* sig_error_string(int code);      /* static string; cudaGetErrorString for code > 0 */
+/* bytes of the ctx buffer for (kind, B, L, d); 0 if the shape is unsupported */
+size_t sig_ctx_bytes(int kind, int B, int L, int d);
+
+/* ---- SIM: Select_Interactive_Module.forward (useA.py:454-476) ---------- */
+/* out  [B,3d] in tokens' dtype; masks fp32 [3,B,L] (last_masks, useA.py:323).
+ * k1 = TOPK, k2 = 2*TOPK (useA.py:42-43), both clipped to the row length;
+ * max_keep = int(L*keep_ratio) or -1 when keep_ratio is None (useA.py:254-256). */
+int sig_sim_fwd(const sig_tokens* tok, const sig_sim_params* p, int k1, int k2, int max_keep,
+                void* out, float* masks, void* ctx, size_t ctx_bytes,
+                unsigned flags, int device, void* stream);
+/* dout [B,3d] tokens' dtype.  Writes dpatch/dcls and all sig_sim_param_grads. */
+int sig_sim_bwd(const sig_tokens* tok, const sig_sim_params* p, const void* dout,
+                const sig_token_grads* dtok, const sig_sim_param_grads* dp,
+                void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
+
+/* ---- TokenSelection (useA.py:50-325) ----------------------------------- */
+/* which: 1 = intra_modal_token_selection (:50), 2 = inter_modal_token_selection (:98),
+ * 3 = forward's union (+ keep_ratio) (:223-314).  masks fp32 [3,B,L].
+ * selected (optional, NULL to skip): three [B,L,d] contiguous maps in tokens' dtype,
+ * laid out [3,B,L,d] = patches * mask (:318-320). */
+int sig_sim_select_fwd(const sig_tokens* tok, const sig_sim_params* p, int which,
+                       int k1, int k2, int max_keep, float* masks, void* selected,
+                       void* ctx, size_t ctx_bytes, int device, void* stream);
+/* Test seam: selection from caller-supplied fp32 scores, ties -> lowest index.
+ * intra [3,B,L] (softmax scores, useA.py:72-74), inter [3,B,2L] (D_m, useA.py:136-151),
+ * raw [3,B,L] (cls.patch, only read when max_keep >= 0).  masks fp32 [3,B,L] as `which`. */
+int sig_sim_select_from_scores(const float* intra, const float* inter, const float* raw,
+                               int B, int L, int which, int k1, int k2, int max_keep,
+                               float* masks, int device, void* stream);
+/* dpatch = dselected * mask (backward of useA.py:318-320); dselected [3,B,L,d] contiguous */
+int sig_mask_mul_bwd(const void* dselected, const float* masks, int dtype, int B, int L, int d,
+                     const sig_token_grads* dtok, int device, void* stream);
+
+/* ---- ModalInteractive.forward (useA.py:364-411) on arbitrary K/V tokens - */
+/* tok->patch = the three "selected" maps, tok->cls = CLS tokens; masks may be NULL
+ * (all tokens participate) or fp32 [3,B,L] (token rows are multiplied by it). */
+int sig_sim_attn_fwd(const sig_tokens* tok, const sig_sim_params* p, const float* masks,
+                     void* out, void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
+int sig_sim_attn_bwd(const sig_tokens* tok, const sig_sim_params* p, const float* masks,
+                     const void* dout, const sig_token_grads* dtok, const sig_sim_param_grads* dp,
+                     void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
+
+/* ---- AlignmentM.forward (useB.py:169-190) ------------------------------ */
+/* losses[0] = Cls_Align (GAM, useB.py:76-126), losses[1] = patch_Align (LAM, useB.py:128-167;
+ * skipped when do_lam == 0, i.e. stage == "CLS").  grid h x w with h*w == L. */
+int sig_align_fwd(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam,
+                  float* losses, void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
+/* dlosses: device fp32 [2] (upstream gradients of the two scalars). */
+int sig_align_bwd(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam,
+                  const float* dlosses, const sig_token_grads* dtok, const sig_align_param_grads* dp,
+                  void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
+
+/* ---- DA_sample.forward (DAS.py:107-165), one modality ------------------- */
+/* x: channels-last [B,h*w,d] view (stride_b, stride_l elements); params index m of `p`.
+ * sampled: fp32 [B,Hk*Wk,d] contiguous (Hk=h/4, Wk=w/4). */
+int sig_das_fwd(const void* x, int64_t stride_b, int64_t stride_l, int dtype, int B, int h, int w, int d,
+                const sig_align_params* p, int m, float* sampled,
+                void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
+/* dsampled fp32 [B,Hk*Wk,d]; dx: same geometry/dtype as x (overwritten); parameter grads index m of dp */
+int sig_das_bwd(const void* x, int64_t stride_b, int64_t stride_l, int dtype, int B, int h, int w, int d,
+                const sig_align_params* p, int m, const float* dsampled, void* dx,
+                const sig_align_param_grads* dp, void* ctx, size_t ctx_bytes,
+                unsigned flags, int device, void* stream);
+
+/* ---- utils/volume.py:14 volume_computation3 ---------------------------- */
+/* l [B1,d], v,a [B2,d] fp32 contiguous -> vol [B1,B2] fp32 = sqrt|det Gram(l_i, v_j, a_j)| */
+size_t sig_volume3_ws_bytes(int B1, int B2);   /* scratch for either call */
+int sig_volume3_fwd(const float* l, const float* v, const float* a, int B1, int B2, int d,
+                    float* vol, void* ws, size_t ws_bytes, int device, void* stream);
+int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int B2, int d,
+                    const float* dvol, float* dl, float* dv, float* da,
+                    void* ws, size_t ws_bytes, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGNAL_B200_H */

@@ -1,0 +1,158 @@
+// extern "C" surface of libsignal_b200.so (see include/signal_b200.h).
+#include "align.h"
+#include "common.cuh"
+#include "sim.h"
+
+namespace {
+struct DeviceGuard {
+  int prev = -1;
+  int rc = 0;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      cudaError_t e = cudaSetDevice(dev);
+      if (e != cudaSuccess) rc = (int)e;
+    }
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
+#define SIG_ENTER(device)          \
+  DeviceGuard guard__(device);     \
+  if (guard__.rc) return guard__.rc; \
+  cudaGetLastError();
+
+extern "C" {
+
+int sig_version(void) { return SIG_ABI_VERSION; }
+
+const char* sig_error_string(int code) {
+  switch (code) {
+    case SIG_OK: return "ok";
+    case SIG_ERR_NULL: return "signal_b200: a required pointer is NULL";
+    case SIG_ERR_SHAPE: return "signal_b200: unsupported shape (B, L<=128, d%64==0, grid h*w==L with h,w multiples of 4 and >= 8, k >= 1)";
+    case SIG_ERR_DTYPE: return "signal_b200: unknown dtype (SIG_F32 or SIG_BF16)";
+    case SIG_ERR_ALIGN: return "signal_b200: pointer or stride not 16-byte aligned";
+    case SIG_ERR_WORKSPACE: return "signal_b200: ctx/workspace buffer too small (see sig_ctx_bytes)";
+    case SIG_ERR_ARCH: return "signal_b200: device is not sm_100";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "signal_b200: unknown error";
+}
+
+size_t sig_ctx_bytes(int kind, int B, int L, int d) {
+  if (B < 1 || L < 1 || L > sig::kMaxL || d < 64 || d % 64) return 0;
+  switch (kind) {
+    case SIG_CTX_SIM:
+    case SIG_CTX_SELECT: return sig::sim_ctx_bytes(B, L, d);
+    case SIG_CTX_ALIGN: return sig::align_ctx_bytes(B, L, d);
+    case SIG_CTX_DAS: return sig::das_ctx_bytes(B, L, d);
+    default: return 0;
+  }
+}
+
+int sig_sim_fwd(const sig_tokens* tok, const sig_sim_params* p, int k1, int k2, int max_keep, void* out, float* masks, void* ctx,
+                size_t ctx_bytes, unsigned flags, int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::sim_forward(tok, p, true, nullptr, k1, k2, max_keep, out, masks, ctx, ctx_bytes, flags, (cudaStream_t)stream);
+}
+
+int sig_sim_bwd(const sig_tokens* tok, const sig_sim_params* p, const void* dout, const sig_token_grads* dtok,
+                const sig_sim_param_grads* dp, void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::sim_backward(tok, p, true, dout, dtok, dp, ctx, ctx_bytes, flags, (cudaStream_t)stream);
+}
+
+int sig_sim_select_fwd(const sig_tokens* tok, const sig_sim_params* p, int which, int k1, int k2, int max_keep, float* masks,
+                       void* selected, void* ctx, size_t ctx_bytes, int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::sim_select(tok, p, which, k1, k2, max_keep, masks, selected, ctx, ctx_bytes, (cudaStream_t)stream);
+}
+
+int sig_sim_select_from_scores(const float* intra, const float* inter, const float* raw, int B, int L, int which, int k1, int k2,
+                               int max_keep, float* masks, int device, void* stream) {
+  SIG_ENTER(device);
+  if (!masks) return SIG_ERR_NULL;
+  if (which < 1 || which > 3 || B < 1 || L < 1 || L > sig::kMaxL || k1 < 1 || k2 < 1 || max_keep > L) return SIG_ERR_SHAPE;
+  if ((which & 1) && !intra) return SIG_ERR_NULL;
+  if ((which & 2) && !inter) return SIG_ERR_NULL;
+  if (which == 3 && max_keep >= 0 && !raw) return SIG_ERR_NULL;
+  return sig::select_from_scores(intra, inter, raw, B, L, which, k1, k2, max_keep, masks, (cudaStream_t)stream);
+}
+
+int sig_mask_mul_bwd(const void* dselected, const float* masks, int dtype, int B, int L, int d, const sig_token_grads* dtok,
+                     int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::mask_mul_bwd(dselected, masks, dtype, B, L, d, dtok, (cudaStream_t)stream);
+}
+
+int sig_sim_attn_fwd(const sig_tokens* tok, const sig_sim_params* p, const float* masks, void* out, void* ctx, size_t ctx_bytes,
+                     unsigned flags, int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::sim_forward(tok, p, false, masks, 0, 0, -1, out, nullptr, ctx, ctx_bytes, flags, (cudaStream_t)stream);
+}
+
+int sig_sim_attn_bwd(const sig_tokens* tok, const sig_sim_params* p, const float* masks, const void* dout,
+                     const sig_token_grads* dtok, const sig_sim_param_grads* dp, void* ctx, size_t ctx_bytes, unsigned flags,
+                     int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::sim_backward(tok, p, masks != nullptr, dout, dtok, dp, ctx, ctx_bytes, flags, (cudaStream_t)stream);
+}
+
+int sig_align_fwd(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
+                  size_t ctx_bytes, unsigned flags, int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::align_forward(tok, p, h, w, do_lam, losses, ctx, ctx_bytes, flags, (cudaStream_t)stream);
+}
+
+int sig_align_bwd(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, const float* dlosses,
+                  const sig_token_grads* dtok, const sig_align_param_grads* dp, void* ctx, size_t ctx_bytes, unsigned flags,
+                  int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::align_backward(tok, p, h, w, do_lam, dlosses, dtok, dp, ctx, ctx_bytes, flags, (cudaStream_t)stream);
+}
+
+int sig_das_fwd(const void* x, int64_t stride_b, int64_t stride_l, int dtype, int B, int h, int w, int d,
+                const sig_align_params* p, int m, float* sampled, void* ctx, size_t ctx_bytes, unsigned flags, int device,
+                void* stream) {
+  SIG_ENTER(device);
+  return sig::das_forward(x, stride_b, stride_l, dtype, B, h, w, d, p, m, sampled, ctx, ctx_bytes, flags, (cudaStream_t)stream);
+}
+
+int sig_das_bwd(const void* x, int64_t stride_b, int64_t stride_l, int dtype, int B, int h, int w, int d,
+                const sig_align_params* p, int m, const float* dsampled, void* dx, const sig_align_param_grads* dp, void* ctx,
+                size_t ctx_bytes, unsigned flags, int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::das_backward(x, stride_b, stride_l, dtype, B, h, w, d, p, m, dsampled, dx, dp, ctx, ctx_bytes, flags,
+                           (cudaStream_t)stream);
+}
+
+size_t sig_volume3_ws_bytes(int B1, int B2) {
+  if (B1 < 1 || B2 < 1) return 0;
+  return sig::volume_ws_floats(B1, B2) * sizeof(float);
+}
+
+int sig_volume3_fwd(const float* l, const float* v, const float* a, int B1, int B2, int d, float* vol, void* ws, size_t ws_bytes,
+                    int device, void* stream) {
+  SIG_ENTER(device);
+  if (!l || !v || !a || !vol || !ws) return SIG_ERR_NULL;
+  if (B1 < 1 || B2 < 1 || d < 1) return SIG_ERR_SHAPE;
+  if (ws_bytes < sig_volume3_ws_bytes(B1, B2)) return SIG_ERR_WORKSPACE;
+  return sig::volume3_forward(l, v, a, B1, B2, d, vol, static_cast<float*>(ws), (cudaStream_t)stream);
+}
+
+int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int B2, int d, const float* dvol, float* dl, float* dv,
+                    float* da, void* ws, size_t ws_bytes, int device, void* stream) {
+  SIG_ENTER(device);
+  if (!l || !v || !a || !dvol || !dl || !dv || !da || !ws) return SIG_ERR_NULL;
+  if (B1 < 1 || B2 < 1 || d < 1) return SIG_ERR_SHAPE;
+  if (ws_bytes < sig_volume3_ws_bytes(B1, B2)) return SIG_ERR_WORKSPACE;
+  return sig::volume3_backward(l, v, a, B1, B2, d, dvol, dl, dv, da, static_cast<float*>(ws), (cudaStream_t)stream);
+}
+
+}  // extern "C"

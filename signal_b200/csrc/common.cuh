@@ -1,0 +1,172 @@
+// Shared device/host helpers for libsignal_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "signal_b200.h"
+
+#define SIG_CHECK_LAUNCH()                         \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return (int)e__;       \
+  } while (0)
+
+#define SIG_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+namespace sig {
+
+constexpr int kHeads = 8;        // useA.py:449
+constexpr int kMaxL = 128;       // patch tokens per modality (make_model.py:67)
+constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default
+constexpr float kLabelSmooth = 0.1f;  // useB.py:121-122
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- scalar conversions ---------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8 consecutive channels -> fp32 registers (16 B load for bf16, 2 x 16 B for fp32).
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 raw;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+// ---- math -------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) {  // nn.GELU() erf form
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {  // Phi(x) + x phi(x)
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ---- reductions ---------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum; `scratch` holds >= 33 floats; result broadcast to all threads.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // scratch may still be read from a previous call
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < nw ? scratch[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < nw ? scratch[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// ---- host-side argument checks ---------------------------------------------------
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t elem_size(int dtype) { return dtype == SIG_BF16 ? 2 : 4; }
+
+inline int check_tokens(const sig_tokens* t, bool need_cls) {
+  if (!t) return SIG_ERR_NULL;
+  if (t->dtype != SIG_F32 && t->dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  if (t->B < 1 || t->B > 4096 || t->L < 1 || t->L > kMaxL || t->d < 64 || t->d > 1024 || (t->d % 64) != 0)
+    return SIG_ERR_SHAPE;
+  const size_t es = elem_size(t->dtype);
+  for (int m = 0; m < 3; ++m) {
+    if (!t->patch[m]) return SIG_ERR_NULL;
+    if (!aligned16(t->patch[m]) || (t->patch_stride_b[m] * es) % 16 || (t->patch_stride_l[m] * es) % 16)
+      return SIG_ERR_ALIGN;
+    if (need_cls) {
+      if (!t->cls[m]) return SIG_ERR_NULL;
+      if (!aligned16(t->cls[m]) || (t->cls_stride_b[m] * es) % 16) return SIG_ERR_ALIGN;
+    }
+  }
+  return 0;
+}
+
+inline int check_token_grads(const sig_token_grads* g, int dtype, bool need_cls) {
+  if (!g) return SIG_ERR_NULL;
+  const size_t es = elem_size(dtype);
+  for (int m = 0; m < 3; ++m) {
+    if (!g->dpatch[m]) return SIG_ERR_NULL;
+    if (!aligned16(g->dpatch[m]) || (g->patch_stride_b[m] * es) % 16 || (g->patch_stride_l[m] * es) % 16)
+      return SIG_ERR_ALIGN;
+    if (need_cls) {
+      if (!g->dcls[m]) return SIG_ERR_NULL;
+    }
+    if (g->dcls[m] && (!aligned16(g->dcls[m]) || (g->cls_stride_b[m] * es) % 16)) return SIG_ERR_ALIGN;
+  }
+  return 0;
+}
+
+// Bump allocator over the caller's ctx buffer (256 B aligned sub-buffers).
+struct Arena {
+  char* base;
+  size_t off;
+  explicit Arena(void* p) : base(static_cast<char*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off += (n * sizeof(T) + 255) & ~size_t(255);
+    return r;
+  }
+};
+
+}  // namespace sig

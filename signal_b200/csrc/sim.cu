@@ -1,0 +1,874 @@
+// SIM -- Select_Interactive_Module (modeling/AddModule/useA.py), fp32 SIMT path.
+//
+// Math (validated against the live reference):
+//  selection  q = W_q cls + b_q ; qt = W_k^T q ; c = q.b_k ;
+//             S[m,j] = softmax_j((qt_m . x_j + c_m)/sqrt(d)) over the 3L tokens   (useA.py:116-129)
+//             intra  = softmax_l(cls_m . x_l / sqrt(d))                            (useA.py:72-74)
+//             rank-select (ties -> lowest index), scatter to the other modalities, union (useA.py:155-251)
+//  attention  per head h: q_h = (W_q^h cls + b_q^h), qt_h = W_k^hT q_h / sqrt(hd), c_h = q_h.b_k^h / sqrt(hd)
+//             s_j = mask_j ? qt_h . x_j + c_h : c_h ; p = softmax_j(s)
+//             xbar_h = sum_j p_j mask_j x_j ; o_h = W_v^h xbar_h + b_v^h            (useA.py:383-388)
+//             out = LN2(y1 + FFN(y1)), y1 = LN1(cls + W_o o + b_o)                  (useA.py:393-408)
+// i.e. the K/V projections are applied to 24 effective queries per sample instead of 384 tokens.
+#include "common.cuh"
+#include "sim.h"
+#include "simt_ops.cuh"
+
+namespace sig {
+
+// ---------------------------------------------------------------------------------------------
+// token conversion: strided T views -> contiguous fp32  Xf[3][B][L][d], clsf[B][3][d]
+// ---------------------------------------------------------------------------------------------
+struct TokPtrs {
+  const void* patch[3];
+  const void* cls[3];
+  int64_t psb[3], psl[3], csb[3];
+};
+
+template <typename T>
+static __global__ void convert_tokens_kernel(TokPtrs tp, int B, int L, int d, float* __restrict__ Xf, float* __restrict__ clsf) {
+  const int m = blockIdx.y;
+  const int64_t row = blockIdx.x;  // [0, B*L) patches, [B*L, B*L+B) cls
+  const T* src;
+  float* dst;
+  if (row < (int64_t)B * L) {
+    const int b = (int)(row / L), l = (int)(row % L);
+    src = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m] + l * tp.psl[m];
+    dst = Xf + (((int64_t)m * B + b) * L + l) * d;
+  } else {
+    if (!clsf || !tp.cls[m]) return;
+    const int b = (int)(row - (int64_t)B * L);
+    src = static_cast<const T*>(tp.cls[m]) + b * tp.csb[m];
+    dst = clsf + ((int64_t)b * 3 + m) * d;
+  }
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
+    float v[8];
+    load8(src + c, v);
+    store8(dst + c, v);
+  }
+}
+
+int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s) {
+  TokPtrs tp;
+  for (int m = 0; m < 3; ++m) {
+    tp.patch[m] = t->patch[m]; tp.cls[m] = t->cls[m];
+    tp.psb[m] = t->patch_stride_b[m]; tp.psl[m] = t->patch_stride_l[m]; tp.csb[m] = t->cls_stride_b[m];
+  }
+  dim3 grid((unsigned)((int64_t)t->B * t->L + t->B), 3);
+  const int threads = t->d / 8 >= 128 ? 128 : 64;
+  if (t->dtype == SIG_BF16)
+    convert_tokens_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(tp, t->B, t->L, t->d, Xf, clsf);
+  else
+    convert_tokens_kernel<float><<<grid, threads, 0, s>>>(tp, t->B, t->L, t->d, Xf, clsf);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// selection scores
+// ---------------------------------------------------------------------------------------------
+// grid (ceil(L/32), 3, B), 256 threads: 8 warps x 4 tokens.  Four dot products per token:
+// the three folded inter-modal queries and the token's own CLS.
+static __global__ void __launch_bounds__(256) sim_scores_kernel(const float* __restrict__ Xf, const float* __restrict__ clsf,
+                                                                const float* __restrict__ qtsel, const float* __restrict__ csel,
+                                                                int B, int L, int d, float* __restrict__ sel_logits,
+                                                                float* __restrict__ intra_raw) {
+  extern __shared__ float qv[];  // [4][d]
+  const int m = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 4 * d; i += blockDim.x) {
+    const int r = i / d, c = i % d;
+    qv[i] = r < 3 ? qtsel[((int64_t)b * 3 + r) * d + c] : clsf[((int64_t)b * 3 + m) * d + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float inv = rsqrtf((float)d);
+  for (int i = 0; i < 4; ++i) {
+    const int l = blockIdx.x * 32 + w * 4 + i;
+    if (l >= L) break;
+    const float* x = Xf + (((int64_t)m * B + b) * L + l) * d;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + c);
+      const float4 q0 = *reinterpret_cast<const float4*>(qv + c);
+      const float4 q1 = *reinterpret_cast<const float4*>(qv + d + c);
+      const float4 q2 = *reinterpret_cast<const float4*>(qv + 2 * d + c);
+      const float4 q3 = *reinterpret_cast<const float4*>(qv + 3 * d + c);
+      a0 += xv.x * q0.x + xv.y * q0.y + xv.z * q0.z + xv.w * q0.w;
+      a1 += xv.x * q1.x + xv.y * q1.y + xv.z * q1.z + xv.w * q1.w;
+      a2 += xv.x * q2.x + xv.y * q2.y + xv.z * q2.z + xv.w * q2.w;
+      a3 += xv.x * q3.x + xv.y * q3.y + xv.z * q3.z + xv.w * q3.w;
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane == 0) {
+      const int64_t base = (int64_t)b * 3 * 3 * L + (int64_t)m * L + l;
+      sel_logits[base] = (a0 + csel[b * 3 + 0]) * inv;
+      sel_logits[base + 3 * L] = (a1 + csel[b * 3 + 1]) * inv;
+      sel_logits[base + 6 * L] = (a2 + csel[b * 3 + 2]) * inv;
+      intra_raw[((int64_t)b * 3 + m) * L + l] = a3;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank-select (shared by the fused path and the from-scores test seam)
+// ---------------------------------------------------------------------------------------------
+// intra [3][L], inter [3][2L] (D_m of useA.py:136-151), raw [3][L]; all in shared memory.
+// mask_out [3][L] (shared).  which: 1 intra, 2 inter, 3 union (+ keep_ratio when max_keep >= 0).
+// rank_i = #{j : s_j > s_i or (s_j == s_i and j < i)}; selected iff rank_i < k.
+static __device__ void select_masks(const float* intra, const float* inter, const float* raw, int L, int which, int k1,
+                                    int k2, int max_keep, unsigned char* sel_inter /*[3][2L]*/, unsigned char* sel_intra /*[3][L]*/,
+                                    float* mask_out /*[3][L]*/) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int kk1 = min(k1, L), kk2 = min(k2, 2 * L);
+  for (int it = tid; it < 3 * L; it += nt) {
+    const int m = it / L, i = it % L;
+    const float* row = intra + m * L;
+    const float si = row[i];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const float sj = row[j];
+      rank += (sj > si) || (sj == si && j < i);
+    }
+    sel_intra[it] = rank < kk1;
+  }
+  for (int it = tid; it < 6 * L; it += nt) {
+    const int q = it / (2 * L), i = it % (2 * L);
+    const float* row = inter + q * 2 * L;
+    const float si = row[i];
+    int rank = 0;
+    for (int j = 0; j < 2 * L; ++j) {
+      const float sj = row[j];
+      rank += (sj > si) || (sj == si && j < i);
+    }
+    sel_inter[it] = rank < kk2;
+  }
+  __syncthreads();
+  // scatter back (useA.py:166-218): query RGB ranks [NIR|TIR], NIR ranks [RGB|TIR], TIR ranks [RGB|NIR]
+  for (int it = tid; it < 3 * L; it += nt) {
+    const int m = it / L, l = it % L;
+    bool c;
+    if (m == 0) c = sel_inter[1 * 2 * L + l] | sel_inter[2 * 2 * L + l];
+    else if (m == 1) c = sel_inter[0 * 2 * L + l] | sel_inter[2 * 2 * L + L + l];
+    else c = sel_inter[0 * 2 * L + L + l] | sel_inter[1 * 2 * L + L + l];
+    const bool s = sel_intra[it];
+    const bool r = which == 1 ? s : (which == 2 ? c : (s | c));
+    mask_out[it] = r ? 1.f : 0.f;
+  }
+  __syncthreads();
+  if (which == 3 && max_keep >= 0) {
+    // useA.py:254-314: order by (selected desc, raw desc, index asc), keep the first max_keep
+    unsigned char* keep = sel_intra;  // reuse
+    for (int it = tid; it < 3 * L; it += nt) {
+      const int m = it / L, i = it % L;
+      const float* mk = mask_out + m * L;
+      const float* rw = raw + m * L;
+      const float mi = mk[i], ri = rw[i];
+      int rank = 0;
+      for (int j = 0; j < L; ++j) {
+        const float mj = mk[j], rj = rw[j];
+        rank += (mj > mi) || (mj == mi && (rj > ri || (rj == ri && j < i)));
+      }
+      keep[it] = rank < max_keep;
+    }
+    __syncthreads();
+    for (int it = tid; it < 3 * L; it += nt) mask_out[it] = keep[it] ? 1.f : 0.f;
+    __syncthreads();
+  }
+}
+
+// grid B, 256 threads.  Softmax the logits into the reference-defined scores, then rank-select.
+static __global__ void __launch_bounds__(256) sim_select_kernel(const float* __restrict__ sel_logits, const float* __restrict__ intra_raw,
+                                                                int B, int L, int d, int which, int k1, int k2, int max_keep,
+                                                                float* __restrict__ masks, float* __restrict__ masks2) {
+  __shared__ float s_inter[3 * 2 * kMaxL], s_intra[3 * kMaxL], s_raw[3 * kMaxL], s_mask[3 * kMaxL];
+  __shared__ float s_full[3 * kMaxL];
+  __shared__ unsigned char f_inter[3 * 2 * kMaxL], f_intra[3 * kMaxL];
+  __shared__ float scratch[33];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float inv = rsqrtf((float)d);
+  for (int q = 0; q < 3; ++q) {
+    // softmax over all 3L keys of query q (useA.py:129)
+    const float* lg = sel_logits + ((int64_t)b * 3 + q) * 3 * L;
+    float mx = -INFINITY;
+    for (int j = tid; j < 3 * L; j += blockDim.x) mx = fmaxf(mx, lg[j]);
+    mx = block_max(mx, scratch);
+    float sm = 0.f;
+    for (int j = tid; j < 3 * L; j += blockDim.x) {
+      const float e = expf(lg[j] - mx);
+      s_full[j] = e;
+      sm += e;
+    }
+    sm = block_sum(sm, scratch);
+    // D_q: drop the query's own modality, keep order (useA.py:136-151)
+    for (int j = tid; j < 3 * L; j += blockDim.x) {
+      const int mj = j / L, l = j % L;
+      if (mj == q) continue;
+      const int slot = (mj > q ? mj - 1 : mj) * L + l;
+      s_inter[q * 2 * L + slot] = s_full[j] / sm;
+    }
+    __syncthreads();
+  }
+  for (int m = 0; m < 3; ++m) {
+    const float* rw = intra_raw + ((int64_t)b * 3 + m) * L;
+    float mx = -INFINITY;
+    for (int l = tid; l < L; l += blockDim.x) mx = fmaxf(mx, rw[l] * inv);
+    mx = block_max(mx, scratch);
+    float sm = 0.f;
+    for (int l = tid; l < L; l += blockDim.x) {
+      const float e = expf(rw[l] * inv - mx);
+      s_intra[m * L + l] = e;
+      s_raw[m * L + l] = rw[l];
+      sm += e;
+    }
+    sm = block_sum(sm, scratch);
+    for (int l = tid; l < L; l += blockDim.x) s_intra[m * L + l] /= sm;
+    __syncthreads();
+  }
+  select_masks(s_intra, s_inter, s_raw, L, which, k1, k2, max_keep, f_inter, f_intra, s_mask);
+  for (int it = tid; it < 3 * L; it += blockDim.x) {
+    const int m = it / L, l = it % L;
+    const float v = s_mask[it];
+    masks[((int64_t)m * B + b) * L + l] = v;
+    if (masks2) masks2[((int64_t)m * B + b) * L + l] = v;
+  }
+}
+
+static __global__ void __launch_bounds__(256) select_from_scores_kernel(const float* __restrict__ intra, const float* __restrict__ inter,
+                                                                        const float* __restrict__ raw, int B, int L, int which, int k1,
+                                                                        int k2, int max_keep, float* __restrict__ masks) {
+  __shared__ float s_inter[3 * 2 * kMaxL], s_intra[3 * kMaxL], s_raw[3 * kMaxL], s_mask[3 * kMaxL];
+  __shared__ unsigned char f_inter[3 * 2 * kMaxL], f_intra[3 * kMaxL];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int it = tid; it < 3 * L; it += blockDim.x) {
+    const int m = it / L, l = it % L;
+    s_intra[it] = intra ? intra[((int64_t)m * B + b) * L + l] : 0.f;
+    s_raw[it] = raw ? raw[((int64_t)m * B + b) * L + l] : 0.f;
+  }
+  for (int it = tid; it < 6 * L; it += blockDim.x) {
+    const int q = it / (2 * L), i = it % (2 * L);
+    s_inter[it] = inter ? inter[((int64_t)q * B + b) * 2 * L + i] : 0.f;
+  }
+  __syncthreads();
+  select_masks(s_intra, s_inter, s_raw, L, which, k1, k2, max_keep, f_inter, f_intra, s_mask);
+  for (int it = tid; it < 3 * L; it += blockDim.x) {
+    const int m = it / L, l = it % L;
+    masks[((int64_t)m * B + b) * L + l] = s_mask[it];
+  }
+}
+
+int select_from_scores(const float* intra, const float* inter, const float* raw, int B, int L, int which, int k1, int k2,
+                       int max_keep, float* masks, cudaStream_t s) {
+  select_from_scores_kernel<<<B, 256, 0, s>>>(intra, inter, raw, B, L, which, k1, k2, max_keep, masks);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+// selected[m][b][l][:] = x * mask  (useA.py:318-320), written contiguous in the token dtype
+template <typename T>
+static __global__ void mask_mul_kernel(const float* __restrict__ Xf, const float* __restrict__ masks, int64_t rows, int d,
+                                       T* __restrict__ selected) {
+  const int64_t row = blockIdx.x;
+  const float mk = masks[row];
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
+    float v[8];
+    load8(Xf + row * d + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= mk;
+    store8(selected + row * d + c, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention over the (masked) tokens, 24 effective queries per sample
+// ---------------------------------------------------------------------------------------------
+// effective query index e = q*8 + h (q = CLS modality, h = head).  A CTA handles heads
+// {2hp, 2hp+1} x 3 queries: local i = hl*3 + q.
+__device__ __forceinline__ int eff_index(int hp, int i) { return (i % 3) * 8 + 2 * hp + i / 3; }
+
+// grid (B, 4), 256 threads, dyn smem: qs[6][d] + lg[6][3L] + msk[3L]
+static __global__ void __launch_bounds__(256) sim_attn_fwd_kernel(const float* __restrict__ Xf, const float* __restrict__ maskf,
+                                                                  const float* __restrict__ qt, const float* __restrict__ cq, int B,
+                                                                  int L, int d, float* __restrict__ xbar, float* __restrict__ amax,
+                                                                  float* __restrict__ asum) {
+  extern __shared__ float smem[];
+  float* qs = smem;               // [6][d]
+  float* lg = qs + 6 * d;         // [6][3L]
+  float* msk = lg + 6 * 3 * L;    // [3L]
+  const int b = blockIdx.x, hp = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int T3 = 3 * L;
+  for (int i = tid; i < 6 * d; i += blockDim.x) {
+    const int r = i / d, c = i % d;
+    qs[i] = qt[((int64_t)b * 24 + eff_index(hp, r)) * d + c];
+  }
+  for (int j = tid; j < T3; j += blockDim.x) {
+    const int m = j / L, l = j % L;
+    msk[j] = maskf ? maskf[((int64_t)m * B + b) * L + l] : 1.f;
+  }
+  __syncthreads();
+  // phase A: logits
+  for (int j = w; j < T3; j += 8) {
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (msk[j] != 0.f) {
+      const int m = j / L, l = j % L;
+      const float* x = Xf + (((int64_t)m * B + b) * L + l) * d;
+      for (int c = lane * 4; c < d; c += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + c);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float4 q = *reinterpret_cast<const float4*>(qs + i * d + c);
+          acc[i] += xv.x * q.x + xv.y * q.y + xv.z * q.z + xv.w * q.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) acc[i] = warp_sum(acc[i]) * msk[j];
+    }
+    if (lane < 6) {
+      float v = acc[0];
+#pragma unroll
+      for (int i = 1; i < 6; ++i) v = lane == i ? acc[i] : v;
+      lg[lane * T3 + j] = v + cq[(int64_t)b * 24 + eff_index(hp, lane)];
+    }
+  }
+  __syncthreads();
+  // phase B: softmax per effective query (one warp per row)
+  if (w < 6) {
+    float* row = lg + w * T3;
+    float mx = -INFINITY;
+    for (int j = lane; j < T3; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sm = 0.f;
+    for (int j = lane; j < T3; j += 32) {
+      const float e = expf(row[j] - mx);
+      row[j] = e;
+      sm += e;
+    }
+    sm = warp_sum(sm);
+    const float r = 1.f / sm;
+    for (int j = lane; j < T3; j += 32) row[j] *= r;
+    if (lane == 0) {
+      amax[(int64_t)b * 24 + eff_index(hp, w)] = mx;
+      asum[(int64_t)b * 24 + eff_index(hp, w)] = sm;
+    }
+  }
+  __syncthreads();
+  // phase C: xbar = sum_j p_j mask_j x_j  (thread per channel)
+  for (int c = tid; c < d; c += blockDim.x) {
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < T3; ++j) {
+      const float mk = msk[j];
+      if (mk == 0.f) continue;
+      const int m = j / L, l = j % L;
+      const float x = Xf[(((int64_t)m * B + b) * L + l) * d + c] * mk;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) acc[i] = fmaf(lg[i * T3 + j], x, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xbar[((int64_t)b * 24 + eff_index(hp, i)) * d + c] = acc[i];
+  }
+}
+
+// grid B, 256 threads; loops over the four head pairs.
+// dyn smem: qs[6][d] + dxs[6][d] + P[6][3L] + dS[6][3L] + msk[3L] + delta[8]
+static __global__ void __launch_bounds__(256) sim_attn_bwd_kernel(const float* __restrict__ Xf, const float* __restrict__ maskf,
+                                                                  const float* __restrict__ qt, const float* __restrict__ cq,
+                                                                  const float* __restrict__ xbar, const float* __restrict__ amax,
+                                                                  const float* __restrict__ asum, const float* __restrict__ dxbar,
+                                                                  int B, int L, int d, float* __restrict__ dqt, float* __restrict__ dXf) {
+  extern __shared__ float smem[];
+  const int T3 = 3 * L;
+  float* qs = smem;
+  float* dxs = qs + 6 * d;
+  float* P = dxs + 6 * d;
+  float* dS = P + 6 * T3;
+  float* msk = dS + 6 * T3;
+  float* delta = msk + T3;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int j = tid; j < T3; j += blockDim.x) {
+    const int m = j / L, l = j % L;
+    msk[j] = maskf ? maskf[((int64_t)m * B + b) * L + l] : 1.f;
+  }
+  for (int hp = 0; hp < 4; ++hp) {
+    __syncthreads();
+    for (int i = tid; i < 6 * d; i += blockDim.x) {
+      const int r = i / d, c = i % d;
+      const int64_t e = (int64_t)b * 24 + eff_index(hp, r);
+      qs[i] = qt[e * d + c];
+      dxs[i] = dxbar[e * d + c];
+    }
+    __syncthreads();
+    if (w < 6) {  // delta_i = dxbar_i . xbar_i
+      const int64_t e = (int64_t)b * 24 + eff_index(hp, w);
+      float a = 0.f;
+      for (int c = lane; c < d; c += 32) a += dxs[w * d + c] * xbar[e * d + c];
+      a = warp_sum(a);
+      if (lane == 0) delta[w] = a;
+    }
+    __syncthreads();
+    // phase A: p and dS per token
+    for (int j = w; j < T3; j += 8) {
+      float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float mk = msk[j];
+      if (mk != 0.f) {
+        const int m = j / L, l = j % L;
+        const float* x = Xf + (((int64_t)m * B + b) * L + l) * d;
+        for (int c = lane * 4; c < d; c += 128) {
+          const float4 xv = *reinterpret_cast<const float4*>(x + c);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const float4 q = *reinterpret_cast<const float4*>(qs + i * d + c);
+            const float4 g = *reinterpret_cast<const float4*>(dxs + i * d + c);
+            s[i] += xv.x * q.x + xv.y * q.y + xv.z * q.z + xv.w * q.w;
+            dp[i] += xv.x * g.x + xv.y * g.y + xv.z * g.z + xv.w * g.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          s[i] = warp_sum(s[i]) * mk;
+          dp[i] = warp_sum(dp[i]) * mk;
+        }
+      }
+      if (lane < 6) {
+        float sv = s[0], dv = dp[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) {
+          sv = lane == i ? s[i] : sv;
+          dv = lane == i ? dp[i] : dv;
+        }
+        const int64_t e = (int64_t)b * 24 + eff_index(hp, lane);
+        const float p = expf(sv + cq[e] - amax[e]) / asum[e];
+        P[lane * T3 + j] = p;
+        dS[lane * T3 + j] = p * (dv - delta[lane]);
+      }
+    }
+    __syncthreads();
+    // phase C1: dx_j = mask_j * sum_i (p_ij dxbar_i + dS_ij qt_i), accumulated over head pairs
+    for (int j = w; j < T3; j += 8) {
+      const int m = j / L, l = j % L;
+      float* dx = dXf + (((int64_t)m * B + b) * L + l) * d;
+      const float mk = msk[j];
+      for (int c = lane * 4; c < d; c += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mk != 0.f) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const float p = P[i * T3 + j], ds = dS[i * T3 + j];
+            const float4 q = *reinterpret_cast<const float4*>(qs + i * d + c);
+            const float4 g = *reinterpret_cast<const float4*>(dxs + i * d + c);
+            acc.x += p * g.x + ds * q.x; acc.y += p * g.y + ds * q.y;
+            acc.z += p * g.z + ds * q.z; acc.w += p * g.w + ds * q.w;
+          }
+          acc.x *= mk; acc.y *= mk; acc.z *= mk; acc.w *= mk;
+          if (hp > 0) {
+            const float4 old = *reinterpret_cast<const float4*>(dx + c);
+            acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+          }
+        }
+        if (mk != 0.f || hp == 0) *reinterpret_cast<float4*>(dx + c) = acc;
+      }
+    }
+    // phase C2: dqt_i = sum_j dS_ij mask_j x_j
+    for (int c = tid; c < d; c += blockDim.x) {
+      float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < T3; ++j) {
+        const float mk = msk[j];
+        if (mk == 0.f) continue;
+        const int m = j / L, l = j % L;
+        const float x = Xf[(((int64_t)m * B + b) * L + l) * d + c] * mk;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc[i] = fmaf(dS[i * T3 + j], x, acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) dqt[((int64_t)b * 24 + eff_index(hp, i)) * d + c] = acc[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient writers (fp32 scratch -> strided token-dtype destinations)
+// ---------------------------------------------------------------------------------------------
+struct GradPtrs {
+  void* dpatch[3];
+  void* dcls[3];
+  int64_t psb[3], psl[3], csb[3];
+  int accumulate;
+};
+
+// grid (B*L + B, 3).  dXf [3][B][L][d] (may be NULL -> zeros), dclsf [B][3][d] (may be NULL -> zeros)
+template <typename T>
+static __global__ void write_token_grads_kernel(GradPtrs gp, const float* __restrict__ dXf, const float* __restrict__ dclsf, int B,
+                                                int L, int d) {
+  const int m = blockIdx.y;
+  const int64_t row = blockIdx.x;
+  const float* src;
+  T* dst;
+  if (row < (int64_t)B * L) {
+    const int b = (int)(row / L), l = (int)(row % L);
+    src = dXf ? dXf + (((int64_t)m * B + b) * L + l) * d : nullptr;
+    dst = static_cast<T*>(gp.dpatch[m]) + b * gp.psb[m] + l * gp.psl[m];
+  } else {
+    if (!gp.dcls[m]) return;
+    const int b = (int)(row - (int64_t)B * L);
+    src = dclsf ? dclsf + ((int64_t)b * 3 + m) * d : nullptr;
+    dst = static_cast<T*>(gp.dcls[m]) + b * gp.csb[m];
+  }
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (src) load8(src + c, v);
+    if (gp.accumulate) {
+      float o[8];
+      load8(dst + c, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += o[i];
+    }
+    store8(dst + c, v);
+  }
+}
+
+int write_token_grads(const sig_token_grads* g, int dtype, const float* dXf, const float* dclsf, int B, int L, int d,
+                      cudaStream_t s) {
+  GradPtrs gp;
+  for (int m = 0; m < 3; ++m) {
+    gp.dpatch[m] = g->dpatch[m]; gp.dcls[m] = g->dcls[m];
+    gp.psb[m] = g->patch_stride_b[m]; gp.psl[m] = g->patch_stride_l[m]; gp.csb[m] = g->cls_stride_b[m];
+  }
+  gp.accumulate = g->accumulate;
+  dim3 grid((unsigned)((int64_t)B * L + B), 3);
+  const int threads = d / 8 >= 128 ? 128 : 64;
+  if (dtype == SIG_BF16)
+    write_token_grads_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(gp, dXf, dclsf, B, L, d);
+  else
+    write_token_grads_kernel<float><<<grid, threads, 0, s>>>(gp, dXf, dclsf, B, L, d);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ctx layout
+// ---------------------------------------------------------------------------------------------
+struct SimCtx {
+  float *Xf, *clsf, *maskf;
+  float *qsel, *qtsel, *csel, *sel_logits, *intra_raw;
+  float *qatt, *qtatt, *catt, *amax, *asum, *xbar, *o, *attn;
+  float *r1, *mu1, *rstd1, *y1, *a1, *h1, *f, *r2, *mu2, *rstd2;
+  // backward scratch
+  float *dr2, *dyx, *dyf, *dh1, *dr1, *dob, *dxbar, *dqt, *dqatt, *dXf;
+  size_t bytes;
+};
+
+static SimCtx sim_ctx(void* base, int B, int L, int d) {
+  Arena a(base);
+  SimCtx c;
+  const size_t R = (size_t)B * 3;
+  c.Xf = a.take<float>((size_t)3 * B * L * d);
+  c.clsf = a.take<float>(R * d);
+  c.maskf = a.take<float>((size_t)3 * B * L);
+  c.qsel = a.take<float>(R * d);
+  c.qtsel = a.take<float>(R * d);
+  c.csel = a.take<float>(R);
+  c.sel_logits = a.take<float>(R * 3 * L);
+  c.intra_raw = a.take<float>(R * L);
+  c.qatt = a.take<float>(R * d);
+  c.qtatt = a.take<float>(R * 8 * d);
+  c.catt = a.take<float>(R * 8);
+  c.amax = a.take<float>(R * 8);
+  c.asum = a.take<float>(R * 8);
+  c.xbar = a.take<float>(R * 8 * d);
+  c.o = a.take<float>(R * d);
+  c.attn = a.take<float>(R * d);
+  c.r1 = a.take<float>(R * d);
+  c.mu1 = a.take<float>(R);
+  c.rstd1 = a.take<float>(R);
+  c.y1 = a.take<float>(R * d);
+  c.a1 = a.take<float>(R * 2 * d);
+  c.h1 = a.take<float>(R * 2 * d);
+  c.f = a.take<float>(R * d);
+  c.r2 = a.take<float>(R * d);
+  c.mu2 = a.take<float>(R);
+  c.rstd2 = a.take<float>(R);
+  c.dr2 = a.take<float>(R * d);
+  c.dyx = a.take<float>(R * d);
+  c.dyf = a.take<float>(R * d);
+  c.dh1 = a.take<float>(R * 2 * d);
+  c.dr1 = a.take<float>(R * d);
+  c.dob = a.take<float>(R * d);
+  c.dxbar = a.take<float>(R * 8 * d);
+  c.dqt = a.take<float>(R * 8 * d);
+  c.dqatt = a.take<float>(R * d);
+  c.dXf = a.take<float>((size_t)3 * B * L * d);
+  c.bytes = a.off;
+  return c;
+}
+
+size_t sim_ctx_bytes(int B, int L, int d) { return sim_ctx(nullptr, B, L, d).bytes; }
+
+// ---------------------------------------------------------------------------------------------
+// orchestration
+// ---------------------------------------------------------------------------------------------
+static int run_selection(const SimCtx& c, const sig_sim_params* p, int B, int L, int d, int which, int k1, int k2, int max_keep,
+                         float* masks_out, cudaStream_t s) {
+  const int R = 3 * B;
+  // q = W_q cls + b_q (useA.py:123); qt = W_k^T q; c = q . b_k
+  SIG_TRY(launch_gemm(gemm_nt(c.clsf, d, p->sel_wq, d, c.qsel, d, p->sel_bq, R, d, d), s));
+  SIG_TRY(launch_gemm(gemm_nn(c.qsel, d, p->sel_wk, d, c.qtsel, d, R, d, d), s));
+  SIG_TRY(launch_gemm(gemm_nt(c.qsel, d, p->sel_bk, d, c.csel, 1, nullptr, R, 1, d), s));
+  dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
+  sim_scores_kernel<<<grid, 256, 4 * d * sizeof(float), s>>>(c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);
+  SIG_CHECK_LAUNCH();
+  sim_select_kernel<<<B, 256, 0, s>>>(c.sel_logits, c.intra_raw, B, L, d, which, k1, k2, max_keep, c.maskf, masks_out);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+static size_t attn_fwd_smem(int L, int d) { return (size_t)(6 * d + 6 * 3 * L + 3 * L) * sizeof(float); }
+static size_t attn_bwd_smem(int L, int d) { return (size_t)(12 * d + 12 * 3 * L + 3 * L + 8) * sizeof(float); }
+
+template <typename OutT>
+static int run_attention_fwd(const SimCtx& c, const sig_sim_params* p, const float* maskf, int B, int L, int d, OutT* out,
+                             cudaStream_t s) {
+  const int R = 3 * B, hd = d / kHeads;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const float* wq = p->in_proj_w;
+  const float* wk = p->in_proj_w + (size_t)d * d;
+  const float* wv = p->in_proj_w + (size_t)2 * d * d;
+  const float* bq = p->in_proj_b;
+  const float* bk = p->in_proj_b + d;
+  const float* bv = p->in_proj_b + 2 * d;
+  // q = W_q cls + b_q  (unscaled; the 1/sqrt(hd) of MHA is folded into qt and c)
+  SIG_TRY(launch_gemm(gemm_nt(c.clsf, d, wq, d, c.qatt, d, bq, R, d, d), s));
+  {  // qt[(b,q),h,:] = scale * q_h W_k^h   (batched over heads)
+    Gemm g = gemm_nn(c.qatt, d, wk, d, c.qtatt, 8 * (int64_t)d, R, d, hd);
+    g.batch = kHeads; g.az = hd; g.bz = (int64_t)hd * d; g.cz = d; g.alpha = scale;
+    SIG_TRY(launch_gemm(g, s));
+  }
+  {  // c[(b,q),h] = scale * q_h . b_k^h
+    Gemm g = gemm_nt(c.qatt, d, bk, hd, c.catt, 8, nullptr, R, 1, hd);
+    g.batch = kHeads; g.az = hd; g.bz = hd; g.cz = 1; g.alpha = scale;
+    SIG_TRY(launch_gemm(g, s));
+  }
+  const size_t sm = attn_fwd_smem(L, d);
+  cudaFuncSetAttribute(sim_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  sim_attn_fwd_kernel<<<dim3(B, 4), 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, B, L, d, c.xbar, c.amax, c.asum);
+  SIG_CHECK_LAUNCH();
+  {  // o_h = W_v^h xbar_h + b_v^h
+    Gemm g = gemm_nt(c.xbar, 8 * (int64_t)d, wv, d, c.o, d, bv, R, hd, d);
+    g.batch = kHeads; g.az = d; g.bz = (int64_t)hd * d; g.cz = hd; g.biasz = hd;
+    SIG_TRY(launch_gemm(g, s));
+  }
+  SIG_TRY(launch_gemm(gemm_nt(c.o, d, p->out_proj_w, d, c.attn, d, p->out_proj_b, R, d, d), s));
+  layernorm_fwd_kernel<float><<<R, 256, 0, s>>>(c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
+  SIG_CHECK_LAUNCH();
+  {
+    Gemm g = gemm_nt(c.y1, d, p->ffn0_w, d, c.h1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d);
+    g.act = 1; g.pre = c.a1;
+    SIG_TRY(launch_gemm(g, s));
+  }
+  SIG_TRY(launch_gemm(gemm_nt(c.h1, 2 * (int64_t)d, p->ffn2_w, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
+  layernorm_fwd_kernel<OutT><<<R, 256, 0, s>>>(c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename InT>
+static int run_attention_bwd(const SimCtx& c, const sig_sim_params* p, const float* maskf, int B, int L, int d, const InT* dout,
+                             const sig_sim_param_grads* g, cudaStream_t s) {
+  const int R = 3 * B, hd = d / kHeads;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const float* wq = p->in_proj_w;
+  const float* wk = p->in_proj_w + (size_t)d * d;
+  const float* wv = p->in_proj_w + (size_t)2 * d * d;
+  float* dwq = g->in_proj_w;
+  float* dwk = g->in_proj_w + (size_t)d * d;
+  float* dwv = g->in_proj_w + (size_t)2 * d * d;
+  // LN2
+  layernorm_bwd_kernel<InT><<<R, 256, 0, s>>>(dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
+  SIG_CHECK_LAUNCH();
+  SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln2_w, 1.f, s));
+  SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln2_b, 1.f, s));
+  // FFN
+  SIG_TRY(launch_colsum(c.dr2, d, R, d, g->ffn2_b, 1.f, s));
+  SIG_TRY(launch_gemm(gemm_tn(c.dr2, d, c.h1, 2 * (int64_t)d, g->ffn2_w, 2 * (int64_t)d, d, 2 * d, R), s));
+  SIG_TRY(launch_gemm(gemm_nn(c.dr2, d, p->ffn2_w, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d), s));
+  {
+    const int64_t n = (int64_t)R * 2 * d;
+    gelu_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(c.dh1, c.a1, c.dh1, n);  // dh1 := da1
+    SIG_CHECK_LAUNCH();
+  }
+  SIG_TRY(launch_colsum(c.dh1, 2 * (int64_t)d, R, 2 * d, g->ffn0_b, 1.f, s));
+  SIG_TRY(launch_gemm(gemm_tn(c.dh1, 2 * (int64_t)d, c.y1, d, g->ffn0_w, d, 2 * d, d, R), s));
+  {  // dy1 = dr2 + da1 W1
+    Gemm gg = gemm_nn(c.dh1, 2 * (int64_t)d, p->ffn0_w, d, c.dr2, d, R, d, 2 * d);
+    gg.accumulate = 1;
+    SIG_TRY(launch_gemm(gg, s));
+  }
+  // LN1
+  layernorm_bwd_kernel<float><<<R, 256, 0, s>>>(c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
+  SIG_CHECK_LAUNCH();
+  SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln1_w, 1.f, s));
+  SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln1_b, 1.f, s));
+  // out_proj
+  SIG_TRY(launch_colsum(c.dr1, d, R, d, g->out_proj_b, 1.f, s));
+  SIG_TRY(launch_gemm(gemm_tn(c.dr1, d, c.o, d, g->out_proj_w, d, d, d, R), s));
+  SIG_TRY(launch_gemm(gemm_nn(c.dr1, d, p->out_proj_w, d, c.dob, d, R, d, d), s));
+  // value projection
+  SIG_TRY(launch_colsum(c.dob, d, R, d, g->in_proj_b + 2 * d, 1.f, s));
+  {  // dW_v^h = do_h^T xbar_h
+    Gemm gg = gemm_tn(c.dob, d, c.xbar, 8 * (int64_t)d, dwv, d, hd, d, R);
+    gg.batch = kHeads; gg.az = hd; gg.bz = d; gg.cz = (int64_t)hd * d;
+    SIG_TRY(launch_gemm(gg, s));
+  }
+  {  // dxbar_h = do_h W_v^h
+    Gemm gg = gemm_nn(c.dob, d, wv, d, c.dxbar, 8 * (int64_t)d, R, d, hd);
+    gg.batch = kHeads; gg.az = hd; gg.bz = (int64_t)hd * d; gg.cz = d;
+    SIG_TRY(launch_gemm(gg, s));
+  }
+  const size_t sm = attn_bwd_smem(L, d);
+  cudaFuncSetAttribute(sim_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  sim_attn_bwd_kernel<<<B, 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, c.xbar, c.amax, c.asum, c.dxbar, B, L, d, c.dqt, c.dXf);
+  SIG_CHECK_LAUNCH();
+  {  // dq_h = scale * dqt_h W_k^hT
+    Gemm gg = gemm_nt(c.dqt, 8 * (int64_t)d, wk, d, c.dqatt, d, nullptr, R, hd, d);
+    gg.batch = kHeads; gg.az = d; gg.bz = (int64_t)hd * d; gg.cz = hd; gg.alpha = scale;
+    SIG_TRY(launch_gemm(gg, s));
+  }
+  {  // dW_k^h = scale * q_h^T dqt_h
+    Gemm gg = gemm_tn(c.qatt, d, c.dqt, 8 * (int64_t)d, dwk, d, hd, d, R);
+    gg.batch = kHeads; gg.az = hd; gg.bz = d; gg.cz = (int64_t)hd * d; gg.alpha = scale;
+    SIG_TRY(launch_gemm(gg, s));
+  }
+  cudaMemsetAsync(g->in_proj_b + d, 0, d * sizeof(float), s);  // key bias: softmax shift invariance => exactly 0
+  SIG_TRY(launch_colsum(c.dqatt, d, R, d, g->in_proj_b, 1.f, s));
+  SIG_TRY(launch_gemm(gemm_tn(c.dqatt, d, c.clsf, d, dwq, d, d, d, R), s));
+  {  // dcls = dr1 (residual) + dq W_q
+    Gemm gg = gemm_nn(c.dqatt, d, wq, d, c.dr1, d, R, d, d);
+    gg.accumulate = 1;
+    SIG_TRY(launch_gemm(gg, s));
+  }
+  return 0;
+}
+
+static int check_sim_params(const sig_sim_params* p, bool need_sel, bool need_attn) {
+  if (!p) return SIG_ERR_NULL;
+  if (need_sel && (!p->sel_wq || !p->sel_bq || !p->sel_wk || !p->sel_bk)) return SIG_ERR_NULL;
+  if (need_attn && (!p->in_proj_w || !p->in_proj_b || !p->out_proj_w || !p->out_proj_b || !p->ffn0_w || !p->ffn0_b ||
+                    !p->ffn2_w || !p->ffn2_b || !p->ln1_w || !p->ln1_b || !p->ln2_w || !p->ln2_b))
+    return SIG_ERR_NULL;
+  return 0;
+}
+
+int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, const float* ext_masks, int k1, int k2,
+                int max_keep, void* out, float* masks_out, void* ctx, size_t ctx_bytes, unsigned flags, cudaStream_t s) {
+  SIG_TRY(check_tokens(tok, true));
+  SIG_TRY(check_sim_params(p, do_select, true));
+  if (!out || !ctx) return SIG_ERR_NULL;
+  if (tok->d % (8 * kHeads) != 0) return SIG_ERR_SHAPE;
+  const int B = tok->B, L = tok->L, d = tok->d;
+  if (ctx_bytes < sim_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
+  if (do_select && (k1 < 1 || k2 < 1 || max_keep > L)) return SIG_ERR_SHAPE;
+  (void)flags;
+  SimCtx c = sim_ctx(ctx, B, L, d);
+  SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));
+  const float* maskf = nullptr;
+  if (do_select) {
+    SIG_TRY(run_selection(c, p, B, L, d, 3, k1, k2, max_keep, masks_out, s));
+    maskf = c.maskf;
+  } else if (ext_masks) {
+    cudaMemcpyAsync(c.maskf, ext_masks, (size_t)3 * B * L * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    maskf = c.maskf;
+  }
+  if (tok->dtype == SIG_BF16)
+    return run_attention_fwd<__nv_bfloat16>(c, p, maskf, B, L, d, static_cast<__nv_bfloat16*>(out), s);
+  return run_attention_fwd<float>(c, p, maskf, B, L, d, static_cast<float*>(out), s);
+}
+
+int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks, const void* dout, const sig_token_grads* dtok,
+                 const sig_sim_param_grads* dp, void* ctx, size_t ctx_bytes, unsigned flags, cudaStream_t s) {
+  SIG_TRY(check_tokens(tok, true));
+  SIG_TRY(check_sim_params(p, false, true));
+  SIG_TRY(check_token_grads(dtok, tok->dtype, true));
+  if (!dout || !ctx || !dp) return SIG_ERR_NULL;
+  if (!dp->in_proj_w || !dp->in_proj_b || !dp->out_proj_w || !dp->out_proj_b || !dp->ffn0_w || !dp->ffn0_b || !dp->ffn2_w ||
+      !dp->ffn2_b || !dp->ln1_w || !dp->ln1_b || !dp->ln2_w || !dp->ln2_b)
+    return SIG_ERR_NULL;
+  const int B = tok->B, L = tok->L, d = tok->d;
+  if (ctx_bytes < sim_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
+  (void)flags;
+  SimCtx c = sim_ctx(ctx, B, L, d);
+  const float* maskf = has_masks ? c.maskf : nullptr;
+  if (tok->dtype == SIG_BF16)
+    SIG_TRY(run_attention_bwd<__nv_bfloat16>(c, p, maskf, B, L, d, static_cast<const __nv_bfloat16*>(dout), dp, s));
+  else
+    SIG_TRY(run_attention_bwd<float>(c, p, maskf, B, L, d, static_cast<const float*>(dout), dp, s));
+  return write_token_grads(dtok, tok->dtype, c.dXf, c.dr1, B, L, d, s);
+}
+
+int sim_select(const sig_tokens* tok, const sig_sim_params* p, int which, int k1, int k2, int max_keep, float* masks,
+               void* selected, void* ctx, size_t ctx_bytes, cudaStream_t s) {
+  SIG_TRY(check_tokens(tok, true));
+  SIG_TRY(check_sim_params(p, true, false));
+  if (!masks || !ctx) return SIG_ERR_NULL;
+  if (which < 1 || which > 3 || k1 < 1 || k2 < 1 || max_keep > tok->L) return SIG_ERR_SHAPE;
+  const int B = tok->B, L = tok->L, d = tok->d;
+  if (ctx_bytes < sim_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
+  SimCtx c = sim_ctx(ctx, B, L, d);
+  SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));
+  SIG_TRY(run_selection(c, p, B, L, d, which, k1, k2, max_keep, masks, s));
+  if (selected) {
+    const int64_t rows = (int64_t)3 * B * L;
+    const int threads = d / 8 >= 128 ? 128 : 64;
+    if (tok->dtype == SIG_BF16)
+      mask_mul_kernel<__nv_bfloat16><<<(unsigned)rows, threads, 0, s>>>(c.Xf, c.maskf, rows, d, static_cast<__nv_bfloat16*>(selected));
+    else
+      mask_mul_kernel<float><<<(unsigned)rows, threads, 0, s>>>(c.Xf, c.maskf, rows, d, static_cast<float*>(selected));
+    SIG_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+// dpatch = dselected * mask
+template <typename T>
+static __global__ void mask_mul_bwd_kernel(const T* __restrict__ dsel, const float* __restrict__ masks, GradPtrs gp, int B, int L,
+                                           int d) {
+  const int m = blockIdx.y;
+  const int64_t row = blockIdx.x;
+  const int b = (int)(row / L), l = (int)(row % L);
+  const int64_t r = ((int64_t)m * B + b) * L + l;
+  const float mk = masks[r];
+  T* dst = static_cast<T*>(gp.dpatch[m]) + b * gp.psb[m] + l * gp.psl[m];
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
+    float v[8];
+    load8(dsel + r * d + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= mk;
+    if (gp.accumulate) {
+      float o[8];
+      load8(dst + c, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += o[i];
+    }
+    store8(dst + c, v);
+  }
+}
+
+int mask_mul_bwd(const void* dselected, const float* masks, int dtype, int B, int L, int d, const sig_token_grads* g,
+                 cudaStream_t s) {
+  if (!dselected || !masks) return SIG_ERR_NULL;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  if (B < 1 || L < 1 || d < 8 || d % 8) return SIG_ERR_SHAPE;
+  SIG_TRY(check_token_grads(g, dtype, false));
+  GradPtrs gp;
+  for (int m = 0; m < 3; ++m) {
+    gp.dpatch[m] = g->dpatch[m]; gp.dcls[m] = nullptr;
+    gp.psb[m] = g->patch_stride_b[m]; gp.psl[m] = g->patch_stride_l[m]; gp.csb[m] = 0;
+  }
+  gp.accumulate = g->accumulate;
+  dim3 grid((unsigned)((int64_t)B * L), 3);
+  const int threads = d / 8 >= 128 ? 128 : 64;
+  if (dtype == SIG_BF16)
+    mask_mul_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(dselected), masks, gp, B, L, d);
+  else
+    mask_mul_bwd_kernel<float><<<grid, threads, 0, s>>>(static_cast<const float*>(dselected), masks, gp, B, L, d);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace sig

@@ -1,0 +1,383 @@
+"""torch.autograd.Function wrappers over the C ABI (signal_b200.lib).
+
+Host-side plumbing only: allocate outputs / saved-state buffers with torch, pass raw
+pointers + strides to libsignal_b200.so on the current CUDA stream, wire gradients.
+Every Function has a *packed* mode whose token inputs are the three [B,1+L,d] token maps
+(CLS = row 0, patches = rows 1.., modeling/meta_arch.py:108-109): the backward kernels
+then write one [B,1+L,d] gradient per modality directly (no per-view zero-fill + add).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L_
+
+_SIM_GRAD_SHAPES = lambda d: [(3 * d, d), (3 * d,), (d, d), (d,), (2 * d, d), (2 * d,), (d, 2 * d), (d,), (d,), (d,), (d,), (d,)]
+
+
+def _carve(flat: torch.Tensor, shapes) -> List[torch.Tensor]:
+    out, off = [], 0
+    for s in shapes:
+        n = 1
+        for x in s:
+            n *= x
+        out.append(flat[off:off + n].view(s))
+        off += (n + 3) // 4 * 4   # keep every view 16-byte aligned
+    return out
+
+
+def _arena(shapes, device) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    total = sum(((int(torch.Size(s).numel()) + 3) // 4 * 4) for s in shapes)
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    return flat, _carve(flat, shapes)
+
+
+def _split_tokens(packed: bool, toks: Sequence[torch.Tensor]):
+    if packed:
+        for t in toks:
+            if t.dim() != 3 or not t.is_contiguous():
+                raise RuntimeError("signal_b200: packed token maps must be contiguous [B,1+L,d]")
+        return [t[:, 1:] for t in toks], [t[:, 0] for t in toks]
+    return list(toks[:3]), list(toks[3:6])
+
+
+def _alloc_token_grads(packed: bool, toks, need_cls: bool):
+    """Returns (returned grads, dpatch views, dcls views or None)."""
+    if packed:
+        full = [torch.empty_like(t) for t in toks]
+        return full, [t[:, 1:] for t in full], [t[:, 0] for t in full]
+    B, L, d = toks[0].shape
+    dp = [torch.empty(B, L, d, dtype=toks[0].dtype, device=toks[0].device) for _ in range(3)]
+    dc = [torch.empty(B, d, dtype=toks[0].dtype, device=toks[0].device) for _ in range(3)] if need_cls else None
+    return dp + (dc if dc else []), dp, dc
+
+
+# ------------------------------------------------------------------------------------------
+# SIM
+# ------------------------------------------------------------------------------------------
+class SimFunction(torch.autograd.Function):
+    """Select_Interactive_Module.forward (useA.py:454-476) -> (out [B,3d], masks fp32 [3,B,L])."""
+
+    @staticmethod
+    def forward(ctx, packed: bool, k1: int, k2: int, max_keep: int, flags: int, *tensors):
+        ntok = 3 if packed else 6
+        toks, params = tensors[:ntok], tensors[ntok:]
+        lib = L_.load()
+        patches, cls = _split_tokens(packed, toks)
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        tok = L_.tokens_struct(patches, cls)
+        prm = L_.sim_params_struct(params)
+        out = torch.empty(B, 3 * d, dtype=patches[0].dtype, device=dev)
+        masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
+        nbytes = L_.ctx_bytes(L_.CTX_SIM, B, L, d)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_sim_fwd(C.byref(tok), C.byref(prm), k1, k2, max_keep, out.data_ptr(), masks.data_ptr(),
+                                     buf.data_ptr(), nbytes, flags, dev.index, L_.stream_ptr(dev)), "sig_sim_fwd")
+        ctx.save_for_backward(*toks, *params, buf)
+        ctx.packed, ctx.ntok, ctx.flags = packed, ntok, flags
+        ctx.mark_non_differentiable(masks)
+        return out, masks
+
+    @staticmethod
+    def backward(ctx, dout, _dmasks):
+        saved = ctx.saved_tensors
+        toks, params, buf = saved[:ctx.ntok], saved[ctx.ntok:-1], saved[-1]
+        lib = L_.load()
+        patches, cls = _split_tokens(ctx.packed, toks)
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        dout = dout.to(patches[0].dtype).contiguous()
+        ret, dpatch, dcls = _alloc_token_grads(ctx.packed, toks, True)
+        _, pg = _arena(_SIM_GRAD_SHAPES(d), dev)
+        tok = L_.tokens_struct(patches, cls)
+        prm = L_.sim_params_struct(params)
+        tg = L_.token_grads_struct(dpatch, dcls)
+        gs = L_.sim_grads_struct(pg)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(prm), dout.data_ptr(), C.byref(tg), C.byref(gs), buf.data_ptr(),
+                                     buf.numel(), ctx.flags, dev.index, L_.stream_ptr(dev)), "sig_sim_bwd")
+        return (None,) * 5 + tuple(ret) + (None,) * 4 + tuple(pg)
+
+
+class AttnFunction(torch.autograd.Function):
+    """ModalInteractive.forward (useA.py:364-411) on arbitrary K/V token maps (no masks)."""
+
+    @staticmethod
+    def forward(ctx, flags: int, *tensors):
+        toks, params = tensors[:6], tensors[6:]
+        lib = L_.load()
+        patches, cls = list(toks[:3]), list(toks[3:6])
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        tok = L_.tokens_struct(patches, cls)
+        prm = L_.sim_params_struct(params)
+        out = torch.empty(B, 3 * d, dtype=patches[0].dtype, device=dev)
+        nbytes = L_.ctx_bytes(L_.CTX_SIM, B, L, d)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_sim_attn_fwd(C.byref(tok), C.byref(prm), None, out.data_ptr(), buf.data_ptr(), nbytes, flags,
+                                          dev.index, L_.stream_ptr(dev)), "sig_sim_attn_fwd")
+        ctx.save_for_backward(*toks, *params, buf)
+        ctx.flags = flags
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = ctx.saved_tensors
+        toks, params, buf = saved[:6], saved[6:-1], saved[-1]
+        lib = L_.load()
+        patches, cls = list(toks[:3]), list(toks[3:6])
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        dout = dout.to(patches[0].dtype).contiguous()
+        ret, dpatch, dcls = _alloc_token_grads(False, toks, True)
+        _, pg = _arena(_SIM_GRAD_SHAPES(d), dev)
+        tok = L_.tokens_struct(patches, cls)
+        prm = L_.sim_params_struct(params)
+        tg = L_.token_grads_struct(dpatch, dcls)
+        gs = L_.sim_grads_struct(pg)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_sim_attn_bwd(C.byref(tok), C.byref(prm), None, dout.data_ptr(), C.byref(tg), C.byref(gs),
+                                          buf.data_ptr(), buf.numel(), ctx.flags, dev.index, L_.stream_ptr(dev)),
+                     "sig_sim_attn_bwd")
+        return (None,) + tuple(ret) + (None,) * 4 + tuple(pg)
+
+
+class SelectFunction(torch.autograd.Function):
+    """TokenSelection.forward (useA.py:223-325) -> (selected x3 [B,L,d], masks fp32 [3,B,L])."""
+
+    @staticmethod
+    def forward(ctx, k1: int, k2: int, max_keep: int, *tensors):
+        toks, params = tensors[:6], tensors[6:]
+        lib = L_.load()
+        patches, cls = list(toks[:3]), list(toks[3:6])
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        tok = L_.tokens_struct(patches, cls)
+        prm = L_.sim_params_struct(list(params) + [params[0]] * 12)   # only the four selection tensors are read
+        masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
+        selected = torch.empty(3, B, L, d, dtype=patches[0].dtype, device=dev)
+        nbytes = L_.ctx_bytes(L_.CTX_SELECT, B, L, d)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_sim_select_fwd(C.byref(tok), C.byref(prm), 3, k1, k2, max_keep, masks.data_ptr(),
+                                            selected.data_ptr(), buf.data_ptr(), nbytes, dev.index, L_.stream_ptr(dev)),
+                     "sig_sim_select_fwd")
+        ctx.save_for_backward(masks)
+        ctx.dtype = patches[0].dtype
+        ctx.mark_non_differentiable(masks)
+        return selected[0], selected[1], selected[2], masks
+
+    @staticmethod
+    def backward(ctx, d0, d1, d2, _dm):
+        (masks,) = ctx.saved_tensors
+        lib = L_.load()
+        _, B, L = masks.shape
+        dev = masks.device
+        d = next(g.shape[-1] for g in (d0, d1, d2) if g is not None)
+        dsel = torch.stack([torch.zeros(B, L, d, dtype=ctx.dtype, device=dev) if g is None else g.to(ctx.dtype)
+                            for g in (d0, d1, d2)]).contiguous()
+        dpatch = [torch.empty(B, L, d, dtype=ctx.dtype, device=dev) for _ in range(3)]
+        tg = L_.token_grads_struct(dpatch, None)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_mask_mul_bwd(dsel.data_ptr(), masks.data_ptr(), L_.SIG_BF16 if ctx.dtype == torch.bfloat16 else L_.SIG_F32,
+                                          B, L, d, C.byref(tg), dev.index, L_.stream_ptr(dev)), "sig_mask_mul_bwd")
+        return (None,) * 3 + tuple(dpatch) + (None,) * 7
+
+
+def select_masks(which: int, patches, cls, sel_params, k1: int, k2: int, max_keep: int = -1) -> torch.Tensor:
+    """intra (1) / inter (2) / union (3) selection masks, fp32 [3,B,L]; not differentiable."""
+    lib = L_.load()
+    patches = [p.detach() for p in patches]
+    cls = [c.detach() for c in cls]
+    B, L, d = patches[0].shape
+    dev = patches[0].device
+    tok = L_.tokens_struct(patches, cls)
+    sel = [p.detach() for p in sel_params]
+    prm = L_.sim_params_struct(sel + [sel[0]] * 12)
+    masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
+    nbytes = L_.ctx_bytes(L_.CTX_SELECT, B, L, d)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L_.check(lib.sig_sim_select_fwd(C.byref(tok), C.byref(prm), which, k1, k2, max_keep, masks.data_ptr(), None,
+                                        buf.data_ptr(), nbytes, dev.index, L_.stream_ptr(dev)), "sig_sim_select_fwd")
+    return masks
+
+
+def select_from_scores(intra: Optional[torch.Tensor], inter: Optional[torch.Tensor], raw: Optional[torch.Tensor],
+                       which: int, k1: int, k2: int, max_keep: int = -1) -> torch.Tensor:
+    """Test seam: rank-select on caller-supplied fp32 scores ([3,B,L], [3,B,2L], [3,B,L])."""
+    lib = L_.load()
+    ref = intra if intra is not None else inter
+    B = ref.shape[1]
+    L = intra.shape[2] if intra is not None else inter.shape[2] // 2
+    dev = ref.device
+    keep = [t.contiguous().float() if t is not None else None for t in (intra, inter, raw)]
+    masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L_.check(lib.sig_sim_select_from_scores(*(None if t is None else t.data_ptr() for t in keep), B, L, which, k1, k2,
+                                                max_keep, masks.data_ptr(), dev.index, L_.stream_ptr(dev)),
+                 "sig_sim_select_from_scores")
+    return masks
+
+
+# ------------------------------------------------------------------------------------------
+# AlignmentM
+# ------------------------------------------------------------------------------------------
+def _align_grad_shapes(d):
+    one = [(d, d, 1, 1), (d,), (d, d, 1, 1), (d,), (d, 1, 4, 4), (d,), (1, d, 1, 1)]
+    return [()] + one * 3
+
+
+class AlignFunction(torch.autograd.Function):
+    """AlignmentM.forward (useB.py:169-190) -> (gam, lam) 0-dim fp32 (lam = 0 when do_lam is False).
+
+    tensors: 3 token maps (packed) or 3 patch maps, then contra_temp, then 7 tensors per
+    modality in lib.ALIGN_MOD_FIELDS order (r, n, t).
+    """
+
+    @staticmethod
+    def forward(ctx, packed: bool, h: int, w: int, do_lam: bool, flags: int, *tensors):
+        toks, params = tensors[:3], tensors[3:]
+        lib = L_.load()
+        patches = [t[:, 1:] for t in toks] if packed else list(toks)
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        tok = L_.tokens_struct(patches, None)
+        mods = [params[1 + 7 * m: 8 + 7 * m] for m in range(3)]
+        for mod in mods:
+            for t in mod:
+                L_._f32c(t)
+        prm = L_.align_params_struct(L_._f32c(params[0]), mods)
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        nbytes = L_.ctx_bytes(L_.CTX_ALIGN, B, L, d)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_align_fwd(C.byref(tok), C.byref(prm), h, w, int(do_lam), losses.data_ptr(), buf.data_ptr(), nbytes,
+                                       flags, dev.index, L_.stream_ptr(dev)), "sig_align_fwd")
+        ctx.save_for_backward(*toks, *params, buf)
+        ctx.cfg = (packed, h, w, do_lam, flags)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, dgam, dlam):
+        packed, h, w, do_lam, flags = ctx.cfg
+        saved = ctx.saved_tensors
+        toks, params, buf = saved[:3], saved[3:-1], saved[-1]
+        lib = L_.load()
+        patches = [t[:, 1:] for t in toks] if packed else list(toks)
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        z = torch.zeros((), dtype=torch.float32, device=dev)
+        dl = torch.stack([z if dgam is None else dgam.float(), z if dlam is None else dlam.float()]).contiguous()
+        if packed:
+            ret = [torch.empty_like(t) for t in toks]
+            dpatch, dcls = [t[:, 1:] for t in ret], [t[:, 0] for t in ret]
+        else:
+            ret = [torch.empty(B, L, d, dtype=toks[0].dtype, device=dev) for _ in range(3)]
+            dpatch, dcls = ret, None
+        flat, pg = _arena(_align_grad_shapes(d), dev)
+        if not do_lam:
+            flat.zero_()
+        tok = L_.tokens_struct(patches, None)
+        mods = [params[1 + 7 * m: 8 + 7 * m] for m in range(3)]
+        prm = L_.align_params_struct(params[0], mods)
+        gmods = [pg[1 + 7 * m: 8 + 7 * m] for m in range(3)]
+        gs = L_.align_params_struct(pg[0], gmods, cls=L_.SigAlignParamGrads)
+        tg = L_.token_grads_struct(dpatch, dcls, accumulate=False, zero_cls=packed)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_align_bwd(C.byref(tok), C.byref(prm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg), C.byref(gs),
+                                       buf.data_ptr(), buf.numel(), flags, dev.index, L_.stream_ptr(dev)), "sig_align_bwd")
+        return (None,) * 5 + tuple(ret) + tuple(pg)
+
+
+class DasFunction(torch.autograd.Function):
+    """DA_sample.forward (DAS.py:107-165) on a channels-last [B,h*w,d] view -> sampled fp32 [B,Hk*Wk,d].
+
+    params: the 7 tensors of one modality in lib.ALIGN_MOD_FIELDS order.
+    """
+
+    @staticmethod
+    def forward(ctx, h: int, w: int, flags: int, x, *params):
+        lib = L_.load()
+        B, L, d = x.shape
+        dev = x.device
+        if x.stride(2) != 1:
+            raise RuntimeError("signal_b200: DA_sample needs a channels-last input view")
+        for t in params:
+            L_._f32c(t)
+        prm = L_.align_params_struct(None, [params])
+        P = (h // 4) * (w // 4)
+        sampled = torch.empty(B, P, d, dtype=torch.float32, device=dev)
+        nbytes = L_.ctx_bytes(L_.CTX_DAS, B, L, d)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_das_fwd(x.data_ptr(), x.stride(0), x.stride(1), L_.dtype_enum(x), B, h, w, d, C.byref(prm), 0,
+                                     sampled.data_ptr(), buf.data_ptr(), nbytes, flags, dev.index, L_.stream_ptr(dev)),
+                     "sig_das_fwd")
+        ctx.save_for_backward(x, *params, buf)
+        ctx.cfg = (h, w, flags)
+        return sampled
+
+    @staticmethod
+    def backward(ctx, dsampled):
+        h, w, flags = ctx.cfg
+        saved = ctx.saved_tensors
+        x, params, buf = saved[0], saved[1:-1], saved[-1]
+        lib = L_.load()
+        B, L, d = x.shape
+        dev = x.device
+        dsampled = dsampled.float().contiguous()
+        dx = torch.empty(B, L, d, dtype=x.dtype, device=dev)
+        shapes = [(d, d, 1, 1), (d,), (d, d, 1, 1), (d,), (d, 1, 4, 4), (d,), (1, d, 1, 1)]
+        _, pg = _arena(shapes, dev)
+        prm = L_.align_params_struct(None, [params])
+        gs = L_.align_params_struct(None, [pg], cls=L_.SigAlignParamGrads)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_das_bwd(x.data_ptr(), x.stride(0), x.stride(1), L_.dtype_enum(x), B, h, w, d, C.byref(prm), 0,
+                                     dsampled.data_ptr(), dx.data_ptr(), C.byref(gs), buf.data_ptr(), buf.numel(), flags,
+                                     dev.index, L_.stream_ptr(dev)), "sig_das_bwd")
+        return (None,) * 3 + (dx,) + tuple(pg)
+
+
+class VolumeFunction(torch.autograd.Function):
+    """utils/volume.py:14 volume_computation3 -> [B1,B2] fp32."""
+
+    @staticmethod
+    def forward(ctx, l, v, a):
+        lib = L_.load()
+        lf, vf, af = (t.float().contiguous() for t in (l, v, a))
+        B1, d = lf.shape
+        B2 = vf.shape[0]
+        dev = lf.device
+        vol = torch.empty(B1, B2, dtype=torch.float32, device=dev)
+        nbytes = lib.sig_volume3_ws_bytes(B1, B2)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_volume3_fwd(lf.data_ptr(), vf.data_ptr(), af.data_ptr(), B1, B2, d, vol.data_ptr(), ws.data_ptr(),
+                                         nbytes, dev.index, L_.stream_ptr(dev)), "sig_volume3_fwd")
+        ctx.save_for_backward(lf, vf, af)
+        ctx.dtypes = (l.dtype, v.dtype, a.dtype)
+        return vol
+
+    @staticmethod
+    def backward(ctx, dvol):
+        lf, vf, af = ctx.saved_tensors
+        lib = L_.load()
+        B1, d = lf.shape
+        B2 = vf.shape[0]
+        dev = lf.device
+        dvol = dvol.float().contiguous()
+        dl, dv, da = torch.empty_like(lf), torch.empty_like(vf), torch.empty_like(af)
+        nbytes = lib.sig_volume3_ws_bytes(B1, B2)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_volume3_bwd(lf.data_ptr(), vf.data_ptr(), af.data_ptr(), B1, B2, d, dvol.data_ptr(), dl.data_ptr(),
+                                         dv.data_ptr(), da.data_ptr(), ws.data_ptr(), nbytes, dev.index, L_.stream_ptr(dev)),
+                     "sig_volume3_bwd")
+        return dl.to(ctx.dtypes[0]), dv.to(ctx.dtypes[1]), da.to(ctx.dtypes[2])

@@ -1,0 +1,213 @@
+"""ctypes binding of libsignal_b200.so (C ABI: include/signal_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (plain nvcc,
+sm_100a).  There is no CPU or PyTorch fallback: if the library is missing or a
+call is rejected, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsignal_b200.so")
+
+SIG_F32, SIG_BF16 = 0, 1
+CTX_SIM, CTX_ALIGN, CTX_SELECT, CTX_DAS = 0, 1, 2, 3
+FLAG_FORCE_SIMT = 1
+
+_VP3 = C.c_void_p * 3
+_I64x3 = C.c_int64 * 3
+
+
+class SigTokens(C.Structure):
+    _fields_ = [("patch", _VP3), ("cls", _VP3), ("patch_stride_b", _I64x3), ("patch_stride_l", _I64x3),
+                ("cls_stride_b", _I64x3), ("dtype", C.c_int32), ("B", C.c_int32), ("L", C.c_int32), ("d", C.c_int32)]
+
+
+class SigTokenGrads(C.Structure):
+    _fields_ = [("dpatch", _VP3), ("dcls", _VP3), ("patch_stride_b", _I64x3), ("patch_stride_l", _I64x3),
+                ("cls_stride_b", _I64x3), ("accumulate", C.c_int32), ("zero_cls", C.c_int32)]
+
+
+SIM_PARAM_FIELDS = ["sel_wq", "sel_bq", "sel_wk", "sel_bk", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b",
+                    "ffn0_w", "ffn0_b", "ffn2_w", "ffn2_b", "ln1_w", "ln1_b", "ln2_w", "ln2_b"]
+SIM_GRAD_FIELDS = SIM_PARAM_FIELDS[4:]
+
+
+class SigSimParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in SIM_PARAM_FIELDS]
+
+
+class SigSimParamGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in SIM_GRAD_FIELDS]
+
+
+ALIGN_MOD_FIELDS = ["proj_q_w", "proj_q_b", "off0_w", "off0_b", "off2_w", "off2_b", "off4_w"]
+
+
+class SigAlignParams(C.Structure):
+    _fields_ = [("contra_temp", C.c_void_p)] + [(n, _VP3) for n in ALIGN_MOD_FIELDS]
+
+
+class SigAlignParamGrads(C.Structure):
+    _fields_ = [("contra_temp", C.c_void_p)] + [(n, _VP3) for n in ALIGN_MOD_FIELDS]
+
+
+_lib = None
+
+# every symbol include/signal_b200.h declares (tests check that the .so exports them all)
+EXPORTS = [
+    "sig_version", "sig_error_string", "sig_ctx_bytes",
+    "sig_sim_fwd", "sig_sim_bwd", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
+    "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
+    "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
+]
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"signal_b200: CUDA extension not built ({LIB_PATH} missing). "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, u, sz, i64 = C.c_void_p, C.c_int, C.c_uint, C.c_size_t, C.c_int64
+    P = C.POINTER
+    lib.sig_version.restype = i
+    lib.sig_error_string.restype = C.c_char_p
+    lib.sig_error_string.argtypes = [i]
+    lib.sig_ctx_bytes.restype = sz
+    lib.sig_ctx_bytes.argtypes = [i, i, i, i]
+    lib.sig_sim_fwd.argtypes = [P(SigTokens), P(SigSimParams), i, i, i, vp, vp, vp, sz, u, i, vp]
+    lib.sig_sim_bwd.argtypes = [P(SigTokens), P(SigSimParams), vp, P(SigTokenGrads), P(SigSimParamGrads), vp, sz, u, i, vp]
+    lib.sig_sim_select_fwd.argtypes = [P(SigTokens), P(SigSimParams), i, i, i, i, vp, vp, vp, sz, i, vp]
+    lib.sig_sim_select_from_scores.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, i, vp]
+    lib.sig_mask_mul_bwd.argtypes = [vp, vp, i, i, i, i, P(SigTokenGrads), i, vp]
+    lib.sig_sim_attn_fwd.argtypes = [P(SigTokens), P(SigSimParams), vp, vp, vp, sz, u, i, vp]
+    lib.sig_sim_attn_bwd.argtypes = [P(SigTokens), P(SigSimParams), vp, vp, P(SigTokenGrads), P(SigSimParamGrads), vp, sz, u, i, vp]
+    lib.sig_align_fwd.argtypes = [P(SigTokens), P(SigAlignParams), i, i, i, vp, vp, sz, u, i, vp]
+    lib.sig_align_bwd.argtypes = [P(SigTokens), P(SigAlignParams), i, i, i, vp, P(SigTokenGrads), P(SigAlignParamGrads), vp, sz, u, i, vp]
+    lib.sig_das_fwd.argtypes = [vp, i64, i64, i, i, i, i, i, P(SigAlignParams), i, vp, vp, sz, u, i, vp]
+    lib.sig_das_bwd.argtypes = [vp, i64, i64, i, i, i, i, i, P(SigAlignParams), i, vp, vp, P(SigAlignParamGrads), vp, sz, u, i, vp]
+    lib.sig_volume3_ws_bytes.restype = sz
+    lib.sig_volume3_ws_bytes.argtypes = [i, i]
+    lib.sig_volume3_fwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, sz, i, vp]
+    lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("sig_error_string", "sig_ctx_bytes", "sig_volume3_ws_bytes"):
+            fn.restype = i
+    if lib.sig_version() != 1:
+        raise RuntimeError("signal_b200: ABI version mismatch between lib.py and libsignal_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().sig_error_string(rc).decode()
+        raise RuntimeError(f"signal_b200.{what} failed (code {rc}): {msg}")
+
+
+def dtype_enum(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return SIG_F32
+    if t.dtype == torch.bfloat16:
+        return SIG_BF16
+    raise RuntimeError(f"signal_b200: unsupported token dtype {t.dtype} (fp32 or bf16; fp16 autocast is not supported)")
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"signal_b200: {what} must be a CUDA tensor (there is no CPU path)")
+
+
+def tokens_struct(patches: Sequence[torch.Tensor], cls: Optional[Sequence[torch.Tensor]]) -> SigTokens:
+    """Describe three strided [B,L,d] patch views (+ optional [B,d] CLS views) without copying."""
+    t = SigTokens()
+    B, L, d = patches[0].shape
+    for m in range(3):
+        p = patches[m]
+        _require_cuda(p, "patch tokens")
+        if p.shape != (B, L, d) or p.dtype != patches[0].dtype or p.stride(2) != 1:
+            raise RuntimeError("signal_b200: patch maps must share shape/dtype and have unit channel stride")
+        t.patch[m] = p.data_ptr()
+        t.patch_stride_b[m] = p.stride(0)
+        t.patch_stride_l[m] = p.stride(1)
+        if cls is not None:
+            g = cls[m]
+            _require_cuda(g, "CLS tokens")
+            if g.shape != (B, d) or g.dtype != p.dtype or g.stride(1) != 1:
+                raise RuntimeError("signal_b200: CLS tokens must be [B,d] views with unit channel stride")
+            t.cls[m] = g.data_ptr()
+            t.cls_stride_b[m] = g.stride(0)
+    t.dtype = dtype_enum(patches[0])
+    t.B, t.L, t.d = B, L, d
+    return t
+
+
+def token_grads_struct(dpatch: Sequence[torch.Tensor], dcls: Optional[Sequence[torch.Tensor]],
+                       accumulate: bool = False, zero_cls: bool = False) -> SigTokenGrads:
+    g = SigTokenGrads()
+    for m in range(3):
+        g.dpatch[m] = dpatch[m].data_ptr()
+        g.patch_stride_b[m] = dpatch[m].stride(0)
+        g.patch_stride_l[m] = dpatch[m].stride(1)
+        if dcls is not None:
+            g.dcls[m] = dcls[m].data_ptr()
+            g.cls_stride_b[m] = dcls[m].stride(0)
+    g.accumulate = int(accumulate)
+    g.zero_cls = int(zero_cls)
+    return g
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise RuntimeError("signal_b200: parameters must be contiguous fp32 CUDA tensors (fp32 masters)")
+    return t
+
+
+def sim_params_struct(params: Sequence[torch.Tensor]) -> SigSimParams:
+    """params in SIM_PARAM_FIELDS order (16 tensors)."""
+    s = SigSimParams()
+    for name, t in zip(SIM_PARAM_FIELDS, params):
+        setattr(s, name, _f32c(t).data_ptr())
+    return s
+
+
+def sim_grads_struct(grads: Sequence[torch.Tensor]) -> SigSimParamGrads:
+    s = SigSimParamGrads()
+    for name, t in zip(SIM_GRAD_FIELDS, grads):
+        setattr(s, name, t.data_ptr())
+    return s
+
+
+def align_params_struct(contra_temp: torch.Tensor, mods: Sequence[Sequence[torch.Tensor]], cls=SigAlignParams):
+    """mods[m] = 7 tensors in ALIGN_MOD_FIELDS order for modality m (r, n, t); entries may be None."""
+    s = cls()
+    s.contra_temp = contra_temp.data_ptr() if contra_temp is not None else None
+    for m, mod in enumerate(mods):
+        if mod is None:
+            continue
+        for name, t in zip(ALIGN_MOD_FIELDS, mod):
+            getattr(s, name)[m] = t.data_ptr()
+    return s
+
+
+def ctx_bytes(kind: int, B: int, L: int, d: int) -> int:
+    n = load().sig_ctx_bytes(kind, B, L, d)
+    if n == 0:
+        raise RuntimeError(f"signal_b200: unsupported shape B={B} L={L} d={d} (L <= 128, d % 64 == 0)")
+    return n
