@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Fusion-head fwd+bwd throughput on B200 (BASELINE.json metric) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dim 768] [--impl reference]
+
+One "step" = Select_Interactive_Module fwd + AlignmentM fwd (GAM + LAM) + backward to the three
+[B,129,d] token maps and all head parameters, on one synthetic RGBNT201 batch (B=128 per GPU,
+bf16 tokens, fp32 master parameters).  N>1 (launched by torchrun, one rank per GPU): the batch
+is sharded (weak scaling, B=128 per rank) and the head gradients are all-reduced with NCCL.
+
+value   : samples/s, tokens already resident in HBM, CUDA-event timed, max over ranks
+e2e     : same step through the nn.Module API starting from pinned HOST token maps (H2D copy of
+          the tokens and D2H read of out + losses inside the timed region)
+roofline: dominant phase of the step (CUDA events recorded by the library around each phase in a
+          profiled pass right after the timed region) against MEASURED_PEAKS.json
+cpu_baseline / --impl reference: the CPU oracle port (oracle/signal_oracle.py, torch CPU ops, all
+          host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fusion_head_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+B_PER_GPU = 128
+L = 128
+GRID = (16, 8)
+TOPK = 80
+NSETS = 4            # token sets rotated through the timed region (4 x 76 MB > 126 MB L2)
+W_GAM, W_LAM = 0.2, 0.2   # configs/RGBNT201/Signal.yml:9-10
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm": j["hbm_gbs"], "tensor_burst": j["bf16_tflops"], "tensor": j["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+def workload_name(d):
+    return f"RGBNT201 fusion head (SIM+GAM+LAM) fwd+bwd, B={B_PER_GPU}/GPU, 3x129 tokens, d={d}, grid 16x8, TOPK={TOPK}, bf16"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port)
+# ---------------------------------------------------------------------------------------------
+def cpu_step_fn(d, B, seed=1234):
+    import torch
+    from oracle import signal_oracle as so
+    from signal_b200 import synthetic as syn
+    sim_p = {k: v.requires_grad_(True) for k, v in syn.make_params(syn.sim_param_shapes(d), seed).items()}
+    al_p = {k: v.requires_grad_(True) for k, v in syn.make_params(syn.align_param_shapes(d), seed + 1).items()}
+    toks = [t.to(torch.bfloat16).float().requires_grad_(True) for t in syn.make_tokens(B, d, seed=seed + 2)]
+    cot = syn.make_cotangent(B, d, seed=seed + 3)
+    leaves = toks + [p for p in sim_p.values()] + [p for p in al_p.values()]
+
+    def step():
+        out, gam, lam, _ = so.head_forward(sim_p, al_p, toks, TOPK, GRID[0], GRID[1])
+        loss = (out * cot).sum() + W_GAM * gam + W_LAM * lam
+        torch.autograd.grad(loss, leaves, allow_unused=True)
+    return step
+
+
+def time_cpu(d, B, steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(d, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bs = 32
+    steps = max(1, min(args.steps, 6))
+    warmup = max(1, min(args.warmup, 2))
+    val, ms, cores = time_cpu(args.dim, Bs, steps, warmup)
+    sample = f"B={Bs} slice of the workload per step, {warmup} warm-up + {steps} timed fwd+bwd steps, fp32, torch CPU ops"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.dim), "note": "CPU oracle port of the reference modules (the reference is "
+                   "pure Python and /root/reference does not travel to the GPU box)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work per phase (per step of B samples); DESIGN.md states the derivation
+# ---------------------------------------------------------------------------------------------
+def phase_work(B, d, s=2):
+    T = 3 * L * d            # token elements per sample
+    g = 3 * d
+    simt_lam_fwd = 3 * (2 * 2 * L * d * d) * B                     # two dense 1x1 convs, three modalities
+    return {
+        # phase: (bound, work, unit)   bytes for hbm, flops for tensor
+        "convert_tokens": ("hbm", B * (T + g) * (s + 4), "B"),
+        "sim_select": ("hbm", B * (T + g) * 4, "B"),
+        "sim_attn_tokens_fwd": ("hbm", B * (T + g) * 4, "B"),
+        "sim_attn_tokens_bwd": ("hbm", B * 2 * T * 4, "B"),
+        "gam_fwd": ("hbm", B * T * 4, "B"),
+        "lam_offsetnet_fwd": ("tensor", simt_lam_fwd, "FLOP"),
+        "lam_offsetnet_bwd": ("tensor", 2 * simt_lam_fwd, "FLOP"),
+        "lam_sample_fwd": ("hbm", B * T * 4 // 4, "B"),
+        "lam_sample_bwd": ("hbm", B * T * 4 // 4, "B"),
+        "align_write": ("hbm", B * T * (4 + s), "B"),
+        "write_token_grads": ("hbm", B * (T + g) * (4 + s), "B"),
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from signal_b200 import lib, modules as M, synthetic as syn
+    lib.load()
+
+    d, B = args.dim, B_PER_GPU
+    sim = M.Select_Interactive_Module(d, k=TOPK)
+    al = M.AlignmentM(d, GRID[0], GRID[1])
+    sim.load_state_dict(syn.make_params(syn.sim_param_shapes(d), 1234))
+    al.load_state_dict(syn.make_params(syn.align_param_shapes(d), 1235))
+    sim, al = sim.to(dev), al.to(dev)
+    params = [p for p in list(sim.parameters()) + list(al.parameters())]
+    # flat gradient arena: .grad tensors are views, one NCCL all-reduce per step
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+
+    host_sets = []
+    for k in range(NSETS):
+        toks = syn.make_tokens(B, d, seed=1234 + 17 * k + 1000 * rank, dtype=torch.bfloat16)
+        host_sets.append([t.pin_memory() for t in toks])
+    dev_sets = [[t.to(dev).requires_grad_(True) for t in hs] for hs in host_sets]
+    cot = syn.make_cotangent(B, d).to(dev, torch.bfloat16)
+    wg = torch.tensor(W_GAM, device=dev)
+    wl = torch.tensor(W_LAM, device=dev)
+
+    def fwd_bwd(toks):
+        patches = [t[:, 1:] for t in toks]
+        cls = [t[:, 0] for t in toks]
+        out = sim(*patches, *cls)
+        gam, lam = al(*patches, stage="together_CLS_Patch")
+        torch.autograd.backward([out, gam, lam], [cot, wg, wl])
+        return out, gam, lam
+
+    def step(i):
+        toks = dev_sets[i % NSETS]
+        for t in toks:
+            t.grad = None
+        flat.zero_()
+        res = fwd_bwd(toks)
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return res
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host tokens -> modules -> host results, same step
+    e2e_steps = max(3, min(args.steps, 20))
+    h2d = 3 * B * (L + 1) * d * 2
+    d2h = B * 3 * d * 2 + 8
+
+    def e2e_step(i):
+        toks = [t.to(dev, non_blocking=True).requires_grad_(True) for t in host_sets[i % NSETS]]
+        flat.zero_()
+        out, gam, lam = fwd_bwd(toks)
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return out.cpu(), torch.stack([gam, lam]).cpu()
+
+    for i in range(3):
+        e2e_step(i)
+    sync_all()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * e2e_steps / (float(t.item()) * 1e-3)
+
+    # ---- profiled pass (rank 0): per-phase CUDA-event times -> roofline of the dominant phase
+    roof, phases = None, None
+    if rank == 0:
+        prof_steps = 5
+        lib.profile_enable(True)
+        for i in range(prof_steps):
+            step(i)
+        torch.cuda.synchronize()
+        lib.profile_enable(False)
+        prof = lib.profile_collect()
+        pk = peaks()
+        work = phase_work(B, d)
+        phases = {k: round(v[0] / prof_steps * 1e3, 1) for k, v in prof.items()}   # us per step
+        tot = sum(phases.values())
+        dom = max(phases, key=phases.get) if phases else None
+        if dom and dom in work:
+            bound, w, _ = work[dom]
+            sec = phases[dom] * 1e-6
+            if bound == "hbm":
+                ach, peak, unit = w / sec / 1e9, pk["hbm"], "GB/s"
+            else:
+                ach, peak, unit = w / sec / 1e12, pk["tensor"], "TFLOP/s"
+            roof = {"kernel": dom, "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": pk["src"],
+                    "share_of_step": round(phases[dom] / tot, 3) if tot else None}
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            Bs = 32
+            v, ms, cores = time_cpu(d, Bs, 3, 1)
+            cpu = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"B={Bs} slice of the workload, 1 warm-up + 3 timed fwd+bwd steps of the CPU oracle port, fp32"}
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(d), "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
+                       "grad_allreduce": "one NCCL all-reduce of the flat head-gradient arena per step" if world > 1 else "n/a"},
+            "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "phases_us": phases,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dim", type=int, default=768, choices=[512, 768])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

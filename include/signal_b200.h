@@ -194,6 +194,14 @@ int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int 
                     const float* dvol, float* dl, float* dv, float* da,
                     void* ws, size_t ws_bytes, int device, void* stream);
 
+/* ---- measurement aids (no effect on results) ------------------------------ */
+/* number of kernel launches the library has enqueued since it was loaded */
+unsigned long long sig_debug_launch_count(void);
+/* per-phase CUDA-event timing: enable, run, then collect (synchronises the recorded events).
+ * names_buf receives '\n'-separated phase names; ms[i]/counts[i] the summed time and scope count. */
+int sig_profile_enable(int on);
+int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,14 @@ def gelu_exact(x: Tensor) -> Tensor:
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """x W^T + b with the leading dims folded into one 2-D matmul (what nn.Linear / a 1x1 conv compute)."""
+    y = x.reshape(-1, x.shape[-1]) @ weight.t()
+    if bias is not None:
+        y = y + bias
+    return y.reshape(*x.shape[:-1], weight.shape[0])
+
+
 def layer_norm(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     """fp32 LayerNorm over the last dim, biased variance -- useA.py:414-423."""
     mu = x.mean(dim=-1, keepdim=True)
@@ -102,8 +110,8 @@ def inter_modal_scores(params: Params, patches: Sequence[Tensor],
     d = patches[0].shape[-1]
     queries = torch.stack(list(cls), dim=1)                       # useA.py:116
     keys = torch.cat(list(patches), dim=1)                        # useA.py:120
-    q = queries @ params[prefix + "W_q.weight"].T + params[prefix + "W_q.bias"]   # :123
-    k = keys @ params[prefix + "W_k.weight"].T + params[prefix + "W_k.bias"]      # :124
+    q = linear(queries, params[prefix + "W_q.weight"], params[prefix + "W_q.bias"])   # :123
+    k = linear(keys, params[prefix + "W_k.weight"], params[prefix + "W_k.bias"])      # :124
     s = torch.einsum("bqd,bjd->bqj", q, k) / math.sqrt(d)         # :128
     return torch.softmax(s, dim=2)                                # :129
 
@@ -182,15 +190,15 @@ def multi_head_cross_attention(params: Params, queries: Tensor, kv: Tensor,
     hd = d // NUM_HEADS
     w = params[prefix + "in_proj_weight"]
     b = params[prefix + "in_proj_bias"]
-    q = queries @ w[:d].T + b[:d]
-    k = kv @ w[d:2 * d].T + b[d:2 * d]
-    v = kv @ w[2 * d:].T + b[2 * d:]
+    q = linear(queries, w[:d], b[:d])
+    k = linear(kv, w[d:2 * d], b[d:2 * d])
+    v = linear(kv, w[2 * d:], b[2 * d:])
     q = q.reshape(B, nq, NUM_HEADS, hd).transpose(1, 2) * math.sqrt(1.0 / hd)
     k = k.reshape(B, -1, NUM_HEADS, hd).transpose(1, 2)
     v = v.reshape(B, -1, NUM_HEADS, hd).transpose(1, 2)
     p = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
     o = (p @ v).transpose(1, 2).reshape(B, nq, d)
-    return o @ params[prefix + "out_proj.weight"].T + params[prefix + "out_proj.bias"]
+    return linear(o, params[prefix + "out_proj.weight"], params[prefix + "out_proj.bias"])
 
 
 def modal_interactive(params: Params, selected: Sequence[Tensor], cls: Sequence[Tensor],
@@ -200,8 +208,8 @@ def modal_interactive(params: Params, selected: Sequence[Tensor], cls: Sequence[
     kv = torch.cat(list(selected), dim=1)                              # :383
     attn = multi_head_cross_attention(params, queries, kv, prefix + "cross_attn.")  # :388
     y1 = layer_norm(queries + attn, params[prefix + "norm1.weight"], params[prefix + "norm1.bias"])  # :393
-    h = gelu_exact(y1 @ params[prefix + "ffn.0.weight"].T + params[prefix + "ffn.0.bias"])
-    f = h @ params[prefix + "ffn.2.weight"].T + params[prefix + "ffn.2.bias"]      # :397
+    h = gelu_exact(linear(y1, params[prefix + "ffn.0.weight"], params[prefix + "ffn.0.bias"]))
+    f = linear(h, params[prefix + "ffn.2.weight"], params[prefix + "ffn.2.bias"])      # :397
     y2 = layer_norm(y1 + f, params[prefix + "norm2.weight"], params[prefix + "norm2.bias"])  # :401
     return torch.cat([y2[:, 0], y2[:, 1], y2[:, 2]], dim=1)            # :408
 
@@ -267,9 +275,9 @@ def das_offsets(params: Params, x_tok: Tensor, h: int, w: int, prefix: str) -> T
     """
     B, L, d = x_tok.shape
     wq = params[prefix + "proj_q.weight"].reshape(d, d)
-    q = x_tok @ wq.T + params[prefix + "proj_q.bias"]
+    q = linear(x_tok, wq, params[prefix + "proj_q.bias"])
     w0 = params[prefix + "conv_offset.0.weight"].reshape(d, d)
-    g = gelu_exact(q @ w0.T + params[prefix + "conv_offset.0.bias"])   # [B, L, d]
+    g = gelu_exact(linear(q, w0, params[prefix + "conv_offset.0.bias"]))   # [B, L, d]
     Hk, Wk = h // DAS_STRIDE, w // DAS_STRIDE
     g = g.reshape(B, Hk, DAS_KSIZE, Wk, DAS_KSIZE, d)
     wdw = params[prefix + "conv_offset.2.weight"].reshape(d, DAS_KSIZE, DAS_KSIZE)

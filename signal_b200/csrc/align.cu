@@ -136,7 +136,10 @@ static __global__ void __launch_bounds__(1024) gam_loss_kernel(const float* __re
       const float v = V[idx], z = -v * itau;
       const float tg = i == j ? tgt_on : tgt_off;
       const float dZ = (0.5f / B) * ((expf(z - rowstat[i]) - tg) + (expf(z - colstat[j]) - tg));
-      tpart += dZ * v * itau * itau;
+      // sum_j (P_row - T)_ij = 0 and sum_i (P_col - T)_ij = 0, so the diagonal volume can be
+      // subtracted without changing the sum; it removes most of the cancellation in fp32
+      tpart += (0.5f / B) * ((expf(z - rowstat[i]) - tg) * (v - V[(int64_t)i * B + i]) +
+                             (expf(z - colstat[j]) - tg) * (v - V[(int64_t)j * B + j])) * itau * itau;
       const float det = gram_det(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]);
       const float dd = ddet_of(-dZ * itau, det, v);
       Wlv[idx] = dd * (-2.f * (lv[idx] * aa[j] - va[j] * la[idx]));
@@ -538,6 +541,7 @@ size_t das_ctx_bytes(int B, int L, int d) { return align_ctx(nullptr, B, L, d, 1
 static int lam_offsets_fwd(const float* X, const sig_align_params* p, int m, const LamMod& lm, const Geo& g, int B, int L, int d,
                            cudaStream_t s) {
   const int BL = B * L;
+  SIG_PHASE("lam_offsetnet_fwd");
   // q = proj_q(x) (DAS.py:129); H = conv_offset[0](q) (DAS.py:58); G = GELU(H)
   SIG_TRY(launch_gemm(gemm_nt(X, d, p->proj_q_w[m], d, lm.Q, d, p->proj_q_b[m], BL, d, d), s));
   {
@@ -554,6 +558,7 @@ static int lam_offsets_fwd(const float* X, const sig_align_params* p, int m, con
 static int lam_offsets_bwd(const float* X, const sig_align_params* p, const sig_align_param_grads* dp, int m, const LamMod& lm,
                            const AlignCtx& c, float* dXdense, const Geo& g, int B, int L, int d, cudaStream_t s) {
   const int BL = B * L;
+  SIG_PHASE("lam_offsetnet_bwd");
   lam_dw_bwd_kernel<<<B * g.P, 256, 0, s>>>(lm.H, lm.U, lm.dO, p->off2_w[m], p->off4_w[m], g, L, d, lm.dU, c.dH);
   SIG_CHECK_LAUNCH();
   lam_dw_param_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(lm.G, lm.U, lm.dU, lm.dO, g, B, L, d, dp->off2_w[m], dp->off2_b[m],
@@ -613,6 +618,8 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   for (int m = 0; m < 3; ++m) t2.cls[m] = nullptr;
   SIG_TRY(convert_tokens(&t2, c.Xf, nullptr, s));
   // ---- GAM
+  {
+  SIG_PHASE("gam_fwd");
   pool_kernel<<<dim3(B, 3), 256, 0, s>>>(c.Xf, B, L, d, c.mean);
   SIG_CHECK_LAUNCH();
   gam_norm_kernel<<<B, 256, 0, s>>>(c.mean, B, d, c.f, c.nrm, c.self4);
@@ -625,6 +632,7 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   gam_loss_kernel<<<1, 1024, 0, s>>>(c.self4, c.lv, c.la, p->contra_temp, B, c.V, c.rowstat, c.colstat, c.Wlv, c.Wla, c.rowA,
                                      c.colC, losses, c.dtau);
   SIG_CHECK_LAUNCH();
+  }
   // ---- LAM
   if (do_lam) {
     const Geo g = make_geo(h, w);
@@ -632,9 +640,11 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
     const int64_t ms = (int64_t)B * g.P * d;
     for (int m = 0; m < 3; ++m) {
       SIG_TRY(lam_offsets_fwd(c.Xf + m * BL * d, p, m, c.mod[m], g, B, L, d, s));
+      SIG_PHASE("lam_sample_fwd");
       lam_sample_fwd_kernel<<<B * g.P, 256, 0, s>>>(c.Xf + m * BL * d, c.mod[m].o, g, L, d, c.S + m * ms);
       SIG_CHECK_LAUNCH();
     }
+    SIG_PHASE("lam_sample_fwd");
     lam_mse_kernel<<<B * g.P, 256, 0, s>>>(c.S, ms, d, c.part);
     SIG_CHECK_LAUNCH();
     sum_kernel<<<1, 256, 0, s>>>(c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
@@ -664,6 +674,8 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
   float* dfr = c.df;
   float* dfn = c.df + (size_t)B * d;
   float* dft = c.df + (size_t)2 * B * d;
+  {
+  SIG_PHASE("gam_bwd");
   SIG_TRY(launch_gemm(gemm_nn(c.Wlv, B, fn, d, dfr, d, B, d, B), s));
   {
     Gemm gg = gemm_nn(c.Wla, B, ft, d, dfr, d, B, d, B);
@@ -676,20 +688,28 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
   SIG_CHECK_LAUNCH();
   scale_scalar_kernel<<<1, 1, 0, s>>>(c.dtau, dlosses, dp->contra_temp);
   SIG_CHECK_LAUNCH();
+  }
   // ---- LAM
   Geo g = make_geo(do_lam ? h : 8, do_lam ? w : 8);
   const int64_t ms = (int64_t)B * g.P * d;
   if (do_lam) {
+    {
+    SIG_PHASE("lam_sample_bwd");
     lam_mse_bwd_kernel<<<B * g.P, 256, 0, s>>>(c.S, ms, d, 2.f / (3.f * (float)B * g.P * d), dlosses + 1, c.dS);
     SIG_CHECK_LAUNCH();
+    }
     for (int m = 0; m < 3; ++m) {
       const float* X = c.Xf + m * BL * d;
+      {
+      SIG_PHASE("lam_sample_bwd");
       lam_sample_bwd_kernel<<<B * g.P, 256, 0, s>>>(X, c.mod[m].o, c.dS + m * ms, g, L, d, c.mod[m].dO);
       SIG_CHECK_LAUNCH();
+      }
       SIG_TRY(lam_offsets_bwd(X, p, dp, m, c.mod[m], c, c.dXf + m * BL * d, g, B, L, d, s));
     }
   }
   // ---- single writer per modality
+  SIG_PHASE("align_write");
   const bool zero_cls = dtok->zero_cls != 0;
   for (int m = 0; m < 3; ++m) {
     const float* dense = do_lam ? c.dXf + m * BL * d : nullptr;

@@ -5,10 +5,12 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "prof.h"
 #include "signal_b200.h"
 
 #define SIG_CHECK_LAUNCH()                         \
   do {                                             \
+    ::sig::prof_count_launch();                    \
     cudaError_t e__ = cudaGetLastError();          \
     if (e__ != cudaSuccess) return (int)e__;       \
   } while (0)

@@ -1,0 +1,90 @@
+#include "prof.h"
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "signal_b200.h"
+
+namespace sig {
+namespace {
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_enabled{0};
+std::mutex g_mu;
+struct Rec {
+  std::string name;
+  cudaEvent_t a, b;
+};
+std::vector<Rec> g_recs;
+}  // namespace
+
+void prof_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : idx(-1), s(stream) {
+  if (!g_enabled.load(std::memory_order_relaxed)) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  Rec r;
+  r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess) return;
+  if (cudaEventCreate(&r.b) != cudaSuccess) { cudaEventDestroy(r.a); return; }
+  cudaEventRecord(r.a, stream);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_recs.push_back(r);
+  idx = (int)g_recs.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (idx < (int)g_recs.size()) cudaEventRecord(g_recs[idx].b, s);
+}
+}  // namespace sig
+
+extern "C" {
+
+unsigned long long sig_debug_launch_count(void) { return sig::g_launches.load(); }
+
+int sig_profile_enable(int on) {
+  sig::g_enabled.store(on ? 1 : 0);
+  return 0;
+}
+
+// Synchronises the recorded events, writes up to `max` aggregated phases ('\n'-separated names
+// into names_buf, summed milliseconds into ms, scope counts into counts) and clears the record.
+int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max) {
+  std::lock_guard<std::mutex> lk(sig::g_mu);
+  std::vector<std::string> names;
+  std::vector<float> sums;
+  std::vector<int> cnt;
+  for (auto& r : sig::g_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&t, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    size_t i = 0;
+    for (; i < names.size(); ++i)
+      if (names[i] == r.name) break;
+    if (i == names.size()) { names.push_back(r.name); sums.push_back(0.f); cnt.push_back(0); }
+    sums[i] += t;
+    cnt[i] += 1;
+  }
+  sig::g_recs.clear();
+  std::string joined;
+  int n = 0;
+  for (size_t i = 0; i < names.size() && n < max; ++i, ++n) {
+    if (joined.size() + names[i].size() + 2 > names_bytes) break;
+    joined += names[i];
+    joined += '\n';
+    ms[n] = sums[i];
+    counts[n] = cnt[i];
+  }
+  if (names_buf && names_bytes) {
+    std::strncpy(names_buf, joined.c_str(), names_bytes - 1);
+    names_buf[names_bytes - 1] = 0;
+  }
+  return n;
+}
+}

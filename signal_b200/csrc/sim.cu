@@ -49,6 +49,7 @@ static __global__ void convert_tokens_kernel(TokPtrs tp, int B, int L, int d, fl
 }
 
 int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s) {
+  SIG_PHASE("convert_tokens");
   TokPtrs tp;
   for (int m = 0; m < 3; ++m) {
     tp.patch[m] = t->patch[m]; tp.cls[m] = t->cls[m];
@@ -526,6 +527,7 @@ static __global__ void write_token_grads_kernel(GradPtrs gp, const float* __rest
 
 int write_token_grads(const sig_token_grads* g, int dtype, const float* dXf, const float* dclsf, int B, int L, int d,
                       cudaStream_t s) {
+  SIG_PHASE("write_token_grads");
   GradPtrs gp;
   for (int m = 0; m < 3; ++m) {
     gp.dpatch[m] = g->dpatch[m]; gp.dcls[m] = g->dcls[m];
@@ -607,6 +609,7 @@ size_t sim_ctx_bytes(int B, int L, int d) { return sim_ctx(nullptr, B, L, d).byt
 static int run_selection(const SimCtx& c, const sig_sim_params* p, int B, int L, int d, int which, int k1, int k2, int max_keep,
                          float* masks_out, cudaStream_t s) {
   const int R = 3 * B;
+  SIG_PHASE("sim_select");
   // q = W_q cls + b_q (useA.py:123); qt = W_k^T q; c = q . b_k
   SIG_TRY(launch_gemm(gemm_nt(c.clsf, d, p->sel_wq, d, c.qsel, d, p->sel_bq, R, d, d), s));
   SIG_TRY(launch_gemm(gemm_nn(c.qsel, d, p->sel_wk, d, c.qtsel, d, R, d, d), s));
@@ -634,6 +637,8 @@ static int run_attention_fwd(const SimCtx& c, const sig_sim_params* p, const flo
   const float* bk = p->in_proj_b + d;
   const float* bv = p->in_proj_b + 2 * d;
   // q = W_q cls + b_q  (unscaled; the 1/sqrt(hd) of MHA is folded into qt and c)
+  {
+  SIG_PHASE("sim_attn_prep");
   SIG_TRY(launch_gemm(gemm_nt(c.clsf, d, wq, d, c.qatt, d, bq, R, d, d), s));
   {  // qt[(b,q),h,:] = scale * q_h W_k^h   (batched over heads)
     Gemm g = gemm_nn(c.qatt, d, wk, d, c.qtatt, 8 * (int64_t)d, R, d, hd);
@@ -645,10 +650,15 @@ static int run_attention_fwd(const SimCtx& c, const sig_sim_params* p, const flo
     g.batch = kHeads; g.az = hd; g.bz = hd; g.cz = 1; g.alpha = scale;
     SIG_TRY(launch_gemm(g, s));
   }
+  }
+  {
+  SIG_PHASE("sim_attn_tokens_fwd");
   const size_t sm = attn_fwd_smem(L, d);
   cudaFuncSetAttribute(sim_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   sim_attn_fwd_kernel<<<dim3(B, 4), 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, B, L, d, c.xbar, c.amax, c.asum);
   SIG_CHECK_LAUNCH();
+  }
+  SIG_PHASE("sim_post");
   {  // o_h = W_v^h xbar_h + b_v^h
     Gemm g = gemm_nt(c.xbar, 8 * (int64_t)d, wv, d, c.o, d, bv, R, hd, d);
     g.batch = kHeads; g.az = d; g.bz = (int64_t)hd * d; g.cz = hd; g.biasz = hd;
@@ -679,6 +689,8 @@ static int run_attention_bwd(const SimCtx& c, const sig_sim_params* p, const flo
   float* dwq = g->in_proj_w;
   float* dwk = g->in_proj_w + (size_t)d * d;
   float* dwv = g->in_proj_w + (size_t)2 * d * d;
+  {
+  SIG_PHASE("sim_post_bwd");
   // LN2
   layernorm_bwd_kernel<InT><<<R, 256, 0, s>>>(dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
   SIG_CHECK_LAUNCH();
@@ -721,10 +733,15 @@ static int run_attention_bwd(const SimCtx& c, const sig_sim_params* p, const flo
     gg.batch = kHeads; gg.az = hd; gg.bz = (int64_t)hd * d; gg.cz = d;
     SIG_TRY(launch_gemm(gg, s));
   }
+  }
+  {
+  SIG_PHASE("sim_attn_tokens_bwd");
   const size_t sm = attn_bwd_smem(L, d);
   cudaFuncSetAttribute(sim_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   sim_attn_bwd_kernel<<<B, 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, c.xbar, c.amax, c.asum, c.dxbar, B, L, d, c.dqt, c.dXf);
   SIG_CHECK_LAUNCH();
+  }
+  SIG_PHASE("sim_attn_prep_bwd");
   {  // dq_h = scale * dqt_h W_k^hT
     Gemm gg = gemm_nt(c.dqt, 8 * (int64_t)d, wk, d, c.dqatt, d, nullptr, R, hd, d);
     gg.batch = kHeads; gg.az = d; gg.bz = (int64_t)hd * d; gg.cz = hd; gg.alpha = scale;

@@ -65,6 +65,7 @@ EXPORTS = [
     "sig_sim_fwd", "sig_sim_bwd", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
+    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect",
 ]
 
 
@@ -101,9 +102,12 @@ def load():
     lib.sig_volume3_ws_bytes.argtypes = [i, i]
     lib.sig_volume3_fwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, sz, i, vp]
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
+    lib.sig_debug_launch_count.restype = C.c_ulonglong
+    lib.sig_profile_enable.argtypes = [i]
+    lib.sig_profile_collect.argtypes = [C.c_char_p, sz, P(C.c_float), P(C.c_int), i]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("sig_error_string", "sig_ctx_bytes", "sig_volume3_ws_bytes"):
+        if name not in ("sig_error_string", "sig_ctx_bytes", "sig_volume3_ws_bytes", "sig_debug_launch_count"):
             fn.restype = i
     if lib.sig_version() != 1:
         raise RuntimeError("signal_b200: ABI version mismatch between lib.py and libsignal_b200.so")
@@ -211,3 +215,23 @@ def ctx_bytes(kind: int, B: int, L: int, d: int) -> int:
     if n == 0:
         raise RuntimeError(f"signal_b200: unsupported shape B={B} L={L} d={d} (L <= 128, d % 64 == 0)")
     return n
+
+
+def launch_count() -> int:
+    """Kernel launches enqueued by the library since it was loaded."""
+    return int(load().sig_debug_launch_count())
+
+
+def profile_enable(on: bool):
+    load().sig_profile_enable(int(on))
+
+
+def profile_collect():
+    """-> {phase: (summed ms, scopes)} for everything recorded since the last collect."""
+    lib = load()
+    names = C.create_string_buffer(4096)
+    ms = (C.c_float * 64)()
+    cnt = (C.c_int * 64)()
+    n = lib.sig_profile_collect(names, 4096, ms, cnt, 64)
+    keys = names.value.decode().split("\n")[:n]
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(keys)}

@@ -54,13 +54,14 @@ def param_tol(key, objective, tol):
     * d(gam)/d(contra_temp) = sum_ij dZ_ij V_ij / tau^2 with sum_j dZ_ij = 0: on iid
       tokens V ~ 1 everywhere, so the sum cancels to ~1e-3 of its terms and the
       reference's own fp32 ``torch.det`` (volume.py:57, fp32 even in the fp64 golden
-      run) shows up as ~3e-4 relative noise.
+      run) shows up as ~3e-4 relative noise; an fp32 evaluation of V (1e-7 relative per
+      entry, times 1/tau^2 = 204, over a result of ~0.05) sits at ~1e-3.  Hence 3e-3.
     * LAM parameter gradients with the offsets pushed into tanh saturation
       (offset_gain >= 25) pass through 1 - tanh(o)^2, which loses digits in fp32: the
       fp32 *reference* deviates from its own fp64 run by ~2e-4 there.
     """
     if key.endswith("contra_temp"):
-        return max(tol, 1e-3)
+        return max(tol, 3e-3)
     if objective == "lam" and tol > 1e-5:
         return max(tol, 5e-4)
     return tol
