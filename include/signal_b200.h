@@ -202,6 +202,13 @@ unsigned long long sig_debug_launch_count(void);
 int sig_profile_enable(int on);
 int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);
 
+/* Unit-test seam for the tcgen05 GEMM core: C = alpha * A . B^T (+bias) (GELU if act), bf16 operands.
+ * mode: 0 row-major [rows,K]; 1 token view [B,128,d] with rows=(b,l), K=d; 2 row-major [K,cols];
+ * 3 token view with K=(b,l), cols=d.  geom = {ld, stride_b, stride_l, rows, cols} (elements). */
+int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const void* B, int b_mode,
+                        const int64_t* b_geom, void* C, int64_t ldc, int out_bf16, const float* bias,
+                        int M, int N, int K, float alpha, int act, int ksplit, int bn, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

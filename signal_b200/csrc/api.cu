@@ -2,6 +2,7 @@
 #include "align.h"
 #include "common.cuh"
 #include "sim.h"
+#include "tc_gemm.h"
 
 namespace {
 struct DeviceGuard {
@@ -153,6 +154,23 @@ int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int 
   if (B1 < 1 || B2 < 1 || d < 1) return SIG_ERR_SHAPE;
   if (ws_bytes < sig_volume3_ws_bytes(B1, B2)) return SIG_ERR_WORKSPACE;
   return sig::volume3_backward(l, v, a, B1, B2, d, dvol, dl, dv, da, static_cast<float*>(ws), (cudaStream_t)stream);
+}
+
+int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const void* B, int b_mode, const int64_t* b_geom,
+                        void* C, int64_t ldc, int out_bf16, const float* bias, int M, int N, int K, float alpha, int act,
+                        int ksplit, int bn, int device, void* stream) {
+  SIG_ENTER(device);
+  if (!A || !B || !C || !a_geom || !b_geom) return SIG_ERR_NULL;
+  sig::TcGemmDesc g = sig::tc_desc();
+  auto fill = [](sig::TcOperand& o, const void* p, int mode, const int64_t* ge) {
+    o.ptr[0] = o.ptr[1] = o.ptr[2] = p; o.mode = mode; o.ld = ge[0]; o.stride_b = ge[1]; o.stride_l = ge[2];
+    o.rows = ge[3]; o.cols = ge[4];
+  };
+  fill(g.A, A, a_mode, a_geom);
+  fill(g.B, B, b_mode, b_geom);
+  g.M = M; g.N = N; g.K = K; g.C[0] = C; g.ldc = ldc; g.out_bf16 = out_bf16; g.bias[0] = bias; g.alpha = alpha;
+  g.act = act; g.ksplit = ksplit; g.bn = bn;
+  return sig::tc_gemm(g, (cudaStream_t)stream);
 }
 
 }  // extern "C"

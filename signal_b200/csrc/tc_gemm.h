@@ -1,0 +1,59 @@
+// Generic bf16 tcgen05 GEMM (TMA-fed, TMEM accumulators, persistent, warp-specialised).
+//   C[z][M,N] = alpha * A[z] . B[z]^T (+ bias[z][n]) (GELU optional), fp32 accumulate,
+// operands described by TMA tensor maps so that strided token views are consumed in place.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sig {
+
+enum TcOpMode : int {
+  TC_K2D = 0,    // row-major [rows, K] matrix, rows = M or N index                (K-major operand)
+  TC_KTOK = 1,   // token view [B, L=128, d]: rows = (b, l), K = d                  (K-major operand, 3-D map)
+  TC_MN2D = 2,   // row-major [K, cols] matrix, cols = M or N index                 (MN-major operand)
+  TC_MNTOK = 3,  // token view [B, L=128, d]: K = (b, l) positions, cols = channels (MN-major operand, 3-D map)
+};
+
+struct TcOperand {
+  const void* ptr[3];       // per batch entry (bf16)
+  int mode;
+  int64_t ld;               // 2-D modes: row pitch in elements
+  int64_t stride_b, stride_l;  // token modes: element strides; B samples of L=128 rows
+  int64_t rows, cols;       // 2-D modes: matrix extents (rows x cols as stored); token modes: rows = B, cols = d
+};
+
+struct TcGemmDesc {
+  TcOperand A, B;
+  int M, N, K, batch;       // batch <= 3
+  void* C[3];
+  int64_t ldc;
+  int out_bf16;             // 0: fp32 C, 1: bf16 C
+  const float* bias[3];     // optional, per n
+  float alpha;
+  int act;                  // 0 none, 1 GELU
+  int ksplit;               // > 1: fp32 atomic accumulation into a pre-zeroed C (no bias / act / bf16)
+  int bn;                   // 128 or 256 (N tile)
+};
+
+inline TcGemmDesc tc_desc() {
+  TcGemmDesc g{};
+  g.batch = 1; g.alpha = 1.f; g.ksplit = 1; g.bn = 128;
+  return g;
+}
+inline TcOperand tc_k2d(const void* p, int64_t rows, int64_t k, int64_t ld) {
+  TcOperand o{}; o.ptr[0] = o.ptr[1] = o.ptr[2] = p; o.mode = TC_K2D; o.ld = ld; o.rows = rows; o.cols = k; return o;
+}
+inline TcOperand tc_mn2d(const void* p, int64_t k, int64_t cols, int64_t ld) {
+  TcOperand o{}; o.ptr[0] = o.ptr[1] = o.ptr[2] = p; o.mode = TC_MN2D; o.ld = ld; o.rows = k; o.cols = cols; return o;
+}
+
+// Enqueue the GEMM on `s`.  Returns 0 / SIG_ERR_* / cudaError_t.
+int tc_gemm(const TcGemmDesc& g, cudaStream_t s);
+
+// bf16 helpers used around the GEMMs
+int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
+// dst[c][r] = bf16(src[r][c]) for a row-major [rows, cols] fp32 matrix
+int transpose_f32_to_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, cudaStream_t s);
+
+}  // namespace sig

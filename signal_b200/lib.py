@@ -65,7 +65,7 @@ EXPORTS = [
     "sig_sim_fwd", "sig_sim_bwd", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
-    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect",
+    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16",
 ]
 
 
@@ -102,6 +102,7 @@ def load():
     lib.sig_volume3_ws_bytes.argtypes = [i, i]
     lib.sig_volume3_fwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, sz, i, vp]
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
+    lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i, vp]
     lib.sig_debug_launch_count.restype = C.c_ulonglong
     lib.sig_profile_enable.argtypes = [i]
     lib.sig_profile_collect.argtypes = [C.c_char_p, sz, P(C.c_float), P(C.c_int), i]
@@ -235,3 +236,21 @@ def profile_collect():
     n = lib.sig_profile_collect(names, 4096, ms, cnt, 64)
     keys = names.value.decode().split("\n")[:n]
     return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(keys)}
+
+
+def debug_gemm_bf16(A, a_mode, B, b_mode, M, N, K, out_bf16=False, bias=None, alpha=1.0, act=0, ksplit=1, bn=128):
+    """Unit-test seam: run the tcgen05 GEMM core on bf16 CUDA tensors, returns C [M,N]."""
+    lib = load()
+
+    def geom(t, mode):
+        if mode in (0, 2):
+            return (C.c_int64 * 5)(t.stride(0), 0, 0, t.shape[0], t.shape[1])
+        return (C.c_int64 * 5)(0, t.stride(0), t.stride(1), t.shape[0], t.shape[2])
+
+    dev = A.device
+    out = torch.zeros(M, N, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.sig_debug_gemm_bf16(A.data_ptr(), a_mode, geom(A, a_mode), B.data_ptr(), b_mode, geom(B, b_mode),
+                                      out.data_ptr(), N, int(out_bf16), None if bias is None else bias.data_ptr(), M, N, K,
+                                      alpha, act, ksplit, bn, dev.index, stream_ptr(dev)), "sig_debug_gemm_bf16")
+    return out
