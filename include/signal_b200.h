@@ -121,8 +121,9 @@ typedef struct sig_align_param_grads {           /* overwritten */
 /* ---- library info ------------------------------------------------------ */
 int sig_version(void);                       /* SIG_ABI_VERSION */
 const char* sig_error_string(int code);      /* static string; cudaGetErrorString for code > 0 */
-/* bytes of the ctx buffer for (kind, B, L, d); 0 if the shape is unsupported */
-size_t sig_ctx_bytes(int kind, int B, int L, int d);
+/* bytes of the ctx buffer for (kind, B, L, d) with tokens of `dtype` and the call's `flags`;
+ * 0 if the shape is unsupported */
+size_t sig_ctx_bytes(int kind, int B, int L, int d, int dtype, unsigned flags);
 
 /* ---- SIM: Select_Interactive_Module.forward (useA.py:454-476) ---------- */
 /* out  [B,3d] in tokens' dtype; masks fp32 [3,B,L] (last_masks, useA.py:323).

@@ -5,8 +5,19 @@
 #include "common.cuh"
 #include "sim.h"
 #include "simt_ops.cuh"
+#include "tc_gemm.h"
 
 namespace sig {
+
+struct TokPtrs3 {
+  const void* patch[3];
+  int64_t psb[3], psl[3];
+};
+struct GradPtrs3 {
+  void* dpatch[3];
+  void* dcls[3];
+  int64_t psb[3], psl[3], csb[3];
+};
 
 // =============================================================================================
 // GAM
@@ -535,6 +546,13 @@ static AlignCtx align_ctx(void* base, int B, int L, int d, int nmod) {
 size_t align_ctx_bytes(int B, int L, int d) { return align_ctx(nullptr, B, L, d, 3).bytes; }
 size_t das_ctx_bytes(int B, int L, int d) { return align_ctx(nullptr, B, L, d, 1).bytes; }
 
+#include "align_tc.inl"
+
+size_t align_ctx_bytes_for(int B, int L, int d, int dtype, unsigned flags) {
+  if (dtype == SIG_BF16 && L == 128 && !(flags & SIG_FLAG_FORCE_SIMT)) return align_tc_ctx(nullptr, B, L, d).bytes;
+  return align_ctx_bytes(B, L, d);
+}
+
 // =============================================================================================
 // orchestration
 // =============================================================================================
@@ -611,8 +629,11 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   if (!p->contra_temp || !losses || !ctx) return SIG_ERR_NULL;
   const int B = tok->B, L = tok->L, d = tok->d;
   if (do_lam) SIG_TRY(check_grid(h, w, L));
+  if (tc_path_ok(tok, flags)) {
+    if (ctx_bytes < align_tc_ctx(nullptr, B, L, d).bytes) return SIG_ERR_WORKSPACE;
+    return align_forward_tc(tok, p, h, w, do_lam, losses, ctx, s);
+  }
   if (ctx_bytes < align_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
-  (void)flags;
   AlignCtx c = align_ctx(ctx, B, L, d, 3);
   sig_tokens t2 = *tok;
   for (int m = 0; m < 3; ++m) t2.cls[m] = nullptr;
@@ -663,8 +684,14 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
   if (!dlosses || !ctx || !dp->contra_temp) return SIG_ERR_NULL;
   const int B = tok->B, L = tok->L, d = tok->d;
   if (do_lam) SIG_TRY(check_grid(h, w, L));
+  if (tc_path_ok(tok, flags)) {
+    if (ctx_bytes < align_tc_ctx(nullptr, B, L, d).bytes) return SIG_ERR_WORKSPACE;
+    for (int m = 1; m < 3; ++m)
+      if (dtok->patch_stride_b[m] != dtok->patch_stride_b[0] || dtok->patch_stride_l[m] != dtok->patch_stride_l[0])
+        return SIG_ERR_SHAPE;
+    return align_backward_tc(tok, p, h, w, do_lam, dlosses, dtok, dp, ctx, s);
+  }
   if (ctx_bytes < align_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
-  (void)flags;
   AlignCtx c = align_ctx(ctx, B, L, d, 3);
   const size_t BL = (size_t)B * L;
   // ---- GAM: d(features), then back through normalise + mean pool (unit upstream; scaled in the writer)

@@ -1,0 +1,555 @@
+// bf16 fast path of AlignmentM (included by align.cu): tokens are consumed in place (strided bf16),
+// the dense 1x1 convolutions of DA_sample run on the tcgen05 GEMM core (tc_gemm.cu) with the two
+// linear maps proj_q -> conv_offset[0] folded into one (DAS.py:129,136: no non-linearity between
+// them), everything else is HBM-bound SIMT code with 16-byte accesses.
+
+// ---- GAM: mean pool straight from the strided token views.  grid (B, 3), 256 threads -------------
+template <typename T>
+static __global__ void __launch_bounds__(256) pool_tok_kernel(TokPtrs3 tp, int B, int L, int d, float* __restrict__ mean) {
+  __shared__ float red[256 * 8];
+  const int b = blockIdx.x, m = blockIdx.y;
+  const int tpr = d / 8;                       // threads per token row
+  const int ngrp = blockDim.x / tpr;           // row groups working in parallel
+  const int grp = threadIdx.x / tpr, c = (threadIdx.x % tpr) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (grp < ngrp) {
+    const T* x = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m];
+    for (int l = grp; l < L; l += ngrp) {
+      float v[8];
+      load8(x + l * tp.psl[m] + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  if (grp == 0) {
+    for (int g2 = 1; g2 < ngrp; ++g2)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += red[(g2 * tpr + threadIdx.x) * 8 + i];
+    const float inv = 1.f / L;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    store8(mean + ((int64_t)m * B + b) * d + c, acc);
+  }
+}
+
+// ---- LAM: depthwise 4x4/s4 conv + GELU + 1x1 -> offset logit, from the bf16 pre-activation H ------
+// grid (B*P, 3), d/8 threads (8 channels each).  U saved (fp32) for backward.
+static __global__ void __launch_bounds__(128) lam_dw_fwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
+                                                                   sig_align_params prm, Geo g, int B, int L, int d,
+                                                                   float* __restrict__ U, float* __restrict__ o) {
+  __shared__ float scratch[33];
+  const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
+  const int py = p / g.Wk, px = p % g.Wk;
+  const float* wdw = prm.off2_w[m];
+  const float* bdw = prm.off2_b[m];
+  const float* w4 = prm.off4_w[m];
+  const __nv_bfloat16* Hm = H + m * hms;
+  float part = 0.f;
+  const int c = threadIdx.x * 8;
+  if (c < d) {
+    float u[8];
+    load8(bdw + c, u);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
+      float h[8];
+      load8(Hm + ((int64_t)b * L + l) * d + c, h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = fmaf(gelu_f(h[i]), wdw[(c + i) * 16 + k], u[i]);
+    }
+    store8(U + ((int64_t)m * B * g.P + bp) * d + c, u);
+    float w[8];
+    load8(w4 + c, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part += gelu_f(u[i]) * w[i];
+  }
+  part = block_sum(part, scratch);
+  if (threadIdx.x == 0) o[(int64_t)m * B * g.P + bp] = part;
+}
+
+// dU = dO * w4 * gelu'(U); dH[b,pos,c] = dU * wdw[c,k] * gelu'(H)  (bf16 out).  grid (B*P, 3)
+static __global__ void __launch_bounds__(128) lam_dw_bwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
+                                                                   const float* __restrict__ U, const float* __restrict__ dO,
+                                                                   sig_align_params prm, Geo g, int B, int L, int d,
+                                                                   float* __restrict__ dU, __nv_bfloat16* __restrict__ dH) {
+  const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
+  const int py = p / g.Wk, px = p % g.Wk;
+  const float* wdw = prm.off2_w[m];
+  const float* w4 = prm.off4_w[m];
+  const int c = threadIdx.x * 8;
+  if (c >= d) return;
+  const int64_t ubase = ((int64_t)m * B * g.P + bp) * d + c;
+  const float go = dO[(int64_t)m * B * g.P + bp];
+  float u[8], w[8], du[8];
+  load8(U + ubase, u);
+  load8(w4 + c, w);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) du[i] = go * w[i] * gelu_grad_f(u[i]);
+  store8(dU + ubase, du);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
+    const int64_t idx = m * hms + ((int64_t)b * L + l) * d + c;
+    float h[8], r[8];
+    load8(H + idx, h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = du[i] * wdw[(c + i) * 16 + k] * gelu_grad_f(h[i]);
+    store8(dH + idx, r);
+  }
+}
+
+// parameter gradients of the offset net tail + bias of the folded conv (deterministic):
+//   dwdw[c,k] = sum dU * gelu(H[pos(p,k)]),  dbdw = sum dU,  dw4 = sum dO * gelu(U),  dbf = sum_pos dH
+// grid (ceil(d/32), 3); 32 channels x 8 row lanes over (b,p)
+static __global__ void __launch_bounds__(256) lam_dw_param_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
+                                                                     const float* __restrict__ U, const float* __restrict__ dU,
+                                                                     const float* __restrict__ dO, sig_align_params prm,
+                                                                     sig_align_param_grads gr, float* __restrict__ dbf, Geo g, int B,
+                                                                     int L, int d) {
+  __shared__ float sm[8][32][20];
+  const int m = blockIdx.y;
+  const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const float* wdw = prm.off2_w[m];
+  float acc[19];
+#pragma unroll
+  for (int i = 0; i < 19; ++i) acc[i] = 0.f;
+  if (c < d) {
+    float wk[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wk[k] = wdw[c * 16 + k];
+    for (int bp = r; bp < B * g.P; bp += 8) {
+      const int b = bp / g.P, p = bp % g.P;
+      const int py = p / g.Wk, px = p % g.Wk;
+      const int64_t ui = ((int64_t)m * B * g.P + bp) * d + c;
+      const float du = dU[ui];
+      acc[16] += du;
+      acc[17] += dO[(int64_t)m * B * g.P + bp] * gelu_f(U[ui]);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
+        const float h = __bfloat162float(H[m * hms + ((int64_t)b * L + l) * d + c]);
+        acc[k] = fmaf(du, gelu_f(h), acc[k]);
+        acc[18] = fmaf(du * wk[k], gelu_grad_f(h), acc[18]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 19; ++i) sm[r][cl][i] = acc[i];
+  __syncthreads();
+  if (r == 0 && c < d) {
+#pragma unroll
+    for (int i = 0; i < 19; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += sm[q][cl][i];
+      if (i < 16) gr.off2_w[m][c * 16 + i] = t;
+      else if (i == 16) gr.off2_b[m][c] = t;
+      else if (i == 17) gr.off4_w[m][c] = t;
+      else dbf[(int64_t)m * d + c] = t;
+    }
+  }
+}
+
+// bilinear sampling straight from the strided token view.  grid (B*P, 3)
+template <typename T>
+static __global__ void __launch_bounds__(128) lam_sample_fwd_tok_kernel(TokPtrs3 tp, const float* __restrict__ o, Geo g, int B, int d,
+                                                                        float* __restrict__ S) {
+  const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
+  const Taps t = make_taps(o[(int64_t)m * B * g.P + bp], p, g);
+  const T* x = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m];
+  const int c = threadIdx.x * 8;
+  if (c >= d) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (t.l[k] >= 0) {
+      float v[8];
+      load8(x + t.l[k] * tp.psl[m] + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(t.wgt[k], v[i], acc[i]);
+    }
+  store8(S + ((int64_t)m * B * g.P + bp) * d + c, acc);
+}
+
+// grid-gradient reduction -> d(offset logit).  grid (B*P, 3)
+template <typename T>
+static __global__ void __launch_bounds__(128) lam_sample_bwd_tok_kernel(TokPtrs3 tp, const float* __restrict__ o,
+                                                                        const float* __restrict__ dS, Geo g, int B, int d,
+                                                                        float* __restrict__ dO) {
+  __shared__ float scratch[33];
+  const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
+  const Taps t = make_taps(o[(int64_t)m * B * g.P + bp], p, g);
+  const T* x = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m];
+  const int c = threadIdx.x * 8;
+  float giy = 0.f, gix = 0.f;
+  if (c < d) {
+    float v[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (t.l[k] >= 0) load8(x + t.l[k] * tp.psl[m] + c, v[k]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
+      }
+    }
+    float ds[8];
+    load8(dS + ((int64_t)m * B * g.P + bp) * d + c, ds);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      giy += ds[i] * ((v[2][i] - v[0][i]) * (1.f - t.wx) + (v[3][i] - v[1][i]) * t.wx);
+      gix += ds[i] * ((v[1][i] - v[0][i]) * (1.f - t.wy) + (v[3][i] - v[2][i]) * t.wy);
+    }
+  }
+  giy = block_sum(giy, scratch);
+  gix = block_sum(gix, scratch);
+  if (threadIdx.x == 0) dO[(int64_t)m * B * g.P + bp] = giy * t.gy + gix * t.gx;
+}
+
+// sparse part of d(patches): every bilinear tap adds w * dS[p,:] to the token row it read.
+// grid (B, 3), d/8 threads; taps are applied one after the other, so no two threads touch the same element.
+template <typename T>
+static __global__ void __launch_bounds__(128) lam_sparse_add_kernel(GradPtrs3 gp, const float* __restrict__ o,
+                                                                    const float* __restrict__ dS, Geo g, int B, int d) {
+  const int m = blockIdx.y, b = blockIdx.x;
+  const int c = threadIdx.x * 8;
+  if (c >= d) return;
+  T* dx = static_cast<T*>(gp.dpatch[m]) + b * gp.psb[m];
+  for (int p = 0; p < g.P; ++p) {
+    const Taps t = make_taps(o[((int64_t)m * B + b) * g.P + p], p, g);
+    float ds[8];
+    load8(dS + (((int64_t)m * B + b) * g.P + p) * d + c, ds);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (t.l[k] >= 0 && t.wgt[k] != 0.f) {
+        float v[8];
+        T* dst = dx + t.l[k] * gp.psl[m] + c;
+        load8(dst, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(t.wgt[k], ds[i], v[i]);
+        store8(dst, v);
+      }
+  }
+}
+
+// zero the CLS gradient rows (packed [B,1+L,d] destination).  grid (B, 3)
+template <typename T>
+static __global__ void zero_cls_kernel(GradPtrs3 gp, int d) {
+  const int m = blockIdx.y, b = blockIdx.x;
+  if (!gp.dcls[m]) return;
+  T* dst = static_cast<T*>(gp.dcls[m]) + b * gp.csb[m];
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) store8(dst + c, z);
+}
+
+// ---- ctx layout of the bf16 path -------------------------------------------------------------------
+struct AlignTcCtx {
+  // GAM (fp32, small)
+  float *mean, *f, *nrm, *self4, *lv, *la, *V, *rowstat, *colstat, *Wlv, *Wla, *rowA, *colC, *dtau, *df, *dmean;
+  // LAM
+  __nv_bfloat16 *W0b, *Wqb, *Wfb, *dWfb;   // [3][d*d]
+  float *bfold, *dWf, *dbf;                // [3][d], [3][d*d], [3][d]
+  __nv_bfloat16 *H, *dH;                   // [3][B*L*d]
+  float *U, *dU, *o, *dO, *S, *dS, *part;
+  size_t bytes;
+};
+
+static AlignTcCtx align_tc_ctx(void* base, int B, int L, int d) {
+  Arena a(base);
+  AlignTcCtx c;
+  const size_t BL = (size_t)B * L, P = (size_t)(L / 16), dd = (size_t)d * d;
+  c.mean = a.take<float>((size_t)3 * B * d);
+  c.f = a.take<float>((size_t)3 * B * d);
+  c.nrm = a.take<float>((size_t)3 * B);
+  c.self4 = a.take<float>((size_t)4 * B);
+  c.lv = a.take<float>((size_t)B * B);
+  c.la = a.take<float>((size_t)B * B);
+  c.V = a.take<float>((size_t)B * B);
+  c.rowstat = a.take<float>((size_t)2 * B);
+  c.colstat = a.take<float>((size_t)2 * B);
+  c.Wlv = a.take<float>((size_t)B * B);
+  c.Wla = a.take<float>((size_t)B * B);
+  c.rowA = a.take<float>((size_t)B);
+  c.colC = a.take<float>((size_t)3 * B);
+  c.dtau = a.take<float>(4);
+  c.df = a.take<float>((size_t)3 * B * d);
+  c.dmean = a.take<float>((size_t)3 * B * d);
+  c.W0b = a.take<__nv_bfloat16>(3 * dd);
+  c.Wqb = a.take<__nv_bfloat16>(3 * dd);
+  c.Wfb = a.take<__nv_bfloat16>(3 * dd);
+  c.dWfb = a.take<__nv_bfloat16>(3 * dd);
+  c.bfold = a.take<float>((size_t)3 * d);
+  c.dWf = a.take<float>(3 * dd);
+  c.dbf = a.take<float>((size_t)3 * d);
+  c.H = a.take<__nv_bfloat16>(3 * BL * d);
+  c.dH = a.take<__nv_bfloat16>(3 * BL * d);
+  c.U = a.take<float>(3 * (size_t)B * P * d);
+  c.dU = a.take<float>(3 * (size_t)B * P * d);
+  c.o = a.take<float>(3 * (size_t)B * P);
+  c.dO = a.take<float>(3 * (size_t)B * P);
+  c.S = a.take<float>(3 * (size_t)B * P * d);
+  c.dS = a.take<float>(3 * (size_t)B * P * d);
+  c.part = a.take<float>((size_t)B * P);
+  c.bytes = a.off;
+  return c;
+}
+
+static TokPtrs3 tok_ptrs3(const sig_tokens* t) {
+  TokPtrs3 tp;
+  for (int m = 0; m < 3; ++m) {
+    tp.patch[m] = t->patch[m];
+    tp.psb[m] = t->patch_stride_b[m];
+    tp.psl[m] = t->patch_stride_l[m];
+  }
+  return tp;
+}
+static GradPtrs3 grad_ptrs3(const sig_token_grads* g) {
+  GradPtrs3 gp;
+  for (int m = 0; m < 3; ++m) {
+    gp.dpatch[m] = g->dpatch[m]; gp.dcls[m] = g->dcls[m];
+    gp.psb[m] = g->patch_stride_b[m]; gp.psl[m] = g->patch_stride_l[m]; gp.csb[m] = g->cls_stride_b[m];
+  }
+  return gp;
+}
+
+static TcOperand tok_operand(const sig_tokens* t, int mode) {
+  TcOperand o{};
+  for (int m = 0; m < 3; ++m) o.ptr[m] = t->patch[m];
+  o.mode = mode;
+  o.stride_b = t->patch_stride_b[0];
+  o.stride_l = t->patch_stride_l[0];
+  o.rows = t->B;
+  o.cols = t->d;
+  return o;
+}
+static TcOperand batched(TcOperand o, const void* base, size_t stride_elems) {
+  for (int m = 0; m < 3; ++m) o.ptr[m] = static_cast<const __nv_bfloat16*>(base) + m * stride_elems;
+  return o;
+}
+
+static bool tc_path_ok(const sig_tokens* t, unsigned flags) {
+  if (flags & SIG_FLAG_FORCE_SIMT) return false;
+  if (t->dtype != SIG_BF16 || t->L != 128) return false;
+  // one 3-D tensor-map geometry for the three modalities
+  for (int m = 1; m < 3; ++m)
+    if (t->patch_stride_b[m] != t->patch_stride_b[0] || t->patch_stride_l[m] != t->patch_stride_l[0]) return false;
+  return true;
+}
+
+static int gam_forward_common(const float* mean, const sig_align_params* p, int B, int d, float* f, float* nrm, float* self4,
+                              float* lv, float* la, float* V, float* rowstat, float* colstat, float* Wlv, float* Wla, float* rowA,
+                              float* colC, float* dtau, float* losses, cudaStream_t s) {
+  gam_norm_kernel<<<B, 256, 0, s>>>(mean, B, d, f, nrm, self4);
+  SIG_CHECK_LAUNCH();
+  const float* fr = f;
+  const float* fn = f + (size_t)B * d;
+  const float* ft = f + (size_t)2 * B * d;
+  SIG_TRY(launch_gemm(gemm_nt(fr, d, fn, d, lv, B, nullptr, B, B, d), s));
+  SIG_TRY(launch_gemm(gemm_nt(fr, d, ft, d, la, B, nullptr, B, B, d), s));
+  gam_loss_kernel<<<1, 1024, 0, s>>>(self4, lv, la, p->contra_temp, B, V, rowstat, colstat, Wlv, Wla, rowA, colC, losses, dtau);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
+                            cudaStream_t s) {
+  const int B = tok->B, L = tok->L, d = tok->d;
+  AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
+  const TokPtrs3 tp = tok_ptrs3(tok);
+  {
+    SIG_PHASE("gam_fwd");
+    pool_tok_kernel<__nv_bfloat16><<<dim3(B, 3), 256, 0, s>>>(tp, B, L, d, c.mean);
+    SIG_CHECK_LAUNCH();
+    SIG_TRY(gam_forward_common(c.mean, p, B, d, c.f, c.nrm, c.self4, c.lv, c.la, c.V, c.rowstat, c.colstat, c.Wlv, c.Wla, c.rowA,
+                               c.colC, c.dtau, losses, s));
+  }
+  if (!do_lam) return 0;
+  const Geo g = make_geo(h, w);
+  const size_t dd = (size_t)d * d, BL = (size_t)B * L;
+  {
+    SIG_PHASE("lam_fold_weights");
+    for (int m = 0; m < 3; ++m) {
+      SIG_TRY(cast_f32_to_bf16(p->off0_w[m], c.W0b + m * dd, dd, s));
+      SIG_TRY(cast_f32_to_bf16(p->proj_q_w[m], c.Wqb + m * dd, dd, s));
+      // b' = W0 bq + b0
+      cudaMemcpyAsync(c.bfold + (size_t)m * d, p->off0_b[m], d * sizeof(float), cudaMemcpyDeviceToDevice, s);
+      Gemm gg = gemm_nt(p->off0_w[m], d, p->proj_q_b[m], d, c.bfold + (size_t)m * d, 1, nullptr, d, 1, d);
+      gg.accumulate = 1;
+      SIG_TRY(launch_gemm(gg, s));
+    }
+    // W' = W0 Wq  (A = W0 [d_out, d_mid] K-major; B[n = d_in, k = d_mid] = Wq[k][n] -> MN-major)
+    TcGemmDesc t = tc_desc();
+    t.A = batched(tc_k2d(nullptr, d, d, d), c.W0b, dd);
+    t.B = batched(tc_mn2d(nullptr, d, d, d), c.Wqb, dd);
+    t.M = d; t.N = d; t.K = d; t.batch = 3;
+    for (int m = 0; m < 3; ++m) t.C[m] = c.Wfb + m * dd;
+    t.ldc = d; t.out_bf16 = 1;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  {
+    SIG_PHASE("lam_offsetnet_fwd");
+    // H = X W'^T + b'   (tokens consumed in place through a 3-D tensor map)
+    TcGemmDesc t = tc_desc();
+    t.A = tok_operand(tok, TC_KTOK);
+    t.B = batched(tc_k2d(nullptr, d, d, d), c.Wfb, dd);
+    t.M = (int)BL; t.N = d; t.K = d; t.batch = 3;
+    for (int m = 0; m < 3; ++m) {
+      t.C[m] = c.H + m * BL * d;
+      t.bias[m] = c.bfold + (size_t)m * d;
+    }
+    t.ldc = d; t.out_bf16 = 1;
+    t.bn = (d % 256 == 0) ? 256 : 128;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  {
+    SIG_PHASE("lam_dwconv_fwd");
+    lam_dw_fwd_tc_kernel<<<dim3(B * g.P, 3), (unsigned)ceil_div(d / 8, 32) * 32, 0, s>>>(c.H, (int64_t)BL * d, *p, g, B, L, d, c.U, c.o);
+    SIG_CHECK_LAUNCH();
+  }
+  {
+    SIG_PHASE("lam_sample_fwd");
+    lam_sample_fwd_tok_kernel<__nv_bfloat16><<<dim3(B * g.P, 3), (unsigned)ceil_div(d / 8, 32) * 32, 0, s>>>(tp, c.o, g, B, d, c.S);
+    SIG_CHECK_LAUNCH();
+    lam_mse_kernel<<<B * g.P, 256, 0, s>>>(c.S, (int64_t)B * g.P * d, d, c.part);
+    SIG_CHECK_LAUNCH();
+    sum_kernel<<<1, 256, 0, s>>>(c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
+    SIG_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, const float* dlosses,
+                             const sig_token_grads* dtok, const sig_align_param_grads* dp, void* ctx, cudaStream_t s) {
+  const int B = tok->B, L = tok->L, d = tok->d;
+  AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
+  const TokPtrs3 tp = tok_ptrs3(tok);
+  const GradPtrs3 gp = grad_ptrs3(dtok);
+  const size_t dd = (size_t)d * d, BL = (size_t)B * L;
+  {
+    SIG_PHASE("gam_bwd");
+    const float* fr = c.f;
+    const float* fn = c.f + (size_t)B * d;
+    const float* ft = c.f + (size_t)2 * B * d;
+    float* dfr = c.df;
+    float* dfn = c.df + (size_t)B * d;
+    float* dft = c.df + (size_t)2 * B * d;
+    SIG_TRY(launch_gemm(gemm_nn(c.Wlv, B, fn, d, dfr, d, B, d, B), s));
+    {
+      Gemm gg = gemm_nn(c.Wla, B, ft, d, dfr, d, B, d, B);
+      gg.accumulate = 1;
+      SIG_TRY(launch_gemm(gg, s));
+    }
+    SIG_TRY(launch_gemm(gemm_tn(c.Wlv, B, fr, d, dfn, d, B, d, B), s));
+    SIG_TRY(launch_gemm(gemm_tn(c.Wla, B, fr, d, dft, d, B, d, B), s));
+    gam_finish_kernel<<<dim3(B, 3), 256, 0, s>>>(c.f, c.nrm, c.rowA, c.colC, c.df, B, L, d, c.dmean);
+    SIG_CHECK_LAUNCH();
+    scale_scalar_kernel<<<1, 1, 0, s>>>(c.dtau, dlosses, dp->contra_temp);
+    SIG_CHECK_LAUNCH();
+  }
+  if (dtok->zero_cls && !dtok->accumulate) {
+    zero_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 64, 0, s>>>(gp, d);
+    SIG_CHECK_LAUNCH();
+  }
+  if (!do_lam) {
+    // GAM only: broadcast rows through the generic writer
+    SIG_PHASE("align_write");
+    const Geo g = make_geo(8, 8);
+    for (int m = 0; m < 3; ++m) {
+      align_write_kernel<__nv_bfloat16><<<(unsigned)BL, 128, 0, s>>>(nullptr, c.dmean + (size_t)m * B * d, dlosses, nullptr, nullptr, g,
+                                                                    B, L, d, static_cast<__nv_bfloat16*>(dtok->dpatch[m]),
+                                                                    dtok->patch_stride_b[m], dtok->patch_stride_l[m], nullptr, 0,
+                                                                    dtok->accumulate);
+      SIG_CHECK_LAUNCH();
+    }
+    return 0;
+  }
+  const Geo g = make_geo(h, w);
+  const unsigned cthreads = (unsigned)ceil_div(d / 8, 32) * 32;
+  {
+    SIG_PHASE("lam_sample_bwd");
+    lam_mse_bwd_kernel<<<B * g.P, 256, 0, s>>>(c.S, (int64_t)B * g.P * d, d, 2.f / (3.f * (float)B * g.P * d), dlosses + 1, c.dS);
+    SIG_CHECK_LAUNCH();
+    lam_sample_bwd_tok_kernel<__nv_bfloat16><<<dim3(B * g.P, 3), cthreads, 0, s>>>(tp, c.o, c.dS, g, B, d, c.dO);
+    SIG_CHECK_LAUNCH();
+  }
+  {
+    SIG_PHASE("lam_dwconv_bwd");
+    lam_dw_bwd_tc_kernel<<<dim3(B * g.P, 3), cthreads, 0, s>>>(c.H, (int64_t)BL * d, c.U, c.dO, *p, g, B, L, d, c.dU, c.dH);
+    SIG_CHECK_LAUNCH();
+    lam_dw_param_tc_kernel<<<dim3((unsigned)ceil_div(d, 32), 3), 256, 0, s>>>(c.H, (int64_t)BL * d, c.U, c.dU, c.dO, *p, *dp, c.dbf, g,
+                                                                              B, L, d);
+    SIG_CHECK_LAUNCH();
+  }
+  {
+    SIG_PHASE("lam_offsetnet_bwd_dx");
+    // d(patches) = dH W' + g_gam * dmean  -> written once, in the token dtype, at the token strides
+    TcGemmDesc t = tc_desc();
+    t.A = batched(tc_k2d(nullptr, (int64_t)BL, d, d), c.dH, BL * d);
+    t.B = batched(tc_mn2d(nullptr, d, d, d), c.Wfb, dd);
+    t.M = (int)BL; t.N = d; t.K = d; t.batch = 3;
+    for (int m = 0; m < 3; ++m) {
+      t.C[m] = dtok->dpatch[m];
+      t.rowvec[m] = c.dmean + (size_t)m * B * d;
+    }
+    t.rowvec_scale = dlosses;
+    t.out_bf16 = 1; t.c_tok = 1;
+    t.c_stride_b = dtok->patch_stride_b[0]; t.c_stride_l = dtok->patch_stride_l[0];
+    t.accumulate = dtok->accumulate;
+    t.bn = (d % 256 == 0) ? 256 : 128;
+    SIG_TRY(tc_gemm(t, s));
+    lam_sparse_add_kernel<__nv_bfloat16><<<dim3(B, 3), cthreads, 0, s>>>(gp, c.o, c.dS, g, B, d);
+    SIG_CHECK_LAUNCH();
+  }
+  {
+    SIG_PHASE("lam_offsetnet_bwd_dw");
+    // dW' = dH^T X  (both operands MN-major: K = all B*L positions), split-K with fp32 atomics
+    cudaMemsetAsync(c.dWf, 0, 3 * dd * sizeof(float), s);
+    TcGemmDesc t = tc_desc();
+    t.A = batched(tc_mn2d(nullptr, (int64_t)BL, d, d), c.dH, BL * d);
+    t.B = tok_operand(tok, TC_MNTOK);
+    t.M = d; t.N = d; t.K = (int)BL; t.batch = 3;
+    for (int m = 0; m < 3; ++m) t.C[m] = c.dWf + m * dd;
+    t.ldc = d;
+    const int tiles = (int)(ceil_div(d, 128) * ceil_div(d, 128)) * 3;
+    int ks = (2 * 148 + tiles - 1) / tiles;
+    if (ks < 1) ks = 1;
+    t.ksplit = ks;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  {
+    SIG_PHASE("lam_unfold_grads");
+    SIG_TRY(cast_f32_to_bf16(c.dWf, c.dWfb, 3 * dd, s));
+    {  // dWq[d_mid, d_in] = W0^T dW'  : A[m = d_mid, k = d_out] = W0[k][m] (MN-major), B[n = d_in, k = d_out] = dW'[k][n] (MN-major)
+      TcGemmDesc t = tc_desc();
+      t.A = batched(tc_mn2d(nullptr, d, d, d), c.W0b, dd);
+      t.B = batched(tc_mn2d(nullptr, d, d, d), c.dWfb, dd);
+      t.M = d; t.N = d; t.K = d; t.batch = 3;
+      for (int m = 0; m < 3; ++m) t.C[m] = dp->proj_q_w[m];
+      t.ldc = d;
+      SIG_TRY(tc_gemm(t, s));
+    }
+    {  // dW0[d_out, d_mid] = dW' Wq^T : A = dW' [d_out, d_in] K-major, B = Wq [d_mid, d_in] K-major
+      TcGemmDesc t = tc_desc();
+      t.A = batched(tc_k2d(nullptr, d, d, d), c.dWfb, dd);
+      t.B = batched(tc_k2d(nullptr, d, d, d), c.Wqb, dd);
+      t.M = d; t.N = d; t.K = d; t.batch = 3;
+      for (int m = 0; m < 3; ++m) t.C[m] = dp->off0_w[m];
+      t.ldc = d;
+      SIG_TRY(tc_gemm(t, s));
+    }
+    for (int m = 0; m < 3; ++m) {
+      // db0 = db' ; dbq = W0^T db'
+      cudaMemcpyAsync(dp->off0_b[m], c.dbf + (size_t)m * d, d * sizeof(float), cudaMemcpyDeviceToDevice, s);
+      Gemm gg{};
+      gg.A = p->off0_w[m]; gg.am = 1; gg.ak = d;            // A(m = d_mid, k = d_out) = W0[k][m]
+      gg.B = c.dbf + (size_t)m * d; gg.bn = 0; gg.bk = 1;   // B(n = 0, k) = db'[k]
+      gg.C = dp->proj_q_b[m]; gg.cm = 1;
+      gg.M = d; gg.N = 1; gg.K = d; gg.batch = 1; gg.alpha = 1.f; gg.ksplit = 1;
+      SIG_TRY(launch_gemm(gg, s));
+    }
+  }
+  return 0;
+}

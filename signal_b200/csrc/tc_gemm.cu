@@ -28,6 +28,11 @@ struct TcKernelParams {
   float alpha;
   int act, ksplit;
   int tiles_m, tiles_n, kblocks;
+  int c_tok;
+  long long c_stride_b, c_stride_l;
+  const float* rowvec[3];
+  const float* rowvec_scale;
+  int accumulate;
 };
 
 template <int BN>
@@ -168,6 +173,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       ptx::tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const float* bias = p.bias[z];
+      const long long row_off = p.c_tok ? (long long)(row >> 7) * p.c_stride_b + (long long)(row & 127) * p.c_stride_l
+                                        : (long long)row * p.ldc;
+      const float* rvec = p.rowvec[z] ? p.rowvec[z] + (long long)(row >> 7) * p.N : nullptr;
+      const float rscale = p.rowvec[z] ? *p.rowvec_scale : 0.f;
+      const bool vec_ok = p.c_tok ? ((p.c_stride_b % 8) == 0 && (p.c_stride_l % 8) == 0) : ((p.ldc % 8) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
           const bool full_cols = col0 + 32 <= p.N;
           if (p.ksplit > 1) {
-            float* dst = static_cast<float*>(p.C[z]) + (long long)row * p.ldc + col0;
+            float* dst = static_cast<float*>(p.C[z]) + row_off + col0;
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
           } else {
@@ -193,28 +203,46 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
             }
+            if (rvec) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] = fmaf(rscale, rvec[col0 + j], v[j]);
+            }
             if (p.out_bf16) {
-              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C[z]) + (long long)row * p.ldc + col0;
-              if (full_cols && (p.ldc % 8) == 0) {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C[z]) + row_off + col0;
+              if (full_cols && vec_ok) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                   float t[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i) t[i] = v[j + i];
+                  if (p.accumulate) {
+                    float o[8];
+                    load8(dst + j, o);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] += o[i];
+                  }
                   store8(dst + j, t);
                 }
               } else {
                 for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
+                  if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(v[j] + (p.accumulate ? __bfloat162float(dst[j]) : 0.f));
               }
             } else {
-              float* dst = static_cast<float*>(p.C[z]) + (long long)row * p.ldc + col0;
-              if (full_cols && (p.ldc % 4) == 0) {
+              float* dst = static_cast<float*>(p.C[z]) + row_off + col0;
+              if (full_cols && vec_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4) {
+                  float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                  if (p.accumulate) {
+                    const float4 o = *reinterpret_cast<const float4*>(dst + j);
+                    t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j) = t;
+                }
               } else {
                 for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) dst[j] = v[j];
+                  if (col0 + j < p.N) dst[j] = v[j] + (p.accumulate ? dst[j] : 0.f);
               }
             }
           }
@@ -307,6 +335,9 @@ int launch(const TcGemmDesc& g, cudaStream_t s) {
   p.a_mode = g.A.mode; p.b_mode = g.B.mode;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.ldc = g.ldc; p.out_bf16 = g.out_bf16; p.alpha = g.alpha; p.act = g.act; p.ksplit = g.ksplit < 1 ? 1 : g.ksplit;
+  p.c_tok = g.c_tok; p.c_stride_b = g.c_stride_b; p.c_stride_l = g.c_stride_l;
+  for (int z = 0; z < g.batch; ++z) p.rowvec[z] = g.rowvec[z];
+  p.rowvec_scale = g.rowvec_scale; p.accumulate = g.accumulate;
   p.tiles_m = (int)ceil_div(g.M, BM);
   p.tiles_n = (int)ceil_div(g.N, BN);
   p.kblocks = (int)ceil_div(g.K, BK);

@@ -34,6 +34,13 @@ struct TcGemmDesc {
   int act;                  // 0 none, 1 GELU
   int ksplit;               // > 1: fp32 atomic accumulation into a pre-zeroed C (no bias / act / bf16)
   int bn;                   // 128 or 256 (N tile)
+  // token-strided output: row = (b, l) with l in [0,128): element (row, n) at C + b*c_stride_b + l*c_stride_l + n
+  int c_tok;
+  int64_t c_stride_b, c_stride_l;
+  // optional per-sample row vector: v += (*rowvec_scale) * rowvec[z][(row / 128) * N + n]
+  const float* rowvec[3];
+  const float* rowvec_scale;
+  int accumulate;           // v += existing C (non split-K)
 };
 
 inline TcGemmDesc tc_desc() {

@@ -73,7 +73,7 @@ class SimFunction(torch.autograd.Function):
         prm = L_.sim_params_struct(params)
         out = torch.empty(B, 3 * d, dtype=patches[0].dtype, device=dev)
         masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
-        nbytes = L_.ctx_bytes(L_.CTX_SIM, B, L, d)
+        nbytes = L_.ctx_bytes(L_.CTX_SIM, B, L, d, L_.dtype_enum(patches[0]), flags)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             L_.check(lib.sig_sim_fwd(C.byref(tok), C.byref(prm), k1, k2, max_keep, out.data_ptr(), masks.data_ptr(),
@@ -117,7 +117,7 @@ class AttnFunction(torch.autograd.Function):
         tok = L_.tokens_struct(patches, cls)
         prm = L_.sim_params_struct(params)
         out = torch.empty(B, 3 * d, dtype=patches[0].dtype, device=dev)
-        nbytes = L_.ctx_bytes(L_.CTX_SIM, B, L, d)
+        nbytes = L_.ctx_bytes(L_.CTX_SIM, B, L, d, L_.dtype_enum(patches[0]), flags)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             L_.check(lib.sig_sim_attn_fwd(C.byref(tok), C.byref(prm), None, out.data_ptr(), buf.data_ptr(), nbytes, flags,
@@ -162,7 +162,7 @@ class SelectFunction(torch.autograd.Function):
         prm = L_.sim_params_struct(list(params) + [params[0]] * 12)   # only the four selection tensors are read
         masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
         selected = torch.empty(3, B, L, d, dtype=patches[0].dtype, device=dev)
-        nbytes = L_.ctx_bytes(L_.CTX_SELECT, B, L, d)
+        nbytes = L_.ctx_bytes(L_.CTX_SELECT, B, L, d, L_.dtype_enum(patches[0]), 0)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             L_.check(lib.sig_sim_select_fwd(C.byref(tok), C.byref(prm), 3, k1, k2, max_keep, masks.data_ptr(),
@@ -201,7 +201,7 @@ def select_masks(which: int, patches, cls, sel_params, k1: int, k2: int, max_kee
     sel = [p.detach() for p in sel_params]
     prm = L_.sim_params_struct(sel + [sel[0]] * 12)
     masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
-    nbytes = L_.ctx_bytes(L_.CTX_SELECT, B, L, d)
+    nbytes = L_.ctx_bytes(L_.CTX_SELECT, B, L, d, L_.dtype_enum(patches[0]), 0)
     buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         L_.check(lib.sig_sim_select_fwd(C.byref(tok), C.byref(prm), which, k1, k2, max_keep, masks.data_ptr(), None,
@@ -255,7 +255,7 @@ class AlignFunction(torch.autograd.Function):
                 L_._f32c(t)
         prm = L_.align_params_struct(L_._f32c(params[0]), mods)
         losses = torch.zeros(2, dtype=torch.float32, device=dev)
-        nbytes = L_.ctx_bytes(L_.CTX_ALIGN, B, L, d)
+        nbytes = L_.ctx_bytes(L_.CTX_ALIGN, B, L, d, L_.dtype_enum(patches[0]), flags)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             L_.check(lib.sig_align_fwd(C.byref(tok), C.byref(prm), h, w, int(do_lam), losses.data_ptr(), buf.data_ptr(), nbytes,
@@ -314,7 +314,7 @@ class DasFunction(torch.autograd.Function):
         prm = L_.align_params_struct(None, [params])
         P = (h // 4) * (w // 4)
         sampled = torch.empty(B, P, d, dtype=torch.float32, device=dev)
-        nbytes = L_.ctx_bytes(L_.CTX_DAS, B, L, d)
+        nbytes = L_.ctx_bytes(L_.CTX_DAS, B, L, d, L_.dtype_enum(x), flags)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             L_.check(lib.sig_das_fwd(x.data_ptr(), x.stride(0), x.stride(1), L_.dtype_enum(x), B, h, w, d, C.byref(prm), 0,

@@ -86,7 +86,7 @@ def load():
     lib.sig_error_string.restype = C.c_char_p
     lib.sig_error_string.argtypes = [i]
     lib.sig_ctx_bytes.restype = sz
-    lib.sig_ctx_bytes.argtypes = [i, i, i, i]
+    lib.sig_ctx_bytes.argtypes = [i, i, i, i, i, u]
     lib.sig_sim_fwd.argtypes = [P(SigTokens), P(SigSimParams), i, i, i, vp, vp, vp, sz, u, i, vp]
     lib.sig_sim_bwd.argtypes = [P(SigTokens), P(SigSimParams), vp, P(SigTokenGrads), P(SigSimParamGrads), vp, sz, u, i, vp]
     lib.sig_sim_select_fwd.argtypes = [P(SigTokens), P(SigSimParams), i, i, i, i, vp, vp, vp, sz, i, vp]
@@ -211,8 +211,8 @@ def align_params_struct(contra_temp: torch.Tensor, mods: Sequence[Sequence[torch
     return s
 
 
-def ctx_bytes(kind: int, B: int, L: int, d: int) -> int:
-    n = load().sig_ctx_bytes(kind, B, L, d)
+def ctx_bytes(kind: int, B: int, L: int, d: int, dtype: int = SIG_F32, flags: int = 0) -> int:
+    n = load().sig_ctx_bytes(kind, B, L, d, dtype, flags)
     if n == 0:
         raise RuntimeError(f"signal_b200: unsupported shape B={B} L={L} d={d} (L <= 128, d % 64 == 0)")
     return n

@@ -71,3 +71,29 @@ def test_full_batch_b128_matches_oracle(d, hw, k):
     flips = int((got["masks"] != ref["masks"]).sum())
     assert flips == 0, f"{flips} mask flips at B=128"
     h.compare_records(got, ref, FP32_TOL, check_masks=False, label=f"B128 d{d}")
+
+
+@pytest.mark.parametrize("name", ["rgbnt201_d512", "rgbnt201_d768", "vehicle_d512"])
+def test_bf16_tensor_core_path_vs_simt_path(name):
+    """Same bf16 inputs through the tcgen05 path and through the fp32 SIMT kernels (FORCE_SIMT)."""
+    from signal_b200 import lib
+    h = _harness()
+    c = gu.CASES[name]
+    sim_p, al_p, toks, cot = gu.case_inputs(c)
+    toks = [t.to(torch.bfloat16) for t in toks]
+    fast = h.cuda_record(c, torch.bfloat16, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
+    slow = h.cuda_record(c, torch.bfloat16, flags=lib.FLAG_FORCE_SIMT, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
+    h.compare_records(fast, slow, BF16_TOL, check_masks=True, label=name + " tc-vs-simt")
+
+
+def test_bf16_full_batch_b128_matches_oracle():
+    """BASELINE.json config #2 (B=128, bf16, d=768) against the fp32 oracle on the rounded inputs."""
+    h = _harness()
+    c = dict(d=768, h=16, w=8, B=128, k=80, keep_ratio=None, gain=30.0, structured=False, seed=4242)
+    sim_p, al_p, toks, cot = gu.case_inputs(c)
+    toks = [t.to(torch.bfloat16) for t in toks]
+    got = h.cuda_record(c, torch.bfloat16, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
+    ref = _oracle_record(c, sim_p, al_p, [t.float() for t in toks], cot)
+    flips = int((got["masks"] != ref["masks"]).sum())
+    assert flips <= 4, f"{flips} mask flips at B=128 bf16"
+    h.compare_records(got, ref, BF16_TOL, check_masks=False, label="B128 d768 bf16")
