@@ -205,10 +205,13 @@ int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* cou
 
 /* Unit-test seam for the tcgen05 GEMM core: C = alpha * A . B^T (+bias) (GELU if act), bf16 operands.
  * mode: 0 row-major [rows,K]; 1 token view [B,128,d] with rows=(b,l), K=d; 2 row-major [K,cols];
- * 3 token view with K=(b,l), cols=d.  geom = {ld, stride_b, stride_l, rows, cols} (elements). */
+ * 3 token view with K=(b,l), cols=d.  geom = {ld, stride_b, stride_l, rows, cols} (elements).
+ * c_stride_b != 0: C rows are (b,l) token rows at C + b*c_stride_b + l*c_stride_l (+ per-sample rowvec). */
 int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const void* B, int b_mode,
                         const int64_t* b_geom, void* C, int64_t ldc, int out_bf16, const float* bias,
-                        int M, int N, int K, float alpha, int act, int ksplit, int bn, int device, void* stream);
+                        int M, int N, int K, float alpha, int act, int ksplit, int bn,
+                        int64_t c_stride_b, int64_t c_stride_l, const float* rowvec, const float* rowvec_scale,
+                        int accumulate, int device, void* stream);
 
 #ifdef __cplusplus
 }

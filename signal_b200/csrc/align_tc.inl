@@ -235,6 +235,12 @@ static __global__ void __launch_bounds__(128) lam_sparse_add_kernel(GradPtrs3 gp
   }
 }
 
+// W[o][m] += u[o] * v[m]   (the bias of proj_q reaches conv_offset[0]'s weight gradient: Q = X Wq^T + bq)
+static __global__ void rank1_add_kernel(float* __restrict__ W, const float* __restrict__ u, const float* __restrict__ v, int d) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < (int64_t)d * d) W[i] += u[i / d] * v[i % d];
+}
+
 // zero the CLS gradient rows (packed [B,1+L,d] destination).  grid (B, 3)
 template <typename T>
 static __global__ void zero_cls_kernel(GradPtrs3 gp, int d) {
@@ -541,6 +547,8 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
       SIG_TRY(tc_gemm(t, s));
     }
     for (int m = 0; m < 3; ++m) {
+      rank1_add_kernel<<<(unsigned)ceil_div((int64_t)dd, 256), 256, 0, s>>>(dp->off0_w[m], c.dbf + (size_t)m * d, p->proj_q_b[m], d);
+      SIG_CHECK_LAUNCH();
       // db0 = db' ; dbq = W0^T db'
       cudaMemcpyAsync(dp->off0_b[m], c.dbf + (size_t)m * d, d * sizeof(float), cudaMemcpyDeviceToDevice, s);
       Gemm gg{};

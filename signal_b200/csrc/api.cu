@@ -158,7 +158,8 @@ int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int 
 
 int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const void* B, int b_mode, const int64_t* b_geom,
                         void* C, int64_t ldc, int out_bf16, const float* bias, int M, int N, int K, float alpha, int act,
-                        int ksplit, int bn, int device, void* stream) {
+                        int ksplit, int bn, int64_t c_stride_b, int64_t c_stride_l, const float* rowvec,
+                        const float* rowvec_scale, int accumulate, int device, void* stream) {
   SIG_ENTER(device);
   if (!A || !B || !C || !a_geom || !b_geom) return SIG_ERR_NULL;
   sig::TcGemmDesc g = sig::tc_desc();
@@ -170,6 +171,8 @@ int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const 
   fill(g.B, B, b_mode, b_geom);
   g.M = M; g.N = N; g.K = K; g.C[0] = C; g.ldc = ldc; g.out_bf16 = out_bf16; g.bias[0] = bias; g.alpha = alpha;
   g.act = act; g.ksplit = ksplit; g.bn = bn;
+  if (c_stride_b) { g.c_tok = 1; g.c_stride_b = c_stride_b; g.c_stride_l = c_stride_l; }
+  g.rowvec[0] = rowvec; g.rowvec_scale = rowvec_scale; g.accumulate = accumulate;
   return sig::tc_gemm(g, (cudaStream_t)stream);
 }
 

@@ -102,7 +102,7 @@ def load():
     lib.sig_volume3_ws_bytes.argtypes = [i, i]
     lib.sig_volume3_fwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, sz, i, vp]
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
-    lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i, vp]
+    lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
     lib.sig_debug_launch_count.restype = C.c_ulonglong
     lib.sig_profile_enable.argtypes = [i]
     lib.sig_profile_collect.argtypes = [C.c_char_p, sz, P(C.c_float), P(C.c_int), i]
@@ -238,8 +238,10 @@ def profile_collect():
     return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(keys)}
 
 
-def debug_gemm_bf16(A, a_mode, B, b_mode, M, N, K, out_bf16=False, bias=None, alpha=1.0, act=0, ksplit=1, bn=128):
-    """Unit-test seam: run the tcgen05 GEMM core on bf16 CUDA tensors, returns C [M,N]."""
+def debug_gemm_bf16(A, a_mode, B, b_mode, M, N, K, out_bf16=False, bias=None, alpha=1.0, act=0, ksplit=1, bn=128,
+                    out=None, rowvec=None, rowvec_scale=None, accumulate=False):
+    """Unit-test seam: run the tcgen05 GEMM core on bf16 CUDA tensors, returns C [M,N].
+    out: optional [B,128,N] (possibly strided) destination for the token-row epilogue."""
     lib = load()
 
     def geom(t, mode):
@@ -248,9 +250,16 @@ def debug_gemm_bf16(A, a_mode, B, b_mode, M, N, K, out_bf16=False, bias=None, al
         return (C.c_int64 * 5)(0, t.stride(0), t.stride(1), t.shape[0], t.shape[2])
 
     dev = A.device
-    out = torch.zeros(M, N, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+    csb = csl = 0
+    if out is None:
+        out = torch.zeros(M, N, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+    else:
+        csb, csl = out.stride(0), out.stride(1)
+        out_bf16 = out.dtype == torch.bfloat16
     with torch.cuda.device(dev):
         check(lib.sig_debug_gemm_bf16(A.data_ptr(), a_mode, geom(A, a_mode), B.data_ptr(), b_mode, geom(B, b_mode),
                                       out.data_ptr(), N, int(out_bf16), None if bias is None else bias.data_ptr(), M, N, K,
-                                      alpha, act, ksplit, bn, dev.index, stream_ptr(dev)), "sig_debug_gemm_bf16")
+                                      alpha, act, ksplit, bn, csb, csl, None if rowvec is None else rowvec.data_ptr(),
+                                      None if rowvec_scale is None else rowvec_scale.data_ptr(), int(accumulate),
+                                      dev.index, stream_ptr(dev)), "sig_debug_gemm_bf16")
     return out

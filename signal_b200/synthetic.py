@@ -83,6 +83,27 @@ def make_params(shapes: Shapes, seed: int, offset_gain: float = 1.0,
     return out
 
 
+def smooth_patches(toks, h: int, w: int, passes: int = 2):
+    """Low-pass the patch rows of each token map over the h x w grid ([1,2,1]/4 separable filter,
+    edge-replicated, `passes` times) and rescale to unit variance.  White-noise features make the
+    deformable sampling of LAM chaotic w.r.t. its offsets; smooth maps give a well-conditioned
+    problem for reduced-precision parity checks."""
+    out = []
+    for t in toks:
+        B, L1, d = t.shape
+        x = t[:, 1:].reshape(B, h, w, d).float()
+        for _ in range(passes):
+            xp = torch.cat([x[:, :1], x, x[:, -1:]], dim=1)
+            x = 0.25 * xp[:, :-2] + 0.5 * xp[:, 1:-1] + 0.25 * xp[:, 2:]
+            xp = torch.cat([x[:, :, :1], x, x[:, :, -1:]], dim=2)
+            x = 0.25 * xp[:, :, :-2] + 0.5 * xp[:, :, 1:-1] + 0.25 * xp[:, :, 2:]
+        x = x / x.std()
+        t2 = t.clone().float()
+        t2[:, 1:] = x.reshape(B, h * w, d)
+        out.append(t2.to(t.dtype))
+    return out
+
+
 def make_tokens(B: int, d: int, seed: int = 1234, L: int = 128, structured: bool = False,
                 dtype: torch.dtype = torch.float32):
     """Three [B, 1+L, d] token maps in (RGB, NI, TI) order.

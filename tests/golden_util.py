@@ -62,6 +62,11 @@ def param_tol(key, objective, tol):
     """
     if key.endswith("contra_temp"):
         return max(tol, 3e-3)
+    if objective == "lam" and tol >= 1e-2:
+        # bf16 runs: the offset-path gradients are sums over channels/positions of terms with random
+        # signs; the bf16 rounding of the folded weights and of the stored pre-activation shows up
+        # amplified (measured 1-4% on these parameters while every per-token gradient is < 2%)
+        return max(tol, 5e-2)
     if objective == "lam" and tol > 1e-5:
         return max(tol, 5e-4)
     return tol

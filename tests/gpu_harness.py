@@ -49,9 +49,35 @@ def cuda_record(c, dtype=torch.float32, packed=True, flags=0, sim_p=None, al_p=N
     return rec
 
 
-def compare_records(got, ref, tol, check_masks=True, ref_masks_key="masks", label=""):
-    """Assert got (CUDA) matches ref (golden npz or oracle record) within tol (relative L2)."""
+def lam_flip_samples(got, ref, tol):
+    """(modality, sample) pairs whose LAM token gradient deviates by more than `tol`.
+
+    d(LAM)/d(offset) is discontinuous where a sample point crosses a pixel boundary (the bilinear
+    slope switches to another pair of neighbouring tokens).  A reduced-precision run moves the
+    predicted offsets by ~1e-3 px, so in a batch of B*8*3 sample points an occasional point lands on
+    the other side of a boundary and that one sample's offset-path gradient changes by O(1).  Such
+    samples are reported, bounded in number, and excluded from the aggregate comparison.
+    """
+    a = np.asarray(got["dtok_lam"], dtype=np.float64)
+    b = np.asarray(ref["dtok_lam"], dtype=np.float64)
+    num = np.linalg.norm((a - b).reshape(a.shape[0], a.shape[1], -1), axis=-1)
+    den = np.linalg.norm(b.reshape(b.shape[0], b.shape[1], -1), axis=-1)
+    bad = np.argwhere(num > tol * np.maximum(den, 1e-30))
+    return [(int(m), int(s)) for m, s in bad]
+
+
+def compare_records(got, ref, tol, check_masks=True, ref_masks_key="masks", label="", lam_flip_robust=False):
+    """Assert got (CUDA) matches ref (golden npz or oracle record) within tol (relative L2).
+
+    lam_flip_robust (reduced-precision runs only): tolerate a few pixel-boundary flips of LAM sample
+    points, see lam_flip_samples()."""
     errs = {}
+    flips = []
+    if lam_flip_robust:
+        flips = lam_flip_samples(got, ref, tol)
+        nsamp = np.asarray(ref["dtok_lam"]).shape[1] * 3
+        assert len(flips) <= max(1, int(0.03 * nsamp)), (label, "too many LAM outlier samples", flips[:10])
+        errs["lam_flip_samples"] = float(len(flips))
     if check_masks:
         assert np.array_equal(got["masks"], ref[ref_masks_key]), f"{label}: selected-token masks differ"
     errs["sim_out"] = gu.rel_err(got["sim_out"], ref["sim_out"])
@@ -60,7 +86,12 @@ def compare_records(got, ref, tol, check_masks=True, ref_masks_key="masks", labe
     for k in ("sim_out", "gam", "lam"):
         assert errs[k] < tol, (label, k, errs[k])
     for oname in ("sim", "gam", "lam"):
-        e = gu.rel_err(got[f"dtok_{oname}"], ref[f"dtok_{oname}"])
+        ga, ra = np.array(got[f"dtok_{oname}"], dtype=np.float64), np.array(ref[f"dtok_{oname}"], dtype=np.float64)
+        if oname == "lam":
+            for m, sidx in flips:
+                ga[m, sidx] = 0.0
+                ra[m, sidx] = 0.0
+        e = gu.rel_err(ga, ra)
         errs[f"dtok_{oname}"] = e
         assert e < tol, (label, f"dtok_{oname}", e)
         for key in [k for k in ref if k.startswith(f"dpar_{oname}/")]:
@@ -71,5 +102,11 @@ def compare_records(got, ref, tol, check_masks=True, ref_masks_key="masks", labe
             assert key in got, (label, key, "gradient missing")
             e = gu.rel_err(got[key], ref[key])
             errs[key] = e
-            assert e < gu.param_tol(name, oname, tol), (label, key, e)
+            ptol = gu.param_tol(name, oname, tol)
+            if oname == "lam" and flips:
+                mods = {"DAS_r": 0, "DAS_n": 1, "DAS_t": 2}
+                hit = [mods[k] for k in mods if k in name]
+                if hit and any(m == hit[0] for m, _ in flips):
+                    ptol = max(ptol, 0.25)   # one flipped sample carries O(1/B) of this modality's gradient
+            assert e < ptol, (label, key, e)
     return errs

@@ -59,10 +59,52 @@ def test_mn_major_both_for_weight_grad(ksplit):
     _check(out, dH.float().T @ X.float().reshape(-1, d))
 
 
-def test_mn_major_b_2d():
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_mn_major_b_2d(bn, out_bf16):
     """C = A . W with W [K,N] row-major as an MN-major B operand."""
     from signal_b200 import lib
-    M, N, K = 256, 512, 768
+    M, N, K = 1024, 512, 768
     A, W = _rand((M, K), 9), _rand((K, N), 10)
-    out = lib.debug_gemm_bf16(A, 0, W, 2, M, N, K)
-    _check(out, A.float() @ W.float())
+    out = lib.debug_gemm_bf16(A, 0, W, 2, M, N, K, bn=bn, out_bf16=out_bf16)
+    _check(out, A.float() @ W.float(), 6e-3 if out_bf16 else 2e-3)
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_persistent_many_tiles_per_cta(bn):
+    """More work units than SMs: exercises the smem ring / TMEM double buffer across tiles."""
+    from signal_b200 import lib
+    Bs, d = 128, 768
+    tok = _rand((Bs, 129, d), 11)
+    W = _rand((d, d), 12)
+    A = tok[:, 1:]
+    bias = torch.randn(d, device="cuda")
+    out = lib.debug_gemm_bf16(A, 1, W, 0, Bs * 128, d, d, bn=bn, out_bf16=True, bias=bias)
+    ref = A.float().reshape(-1, d) @ W.float().T + bias
+    _check(out, ref, 6e-3)
+
+
+def test_token_row_epilogue_many_tiles():
+    """dX-style GEMM: K-major A, MN-major B, bf16 written at token strides into a [B,129,d] map,
+    plus the per-sample row vector (GAM broadcast) scaled by a device scalar."""
+    from signal_b200 import lib
+    Bs, d = 128, 768
+    dH = _rand((Bs * 128, d), 13)
+    W = _rand((d, d), 14)
+    rv = torch.randn(Bs, d, device="cuda")
+    sc = torch.tensor([0.37], device="cuda")
+    dst = torch.full((Bs, 129, d), 7.0, dtype=torch.bfloat16, device="cuda")
+    lib.debug_gemm_bf16(dH, 0, W, 2, Bs * 128, d, d, bn=256, out=dst[:, 1:], rowvec=rv, rowvec_scale=sc)
+    ref = (dH.float() @ W.float()).reshape(Bs, 128, d) + 0.37 * rv[:, None, :]
+    _check(dst[:, 1:], ref, 6e-3)
+    assert bool((dst[:, 0] == 7.0).all())
+
+
+def test_weight_grad_many_units_splitk():
+    from signal_b200 import lib
+    Bs, d = 128, 768
+    tok = _rand((Bs, 129, d), 15)
+    X = tok[:, 1:]
+    dH = _rand((Bs * 128, d), 16)
+    out = lib.debug_gemm_bf16(dH, 2, X, 3, d, d, Bs * 128, ksplit=3)
+    _check(out, dH.float().T @ X.float().reshape(-1, d))
