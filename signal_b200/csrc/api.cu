@@ -49,7 +49,7 @@ const char* sig_error_string(int code) {
 size_t sig_ctx_bytes(int kind, int B, int L, int d, int dtype, unsigned flags) {
   if (B < 1 || L < 1 || L > sig::kMaxL || d < 64 || d % 64) return 0;
   switch (kind) {
-    case SIG_CTX_SIM:
+    case SIG_CTX_SIM: return sig::sim_ctx_bytes_for(B, L, d, dtype, flags);
     case SIG_CTX_SELECT: return sig::sim_ctx_bytes(B, L, d);
     case SIG_CTX_ALIGN: return sig::align_ctx_bytes_for(B, L, d, dtype, flags);
     case SIG_CTX_DAS: return sig::das_ctx_bytes(B, L, d);

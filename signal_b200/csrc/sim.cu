@@ -12,6 +12,7 @@
 // i.e. the K/V projections are applied to 24 effective queries per sample instead of 384 tokens.
 #include "common.cuh"
 #include "sim.h"
+#include "sim_tc.h"
 #include "simt_ops.cuh"
 
 namespace sig {
@@ -65,9 +66,75 @@ int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s) 
   return 0;
 }
 
+// CLS tokens only: strided T views -> clsf[B][3][d] fp32.  grid (B, 3)
+template <typename T>
+static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ clsf) {
+  const int b = blockIdx.x, m = blockIdx.y;
+  const T* src = static_cast<const T*>(tp.cls[m]) + b * tp.csb[m];
+  float* dst = clsf + ((int64_t)b * 3 + m) * d;
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
+    float v[8];
+    load8(src + c, v);
+    store8(dst + c, v);
+  }
+}
+
+static TokPtrs tok_ptrs(const sig_tokens* t) {
+  TokPtrs tp;
+  for (int m = 0; m < 3; ++m) {
+    tp.patch[m] = t->patch[m]; tp.cls[m] = t->cls[m];
+    tp.psb[m] = t->patch_stride_b[m]; tp.psl[m] = t->patch_stride_l[m]; tp.csb[m] = t->cls_stride_b[m];
+  }
+  return tp;
+}
+
 // ---------------------------------------------------------------------------------------------
 // selection scores
 // ---------------------------------------------------------------------------------------------
+// Same four dot products per token as sim_scores_kernel, reading the strided token views in place.
+// grid (ceil(L/32), 3, B), 256 threads: 8 warps x 4 tokens, 8 channels per lane per step (16 B loads).
+template <typename T>
+static __global__ void __launch_bounds__(256) sim_scores_tok_kernel(TokPtrs tp, const float* __restrict__ clsf,
+                                                                    const float* __restrict__ qtsel, const float* __restrict__ csel,
+                                                                    int B, int L, int d, float* __restrict__ sel_logits,
+                                                                    float* __restrict__ intra_raw) {
+  extern __shared__ float qv[];  // [4][d]
+  const int m = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 4 * d; i += blockDim.x) {
+    const int r = i / d, c = i % d;
+    qv[i] = r < 3 ? qtsel[((int64_t)b * 3 + r) * d + c] : clsf[((int64_t)b * 3 + m) * d + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float inv = rsqrtf((float)d);
+  const T* xb = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m];
+  for (int i = 0; i < 4; ++i) {
+    const int l = blockIdx.x * 32 + w * 4 + i;
+    if (l >= L) break;
+    const T* x = xb + l * tp.psl[m];
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane * 8; c < d; c += 256) {
+      float xv[8];
+      load8(x + c, xv);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float qq[8];
+        load8(qv + r * d + c, qq);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) a[r] = fmaf(xv[t], qq[t], a[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[r] = warp_sum(a[r]);
+    if (lane == 0) {
+      const int64_t base = (int64_t)b * 3 * 3 * L + (int64_t)m * L + l;
+      sel_logits[base] = (a[0] + csel[b * 3 + 0]) * inv;
+      sel_logits[base + 3 * L] = (a[1] + csel[b * 3 + 1]) * inv;
+      sel_logits[base + 6 * L] = (a[2] + csel[b * 3 + 2]) * inv;
+      intra_raw[((int64_t)b * 3 + m) * L + l] = a[3];
+    }
+  }
+}
 // grid (ceil(L/32), 3, B), 256 threads: 8 warps x 4 tokens.  Four dot products per token:
 // the three folded inter-modal queries and the token's own CLS.
 static __global__ void __launch_bounds__(256) sim_scores_kernel(const float* __restrict__ Xf, const float* __restrict__ clsf,
@@ -544,6 +611,31 @@ int write_token_grads(const sig_token_grads* g, int dtype, const float* dXf, con
   return 0;
 }
 
+// dcls[m][b] (+)= dclsf[b][m]   grid (B, 3)
+template <typename T>
+static __global__ void write_cls_grads_kernel(GradPtrs gp, const float* __restrict__ dclsf, int d) {
+  const int b = blockIdx.x, m = blockIdx.y;
+  if (!gp.dcls[m]) return;
+  T* dst = static_cast<T*>(gp.dcls[m]) + b * gp.csb[m];
+  const float* src = dclsf + ((int64_t)b * 3 + m) * d;
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
+    float v[8];
+    load8(src + c, v);
+    if (gp.accumulate) {
+      float o[8];
+      load8(dst + c, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += o[i];
+    }
+    store8(dst + c, v);
+  }
+}
+
+static __global__ void fill_kernel(float* __restrict__ p, float v, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ctx layout
 // ---------------------------------------------------------------------------------------------
@@ -554,14 +646,19 @@ struct SimCtx {
   float *r1, *mu1, *rstd1, *y1, *a1, *h1, *f, *r2, *mu2, *rstd2;
   // backward scratch
   float *dr2, *dyx, *dyf, *dh1, *dr1, *dob, *dxbar, *dqt, *dqatt, *dXf;
+  // tensor-core (bf16) token path
+  bool tc;
+  __nv_bfloat16 *DXQT, *Ptok, *PT, *PdS, *dST;
+  float *S32, *delta;
   size_t bytes;
 };
 
-static SimCtx sim_ctx(void* base, int B, int L, int d) {
+static SimCtx sim_ctx(void* base, int B, int L, int d, bool tc = false) {
   Arena a(base);
   SimCtx c;
+  c.tc = tc;
   const size_t R = (size_t)B * 3;
-  c.Xf = a.take<float>((size_t)3 * B * L * d);
+  c.Xf = a.take<float>(tc ? 0 : (size_t)3 * B * L * d);
   c.clsf = a.take<float>(R * d);
   c.maskf = a.take<float>((size_t)3 * B * L);
   c.qsel = a.take<float>(R * d);
@@ -596,18 +693,39 @@ static SimCtx sim_ctx(void* base, int B, int L, int d) {
   c.dxbar = a.take<float>(R * 8 * d);
   c.dqt = a.take<float>(R * 8 * d);
   c.dqatt = a.take<float>(R * d);
-  c.dXf = a.take<float>((size_t)3 * B * L * d);
+  c.dXf = a.take<float>(tc ? 0 : (size_t)3 * B * L * d);
+  c.DXQT = a.take<__nv_bfloat16>(tc ? (size_t)B * 64 * d : 0);
+  c.Ptok = a.take<__nv_bfloat16>(tc ? (size_t)B * 384 * 32 : 0);
+  c.PT = a.take<__nv_bfloat16>(tc ? (size_t)B * 32 * 384 : 0);
+  c.PdS = a.take<__nv_bfloat16>(tc ? (size_t)B * 384 * 64 : 0);
+  c.dST = a.take<__nv_bfloat16>(tc ? (size_t)B * 32 * 384 : 0);
+  c.S32 = a.take<float>(tc ? (size_t)B * 384 * 32 : 0);
+  c.delta = a.take<float>(tc ? (size_t)B * 32 : 0);
   c.bytes = a.off;
   return c;
 }
 
 size_t sim_ctx_bytes(int B, int L, int d) { return sim_ctx(nullptr, B, L, d).bytes; }
 
+static bool sim_tc_ok(int dtype, int L, unsigned flags) {
+  return dtype == SIG_BF16 && L == 128 && !(flags & SIG_FLAG_FORCE_SIMT);
+}
+size_t sim_ctx_bytes_for(int B, int L, int d, int dtype, unsigned flags) {
+  return sim_ctx(nullptr, B, L, d, sim_tc_ok(dtype, L, flags)).bytes;
+}
+
+static SimTcBufs tc_bufs(const SimCtx& c, const float* maskf) {
+  SimTcBufs k{};
+  k.maskf = maskf; k.qtatt = c.qtatt; k.catt = c.catt; k.DXQT = c.DXQT; k.S32 = c.S32; k.Ptok = c.Ptok; k.PT = c.PT;
+  k.xbar = c.xbar; k.dxbar = c.dxbar; k.delta = c.delta; k.PdS = c.PdS; k.dST = c.dST; k.dqt = c.dqt;
+  return k;
+}
+
 // ---------------------------------------------------------------------------------------------
 // orchestration
 // ---------------------------------------------------------------------------------------------
-static int run_selection(const SimCtx& c, const sig_sim_params* p, int B, int L, int d, int which, int k1, int k2, int max_keep,
-                         float* masks_out, cudaStream_t s) {
+static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_params* p, int B, int L, int d, int which, int k1,
+                         int k2, int max_keep, float* masks_out, cudaStream_t s) {
   const int R = 3 * B;
   SIG_PHASE("sim_select");
   // q = W_q cls + b_q (useA.py:123); qt = W_k^T q; c = q . b_k
@@ -615,7 +733,11 @@ static int run_selection(const SimCtx& c, const sig_sim_params* p, int B, int L,
   SIG_TRY(launch_gemm(gemm_nn(c.qsel, d, p->sel_wk, d, c.qtsel, d, R, d, d), s));
   SIG_TRY(launch_gemm(gemm_nt(c.qsel, d, p->sel_bk, d, c.csel, 1, nullptr, R, 1, d), s));
   dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
-  sim_scores_kernel<<<grid, 256, 4 * d * sizeof(float), s>>>(c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);
+  if (c.tc)
+    sim_scores_tok_kernel<__nv_bfloat16><<<grid, 256, 4 * d * sizeof(float), s>>>(tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
+                                                                                 c.sel_logits, c.intra_raw);
+  else
+    sim_scores_kernel<<<grid, 256, 4 * d * sizeof(float), s>>>(c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);
   SIG_CHECK_LAUNCH();
   sim_select_kernel<<<B, 256, 0, s>>>(c.sel_logits, c.intra_raw, B, L, d, which, k1, k2, max_keep, c.maskf, masks_out);
   SIG_CHECK_LAUNCH();
@@ -626,8 +748,8 @@ static size_t attn_fwd_smem(int L, int d) { return (size_t)(6 * d + 6 * 3 * L + 
 static size_t attn_bwd_smem(int L, int d) { return (size_t)(12 * d + 12 * 3 * L + 3 * L + 8) * sizeof(float); }
 
 template <typename OutT>
-static int run_attention_fwd(const SimCtx& c, const sig_sim_params* p, const float* maskf, int B, int L, int d, OutT* out,
-                             cudaStream_t s) {
+static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_sim_params* p, const float* maskf, int B, int L,
+                             int d, OutT* out, cudaStream_t s) {
   const int R = 3 * B, hd = d / kHeads;
   const float scale = 1.0f / sqrtf((float)hd);
   const float* wq = p->in_proj_w;
@@ -653,10 +775,14 @@ static int run_attention_fwd(const SimCtx& c, const sig_sim_params* p, const flo
   }
   {
   SIG_PHASE("sim_attn_tokens_fwd");
-  const size_t sm = attn_fwd_smem(L, d);
-  cudaFuncSetAttribute(sim_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  sim_attn_fwd_kernel<<<dim3(B, 4), 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, B, L, d, c.xbar, c.amax, c.asum);
-  SIG_CHECK_LAUNCH();
+  if (c.tc) {
+    SIG_TRY(sim_tc_tokens_fwd(tok, tc_bufs(c, maskf), s));
+  } else {
+    const size_t sm = attn_fwd_smem(L, d);
+    cudaFuncSetAttribute(sim_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    sim_attn_fwd_kernel<<<dim3(B, 4), 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, B, L, d, c.xbar, c.amax, c.asum);
+    SIG_CHECK_LAUNCH();
+  }
   }
   SIG_PHASE("sim_post");
   {  // o_h = W_v^h xbar_h + b_v^h
@@ -679,8 +805,9 @@ static int run_attention_fwd(const SimCtx& c, const sig_sim_params* p, const flo
 }
 
 template <typename InT>
-static int run_attention_bwd(const SimCtx& c, const sig_sim_params* p, const float* maskf, int B, int L, int d, const InT* dout,
-                             const sig_sim_param_grads* g, cudaStream_t s) {
+static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_token_grads* dtok, const sig_sim_params* p,
+                             const float* maskf, int B, int L, int d, const InT* dout, const sig_sim_param_grads* g,
+                             cudaStream_t s) {
   const int R = 3 * B, hd = d / kHeads;
   const float scale = 1.0f / sqrtf((float)hd);
   const float* wq = p->in_proj_w;
@@ -736,10 +863,14 @@ static int run_attention_bwd(const SimCtx& c, const sig_sim_params* p, const flo
   }
   {
   SIG_PHASE("sim_attn_tokens_bwd");
-  const size_t sm = attn_bwd_smem(L, d);
-  cudaFuncSetAttribute(sim_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  sim_attn_bwd_kernel<<<B, 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, c.xbar, c.amax, c.asum, c.dxbar, B, L, d, c.dqt, c.dXf);
-  SIG_CHECK_LAUNCH();
+  if (c.tc) {
+    SIG_TRY(sim_tc_tokens_bwd(tok, tc_bufs(c, maskf), dtok, s));
+  } else {
+    const size_t sm = attn_bwd_smem(L, d);
+    cudaFuncSetAttribute(sim_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    sim_attn_bwd_kernel<<<B, 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, c.xbar, c.amax, c.asum, c.dxbar, B, L, d, c.dqt, c.dXf);
+    SIG_CHECK_LAUNCH();
+  }
   }
   SIG_PHASE("sim_attn_prep_bwd");
   {  // dq_h = scale * dqt_h W_k^hT
@@ -779,22 +910,32 @@ int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, 
   if (!out || !ctx) return SIG_ERR_NULL;
   if (tok->d % (8 * kHeads) != 0) return SIG_ERR_SHAPE;
   const int B = tok->B, L = tok->L, d = tok->d;
-  if (ctx_bytes < sim_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
+  const bool tcp = sim_tc_ok(tok->dtype, L, flags);
+  if (ctx_bytes < sim_ctx(nullptr, B, L, d, tcp).bytes) return SIG_ERR_WORKSPACE;
   if (do_select && (k1 < 1 || k2 < 1 || max_keep > L)) return SIG_ERR_SHAPE;
-  (void)flags;
-  SimCtx c = sim_ctx(ctx, B, L, d);
-  SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));
+  SimCtx c = sim_ctx(ctx, B, L, d, tcp);
+  if (tcp) {
+    SIG_PHASE("convert_tokens");
+    gather_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(tok_ptrs(tok), d, c.clsf);
+    SIG_CHECK_LAUNCH();
+  } else {
+    SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));
+  }
   const float* maskf = nullptr;
   if (do_select) {
-    SIG_TRY(run_selection(c, p, B, L, d, 3, k1, k2, max_keep, masks_out, s));
+    SIG_TRY(run_selection(c, tok, p, B, L, d, 3, k1, k2, max_keep, masks_out, s));
     maskf = c.maskf;
   } else if (ext_masks) {
     cudaMemcpyAsync(c.maskf, ext_masks, (size_t)3 * B * L * sizeof(float), cudaMemcpyDeviceToDevice, s);
     maskf = c.maskf;
+  } else if (tcp) {
+    fill_kernel<<<(unsigned)ceil_div((int64_t)3 * B * L, 256), 256, 0, s>>>(c.maskf, 1.f, (int64_t)3 * B * L);
+    SIG_CHECK_LAUNCH();
+    maskf = c.maskf;
   }
   if (tok->dtype == SIG_BF16)
-    return run_attention_fwd<__nv_bfloat16>(c, p, maskf, B, L, d, static_cast<__nv_bfloat16*>(out), s);
-  return run_attention_fwd<float>(c, p, maskf, B, L, d, static_cast<float*>(out), s);
+    return run_attention_fwd<__nv_bfloat16>(c, tok, p, maskf, B, L, d, static_cast<__nv_bfloat16*>(out), s);
+  return run_attention_fwd<float>(c, tok, p, maskf, B, L, d, static_cast<float*>(out), s);
 }
 
 int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks, const void* dout, const sig_token_grads* dtok,
@@ -807,14 +948,27 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
       !dp->ffn2_b || !dp->ln1_w || !dp->ln1_b || !dp->ln2_w || !dp->ln2_b)
     return SIG_ERR_NULL;
   const int B = tok->B, L = tok->L, d = tok->d;
-  if (ctx_bytes < sim_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
-  (void)flags;
-  SimCtx c = sim_ctx(ctx, B, L, d);
-  const float* maskf = has_masks ? c.maskf : nullptr;
+  const bool tcp = sim_tc_ok(tok->dtype, L, flags);
+  if (ctx_bytes < sim_ctx(nullptr, B, L, d, tcp).bytes) return SIG_ERR_WORKSPACE;
+  SimCtx c = sim_ctx(ctx, B, L, d, tcp);
+  const float* maskf = (has_masks || tcp) ? c.maskf : nullptr;
   if (tok->dtype == SIG_BF16)
-    SIG_TRY(run_attention_bwd<__nv_bfloat16>(c, p, maskf, B, L, d, static_cast<const __nv_bfloat16*>(dout), dp, s));
+    SIG_TRY(run_attention_bwd<__nv_bfloat16>(c, tok, dtok, p, maskf, B, L, d, static_cast<const __nv_bfloat16*>(dout), dp, s));
   else
-    SIG_TRY(run_attention_bwd<float>(c, p, maskf, B, L, d, static_cast<const float*>(dout), dp, s));
+    SIG_TRY(run_attention_bwd<float>(c, tok, dtok, p, maskf, B, L, d, static_cast<const float*>(dout), dp, s));
+  if (tcp) {
+    // the token-gradient GEMM already wrote d(patches) at the token strides; only the CLS rows remain
+    SIG_PHASE("write_token_grads");
+    GradPtrs gp;
+    for (int m = 0; m < 3; ++m) {
+      gp.dpatch[m] = dtok->dpatch[m]; gp.dcls[m] = dtok->dcls[m];
+      gp.psb[m] = dtok->patch_stride_b[m]; gp.psl[m] = dtok->patch_stride_l[m]; gp.csb[m] = dtok->cls_stride_b[m];
+    }
+    gp.accumulate = dtok->accumulate;
+    write_cls_grads_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(gp, c.dr1, d);
+    SIG_CHECK_LAUNCH();
+    return 0;
+  }
   return write_token_grads(dtok, tok->dtype, c.dXf, c.dr1, B, L, d, s);
 }
 
@@ -828,7 +982,7 @@ int sim_select(const sig_tokens* tok, const sig_sim_params* p, int which, int k1
   if (ctx_bytes < sim_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
   SimCtx c = sim_ctx(ctx, B, L, d);
   SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));
-  SIG_TRY(run_selection(c, p, B, L, d, which, k1, k2, max_keep, masks, s));
+  SIG_TRY(run_selection(c, tok, p, B, L, d, which, k1, k2, max_keep, masks, s));
   if (selected) {
     const int64_t rows = (int64_t)3 * B * L;
     const int threads = d / 8 >= 128 ? 128 : 64;

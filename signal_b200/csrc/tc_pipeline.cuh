@@ -1,0 +1,172 @@
+// Warp-specialised tcgen05 pipeline skeleton shared by the tensor-core kernels.
+//
+//   warp 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled shared-memory ring, mbarrier complete_tx)
+//   warp 1 : MMA issuer    (one thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM, tcgen05.commit)
+//   warp 2 : TMEM allocator
+//   warps 4-7 : epilogue   (tcgen05.ld of the accumulator, problem-specific math, global stores)
+//
+// Persistent: CTA i processes work units i, i+grid, ...; the smem ring and the two TMEM accumulator
+// buffers run continuously across units, so the epilogue of unit n overlaps the MMAs of unit n+1.
+//
+// A Problem supplies: Params (kernel argument, holds the CUtensorMaps), kAMn/kBMn (operand
+// major-ness), num_units(), krange(), load() (issue the TMA copies of one k-block) and epilogue().
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sig {
+namespace tc {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kThreads = 256;
+constexpr int kABytes = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN <= 32 ? 8 : (BN <= 128 ? 6 : 4);
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// Loads one operand tile of `extent` M/N-rows for k-block starting at element k0.
+//   K-major  : smem rows = M/N index, 128 B (64 bf16 of K) per row
+//   MN-major : 64-element M/N chunks of [64 K-rows x 128 B], chunk j at dst + j*8192
+__device__ __forceinline__ void load_kmajor_2d(const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int k0, int row0) {
+  ptx::tma_load_2d(dst, tm, bar, k0, row0);
+}
+__device__ __forceinline__ void load_kmajor_tok(const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int k0, int sample, int nsamples) {
+  for (int j = 0; j < nsamples; ++j) ptx::tma_load_3d(dst + j * 128 * BK * 2, tm, bar, k0, 0, sample + j);
+}
+__device__ __forceinline__ void load_mnmajor_2d(const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int mn0, int krow0, int extent) {
+  for (int j = 0; j < extent / 64; ++j) ptx::tma_load_2d(dst + j * 64 * BK * 2, tm, bar, mn0 + 64 * j, krow0);
+}
+__device__ __forceinline__ void load_mnmajor_tok(const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int mn0, int l0, int sample, int extent) {
+  for (int j = 0; j < extent / 64; ++j) ptx::tma_load_3d(dst + j * 64 * BK * 2, tm, bar, mn0 + 64 * j, l0, sample);
+}
+
+template <int BN, class Problem>
+__global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_constant__ typename Problem::Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // 1024 B aligned (128B-swizzle atoms)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_units = Problem::num_units(p);
+
+  if (warp == 0 && lane == 0) Problem::prefetch(p);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      int kb0, kb1;
+      Problem::krange(p, unit, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const uint32_t stage = it % C::kStages, ph = (it / C::kStages) & 1;
+        ptx::mbar_wait(&empty[stage], ph ^ 1);
+        ptx::mbar_expect_tx(&full[stage], C::kStageBytes);
+        uint8_t* sa = smem + stage * C::kStageBytes;
+        Problem::load(p, unit, kb, sa, sa + kABytes, &full[stage]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================= MMA issuer =================
+    constexpr int a_mn = Problem::kAMn, b_mn = Problem::kBMn;
+    const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, a_mn, b_mn);
+    // K-major: 8-row groups 1024 B apart (SBO); one UMMA_K (16 bf16) = 32 B inside the 128 B swizzle row.
+    // MN-major: 64-element chunks 8192 B apart (LBO); 8 K-rows = 1024 B (SBO); one UMMA_K = 16 rows = 2048 B.
+    constexpr uint32_t a_lbo = a_mn ? 64 * 128 : 16, b_lbo = b_mn ? 64 * 128 : 16;
+    constexpr uint32_t a_kstep = a_mn ? 16 * 128 : 32, b_kstep = b_mn ? 16 * 128 : 32;
+    uint32_t it = 0, tcount = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++tcount) {
+      int kb0, kb1;
+      Problem::krange(p, unit, kb0, kb1);
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty[acc], aph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const uint32_t stage = it % C::kStages, ph = (it / C::kStages) & 1;
+        ptx::mbar_wait(&full[stage], ph);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(smem + stage * C::kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = ptx::make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024);
+          const uint64_t db = ptx::make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024);
+          ptx::umma_bf16(d_tmem, da, db, idesc, kb > kb0 || k > 0);
+        }
+        ptx::umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
+      }
+      ptx::umma_commit(&tmem_full[acc]);   // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      ptx::mbar_wait(&tmem_full[acc], aph);
+      ptx::tc_fence_after();
+      Problem::epilogue(p, unit, tmem_base + acc * BN + ((uint32_t)(q * 32) << 16), q, lane);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ---- host helpers -------------------------------------------------------------------------------
+// bf16 tensor maps with 128B swizzle.  2-D: row-major [rows, cols] with pitch ld (elements), box
+// [box_rows x 64].  Token view: [B, 128, d] with element strides, box [1 x box_rows x 64].
+int make_map_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out);
+int make_map_tok(const void* ptr, int64_t B, int64_t d, int64_t stride_b, int64_t stride_l, int box_rows, CUtensorMap* out);
+int num_sms();
+
+template <int BN, class Problem>
+int launch(const typename Problem::Params& p, int units, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(pipeline_kernel<BN, Problem>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    attr_set = true;
+  }
+  if (units <= 0) return 0;
+  const int grid = units < num_sms() ? units : num_sms();
+  pipeline_kernel<BN, Problem><<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(p);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace sig
