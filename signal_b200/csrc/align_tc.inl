@@ -70,87 +70,81 @@ static __global__ void __launch_bounds__(128) lam_dw_fwd_tc_kernel(const __nv_bf
   if (threadIdx.x == 0) o[(int64_t)m * B * g.P + bp] = part;
 }
 
-// dU = dO * w4 * gelu'(U); dH[b,pos,c] = dU * wdw[c,k] * gelu'(H)  (bf16 out).  grid (B*P, 3)
-static __global__ void __launch_bounds__(128) lam_dw_bwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
+// Backward of the offset-net tail, one pass over H:
+//   dU = dO * w4 * gelu'(U);  dH[b,pos,c] = dU * wdw[c,k] * gelu'(H[b,pos,c])   (bf16 out)
+// and per-CTA partial sums of the parameter gradients
+//   dwdw[c,k] += dU * gelu(H[pos(p,k)]),  dbdw += dU,  dw4 += dO * gelu(U),  dbf += dH
+// grid (ceil(B*P / kDwPairs), 3), d/2 threads (2 channels each).  part: [3][nchunk][19][d]
+constexpr int kDwPairs = 8;
+static __global__ void __launch_bounds__(512) lam_dw_bwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
                                                                    const float* __restrict__ U, const float* __restrict__ dO,
                                                                    sig_align_params prm, Geo g, int B, int L, int d,
-                                                                   float* __restrict__ dU, __nv_bfloat16* __restrict__ dH) {
-  const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
-  const int py = p / g.Wk, px = p % g.Wk;
-  const float* wdw = prm.off2_w[m];
-  const float* w4 = prm.off4_w[m];
-  const int c = threadIdx.x * 8;
+                                                                   __nv_bfloat16* __restrict__ dH, float* __restrict__ part) {
+  const int m = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int c = threadIdx.x * 2;
   if (c >= d) return;
-  const int64_t ubase = ((int64_t)m * B * g.P + bp) * d + c;
-  const float go = dO[(int64_t)m * B * g.P + bp];
-  float u[8], w[8], du[8];
-  load8(U + ubase, u);
-  load8(w4 + c, w);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) du[i] = go * w[i] * gelu_grad_f(u[i]);
-  store8(dU + ubase, du);
+  const float* wdw = prm.off2_w[m];
+  const float2 w4 = *reinterpret_cast<const float2*>(prm.off4_w[m] + c);
+  float wk0[16], wk1[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
-    const int64_t idx = m * hms + ((int64_t)b * L + l) * d + c;
-    float h[8], r[8];
-    load8(H + idx, h);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = du[i] * wdw[(c + i) * 16 + k] * gelu_grad_f(h[i]);
-    store8(dH + idx, r);
+    wk0[k] = wdw[c * 16 + k];
+    wk1[k] = wdw[(c + 1) * 16 + k];
   }
+  float a0[19], a1[19];
+#pragma unroll
+  for (int i = 0; i < 19; ++i) a0[i] = a1[i] = 0.f;
+  const int bp_end = min(B * g.P, (chunk + 1) * kDwPairs);
+  for (int bp = chunk * kDwPairs; bp < bp_end; ++bp) {
+    const int b = bp / g.P, p = bp % g.P;
+    const int py = p / g.Wk, px = p % g.Wk;
+    const int64_t ui = ((int64_t)m * B * g.P + bp) * d + c;
+    const float go = dO[(int64_t)m * B * g.P + bp];
+    const float2 u = *reinterpret_cast<const float2*>(U + ui);
+    const float du0 = go * w4.x * gelu_grad_f(u.x), du1 = go * w4.y * gelu_grad_f(u.y);
+    a0[16] += du0; a1[16] += du1;
+    a0[17] += go * gelu_f(u.x); a1[17] += go * gelu_f(u.y);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
+      const int64_t idx = m * hms + ((int64_t)b * L + l) * d + c;
+      const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(H + idx);
+      const float h0 = __low2float(hv), h1 = __high2float(hv);
+      // gelu(h) = h * cdf, gelu'(h) = cdf + h * pdf : one erf and one exp per element
+      const float c0 = 0.5f * (1.0f + erff(h0 * 0.70710678118654752440f)), c1 = 0.5f * (1.0f + erff(h1 * 0.70710678118654752440f));
+      const float g0 = c0 + h0 * 0.39894228040143267794f * __expf(-0.5f * h0 * h0);
+      const float g1 = c1 + h1 * 0.39894228040143267794f * __expf(-0.5f * h1 * h1);
+      const float dh0 = du0 * wk0[k] * g0, dh1 = du1 * wk1[k] * g1;
+      *reinterpret_cast<__nv_bfloat162*>(dH + idx) = __floats2bfloat162_rn(dh0, dh1);
+      a0[k] = fmaf(du0, h0 * c0, a0[k]);
+      a1[k] = fmaf(du1, h1 * c1, a1[k]);
+      a0[18] += dh0; a1[18] += dh1;
+    }
+  }
+  float* dst = part + (((int64_t)m * nchunk + chunk) * 19) * d + c;
+#pragma unroll
+  for (int i = 0; i < 19; ++i) *reinterpret_cast<float2*>(dst + (int64_t)i * d) = make_float2(a0[i], a1[i]);
 }
 
-// parameter gradients of the offset net tail + bias of the folded conv (deterministic):
-//   dwdw[c,k] = sum dU * gelu(H[pos(p,k)]),  dbdw = sum dU,  dw4 = sum dO * gelu(U),  dbf = sum_pos dH
-// grid (ceil(d/32), 3); 32 channels x 8 row lanes over (b,p)
-static __global__ void __launch_bounds__(256) lam_dw_param_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
-                                                                     const float* __restrict__ U, const float* __restrict__ dU,
-                                                                     const float* __restrict__ dO, sig_align_params prm,
-                                                                     sig_align_param_grads gr, float* __restrict__ dbf, Geo g, int B,
-                                                                     int L, int d) {
-  __shared__ float sm[8][32][20];
-  const int m = blockIdx.y;
-  const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  const float* wdw = prm.off2_w[m];
-  float acc[19];
-#pragma unroll
-  for (int i = 0; i < 19; ++i) acc[i] = 0.f;
-  if (c < d) {
-    float wk[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) wk[k] = wdw[c * 16 + k];
-    for (int bp = r; bp < B * g.P; bp += 8) {
-      const int b = bp / g.P, p = bp % g.P;
-      const int py = p / g.Wk, px = p % g.Wk;
-      const int64_t ui = ((int64_t)m * B * g.P + bp) * d + c;
-      const float du = dU[ui];
-      acc[16] += du;
-      acc[17] += dO[(int64_t)m * B * g.P + bp] * gelu_f(U[ui]);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
-        const float h = __bfloat162float(H[m * hms + ((int64_t)b * L + l) * d + c]);
-        acc[k] = fmaf(du, gelu_f(h), acc[k]);
-        acc[18] = fmaf(du * wk[k], gelu_grad_f(h), acc[18]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 19; ++i) sm[r][cl][i] = acc[i];
+// deterministic reduction of the partials into the parameter gradients.  grid (ceil(d/64), 19, 3), 256 threads:
+// 64 channels x 4 chunk lanes
+static __global__ void __launch_bounds__(256) lam_dw_param_reduce_kernel(const float* __restrict__ part, int nchunk,
+                                                                         sig_align_param_grads gr, float* __restrict__ dbf, int d) {
+  __shared__ float sm[4][64];
+  const int m = blockIdx.z, i = blockIdx.y;
+  const int cl = threadIdx.x & 63, r = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  float acc = 0.f;
+  if (c < d)
+    for (int ch = r; ch < nchunk; ch += 4) acc += part[(((int64_t)m * nchunk + ch) * 19 + i) * d + c];
+  sm[r][cl] = acc;
   __syncthreads();
   if (r == 0 && c < d) {
-#pragma unroll
-    for (int i = 0; i < 19; ++i) {
-      float t = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += sm[q][cl][i];
-      if (i < 16) gr.off2_w[m][c * 16 + i] = t;
-      else if (i == 16) gr.off2_b[m][c] = t;
-      else if (i == 17) gr.off4_w[m][c] = t;
-      else dbf[(int64_t)m * d + c] = t;
-    }
+    const float t = sm[0][cl] + sm[1][cl] + sm[2][cl] + sm[3][cl];
+    if (i < 16) gr.off2_w[m][c * 16 + i] = t;
+    else if (i == 16) gr.off2_b[m][c] = t;
+    else if (i == 17) gr.off4_w[m][c] = t;
+    else dbf[(int64_t)m * d + c] = t;
   }
 }
 
@@ -241,6 +235,37 @@ static __global__ void rank1_add_kernel(float* __restrict__ W, const float* __re
   if (i < (int64_t)d * d) W[i] += u[i / d] * v[i % d];
 }
 
+// y[i] = (add ? add[i] : 0) + sum_k W(i,k) x[k];  W(i,k) = W[i*ws_i + k*ws_k].  One warp per output.  grid ceil(n/8), 256 threads
+static __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ W, int64_t ws_i, int64_t ws_k,
+                                                          const float* __restrict__ x, const float* __restrict__ add, int n, int kdim,
+                                                          float* __restrict__ y) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int k = lane; k < kdim; k += 32) a = fmaf(W[i * ws_i + k * ws_k], x[k], a);
+  a = warp_sum(a);
+  if (lane == 0) y[i] = a + (add ? add[i] : 0.f);
+}
+
+// y[i] = sum_k W[k*ld + i] x[k]  (W^T x with coalesced row reads).  grid ceil(n/32), 256 threads = 32 outputs x 8 k-lanes
+static __global__ void __launch_bounds__(256) gemv_t_kernel(const float* __restrict__ W, int64_t ld, const float* __restrict__ x, int n,
+                                                            int kdim, float* __restrict__ y) {
+  __shared__ float sm[8][33];
+  const int il = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
+  float a = 0.f;
+  if (i < n)
+    for (int k = r; k < kdim; k += 8) a = fmaf(W[k * ld + i], x[k], a);
+  sm[r][il] = a;
+  __syncthreads();
+  if (r == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][il];
+    y[i] = t;
+  }
+}
+
 // zero the CLS gradient rows (packed [B,1+L,d] destination).  grid (B, 3)
 template <typename T>
 static __global__ void zero_cls_kernel(GradPtrs3 gp, int d) {
@@ -259,7 +284,7 @@ struct AlignTcCtx {
   __nv_bfloat16 *W0b, *Wqb, *Wfb, *dWfb;   // [3][d*d]
   float *bfold, *dWf, *dbf;                // [3][d], [3][d*d], [3][d]
   __nv_bfloat16 *H, *dH;                   // [3][B*L*d]
-  float *U, *dU, *o, *dO, *S, *dS, *part;
+  float *U, *dwpart, *o, *dO, *S, *dS, *part;
   size_t bytes;
 };
 
@@ -293,7 +318,7 @@ static AlignTcCtx align_tc_ctx(void* base, int B, int L, int d) {
   c.H = a.take<__nv_bfloat16>(3 * BL * d);
   c.dH = a.take<__nv_bfloat16>(3 * BL * d);
   c.U = a.take<float>(3 * (size_t)B * P * d);
-  c.dU = a.take<float>(3 * (size_t)B * P * d);
+  c.dwpart = a.take<float>(3 * (size_t)ceil_div((int64_t)B * P, kDwPairs) * 19 * d);
   c.o = a.take<float>(3 * (size_t)B * P);
   c.dO = a.take<float>(3 * (size_t)B * P);
   c.S = a.take<float>(3 * (size_t)B * P * d);
@@ -331,10 +356,7 @@ static TcOperand tok_operand(const sig_tokens* t, int mode) {
   o.cols = t->d;
   return o;
 }
-static TcOperand batched(TcOperand o, const void* base, size_t stride_elems) {
-  for (int m = 0; m < 3; ++m) o.ptr[m] = static_cast<const __nv_bfloat16*>(base) + m * stride_elems;
-  return o;
-}
+static TcOperand batched(TcOperand o, const void* base, size_t stride_elems) { return tc_batched(o, base, stride_elems, 3); }
 
 static bool tc_path_ok(const sig_tokens* t, unsigned flags) {
   if (flags & SIG_FLAG_FORCE_SIMT) return false;
@@ -381,10 +403,9 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
       SIG_TRY(cast_f32_to_bf16(p->off0_w[m], c.W0b + m * dd, dd, s));
       SIG_TRY(cast_f32_to_bf16(p->proj_q_w[m], c.Wqb + m * dd, dd, s));
       // b' = W0 bq + b0
-      cudaMemcpyAsync(c.bfold + (size_t)m * d, p->off0_b[m], d * sizeof(float), cudaMemcpyDeviceToDevice, s);
-      Gemm gg = gemm_nt(p->off0_w[m], d, p->proj_q_b[m], d, c.bfold + (size_t)m * d, 1, nullptr, d, 1, d);
-      gg.accumulate = 1;
-      SIG_TRY(launch_gemm(gg, s));
+      gemv_kernel<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(p->off0_w[m], d, 1, p->proj_q_b[m], p->off0_b[m], d, d,
+                                                          c.bfold + (size_t)m * d);
+      SIG_CHECK_LAUNCH();
     }
     // W' = W0 Wq  (A = W0 [d_out, d_mid] K-major; B[n = d_in, k = d_mid] = Wq[k][n] -> MN-major)
     TcGemmDesc t = tc_desc();
@@ -483,10 +504,11 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   }
   {
     SIG_PHASE("lam_dwconv_bwd");
-    lam_dw_bwd_tc_kernel<<<dim3(B * g.P, 3), cthreads, 0, s>>>(c.H, (int64_t)BL * d, c.U, c.dO, *p, g, B, L, d, c.dU, c.dH);
+    const int nchunk = (int)ceil_div((int64_t)B * g.P, kDwPairs);
+    lam_dw_bwd_tc_kernel<<<dim3(nchunk, 3), (unsigned)ceil_div(d / 2, 32) * 32, 0, s>>>(c.H, (int64_t)BL * d, c.U, c.dO, *p, g, B, L, d,
+                                                                                      c.dH, c.dwpart);
     SIG_CHECK_LAUNCH();
-    lam_dw_param_tc_kernel<<<dim3((unsigned)ceil_div(d, 32), 3), 256, 0, s>>>(c.H, (int64_t)BL * d, c.U, c.dU, c.dO, *p, *dp, c.dbf, g,
-                                                                              B, L, d);
+    lam_dw_param_reduce_kernel<<<dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s>>>(c.dwpart, nchunk, *dp, c.dbf, d);
     SIG_CHECK_LAUNCH();
   }
   {
@@ -551,12 +573,8 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
       SIG_CHECK_LAUNCH();
       // db0 = db' ; dbq = W0^T db'
       cudaMemcpyAsync(dp->off0_b[m], c.dbf + (size_t)m * d, d * sizeof(float), cudaMemcpyDeviceToDevice, s);
-      Gemm gg{};
-      gg.A = p->off0_w[m]; gg.am = 1; gg.ak = d;            // A(m = d_mid, k = d_out) = W0[k][m]
-      gg.B = c.dbf + (size_t)m * d; gg.bn = 0; gg.bk = 1;   // B(n = 0, k) = db'[k]
-      gg.C = dp->proj_q_b[m]; gg.cm = 1;
-      gg.M = d; gg.N = 1; gg.K = d; gg.batch = 1; gg.alpha = 1.f; gg.ksplit = 1;
-      SIG_TRY(launch_gemm(gg, s));
+      gemv_t_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(p->off0_w[m], d, c.dbf + (size_t)m * d, d, d, dp->proj_q_b[m]);
+      SIG_CHECK_LAUNCH();
     }
   }
   return 0;

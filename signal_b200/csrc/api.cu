@@ -164,7 +164,7 @@ int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const 
   if (!A || !B || !C || !a_geom || !b_geom) return SIG_ERR_NULL;
   sig::TcGemmDesc g = sig::tc_desc();
   auto fill = [](sig::TcOperand& o, const void* p, int mode, const int64_t* ge) {
-    o.ptr[0] = o.ptr[1] = o.ptr[2] = p; o.mode = mode; o.ld = ge[0]; o.stride_b = ge[1]; o.stride_l = ge[2];
+    for (int i = 0; i < 8; ++i) o.ptr[i] = p; o.mode = mode; o.ld = ge[0]; o.stride_b = ge[1]; o.stride_l = ge[2];
     o.rows = ge[3]; o.cols = ge[4];
   };
   fill(g.A, A, a_mode, a_geom);

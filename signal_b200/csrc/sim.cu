@@ -14,6 +14,7 @@
 #include "sim.h"
 #include "sim_tc.h"
 #include "simt_ops.cuh"
+#include "tc_gemm.h"
 
 namespace sig {
 
@@ -68,7 +69,7 @@ int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s) 
 
 // CLS tokens only: strided T views -> clsf[B][3][d] fp32.  grid (B, 3)
 template <typename T>
-static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ clsf) {
+static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ clsf, __nv_bfloat16* __restrict__ clsb) {
   const int b = blockIdx.x, m = blockIdx.y;
   const T* src = static_cast<const T*>(tp.cls[m]) + b * tp.csb[m];
   float* dst = clsf + ((int64_t)b * 3 + m) * d;
@@ -76,6 +77,7 @@ static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ 
     float v[8];
     load8(src + c, v);
     store8(dst + c, v);
+    if (clsb) store8(clsb + ((int64_t)b * 3 + m) * d + c, v);
   }
 }
 
@@ -650,6 +652,7 @@ struct SimCtx {
   bool tc;
   __nv_bfloat16 *DXQT, *Ptok, *PT, *PdS, *dST;
   float *S32, *delta;
+  __nv_bfloat16 *Wb, *clsb, *qattb, *xbarb, *ob, *y1b, *h1b, *dr2b, *da1b, *dr1b, *dobb, *dqtb, *dqattb;
   size_t bytes;
 };
 
@@ -701,6 +704,19 @@ static SimCtx sim_ctx(void* base, int B, int L, int d, bool tc = false) {
   c.dST = a.take<__nv_bfloat16>(tc ? (size_t)B * 32 * 384 : 0);
   c.S32 = a.take<float>(tc ? (size_t)B * 384 * 32 : 0);
   c.delta = a.take<float>(tc ? (size_t)B * 32 : 0);
+  c.Wb = a.take<__nv_bfloat16>(tc ? (size_t)8 * d * d : 0);
+  c.clsb = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.qattb = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.xbarb = a.take<__nv_bfloat16>(tc ? R * 8 * d : 0);
+  c.ob = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.y1b = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.h1b = a.take<__nv_bfloat16>(tc ? R * 2 * d : 0);
+  c.dr2b = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.da1b = a.take<__nv_bfloat16>(tc ? R * 2 * d : 0);
+  c.dr1b = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.dobb = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.dqtb = a.take<__nv_bfloat16>(tc ? R * 8 * d : 0);
+  c.dqattb = a.take<__nv_bfloat16>(tc ? R * d : 0);
   c.bytes = a.off;
   return c;
 }
@@ -720,6 +736,8 @@ static SimTcBufs tc_bufs(const SimCtx& c, const float* maskf) {
   k.xbar = c.xbar; k.dxbar = c.dxbar; k.delta = c.delta; k.PdS = c.PdS; k.dST = c.dST; k.dqt = c.dqt;
   return k;
 }
+
+#include "sim_mlp_tc.inl"
 
 // ---------------------------------------------------------------------------------------------
 // orchestration
@@ -758,6 +776,18 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
   const float* bq = p->in_proj_b;
   const float* bk = p->in_proj_b + d;
   const float* bv = p->in_proj_b + 2 * d;
+  if (c.tc) {
+    {
+      SIG_PHASE("sim_attn_prep");
+      SIG_TRY(attn_prep_tc(c, p, B, d, s));
+    }
+    {
+      SIG_PHASE("sim_attn_tokens_fwd");
+      SIG_TRY(sim_tc_tokens_fwd(tok, tc_bufs(c, maskf), s));
+    }
+    SIG_PHASE("sim_post");
+    return attn_post_tc<OutT>(c, p, B, d, out, s);
+  }
   // q = W_q cls + b_q  (unscaled; the 1/sqrt(hd) of MHA is folded into qt and c)
   {
   SIG_PHASE("sim_attn_prep");
@@ -816,6 +846,18 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
   float* dwq = g->in_proj_w;
   float* dwk = g->in_proj_w + (size_t)d * d;
   float* dwv = g->in_proj_w + (size_t)2 * d * d;
+  if (c.tc) {
+    {
+      SIG_PHASE("sim_post_bwd");
+      SIG_TRY((attn_post_bwd_tc<InT>(c, p, B, d, dout, g, s)));
+    }
+    {
+      SIG_PHASE("sim_attn_tokens_bwd");
+      SIG_TRY(sim_tc_tokens_bwd(tok, tc_bufs(c, maskf), dtok, s));
+    }
+    SIG_PHASE("sim_attn_prep_bwd");
+    return attn_prep_bwd_tc(c, p, B, d, g, s);
+  }
   {
   SIG_PHASE("sim_post_bwd");
   // LN2
@@ -916,7 +958,7 @@ int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, 
   SimCtx c = sim_ctx(ctx, B, L, d, tcp);
   if (tcp) {
     SIG_PHASE("convert_tokens");
-    gather_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(tok_ptrs(tok), d, c.clsf);
+    gather_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(tok_ptrs(tok), d, c.clsf, c.clsb);
     SIG_CHECK_LAUNCH();
   } else {
     SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));

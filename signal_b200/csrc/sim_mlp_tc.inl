@@ -1,0 +1,232 @@
+// bf16 tensor-core versions of the small dense layers around the SIM token kernels
+// (q / folded-query prep, value + output projections, FFN; useA.py:388-401) -- included by sim.cu.
+// Activations keep an fp32 master (LayerNorm, residuals, softmax statistics run in fp32) and a bf16
+// shadow that feeds the next tcgen05 GEMM; weights are cast to bf16 once per call.
+
+static TcGemmDesc lin_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, float* C, int64_t ldc,
+                         const float* bias, int M, int N, int K) {
+  TcGemmDesc t = tc_desc();
+  t.A = tc_k2d(A, M, K, lda);
+  t.B = tc_k2d(W, N, K, ldw);
+  t.M = M; t.N = N; t.K = K;
+  t.C[0] = C; t.ldc = ldc; t.bias[0] = bias;
+  return t;
+}
+// C[M,N] = A[M,K] Wm[K,N]
+static TcGemmDesc lin_nn(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wm, int64_t ldw, float* C, int64_t ldc, int M,
+                         int N, int K) {
+  TcGemmDesc t = tc_desc();
+  t.A = tc_k2d(A, M, K, lda);
+  t.B = tc_mn2d(Wm, K, N, ldw);
+  t.M = M; t.N = N; t.K = K;
+  t.C[0] = C; t.ldc = ldc;
+  return t;
+}
+// C[M,N] = A[K,M]^T Bm[K,N]
+static TcGemmDesc lin_tn(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bm, int64_t ldb, float* C, int64_t ldc, int M,
+                         int N, int K) {
+  TcGemmDesc t = tc_desc();
+  t.A = tc_mn2d(A, K, M, lda);
+  t.B = tc_mn2d(Bm, K, N, ldb);
+  t.M = M; t.N = N; t.K = K;
+  t.C[0] = C; t.ldc = ldc;
+  return t;
+}
+// per-head batch: entry h uses pointers base + h * stride (elements)
+static void per_head(TcOperand& o, const __nv_bfloat16* base, int64_t stride) {
+  for (int h = 0; h < kHeads; ++h) o.ptr[h] = base + h * stride;
+}
+
+// c[(b,q),h] = scale * q_h . b_k^h   grid R, 256 threads (one warp per head)
+static __global__ void __launch_bounds__(256) catt_kernel(const float* __restrict__ qatt, const float* __restrict__ bk, int d, float scale,
+                                                          float* __restrict__ catt) {
+  const int64_t row = blockIdx.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, hd = d / kHeads;
+  float a = 0.f;
+  for (int c = lane; c < hd; c += 32) a = fmaf(qatt[row * d + h * hd + c], bk[h * hd + c], a);
+  a = warp_sum(a);
+  if (lane == 0) catt[row * 8 + h] = a * scale;
+}
+
+// da = dh * gelu'(a) in place (fp32) + bf16 shadow
+static __global__ void gelu_bwd_shadow_kernel(float* dh, const float* __restrict__ a, __nv_bfloat16* __restrict__ shadow, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = dh[i] * gelu_grad_f(a[i]);
+    dh[i] = v;
+    shadow[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static int cast_sim_weights(const SimCtx& c, const sig_sim_params* p, int d, cudaStream_t s) {
+  const size_t dd = (size_t)d * d;
+  SIG_TRY(cast_f32_to_bf16(p->in_proj_w, c.Wb, 3 * dd, s));
+  SIG_TRY(cast_f32_to_bf16(p->out_proj_w, c.Wb + 3 * dd, dd, s));
+  SIG_TRY(cast_f32_to_bf16(p->ffn0_w, c.Wb + 4 * dd, 2 * dd, s));
+  SIG_TRY(cast_f32_to_bf16(p->ffn2_w, c.Wb + 6 * dd, 2 * dd, s));
+  return 0;
+}
+
+static int attn_prep_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, cudaStream_t s) {
+  const int R = 3 * B, hd = d / kHeads;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const size_t dd = (size_t)d * d;
+  const __nv_bfloat16* wqb = c.Wb;
+  const __nv_bfloat16* wkb = c.Wb + dd;
+  SIG_TRY(cast_sim_weights(c, p, d, s));
+  {  // q = W_q cls + b_q  (fp32 + bf16 shadow)
+    TcGemmDesc t = lin_nt(c.clsb, d, wqb, d, c.qatt, d, p->in_proj_b, R, d, d);
+    t.C2[0] = c.qattb; t.ldc2 = d;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  {  // qt[(b,q),h,:] = scale * q_h W_k^h
+    TcGemmDesc t = lin_nn(c.qattb, d, wkb, d, c.qtatt, 8 * (int64_t)d, R, d, hd);
+    t.batch = kHeads; t.alpha = scale;
+    per_head(t.A, c.qattb, hd);
+    per_head(t.B, wkb, (int64_t)hd * d);
+    for (int h = 0; h < kHeads; ++h) t.C[h] = c.qtatt + (size_t)h * d;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  catt_kernel<<<R, 256, 0, s>>>(c.qatt, p->in_proj_b + d, d, scale, c.catt);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename OutT>
+static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, OutT* out, cudaStream_t s) {
+  const int R = 3 * B, hd = d / kHeads;
+  const size_t dd = (size_t)d * d;
+  const __nv_bfloat16* wvb = c.Wb + 2 * dd;
+  const __nv_bfloat16* wob = c.Wb + 3 * dd;
+  const __nv_bfloat16* w1b = c.Wb + 4 * dd;
+  const __nv_bfloat16* w2b = c.Wb + 6 * dd;
+  SIG_TRY(cast_f32_to_bf16(c.xbar, c.xbarb, (int64_t)R * 8 * d, s));
+  {  // o_h = W_v^h xbar_h + b_v^h
+    TcGemmDesc t = lin_nt(c.xbarb, 8 * (int64_t)d, wvb, d, c.o, d, nullptr, R, hd, d);
+    t.batch = kHeads;
+    per_head(t.A, c.xbarb, d);
+    per_head(t.B, wvb, (int64_t)hd * d);
+    t.ldc2 = d;
+    for (int h = 0; h < kHeads; ++h) {
+      t.C[h] = c.o + (size_t)h * hd;
+      t.bias[h] = p->in_proj_b + 2 * d + h * hd;
+      t.C2[h] = c.ob + (size_t)h * hd;
+    }
+    SIG_TRY(tc_gemm(t, s));
+  }
+  SIG_TRY(tc_gemm(lin_nt(c.ob, d, wob, d, c.attn, d, p->out_proj_b, R, d, d), s));
+  layernorm_fwd_kernel<float><<<R, 256, 0, s>>>(c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
+  SIG_CHECK_LAUNCH();
+  SIG_TRY(cast_f32_to_bf16(c.y1, c.y1b, (int64_t)R * d, s));
+  {
+    TcGemmDesc t = lin_nt(c.y1b, d, w1b, d, c.h1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d);
+    t.act = 1; t.pre[0] = c.a1; t.C2[0] = c.h1b; t.ldc2 = 2 * (int64_t)d;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  SIG_TRY(tc_gemm(lin_nt(c.h1b, 2 * (int64_t)d, w2b, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
+  layernorm_fwd_kernel<OutT><<<R, 256, 0, s>>>(c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename InT>
+static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, const InT* dout, const sig_sim_param_grads* g,
+                            cudaStream_t s) {
+  const int R = 3 * B, hd = d / kHeads;
+  const size_t dd = (size_t)d * d;
+  const __nv_bfloat16* wvb = c.Wb + 2 * dd;
+  const __nv_bfloat16* wob = c.Wb + 3 * dd;
+  const __nv_bfloat16* w1b = c.Wb + 4 * dd;
+  const __nv_bfloat16* w2b = c.Wb + 6 * dd;
+  float* dwv = g->in_proj_w + 2 * dd;
+  SIG_TRY(cast_sim_weights(c, p, d, s));   // backward may run long after forward: do not rely on the forward copy
+  layernorm_bwd_kernel<InT><<<R, 256, 0, s>>>(dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
+  SIG_CHECK_LAUNCH();
+  SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln2_w, 1.f, s));
+  SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln2_b, 1.f, s));
+  SIG_TRY(launch_colsum(c.dr2, d, R, d, g->ffn2_b, 1.f, s));
+  SIG_TRY(cast_f32_to_bf16(c.dr2, c.dr2b, (int64_t)R * d, s));
+  SIG_TRY(tc_gemm(lin_tn(c.dr2b, d, c.h1b, 2 * (int64_t)d, g->ffn2_w, 2 * (int64_t)d, d, 2 * d, R), s));       // dW2 = dr2^T h1
+  SIG_TRY(tc_gemm(lin_nn(c.dr2b, d, w2b, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d), s));              // dh1 = dr2 W2
+  {
+    const int64_t n = (int64_t)R * 2 * d;
+    gelu_bwd_shadow_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(c.dh1, c.a1, c.da1b, n);
+    SIG_CHECK_LAUNCH();
+  }
+  SIG_TRY(launch_colsum(c.dh1, 2 * (int64_t)d, R, 2 * d, g->ffn0_b, 1.f, s));
+  SIG_TRY(tc_gemm(lin_tn(c.da1b, 2 * (int64_t)d, c.y1b, d, g->ffn0_w, d, 2 * d, d, R), s));                     // dW1 = da1^T y1
+  {  // dy1 = dr2 + da1 W1
+    TcGemmDesc t = lin_nn(c.da1b, 2 * (int64_t)d, w1b, d, c.dr2, d, R, d, 2 * d);
+    t.accumulate = 1;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  layernorm_bwd_kernel<float><<<R, 256, 0, s>>>(c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
+  SIG_CHECK_LAUNCH();
+  SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln1_w, 1.f, s));
+  SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln1_b, 1.f, s));
+  SIG_TRY(launch_colsum(c.dr1, d, R, d, g->out_proj_b, 1.f, s));
+  SIG_TRY(cast_f32_to_bf16(c.dr1, c.dr1b, (int64_t)R * d, s));
+  SIG_TRY(tc_gemm(lin_tn(c.dr1b, d, c.ob, d, g->out_proj_w, d, d, d, R), s));                                    // dWo = dr1^T o
+  {  // do = dr1 Wo
+    TcGemmDesc t = lin_nn(c.dr1b, d, wob, d, c.dob, d, R, d, d);
+    t.C2[0] = c.dobb; t.ldc2 = d;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  SIG_TRY(launch_colsum(c.dob, d, R, d, g->in_proj_b + 2 * d, 1.f, s));
+  {  // dW_v^h = do_h^T xbar_h
+    TcGemmDesc t = lin_tn(c.dobb, d, c.xbarb, 8 * (int64_t)d, dwv, d, hd, d, R);
+    t.batch = kHeads;
+    per_head(t.A, c.dobb, hd);
+    per_head(t.B, c.xbarb, d);
+    for (int h = 0; h < kHeads; ++h) t.C[h] = dwv + (size_t)h * hd * d;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  {  // dxbar_h = do_h W_v^h
+    TcGemmDesc t = lin_nn(c.dobb, d, wvb, d, c.dxbar, 8 * (int64_t)d, R, d, hd);
+    t.batch = kHeads;
+    per_head(t.A, c.dobb, hd);
+    per_head(t.B, wvb, (int64_t)hd * d);
+    for (int h = 0; h < kHeads; ++h) t.C[h] = c.dxbar + (size_t)h * d;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  return 0;
+}
+
+static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, const sig_sim_param_grads* g, cudaStream_t s) {
+  const int R = 3 * B, hd = d / kHeads;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const size_t dd = (size_t)d * d;
+  const __nv_bfloat16* wqb = c.Wb;
+  const __nv_bfloat16* wkb = c.Wb + dd;
+  float* dwq = g->in_proj_w;
+  float* dwk = g->in_proj_w + dd;
+  SIG_TRY(cast_f32_to_bf16(c.dqt, c.dqtb, (int64_t)R * 8 * d, s));
+  {  // dq_h = scale * dqt_h W_k^hT
+    TcGemmDesc t = lin_nt(c.dqtb, 8 * (int64_t)d, wkb, d, c.dqatt, d, nullptr, R, hd, d);
+    t.batch = kHeads; t.alpha = scale; t.ldc2 = d;
+    per_head(t.A, c.dqtb, d);
+    per_head(t.B, wkb, (int64_t)hd * d);
+    for (int h = 0; h < kHeads; ++h) {
+      t.C[h] = c.dqatt + (size_t)h * hd;
+      t.C2[h] = c.dqattb + (size_t)h * hd;
+    }
+    SIG_TRY(tc_gemm(t, s));
+  }
+  {  // dW_k^h = scale * q_h^T dqt_h
+    TcGemmDesc t = lin_tn(c.qattb, d, c.dqtb, 8 * (int64_t)d, dwk, d, hd, d, R);
+    t.batch = kHeads; t.alpha = scale;
+    per_head(t.A, c.qattb, hd);
+    per_head(t.B, c.dqtb, d);
+    for (int h = 0; h < kHeads; ++h) t.C[h] = dwk + (size_t)h * hd * d;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  cudaMemsetAsync(g->in_proj_b + d, 0, d * sizeof(float), s);  // key bias: softmax shift invariance => exactly 0
+  SIG_TRY(launch_colsum(c.dqatt, d, R, d, g->in_proj_b, 1.f, s));
+  SIG_TRY(tc_gemm(lin_tn(c.dqattb, d, c.clsb, d, dwq, d, d, d, R), s));                                           // dWq = dq^T cls
+  {  // dcls = dr1 (residual) + dq W_q
+    TcGemmDesc t = lin_nn(c.dqattb, d, wqb, d, c.dr1, d, R, d, d);
+    t.accumulate = 1;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  return 0;
+}

@@ -74,21 +74,24 @@ using tc::BK;
 using tc::BM;
 
 struct TcKernelParams {
-  CUtensorMap ta[3], tb[3];
+  CUtensorMap ta[8], tb[8];
   int a_mode, b_mode;
   int M, N, K, batch;
-  void* C[3];
+  void* C[8];
   long long ldc;
   int out_bf16;
-  const float* bias[3];
+  const float* bias[8];
   float alpha;
   int act, ksplit;
   int tiles_m, tiles_n, kblocks;
   int c_tok;
   long long c_stride_b, c_stride_l;
-  const float* rowvec[3];
+  const float* rowvec[8];
   const float* rowvec_scale;
   int accumulate;
+  void* C2[8];
+  long long ldc2;
+  float* pre[8];
 };
 
 template <int BN, bool AMN, bool BMN>
@@ -163,6 +166,11 @@ struct GemmProblem {
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) v[j] += bias[col0 + j];
             }
+            if (p.pre[z]) {
+              float* pd = p.pre[z] + (long long)row * p.ldc + col0;
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) pd[j] = v[j];
+            }
             if (p.act == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
@@ -171,6 +179,11 @@ struct GemmProblem {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) v[j] = fmaf(rscale, rvec[col0 + j], v[j]);
+            }
+            if (p.C2[z]) {
+              __nv_bfloat16* d2 = static_cast<__nv_bfloat16*>(p.C2[z]) + (long long)row * p.ldc2 + col0;
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) d2[j] = __float2bfloat16_rn(v[j]);
             }
             if (p.out_bf16) {
               __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C[z]) + row_off + col0;
@@ -229,13 +242,15 @@ int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
     p.C[z] = g.C[z];
     p.bias[z] = g.bias[z];
     p.rowvec[z] = g.rowvec[z];
+    p.C2[z] = g.C2[z];
+    p.pre[z] = g.pre[z];
     if (!g.C[z]) return SIG_ERR_NULL;
   }
   p.a_mode = g.A.mode; p.b_mode = g.B.mode;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.ldc = g.ldc; p.out_bf16 = g.out_bf16; p.alpha = g.alpha; p.act = g.act; p.ksplit = g.ksplit < 1 ? 1 : g.ksplit;
   p.c_tok = g.c_tok; p.c_stride_b = g.c_stride_b; p.c_stride_l = g.c_stride_l;
-  p.rowvec_scale = g.rowvec_scale; p.accumulate = g.accumulate;
+  p.rowvec_scale = g.rowvec_scale; p.accumulate = g.accumulate; p.ldc2 = g.ldc2;
   p.tiles_m = (int)ceil_div(g.M, BM);
   p.tiles_n = (int)ceil_div(g.N, BN);
   p.kblocks = (int)ceil_div(g.K, BK);
@@ -251,8 +266,7 @@ int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
 }  // namespace
 
 int tc_gemm(const TcGemmDesc& g, cudaStream_t s) {
-  if (g.M < 1 || g.N < 1 || g.K < 1 || g.batch < 1 || g.batch > 3) return SIG_ERR_SHAPE;
-  if (g.K % 8) return SIG_ERR_SHAPE;
+  if (g.M < 1 || g.N < 1 || g.K < 1 || g.batch < 1 || g.batch > 8) return SIG_ERR_SHAPE;
   if (g.ksplit > 1 && (g.out_bf16 || g.act)) return SIG_ERR_SHAPE;
   if (g.bn == 256) return launch_gemm_bn<256>(g, s);
   return launch_gemm_bn<128>(g, s);

@@ -16,7 +16,7 @@ enum TcOpMode : int {
 };
 
 struct TcOperand {
-  const void* ptr[3];       // per batch entry (bf16)
+  const void* ptr[8];       // per batch entry (bf16)
   int mode;
   int64_t ld;               // 2-D modes: row pitch in elements
   int64_t stride_b, stride_l;  // token modes: element strides; B samples of L=128 rows
@@ -25,11 +25,11 @@ struct TcOperand {
 
 struct TcGemmDesc {
   TcOperand A, B;
-  int M, N, K, batch;       // batch <= 3
-  void* C[3];
+  int M, N, K, batch;       // batch <= 8
+  void* C[8];
   int64_t ldc;
   int out_bf16;             // 0: fp32 C, 1: bf16 C
-  const float* bias[3];     // optional, per n
+  const float* bias[8];     // optional, per n
   float alpha;
   int act;                  // 0 none, 1 GELU
   int ksplit;               // > 1: fp32 atomic accumulation into a pre-zeroed C (no bias / act / bf16)
@@ -38,9 +38,12 @@ struct TcGemmDesc {
   int c_tok;
   int64_t c_stride_b, c_stride_l;
   // optional per-sample row vector: v += (*rowvec_scale) * rowvec[z][(row / 128) * N + n]
-  const float* rowvec[3];
+  const float* rowvec[8];
   const float* rowvec_scale;
   int accumulate;           // v += existing C (non split-K)
+  void* C2[8];              // optional bf16 copy of the stored value (row pitch ldc2)
+  int64_t ldc2;
+  float* pre[8];            // optional fp32 copy of the value before the activation (row pitch ldc)
 };
 
 inline TcGemmDesc tc_desc() {
@@ -49,10 +52,16 @@ inline TcGemmDesc tc_desc() {
   return g;
 }
 inline TcOperand tc_k2d(const void* p, int64_t rows, int64_t k, int64_t ld) {
-  TcOperand o{}; o.ptr[0] = o.ptr[1] = o.ptr[2] = p; o.mode = TC_K2D; o.ld = ld; o.rows = rows; o.cols = k; return o;
+  TcOperand o{}; for (int i = 0; i < 8; ++i) o.ptr[i] = p; o.mode = TC_K2D; o.ld = ld; o.rows = rows; o.cols = k; return o;
 }
 inline TcOperand tc_mn2d(const void* p, int64_t k, int64_t cols, int64_t ld) {
-  TcOperand o{}; o.ptr[0] = o.ptr[1] = o.ptr[2] = p; o.mode = TC_MN2D; o.ld = ld; o.rows = k; o.cols = cols; return o;
+  TcOperand o{}; for (int i = 0; i < 8; ++i) o.ptr[i] = p; o.mode = TC_MN2D; o.ld = ld; o.rows = k; o.cols = cols; return o;
+}
+
+// per-batch base pointers: entry z = base + z * stride_elems (bf16 elements)
+inline TcOperand tc_batched(TcOperand o, const void* base, size_t stride_elems, int n = 3) {
+  for (int z = 0; z < n; ++z) o.ptr[z] = static_cast<const __nv_bfloat16*>(base) + z * stride_elems;
+  return o;
 }
 
 // Enqueue the GEMM on `s`.  Returns 0 / SIG_ERR_* / cudaError_t.
