@@ -206,12 +206,18 @@ def run_gpu(args):
     al.load_state_dict(syn.make_params(syn.align_param_shapes(d), 1235))
     sim, al = sim.to(dev), al.to(dev)
     params = [p for p in list(sim.parameters()) + list(al.parameters())]
-    # flat gradient arena: .grad tensors are views, one NCCL all-reduce per step
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    # each backward returns its parameter gradients as views of ONE flat fp32 arena (one for SIM, one
+    # for AlignM); autograd adopts those views as .grad, so data parallel needs two all-reduces per step
+
+    def allreduce_grads():
+        bases = {}
+        for p in params:
+            if p.grad is not None:
+                b = p.grad._base if p.grad._base is not None else p.grad
+                bases[id(b)] = b
+        for b in bases.values():
+            dist.all_reduce(b)
+            b.div_(world)
 
     host_sets = []
     for k in range(NSETS):
@@ -234,11 +240,11 @@ def run_gpu(args):
         toks = dev_sets[i % NSETS]
         for t in toks:
             t.grad = None
-        flat.zero_()
+        for p in params:
+            p.grad = None
         res = fwd_bwd(toks)
         if world > 1:
-            dist.all_reduce(flat)
-            flat.div_(world)
+            allreduce_grads()
         return res
 
     def sync_all():
@@ -275,11 +281,11 @@ def run_gpu(args):
 
     def e2e_step(i):
         toks = [t.to(dev, non_blocking=True).requires_grad_(True) for t in host_sets[i % NSETS]]
-        flat.zero_()
+        for p in params:
+            p.grad = None
         out, gam, lam = fwd_bwd(toks)
         if world > 1:
-            dist.all_reduce(flat)
-            flat.div_(world)
+            allreduce_grads()
         return out.cpu(), torch.stack([gam, lam]).cpu()
 
     for i in range(3):
@@ -336,7 +342,7 @@ def run_gpu(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(d), "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
-                       "grad_allreduce": "one NCCL all-reduce of the flat head-gradient arena per step" if world > 1 else "n/a"},
+                       "grad_allreduce": "NCCL all-reduce of the two flat head-gradient arenas (SIM, AlignM) per step" if world > 1 else "n/a"},
             "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,

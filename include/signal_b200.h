@@ -77,6 +77,18 @@ typedef struct sig_token_grads {
   int32_t zero_cls;              /* AlignM: also write zeros to dcls rows when dcls != NULL */
 } sig_token_grads;
 
+/* Optional cache of the frozen token_selection parameters folded together (they never receive a
+ * gradient -- selection is not differentiable, useA.py:79-93 -- so the product only changes when a
+ * checkpoint is loaded):  M = W_k^T W_q,  v = W_k^T b_q,  u = W_q^T b_k,  s0 = b_q . b_k,  so that
+ * W_k^T (W_q cls + b_q) = M cls + v  and  (W_q cls + b_q) . b_k = u . cls + s0  (useA.py:123-128).
+ * Filled by sig_sim_fold_selection; the caller re-runs it whenever those four tensors change. */
+typedef struct sig_sel_fold {
+  const void* m_hl;    /* bf16 [d, 2d]: row n = [hi(M[n,:]) | lo(M[n,:])], M = hi + lo (split bf16) */
+  const float* v;      /* [d] */
+  const float* u;      /* [d] */
+  const float* s0;     /* [1] */
+} sig_sel_fold;
+
 /* Select_Interactive_Module parameters (modeling/AddModule/useA.py:33-48,340-361).
  * token_selection.W_v is never used by the reference forward (useA.py:48) and is absent. */
 typedef struct sig_sim_params {
@@ -88,6 +100,7 @@ typedef struct sig_sim_params {
   const float* ffn2_w; const float* ffn2_b;       /* ffn.2 [d,2d],[d] */
   const float* ln1_w; const float* ln1_b;         /* norm1 [d] */
   const float* ln2_w; const float* ln2_b;         /* norm2 [d] */
+  const sig_sel_fold* sel_fold;                   /* optional (NULL: fold on the fly in fp32) */
 } sig_sim_params;
 
 /* Gradients of the trainable SIM parameters (token_selection.* never receive
@@ -136,6 +149,11 @@ int sig_sim_fwd(const sig_tokens* tok, const sig_sim_params* p, int k1, int k2, 
 int sig_sim_bwd(const sig_tokens* tok, const sig_sim_params* p, const void* dout,
                 const sig_token_grads* dtok, const sig_sim_param_grads* dp,
                 void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
+
+/* Fill a sig_sel_fold from p->sel_wq/sel_bq/sel_wk/sel_bk.  m_hl bf16 [d,2d], v/u fp32 [d], s0 fp32 [1];
+ * ws: scratch of d*d floats. */
+int sig_sim_fold_selection(const sig_sim_params* p, int d, void* m_hl, float* v, float* u, float* s0,
+                           void* ws, size_t ws_bytes, int device, void* stream);
 
 /* ---- TokenSelection (useA.py:50-325) ----------------------------------- */
 /* which: 1 = intra_modal_token_selection (:50), 2 = inter_modal_token_selection (:98),

@@ -235,37 +235,6 @@ static __global__ void rank1_add_kernel(float* __restrict__ W, const float* __re
   if (i < (int64_t)d * d) W[i] += u[i / d] * v[i % d];
 }
 
-// y[i] = (add ? add[i] : 0) + sum_k W(i,k) x[k];  W(i,k) = W[i*ws_i + k*ws_k].  One warp per output.  grid ceil(n/8), 256 threads
-static __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ W, int64_t ws_i, int64_t ws_k,
-                                                          const float* __restrict__ x, const float* __restrict__ add, int n, int kdim,
-                                                          float* __restrict__ y) {
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= n) return;
-  float a = 0.f;
-  for (int k = lane; k < kdim; k += 32) a = fmaf(W[i * ws_i + k * ws_k], x[k], a);
-  a = warp_sum(a);
-  if (lane == 0) y[i] = a + (add ? add[i] : 0.f);
-}
-
-// y[i] = sum_k W[k*ld + i] x[k]  (W^T x with coalesced row reads).  grid ceil(n/32), 256 threads = 32 outputs x 8 k-lanes
-static __global__ void __launch_bounds__(256) gemv_t_kernel(const float* __restrict__ W, int64_t ld, const float* __restrict__ x, int n,
-                                                            int kdim, float* __restrict__ y) {
-  __shared__ float sm[8][33];
-  const int il = threadIdx.x & 31, r = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + il;
-  float a = 0.f;
-  if (i < n)
-    for (int k = r; k < kdim; k += 8) a = fmaf(W[k * ld + i], x[k], a);
-  sm[r][il] = a;
-  __syncthreads();
-  if (r == 0 && i < n) {
-    float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) t += sm[q][il];
-    y[i] = t;
-  }
-}
-
 // zero the CLS gradient rows (packed [B,1+L,d] destination).  grid (B, 3)
 template <typename T>
 static __global__ void zero_cls_kernel(GradPtrs3 gp, int d) {
@@ -280,6 +249,8 @@ static __global__ void zero_cls_kernel(GradPtrs3 gp, int d) {
 struct AlignTcCtx {
   // GAM (fp32, small)
   float *mean, *f, *nrm, *self4, *lv, *la, *V, *rowstat, *colstat, *Wlv, *Wla, *rowA, *colC, *dtau, *df, *dmean;
+  float *gstat, *lossp, *dtaup;
+  __nv_bfloat16 *fb, *fA, *fB, *WW;
   // LAM
   __nv_bfloat16 *W0b, *Wqb, *Wfb, *dWfb;   // [3][d*d]
   float *bfold, *dWf, *dbf;                // [3][d], [3][d*d], [3][d]
@@ -308,6 +279,13 @@ static AlignTcCtx align_tc_ctx(void* base, int B, int L, int d) {
   c.dtau = a.take<float>(4);
   c.df = a.take<float>((size_t)3 * B * d);
   c.dmean = a.take<float>((size_t)3 * B * d);
+  c.gstat = a.take<float>((size_t)2 * B);
+  c.lossp = a.take<float>((size_t)2 * B);
+  c.dtaup = a.take<float>((size_t)B);
+  c.fb = a.take<__nv_bfloat16>((size_t)3 * B * d);
+  c.fA = a.take<__nv_bfloat16>((size_t)B * 3 * d);
+  c.fB = a.take<__nv_bfloat16>((size_t)2 * B * 3 * d);
+  c.WW = a.take<__nv_bfloat16>((size_t)B * 2 * ((B + 7) / 8 * 8));
   c.W0b = a.take<__nv_bfloat16>(3 * dd);
   c.Wqb = a.take<__nv_bfloat16>(3 * dd);
   c.Wfb = a.take<__nv_bfloat16>(3 * dd);
@@ -367,19 +345,170 @@ static bool tc_path_ok(const sig_tokens* t, unsigned flags) {
   return true;
 }
 
-static int gam_forward_common(const float* mean, const sig_align_params* p, int B, int d, float* f, float* nrm, float* self4,
-                              float* lv, float* la, float* V, float* rowstat, float* colstat, float* Wlv, float* Wla, float* rowA,
-                              float* colC, float* dtau, float* losses, cudaStream_t s) {
-  gam_norm_kernel<<<B, 256, 0, s>>>(mean, B, d, f, nrm, self4);
-  SIG_CHECK_LAUNCH();
-  const float* fr = f;
-  const float* fn = f + (size_t)B * d;
-  const float* ft = f + (size_t)2 * B * d;
-  SIG_TRY(launch_gemm(gemm_nt(fr, d, fn, d, lv, B, nullptr, B, B, d), s));
-  SIG_TRY(launch_gemm(gemm_nt(fr, d, ft, d, la, B, nullptr, B, B, d), s));
-  gam_loss_kernel<<<1, 1024, 0, s>>>(self4, lv, la, p->contra_temp, B, V, rowstat, colstat, Wlv, Wla, rowA, colC, losses, dtau);
-  SIG_CHECK_LAUNCH();
-  return 0;
+// ---- GAM on the bf16 path -----------------------------------------------------------------------
+// The B x B Gram entries lv = f_r f_n^T, la = f_r f_t^T feed a 3x3 determinant that cancels heavily
+// when the modalities align, so they must not be rounded to bf16.  They run on the tensor cores as a
+// 3-term split-bf16 product (x = hi + lo: hi*hi + hi*lo + lo*hi, fp32 accumulate, error ~2^-16):
+// operands are written as [hi | hi | lo] (A side) and [hi | lo | hi] (B side) along K.
+// grid B, 256 threads.  Also writes f (fp32), fb (plain bf16) and the per-sample Gram entries.
+static __global__ void __launch_bounds__(256) gam_norm_split_kernel(const float* __restrict__ mean, int B, int d, float* __restrict__ f,
+                                                                    __nv_bfloat16* __restrict__ fb, __nv_bfloat16* __restrict__ fA,
+                                                                    __nv_bfloat16* __restrict__ fB, float* __restrict__ nrm,
+                                                                    float* __restrict__ self4) {
+  __shared__ float scratch[33];
+  const int b = blockIdx.x;
+  float inv[3];
+  for (int m = 0; m < 3; ++m) {
+    const float* x = mean + ((int64_t)m * B + b) * d;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) s += x[c] * x[c];
+    s = sqrtf(block_sum(s, scratch));
+    const float dn = fmaxf(s, 1e-12f);
+    inv[m] = 1.f / dn;
+    if (threadIdx.x == 0) nrm[m * B + b] = dn;
+  }
+  float ll = 0.f, vv = 0.f, aa = 0.f, va = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      v[m] = mean[((int64_t)m * B + b) * d + c] * inv[m];
+      f[((int64_t)m * B + b) * d + c] = v[m];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v[m]);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v[m] - __bfloat162float(hi));
+      fb[((int64_t)m * B + b) * d + c] = hi;
+      if (m == 0) {
+        __nv_bfloat16* a = fA + (int64_t)b * 3 * d + c;
+        a[0] = hi; a[d] = hi; a[2 * d] = lo;
+      } else {
+        __nv_bfloat16* q = fB + ((int64_t)(m - 1) * B + b) * 3 * d + c;
+        q[0] = hi; q[d] = lo; q[2 * d] = hi;
+      }
+    }
+    ll += v[0] * v[0]; vv += v[1] * v[1]; aa += v[2] * v[2]; va += v[1] * v[2];
+  }
+  ll = block_sum(ll, scratch); vv = block_sum(vv, scratch);
+  aa = block_sum(aa, scratch); va = block_sum(va, scratch);
+  if (threadIdx.x == 0) {
+    self4[0 * B + b] = ll; self4[1 * B + b] = vv; self4[2 * B + b] = aa; self4[3 * B + b] = va;
+  }
+}
+
+// Stage 1 of the contrastive loss: block r < B handles row r of Z = -V/tau (log-sum-exp, mean, loss
+// term), block r >= B handles column r - B.  grid 2B, 128 threads.  stat[r] = lse, lossp[r] = loss term.
+static __global__ void __launch_bounds__(128) gam_stats_kernel(const float* __restrict__ self4, const float* __restrict__ lv,
+                                                               const float* __restrict__ la, const float* __restrict__ tau_p, int B,
+                                                               float* __restrict__ stat, float* __restrict__ lossp) {
+  __shared__ float scratch[33];
+  const float* ll = self4;
+  const float* vv = self4 + B;
+  const float* aa = self4 + 2 * B;
+  const float* va = self4 + 3 * B;
+  const float itau = 1.f / *tau_p;
+  const int r = blockIdx.x;
+  const bool is_row = r < B;
+  const int i0 = is_row ? r : r - B;
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < B; t += blockDim.x) {
+    const int i = is_row ? i0 : t, j = is_row ? t : i0;
+    const int64_t idx = (int64_t)i * B + j;
+    mx = fmaxf(mx, -sqrtf(fabsf(gram_det(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]))) * itau);
+  }
+  mx = block_max(mx, scratch);
+  float se = 0.f, sz = 0.f, zd = 0.f;
+  for (int t = threadIdx.x; t < B; t += blockDim.x) {
+    const int i = is_row ? i0 : t, j = is_row ? t : i0;
+    const int64_t idx = (int64_t)i * B + j;
+    const float z = -sqrtf(fabsf(gram_det(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]))) * itau;
+    se += expf(z - mx);
+    sz += z;
+    if (i == j) zd = z;
+  }
+  se = block_sum(se, scratch);
+  sz = block_sum(sz, scratch);
+  zd = block_sum(zd, scratch);
+  if (threadIdx.x == 0) {
+    const float lse = mx + logf(se);
+    stat[r] = lse;
+    lossp[r] = (1.f - kLabelSmooth) * (lse - zd) + kLabelSmooth * (lse - sz / B);
+  }
+}
+
+// Stage 2: block r < B: row r of the coefficient matrices Wlv, Wla (fp32 + bf16 [B, 2*Bp] side by side, Bp = B rounded up to 8),
+// rowA[r] and the row's share of d(tau); block r >= B: column sums colC[0..2][r - B].  grid 2B, 128 threads.
+static __global__ void __launch_bounds__(128) gam_coef_kernel(const float* __restrict__ self4, const float* __restrict__ lv,
+                                                              const float* __restrict__ la, const float* __restrict__ tau_p,
+                                                              const float* __restrict__ stat, int B, int Bp, float* __restrict__ Wlv,
+                                                              float* __restrict__ Wla, __nv_bfloat16* __restrict__ WW,
+                                                              float* __restrict__ rowA, float* __restrict__ colC,
+                                                              float* __restrict__ dtaup) {
+  __shared__ float scratch[33];
+  const float* ll = self4;
+  const float* vv = self4 + B;
+  const float* aa = self4 + 2 * B;
+  const float* va = self4 + 3 * B;
+  const float itau = 1.f / *tau_p;
+  const float tgt_off = kLabelSmooth / B, tgt_on = 1.f - kLabelSmooth + kLabelSmooth / B;
+  const int r = blockIdx.x;
+  const bool is_row = r < B;
+  const int i0 = is_row ? r : r - B;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, tp = 0.f;
+  for (int t = threadIdx.x; t < B; t += blockDim.x) {
+    const int i = is_row ? i0 : t, j = is_row ? t : i0;
+    const int64_t idx = (int64_t)i * B + j;
+    const float det = gram_det(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]);
+    const float v = sqrtf(fabsf(det)), z = -v * itau;
+    const float tg = i == j ? tgt_on : tgt_off;
+    const float pr = expf(z - stat[i]) - tg, pc = expf(z - stat[B + j]) - tg;
+    const float dZ = (0.5f / B) * (pr + pc);
+    const float dd = ddet_of(-dZ * itau, det, v);
+    if (is_row) {
+      const float wl = dd * (-2.f * (lv[idx] * aa[j] - va[j] * la[idx]));
+      const float wa = dd * (2.f * (lv[idx] * va[j] - vv[j] * la[idx]));
+      Wlv[idx] = wl;
+      Wla[idx] = wa;
+      WW[(int64_t)i * 2 * Bp + j] = __float2bfloat16_rn(wl);
+      WW[(int64_t)i * 2 * Bp + Bp + j] = __float2bfloat16_rn(wa);
+      s0 += dd * (vv[j] * aa[j] - va[j] * va[j]);
+      // d(tau): subtract the diagonal volumes (sum_j pr = 0, sum_i pc = 0) to avoid fp32 cancellation
+      const float vii = sqrtf(fabsf(gram_det(ll[i], vv[i], aa[i], va[i], lv[(int64_t)i * B + i], la[(int64_t)i * B + i])));
+      const float vjj = sqrtf(fabsf(gram_det(ll[j], vv[j], aa[j], va[j], lv[(int64_t)j * B + j], la[(int64_t)j * B + j])));
+      tp += (0.5f / B) * (pr * (v - vii) + pc * (v - vjj)) * itau * itau;
+    } else {
+      s0 += dd * (ll[i] * aa[j] - la[idx] * la[idx]);
+      s1 += dd * (-2.f * (ll[i] * va[j] - lv[idx] * la[idx]));
+      s2 += dd * (ll[i] * vv[j] - lv[idx] * lv[idx]);
+    }
+  }
+  s0 = block_sum(s0, scratch);
+  if (is_row) {
+    tp = block_sum(tp, scratch);
+    if (threadIdx.x == 0) {
+      rowA[i0] = s0;
+      dtaup[i0] = tp;
+    }
+  } else {
+    s1 = block_sum(s1, scratch);
+    s2 = block_sum(s2, scratch);
+    if (threadIdx.x == 0) {
+      colC[0 * B + i0] = s0; colC[1 * B + i0] = s1; colC[2 * B + i0] = s2;
+    }
+  }
+}
+
+// loss = (0.5/B) * sum lossp[0..2B) ; dtau = sum dtaup[0..B)
+static __global__ void __launch_bounds__(256) gam_final_kernel(const float* __restrict__ lossp, const float* __restrict__ dtaup, int B,
+                                                               float* __restrict__ loss, float* __restrict__ dtau) {
+  __shared__ float scratch[33];
+  float a = 0.f, t = 0.f;
+  for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) a += lossp[i];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) t += dtaup[i];
+  a = block_sum(a, scratch);
+  t = block_sum(t, scratch);
+  if (threadIdx.x == 0) {
+    *loss = a * (0.5f / B);
+    *dtau = t;
+  }
 }
 
 static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
@@ -391,8 +520,22 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     SIG_PHASE("gam_fwd");
     pool_tok_kernel<__nv_bfloat16><<<dim3(B, 3), 256, 0, s>>>(tp, B, L, d, c.mean);
     SIG_CHECK_LAUNCH();
-    SIG_TRY(gam_forward_common(c.mean, p, B, d, c.f, c.nrm, c.self4, c.lv, c.la, c.V, c.rowstat, c.colstat, c.Wlv, c.Wla, c.rowA,
-                               c.colC, c.dtau, losses, s));
+    gam_norm_split_kernel<<<B, 256, 0, s>>>(c.mean, B, d, c.f, c.fb, c.fA, c.fB, c.nrm, c.self4);
+    SIG_CHECK_LAUNCH();
+    {  // lv = f_r f_n^T, la = f_r f_t^T  (split-bf16, K = 3d)
+      TcGemmDesc t = tc_desc();
+      t.A = tc_k2d(c.fA, B, 3 * d, 3 * d);
+      t.B = tc_batched(tc_k2d(nullptr, B, 3 * d, 3 * d), c.fB, (size_t)B * 3 * d, 2);
+      t.M = B; t.N = B; t.K = 3 * d; t.batch = 2;
+      t.C[0] = c.lv; t.C[1] = c.la; t.ldc = B;
+      SIG_TRY(tc_gemm(t, s));
+    }
+    gam_stats_kernel<<<2 * B, 128, 0, s>>>(c.self4, c.lv, c.la, p->contra_temp, B, c.gstat, c.lossp);
+    SIG_CHECK_LAUNCH();
+    gam_coef_kernel<<<2 * B, 128, 0, s>>>(c.self4, c.lv, c.la, p->contra_temp, c.gstat, B, (B + 7) / 8 * 8, c.Wlv, c.Wla, c.WW, c.rowA, c.colC, c.dtaup);
+    SIG_CHECK_LAUNCH();
+    gam_final_kernel<<<1, 256, 0, s>>>(c.lossp, c.dtaup, B, losses, c.dtau);
+    SIG_CHECK_LAUNCH();
   }
   if (!do_lam) return 0;
   const Geo g = make_geo(h, w);
@@ -463,14 +606,25 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     float* dfr = c.df;
     float* dfn = c.df + (size_t)B * d;
     float* dft = c.df + (size_t)2 * B * d;
-    SIG_TRY(launch_gemm(gemm_nn(c.Wlv, B, fn, d, dfr, d, B, d, B), s));
-    {
-      Gemm gg = gemm_nn(c.Wla, B, ft, d, dfr, d, B, d, B);
-      gg.accumulate = 1;
-      SIG_TRY(launch_gemm(gg, s));
+    (void)fr; (void)fn; (void)ft;
+    const int Bp = (B + 7) / 8 * 8;
+    for (int half = 0; half < 2; ++half) {  // df_r = Wlv f_n + Wla f_t
+      TcGemmDesc t = tc_desc();
+      t.A = tc_k2d(c.WW + half * Bp, B, B, 2 * Bp);
+      t.B = tc_mn2d(c.fb + (size_t)(1 + half) * B * d, B, d, d);
+      t.M = B; t.N = d; t.K = B;
+      t.C[0] = dfr; t.ldc = d; t.accumulate = half;
+      SIG_TRY(tc_gemm(t, s));
     }
-    SIG_TRY(launch_gemm(gemm_tn(c.Wlv, B, fr, d, dfn, d, B, d, B), s));
-    SIG_TRY(launch_gemm(gemm_tn(c.Wla, B, fr, d, dft, d, B, d, B), s));
+    {  // df_n = Wlv^T f_r, df_t = Wla^T f_r
+      TcGemmDesc t = tc_desc();
+      t.A = tc_mn2d(c.WW, B, B, 2 * Bp);
+      t.A.ptr[1] = c.WW + Bp;
+      t.B = tc_mn2d(c.fb, B, d, d);
+      t.M = B; t.N = d; t.K = B; t.batch = 2;
+      t.C[0] = dfn; t.C[1] = dft; t.ldc = d;
+      SIG_TRY(tc_gemm(t, s));
+    }
     gam_finish_kernel<<<dim3(B, 3), 256, 0, s>>>(c.f, c.nrm, c.rowA, c.colC, c.df, B, L, d, c.dmean);
     SIG_CHECK_LAUNCH();
     scale_scalar_kernel<<<1, 1, 0, s>>>(c.dtau, dlosses, dp->contra_temp);

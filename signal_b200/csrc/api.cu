@@ -69,6 +69,15 @@ int sig_sim_bwd(const sig_tokens* tok, const sig_sim_params* p, const void* dout
   return sig::sim_backward(tok, p, true, dout, dtok, dp, ctx, ctx_bytes, flags, (cudaStream_t)stream);
 }
 
+int sig_sim_fold_selection(const sig_sim_params* p, int d, void* m_hl, float* v, float* u, float* s0, void* ws, size_t ws_bytes,
+                           int device, void* stream) {
+  SIG_ENTER(device);
+  if (!p || !p->sel_wq || !p->sel_bq || !p->sel_wk || !p->sel_bk || !m_hl || !v || !u || !s0 || !ws) return SIG_ERR_NULL;
+  if (d < 64 || d % 64) return SIG_ERR_SHAPE;
+  if (ws_bytes < (size_t)d * d * sizeof(float)) return SIG_ERR_WORKSPACE;
+  return sig::sim_fold_selection(p, d, m_hl, v, u, s0, static_cast<float*>(ws), (cudaStream_t)stream);
+}
+
 int sig_sim_select_fwd(const sig_tokens* tok, const sig_sim_params* p, int which, int k1, int k2, int max_keep, float* masks,
                        void* selected, void* ctx, size_t ctx_bytes, int device, void* stream) {
   SIG_ENTER(device);

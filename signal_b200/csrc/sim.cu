@@ -69,7 +69,8 @@ int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s) 
 
 // CLS tokens only: strided T views -> clsf[B][3][d] fp32.  grid (B, 3)
 template <typename T>
-static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ clsf, __nv_bfloat16* __restrict__ clsb) {
+static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ clsf, __nv_bfloat16* __restrict__ clsb,
+                                         __nv_bfloat16* __restrict__ clsb2) {
   const int b = blockIdx.x, m = blockIdx.y;
   const T* src = static_cast<const T*>(tp.cls[m]) + b * tp.csb[m];
   float* dst = clsf + ((int64_t)b * 3 + m) * d;
@@ -78,7 +79,41 @@ static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ 
     load8(src + c, v);
     store8(dst + c, v);
     if (clsb) store8(clsb + ((int64_t)b * 3 + m) * d + c, v);
+    if (clsb2) {  // [cls | cls]: A operand of the split-bf16 product with [M_hi | M_lo]
+      store8(clsb2 + ((int64_t)b * 3 + m) * 2 * d + c, v);
+      store8(clsb2 + ((int64_t)b * 3 + m) * 2 * d + d + c, v);
+    }
   }
+}
+
+// csel[r] = cls[r] . u + s0   grid R, 128 threads
+static __global__ void __launch_bounds__(128) csel_fold_kernel(const float* __restrict__ clsf, const float* __restrict__ u,
+                                                               const float* __restrict__ s0, int d, float* __restrict__ csel) {
+  __shared__ float scratch[33];
+  const int64_t r = blockIdx.x;
+  float a = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) a = fmaf(clsf[r * d + c], u[c], a);
+  a = block_sum(a, scratch);
+  if (threadIdx.x == 0) csel[r] = a + *s0;
+}
+
+// out[n][0:d] = hi(M[n][:]), out[n][d:2d] = lo(M[n][:]);  grid d, 128 threads
+static __global__ void split_hl_kernel(const float* __restrict__ M, int d, __nv_bfloat16* __restrict__ out) {
+  const int64_t n = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = M[n * d + c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[n * 2 * d + c] = hi;
+    out[n * 2 * d + d + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+static __global__ void dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ out) {
+  __shared__ float scratch[33];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(a[i], b[i], s);
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) *out = s;
 }
 
 static TokPtrs tok_ptrs(const sig_tokens* t) {
@@ -652,6 +687,7 @@ struct SimCtx {
   bool tc;
   __nv_bfloat16 *DXQT, *Ptok, *PT, *PdS, *dST;
   float *S32, *delta;
+  __nv_bfloat16 *clsb2;
   __nv_bfloat16 *Wb, *clsb, *qattb, *xbarb, *ob, *y1b, *h1b, *dr2b, *da1b, *dr1b, *dobb, *dqtb, *dqattb;
   size_t bytes;
 };
@@ -706,6 +742,7 @@ static SimCtx sim_ctx(void* base, int B, int L, int d, bool tc = false) {
   c.delta = a.take<float>(tc ? (size_t)B * 32 : 0);
   c.Wb = a.take<__nv_bfloat16>(tc ? (size_t)8 * d * d : 0);
   c.clsb = a.take<__nv_bfloat16>(tc ? R * d : 0);
+  c.clsb2 = a.take<__nv_bfloat16>(tc ? R * 2 * d : 0);
   c.qattb = a.take<__nv_bfloat16>(tc ? R * d : 0);
   c.xbarb = a.take<__nv_bfloat16>(tc ? R * 8 * d : 0);
   c.ob = a.take<__nv_bfloat16>(tc ? R * d : 0);
@@ -746,10 +783,23 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
                          int k2, int max_keep, float* masks_out, cudaStream_t s) {
   const int R = 3 * B;
   SIG_PHASE("sim_select");
-  // q = W_q cls + b_q (useA.py:123); qt = W_k^T q; c = q . b_k
-  SIG_TRY(launch_gemm(gemm_nt(c.clsf, d, p->sel_wq, d, c.qsel, d, p->sel_bq, R, d, d), s));
-  SIG_TRY(launch_gemm(gemm_nn(c.qsel, d, p->sel_wk, d, c.qtsel, d, R, d, d), s));
-  SIG_TRY(launch_gemm(gemm_nt(c.qsel, d, p->sel_bk, d, c.csel, 1, nullptr, R, 1, d), s));
+  if (c.tc && p->sel_fold) {
+    // qt = M cls + v on the tensor cores: cls is exact in bf16, M = hi + lo  ->  [cls | cls] . [M_hi | M_lo]^T
+    const sig_sel_fold* f = p->sel_fold;
+    TcGemmDesc t = tc_desc();
+    t.A = tc_k2d(c.clsb2, R, 2 * d, 2 * d);
+    t.B = tc_k2d(f->m_hl, d, 2 * d, 2 * d);
+    t.M = R; t.N = d; t.K = 2 * d;
+    t.C[0] = c.qtsel; t.ldc = d; t.bias[0] = f->v;
+    SIG_TRY(tc_gemm(t, s));
+    csel_fold_kernel<<<R, 128, 0, s>>>(c.clsf, f->u, f->s0, d, c.csel);
+    SIG_CHECK_LAUNCH();
+  } else {
+    // q = W_q cls + b_q (useA.py:123); qt = W_k^T q; c = q . b_k
+    SIG_TRY(launch_gemm(gemm_nt(c.clsf, d, p->sel_wq, d, c.qsel, d, p->sel_bq, R, d, d), s));
+    SIG_TRY(launch_gemm(gemm_nn(c.qsel, d, p->sel_wk, d, c.qtsel, d, R, d, d), s));
+    SIG_TRY(launch_gemm(gemm_nt(c.qsel, d, p->sel_bk, d, c.csel, 1, nullptr, R, 1, d), s));
+  }
   dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
   if (c.tc)
     sim_scores_tok_kernel<__nv_bfloat16><<<grid, 256, 4 * d * sizeof(float), s>>>(tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
@@ -945,6 +995,20 @@ static int check_sim_params(const sig_sim_params* p, bool need_sel, bool need_at
   return 0;
 }
 
+int sim_fold_selection(const sig_sim_params* p, int d, void* m_hl, float* v, float* u, float* s0, float* ws, cudaStream_t s) {
+  // M[n][k] = sum_j W_k[j][n] W_q[j][k]
+  SIG_TRY(launch_gemm(gemm_tn(p->sel_wk, d, p->sel_wq, d, ws, d, d, d, d), s));
+  split_hl_kernel<<<d, 128, 0, s>>>(ws, d, static_cast<__nv_bfloat16*>(m_hl));
+  SIG_CHECK_LAUNCH();
+  gemv_t_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(p->sel_wk, d, p->sel_bq, d, d, v);   // v = W_k^T b_q
+  SIG_CHECK_LAUNCH();
+  gemv_t_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(p->sel_wq, d, p->sel_bk, d, d, u);   // u = W_q^T b_k
+  SIG_CHECK_LAUNCH();
+  dot_kernel<<<1, 256, 0, s>>>(p->sel_bq, p->sel_bk, d, s0);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
 int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, const float* ext_masks, int k1, int k2,
                 int max_keep, void* out, float* masks_out, void* ctx, size_t ctx_bytes, unsigned flags, cudaStream_t s) {
   SIG_TRY(check_tokens(tok, true));
@@ -958,7 +1022,7 @@ int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, 
   SimCtx c = sim_ctx(ctx, B, L, d, tcp);
   if (tcp) {
     SIG_PHASE("convert_tokens");
-    gather_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(tok_ptrs(tok), d, c.clsf, c.clsb);
+    gather_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(tok_ptrs(tok), d, c.clsf, c.clsb, c.clsb2);
     SIG_CHECK_LAUNCH();
   } else {
     SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));

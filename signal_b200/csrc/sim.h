@@ -5,6 +5,7 @@
 namespace sig {
 size_t sim_ctx_bytes(int B, int L, int d);
 size_t sim_ctx_bytes_for(int B, int L, int d, int dtype, unsigned flags);
+int sim_fold_selection(const sig_sim_params* p, int d, void* m_hl, float* v, float* u, float* s0, float* ws, cudaStream_t s);
 int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s);
 int write_token_grads(const sig_token_grads* g, int dtype, const float* dXf, const float* dclsf, int B, int L, int d,
                       cudaStream_t s);

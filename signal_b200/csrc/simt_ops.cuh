@@ -253,4 +253,36 @@ static __global__ void add_kernel(const float* __restrict__ a, const float* __re
   if (i < n) y[i] = a[i] + b[i];
 }
 
+// y[i] = (add ? add[i] : 0) + sum_k W(i,k) x[k];  W(i,k) = W[i*ws_i + k*ws_k].  One warp per output.  grid ceil(n/8), 256 threads
+static __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ W, int64_t ws_i, int64_t ws_k,
+                                                          const float* __restrict__ x, const float* __restrict__ add, int n, int kdim,
+                                                          float* __restrict__ y) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int k = lane; k < kdim; k += 32) a = fmaf(W[i * ws_i + k * ws_k], x[k], a);
+  a = warp_sum(a);
+  if (lane == 0) y[i] = a + (add ? add[i] : 0.f);
+}
+
+// y[i] = sum_k W[k*ld + i] x[k]  (W^T x with coalesced row reads).  grid ceil(n/32), 256 threads = 32 outputs x 8 k-lanes
+static __global__ void __launch_bounds__(256) gemv_t_kernel(const float* __restrict__ W, int64_t ld, const float* __restrict__ x, int n,
+                                                            int kdim, float* __restrict__ y) {
+  __shared__ float sm[8][33];
+  const int il = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
+  float a = 0.f;
+  if (i < n)
+    for (int k = r; k < kdim; k += 8) a = fmaf(W[k * ld + i], x[k], a);
+  sm[r][il] = a;
+  __syncthreads();
+  if (r == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][il];
+    y[i] = t;
+  }
+}
+
+
 }  // namespace sig

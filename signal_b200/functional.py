@@ -63,14 +63,17 @@ class SimFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, packed: bool, k1: int, k2: int, max_keep: int, flags: int, *tensors):
+        # tensors: 3 (packed) or 6 token tensors, 16 parameters, then optionally the 4 tensors of the
+        # folded-selection cache (lib.fold_selection)
         ntok = 3 if packed else 6
-        toks, params = tensors[:ntok], tensors[ntok:]
+        toks, params, fold = tensors[:ntok], tensors[ntok:ntok + 16], tensors[ntok + 16:]
         lib = L_.load()
         patches, cls = _split_tokens(packed, toks)
         B, L, d = patches[0].shape
         dev = patches[0].device
         tok = L_.tokens_struct(patches, cls)
-        prm = L_.sim_params_struct(params)
+        prm = L_.sim_params_struct(params, fold if len(fold) == 4 else None)
+        ctx.nfold = len(fold)
         out = torch.empty(B, 3 * d, dtype=patches[0].dtype, device=dev)
         masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
         nbytes = L_.ctx_bytes(L_.CTX_SIM, B, L, d, L_.dtype_enum(patches[0]), flags)
@@ -101,7 +104,7 @@ class SimFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(prm), dout.data_ptr(), C.byref(tg), C.byref(gs), buf.data_ptr(),
                                      buf.numel(), ctx.flags, dev.index, L_.stream_ptr(dev)), "sig_sim_bwd")
-        return (None,) * 5 + tuple(ret) + (None,) * 4 + tuple(pg)
+        return (None,) * 5 + tuple(ret) + (None,) * 4 + tuple(pg) + (None,) * ctx.nfold
 
 
 class AttnFunction(torch.autograd.Function):

@@ -38,8 +38,12 @@ SIM_PARAM_FIELDS = ["sel_wq", "sel_bq", "sel_wk", "sel_bk", "in_proj_w", "in_pro
 SIM_GRAD_FIELDS = SIM_PARAM_FIELDS[4:]
 
 
+class SigSelFold(C.Structure):
+    _fields_ = [("m_hl", C.c_void_p), ("v", C.c_void_p), ("u", C.c_void_p), ("s0", C.c_void_p)]
+
+
 class SigSimParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in SIM_PARAM_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in SIM_PARAM_FIELDS] + [("sel_fold", C.POINTER(SigSelFold))]
 
 
 class SigSimParamGrads(C.Structure):
@@ -62,7 +66,7 @@ _lib = None
 # every symbol include/signal_b200.h declares (tests check that the .so exports them all)
 EXPORTS = [
     "sig_version", "sig_error_string", "sig_ctx_bytes",
-    "sig_sim_fwd", "sig_sim_bwd", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
+    "sig_sim_fwd", "sig_sim_bwd", "sig_sim_fold_selection", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
     "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16",
@@ -89,6 +93,7 @@ def load():
     lib.sig_ctx_bytes.argtypes = [i, i, i, i, i, u]
     lib.sig_sim_fwd.argtypes = [P(SigTokens), P(SigSimParams), i, i, i, vp, vp, vp, sz, u, i, vp]
     lib.sig_sim_bwd.argtypes = [P(SigTokens), P(SigSimParams), vp, P(SigTokenGrads), P(SigSimParamGrads), vp, sz, u, i, vp]
+    lib.sig_sim_fold_selection.argtypes = [P(SigSimParams), i, vp, vp, vp, vp, vp, sz, i, vp]
     lib.sig_sim_select_fwd.argtypes = [P(SigTokens), P(SigSimParams), i, i, i, i, vp, vp, vp, sz, i, vp]
     lib.sig_sim_select_from_scores.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, i, vp]
     lib.sig_mask_mul_bwd.argtypes = [vp, vp, i, i, i, i, P(SigTokenGrads), i, vp]
@@ -184,12 +189,33 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def sim_params_struct(params: Sequence[torch.Tensor]) -> SigSimParams:
-    """params in SIM_PARAM_FIELDS order (16 tensors)."""
+def sim_params_struct(params: Sequence[torch.Tensor], fold: Optional[Sequence[torch.Tensor]] = None) -> SigSimParams:
+    """params in SIM_PARAM_FIELDS order (16 tensors); fold = optional (m_hl, v, u, s0) selection cache."""
     s = SigSimParams()
     for name, t in zip(SIM_PARAM_FIELDS, params):
         setattr(s, name, _f32c(t).data_ptr())
+    if fold is not None:
+        f = SigSelFold(*(t.data_ptr() for t in fold))
+        s._fold_keepalive = f
+        s.sel_fold = C.pointer(f)
     return s
+
+
+def fold_selection(sel_params: Sequence[torch.Tensor]):
+    """(m_hl bf16 [d,2d], v, u, s0) for the four frozen token_selection tensors (W_q.w, W_q.b, W_k.w, W_k.b)."""
+    lib = load()
+    wq = sel_params[0]
+    d, dev = wq.shape[0], wq.device
+    prm = sim_params_struct([p.detach() for p in sel_params] + [sel_params[0].detach()] * 12)
+    m_hl = torch.empty(d, 2 * d, dtype=torch.bfloat16, device=dev)
+    v = torch.empty(d, dtype=torch.float32, device=dev)
+    u = torch.empty(d, dtype=torch.float32, device=dev)
+    s0 = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = torch.empty(d * d, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.sig_sim_fold_selection(C.byref(prm), d, m_hl.data_ptr(), v.data_ptr(), u.data_ptr(), s0.data_ptr(),
+                                         ws.data_ptr(), ws.numel() * 4, dev.index, stream_ptr(dev)), "sig_sim_fold_selection")
+    return m_hl, v, u, s0
 
 
 def sim_grads_struct(grads: Sequence[torch.Tensor]) -> SigSimParamGrads:

@@ -79,6 +79,19 @@ class TokenSelection(nn.Module):
     def _sel_params(self):
         return [self.W_q.weight, self.W_q.bias, self.W_k.weight, self.W_k.bias]
 
+    def _selection_fold(self):
+        """Cached fold of the four frozen selection tensors (they never receive gradients; the cache is
+        rebuilt when any of them is modified in place, replaced, or moved)."""
+        sel = self._sel_params()
+        key = tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in sel)
+        cache = self.__dict__.get("_fold_cache")
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                from . import lib as L_
+                cache = (key, L_.fold_selection([p.detach() for p in sel]))
+            self.__dict__["_fold_cache"] = cache
+        return cache[1]
+
     def _max_keep(self, L):
         return -1 if self.keep_ratio is None else int(L * self.keep_ratio)
 
@@ -146,6 +159,8 @@ class Select_Interactive_Module(nn.Module):
             return mi(*sel, rgb_global, nir_global, tir_global)
         L = rgb_patches.size(1)
         params = [p.detach() for p in ts._sel_params()] + mi._attn_params()
+        if rgb_patches.dtype == torch.bfloat16 and not (self.flags & 1):
+            params = params + list(ts._selection_fold())
         bases = None
         if self.fuse_views:
             bases = [_packed_base(p, g) for p, g in ((rgb_patches, rgb_global), (nir_patches, nir_global), (tir_patches, tir_global))]
