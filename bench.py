@@ -115,7 +115,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -156,22 +156,21 @@ class ClockSampler:
 # algorithmic work per phase (per step of B samples); DESIGN.md states the derivation
 # ---------------------------------------------------------------------------------------------
 def phase_work(B, d, s=2):
+    """Algorithmic work per step of the bf16 path, as implemented.
+    T*s = bytes of one sample's patch tokens; the folded offset net is ONE d x d GEMM per modality."""
     T = 3 * L * d            # token elements per sample
-    g = 3 * d
-    simt_lam_fwd = 3 * (2 * 2 * L * d * d) * B                     # two dense 1x1 convs, three modalities
+    gemm = 3 * 2 * L * d * d * B                                   # folded 1x1 conv, three modalities
     return {
-        # phase: (bound, work, unit)   bytes for hbm, flops for tensor
-        "convert_tokens": ("hbm", B * (T + g) * (s + 4), "B"),
-        "sim_select": ("hbm", B * (T + g) * 4, "B"),
-        "sim_attn_tokens_fwd": ("hbm", B * (T + g) * 4, "B"),
-        "sim_attn_tokens_bwd": ("hbm", B * 2 * T * 4, "B"),
-        "gam_fwd": ("hbm", B * T * 4, "B"),
-        "lam_offsetnet_fwd": ("tensor", simt_lam_fwd, "FLOP"),
-        "lam_offsetnet_bwd": ("tensor", 2 * simt_lam_fwd, "FLOP"),
-        "lam_sample_fwd": ("hbm", B * T * 4 // 4, "B"),
-        "lam_sample_bwd": ("hbm", B * T * 4 // 4, "B"),
-        "align_write": ("hbm", B * T * (4 + s), "B"),
-        "write_token_grads": ("hbm", B * (T + g) * (4 + s), "B"),
+        # phase: (bound, work)   bytes for hbm, flops for tensor
+        "lam_offsetnet_fwd": ("tensor", gemm),                     # H = X W'^T
+        "lam_offsetnet_bwd_dx": ("tensor", gemm),                  # dX = dH W'
+        "lam_offsetnet_bwd_dw": ("tensor", gemm),                  # dW' = dH^T X
+        "lam_dwconv_fwd": ("hbm", B * T * s),                      # read H
+        "lam_dwconv_bwd": ("hbm", 2 * B * T * s),                  # read H, write dH
+        "sim_select": ("hbm", B * T * s),                          # one pass over the tokens
+        "sim_attn_tokens_fwd": ("hbm", 2 * B * T * s),             # logits pass + pooling pass
+        "sim_attn_tokens_bwd": ("hbm", 3 * B * T * s),             # dP pass + dQ pass + d(patches) write
+        "gam_fwd": ("hbm", B * T * s),                             # mean pool
     }
 
 
@@ -252,9 +251,35 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    eager_step = step
     for i in range(max(args.warmup, 3)):
         step(i)
     sync_all()
+    graph_launches = None
+    if args.graph:
+        # capture one CUDA graph per token set (static inputs); replay = the same module calls,
+        # without per-launch host work.  The library is capturable: no syncs, no allocations.
+        graphs = []
+        for k in range(NSETS):
+            for t in dev_sets[k]:
+                t.grad = None
+            for p in params:
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            lb = lib.launch_count()
+            with torch.cuda.graph(g):
+                fwd_bwd(dev_sets[k])
+                if world > 1:
+                    allreduce_grads()
+            graph_launches = lib.launch_count() - lb
+            graphs.append(g)
+
+        def step(i):
+            graphs[i % NSETS].replay()
+
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -265,7 +290,7 @@ def run_gpu(args):
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
-    launches = lib.launch_count() - l0
+    launches = lib.launch_count() - l0 if graph_launches is None else graph_launches * args.steps
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -307,7 +332,7 @@ def run_gpu(args):
         prof_steps = 5
         lib.profile_enable(True)
         for i in range(prof_steps):
-            step(i)
+            eager_step(i)
         torch.cuda.synchronize()
         lib.profile_enable(False)
         prof = lib.profile_collect()
@@ -315,9 +340,10 @@ def run_gpu(args):
         work = phase_work(B, d)
         phases = {k: round(v[0] / prof_steps * 1e3, 1) for k, v in prof.items()}   # us per step
         tot = sum(phases.values())
-        dom = max(phases, key=phases.get) if phases else None
-        if dom and dom in work:
-            bound, w, _ = work[dom]
+        known = {k: v for k, v in phases.items() if k in work}
+        dom = max(known, key=known.get) if known else None
+        if dom:
+            bound, w = work[dom]
             sec = phases[dom] * 1e-6
             if bound == "hbm":
                 ach, peak, unit = w / sec / 1e9, pk["hbm"], "GB/s"
@@ -341,7 +367,7 @@ def run_gpu(args):
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(d), "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
+                       "launch": "cuda_graph_replay" if args.graph else "eager", "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
                        "grad_allreduce": "NCCL all-reduce of the two flat head-gradient arenas (SIM, AlignM) per step" if world > 1 else "n/a"},
             "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
@@ -358,11 +384,12 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dim", type=int, default=768, choices=[512, 768])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager module calls instead of CUDA-graph replays")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -36,38 +36,48 @@ static __global__ void __launch_bounds__(256) pool_tok_kernel(TokPtrs3 tp, int B
 }
 
 // ---- LAM: depthwise 4x4/s4 conv + GELU + 1x1 -> offset logit, from the bf16 pre-activation H ------
-// grid (B*P, 3), d/8 threads (8 channels each).  U saved (fp32) for backward.
-static __global__ void __launch_bounds__(128) lam_dw_fwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
+// grid (ceil(B*P / kDwPairs), 3), d/2 threads (2 channels each; the 16 depthwise taps of both channels
+// stay in registers across the CTA's sample points).  U saved (fp32) for backward.
+constexpr int kDwPairs = 8;
+static __global__ void __launch_bounds__(512) lam_dw_fwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
                                                                    sig_align_params prm, Geo g, int B, int L, int d,
                                                                    float* __restrict__ U, float* __restrict__ o) {
   __shared__ float scratch[33];
-  const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
-  const int py = p / g.Wk, px = p % g.Wk;
+  const int m = blockIdx.y, chunk = blockIdx.x;
+  const int c = threadIdx.x * 2;
+  const bool active = c < d;
   const float* wdw = prm.off2_w[m];
-  const float* bdw = prm.off2_b[m];
-  const float* w4 = prm.off4_w[m];
-  const __nv_bfloat16* Hm = H + m * hms;
-  float part = 0.f;
-  const int c = threadIdx.x * 8;
-  if (c < d) {
-    float u[8];
-    load8(bdw + c, u);
+  float wk0[16], wk1[16];
+  float2 w4 = make_float2(0.f, 0.f), bd = make_float2(0.f, 0.f);
+  if (active) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
-      float h[8];
-      load8(Hm + ((int64_t)b * L + l) * d + c, h);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) u[i] = fmaf(gelu_f(h[i]), wdw[(c + i) * 16 + k], u[i]);
+      wk0[k] = wdw[c * 16 + k];
+      wk1[k] = wdw[(c + 1) * 16 + k];
     }
-    store8(U + ((int64_t)m * B * g.P + bp) * d + c, u);
-    float w[8];
-    load8(w4 + c, w);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) part += gelu_f(u[i]) * w[i];
+    w4 = *reinterpret_cast<const float2*>(prm.off4_w[m] + c);
+    bd = *reinterpret_cast<const float2*>(prm.off2_b[m] + c);
   }
-  part = block_sum(part, scratch);
-  if (threadIdx.x == 0) o[(int64_t)m * B * g.P + bp] = part;
+  const int bp_end = min(B * g.P, (chunk + 1) * kDwPairs);
+  for (int bp = chunk * kDwPairs; bp < bp_end; ++bp) {
+    const int b = bp / g.P, p = bp % g.P;
+    const int py = p / g.Wk, px = p % g.Wk;
+    float part = 0.f;
+    if (active) {
+      float u0 = bd.x, u1 = bd.y;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
+        const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(H + m * hms + ((int64_t)b * L + l) * d + c);
+        u0 = fmaf(gelu_fast_f(__low2float(hv)), wk0[k], u0);
+        u1 = fmaf(gelu_fast_f(__high2float(hv)), wk1[k], u1);
+      }
+      *reinterpret_cast<float2*>(U + ((int64_t)m * B * g.P + bp) * d + c) = make_float2(u0, u1);
+      part = gelu_fast_f(u0) * w4.x + gelu_fast_f(u1) * w4.y;
+    }
+    part = block_sum(part, scratch);
+    if (threadIdx.x == 0) o[(int64_t)m * B * g.P + bp] = part;
+  }
 }
 
 // Backward of the offset-net tail, one pass over H:
@@ -75,7 +85,6 @@ static __global__ void __launch_bounds__(128) lam_dw_fwd_tc_kernel(const __nv_bf
 // and per-CTA partial sums of the parameter gradients
 //   dwdw[c,k] += dU * gelu(H[pos(p,k)]),  dbdw += dU,  dw4 += dO * gelu(U),  dbf += dH
 // grid (ceil(B*P / kDwPairs), 3), d/2 threads (2 channels each).  part: [3][nchunk][19][d]
-constexpr int kDwPairs = 8;
 static __global__ void __launch_bounds__(512) lam_dw_bwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
                                                                    const float* __restrict__ U, const float* __restrict__ dO,
                                                                    sig_align_params prm, Geo g, int B, int L, int d,
@@ -101,23 +110,25 @@ static __global__ void __launch_bounds__(512) lam_dw_bwd_tc_kernel(const __nv_bf
     const int64_t ui = ((int64_t)m * B * g.P + bp) * d + c;
     const float go = dO[(int64_t)m * B * g.P + bp];
     const float2 u = *reinterpret_cast<const float2*>(U + ui);
-    const float du0 = go * w4.x * gelu_grad_f(u.x), du1 = go * w4.y * gelu_grad_f(u.y);
+    float gu0, dgu0, gu1, dgu1;
+    gelu_fast(u.x, gu0, dgu0);
+    gelu_fast(u.y, gu1, dgu1);
+    const float du0 = go * w4.x * dgu0, du1 = go * w4.y * dgu1;
     a0[16] += du0; a1[16] += du1;
-    a0[17] += go * gelu_f(u.x); a1[17] += go * gelu_f(u.y);
+    a0[17] += go * gu0; a1[17] += go * gu1;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
       const int64_t idx = m * hms + ((int64_t)b * L + l) * d + c;
       const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(H + idx);
       const float h0 = __low2float(hv), h1 = __high2float(hv);
-      // gelu(h) = h * cdf, gelu'(h) = cdf + h * pdf : one erf and one exp per element
-      const float c0 = 0.5f * (1.0f + erff(h0 * 0.70710678118654752440f)), c1 = 0.5f * (1.0f + erff(h1 * 0.70710678118654752440f));
-      const float g0 = c0 + h0 * 0.39894228040143267794f * __expf(-0.5f * h0 * h0);
-      const float g1 = c1 + h1 * 0.39894228040143267794f * __expf(-0.5f * h1 * h1);
-      const float dh0 = du0 * wk0[k] * g0, dh1 = du1 * wk1[k] * g1;
+      float gh0, dgh0, gh1, dgh1;   // gelu and gelu' share one exp and one reciprocal per element
+      gelu_fast(h0, gh0, dgh0);
+      gelu_fast(h1, gh1, dgh1);
+      const float dh0 = du0 * wk0[k] * dgh0, dh1 = du1 * wk1[k] * dgh1;
       *reinterpret_cast<__nv_bfloat162*>(dH + idx) = __floats2bfloat162_rn(dh0, dh1);
-      a0[k] = fmaf(du0, h0 * c0, a0[k]);
-      a1[k] = fmaf(du1, h1 * c1, a1[k]);
+      a0[k] = fmaf(du0, gh0, a0[k]);
+      a1[k] = fmaf(du1, gh1, a1[k]);
       a0[18] += dh0; a1[18] += dh1;
     }
   }
@@ -576,7 +587,8 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   }
   {
     SIG_PHASE("lam_dwconv_fwd");
-    lam_dw_fwd_tc_kernel<<<dim3(B * g.P, 3), (unsigned)ceil_div(d / 8, 32) * 32, 0, s>>>(c.H, (int64_t)BL * d, *p, g, B, L, d, c.U, c.o);
+    lam_dw_fwd_tc_kernel<<<dim3((unsigned)ceil_div((int64_t)B * g.P, kDwPairs), 3), (unsigned)ceil_div(d / 2, 32) * 32, 0, s>>>(
+        c.H, (int64_t)BL * d, *p, g, B, L, d, c.U, c.o);
     SIG_CHECK_LAUNCH();
   }
   {

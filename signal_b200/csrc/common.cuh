@@ -80,6 +80,27 @@ __device__ __forceinline__ float gelu_grad_f(float x) {  // Phi(x) + x phi(x)
   return cdf + x * pdf;
 }
 
+// Fast GELU value + derivative for the bf16 path: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7),
+// sharing exp(-x^2/2) between the cdf and the pdf.  No branches, two MUFU ops per element.
+__device__ __forceinline__ void gelu_fast(float x, float& g, float& dg) {
+  const float ay = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ay, 1.0f));
+  const float e = __expf(-0.5f * x * x);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float half_tail = 0.5f * poly * t * e;          // 0.5 * (1 - erf(|y|))
+  const float cdf = x >= 0.f ? 1.0f - half_tail : half_tail;
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  float g, dg;
+  gelu_fast(x, g, dg);
+  return g;
+}
+
 // ---- reductions ---------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
