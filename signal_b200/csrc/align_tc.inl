@@ -36,17 +36,38 @@ static __global__ void __launch_bounds__(256) pool_tok_kernel(TokPtrs3 tp, int B
 }
 
 // ---- LAM: depthwise 4x4/s4 conv + GELU + 1x1 -> offset logit, from the bf16 pre-activation H ------
-// grid (ceil(B*P / kDwPairs), 3), d/2 threads (2 channels each; the 16 depthwise taps of both channels
-// stay in registers across the CTA's sample points).  U saved (fp32) for backward.
+// A CTA walks kDwPairs sample points; the 16 window rows of H of the next point ([16][d] bf16) are
+// staged into shared memory with cp.async while the current point is being processed (double buffer).
+// Thread t owns channels 2t, 2t+1; its 2 x 16 depthwise taps stay in registers.
 constexpr int kDwPairs = 8;
+
+__device__ __forceinline__ void dw_stage_window(const __nv_bfloat16* __restrict__ Hm, __nv_bfloat16* buf, const Geo& g, int bp, int L,
+                                                int d) {
+  const int b = bp / g.P, p = bp % g.P;
+  const int py = p / g.Wk, px = p % g.Wk;
+  const int cpr = d / 8;                               // 16-byte chunks per row
+  for (int i = threadIdx.x; i < 16 * cpr; i += blockDim.x) {
+    const int k = i / cpr, ch = i % cpr;
+    const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
+    cp_async_16(buf + k * d + ch * 8, Hm + ((int64_t)b * L + l) * d + ch * 8);
+  }
+}
+
+// grid (ceil(B*P / kDwPairs), 3), d/2 threads, dyn smem 2*16*d bf16.  U saved (fp32) for backward.
 static __global__ void __launch_bounds__(512) lam_dw_fwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
                                                                    sig_align_params prm, Geo g, int B, int L, int d,
                                                                    float* __restrict__ U, float* __restrict__ o) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(dw_smem);
   __shared__ float scratch[33];
   const int m = blockIdx.y, chunk = blockIdx.x;
   const int c = threadIdx.x * 2;
   const bool active = c < d;
+  const __nv_bfloat16* Hm = H + m * hms;
   const float* wdw = prm.off2_w[m];
+  const int bp0 = chunk * kDwPairs, bp_end = min(B * g.P, bp0 + kDwPairs);
+  dw_stage_window(Hm, stage, g, bp0, L, d);
+  cp_async_commit();
   float wk0[16], wk1[16];
   float2 w4 = make_float2(0.f, 0.f), bd = make_float2(0.f, 0.f);
   if (active) {
@@ -58,29 +79,30 @@ static __global__ void __launch_bounds__(512) lam_dw_fwd_tc_kernel(const __nv_bf
     w4 = *reinterpret_cast<const float2*>(prm.off4_w[m] + c);
     bd = *reinterpret_cast<const float2*>(prm.off2_b[m] + c);
   }
-  const int bp_end = min(B * g.P, (chunk + 1) * kDwPairs);
-  for (int bp = chunk * kDwPairs; bp < bp_end; ++bp) {
-    const int b = bp / g.P, p = bp % g.P;
-    const int py = p / g.Wk, px = p % g.Wk;
+  for (int bp = bp0; bp < bp_end; ++bp) {
+    const __nv_bfloat16* cur = stage + ((bp - bp0) & 1) * 16 * d;
+    if (bp + 1 < bp_end) dw_stage_window(Hm, stage + ((bp + 1 - bp0) & 1) * 16 * d, g, bp + 1, L, d);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
     float part = 0.f;
     if (active) {
       float u0 = bd.x, u1 = bd.y;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
-        const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(H + m * hms + ((int64_t)b * L + l) * d + c);
-        u0 = fmaf(gelu_fast_f(__low2float(hv)), wk0[k], u0);
-        u1 = fmaf(gelu_fast_f(__high2float(hv)), wk1[k], u1);
+        const uint32_t hv = *reinterpret_cast<const uint32_t*>(cur + k * d + c);
+        u0 = fmaf(gelu_fast_f(bf16lo_to_f32(hv)), wk0[k], u0);
+        u1 = fmaf(gelu_fast_f(bf16hi_to_f32(hv)), wk1[k], u1);
       }
       *reinterpret_cast<float2*>(U + ((int64_t)m * B * g.P + bp) * d + c) = make_float2(u0, u1);
       part = gelu_fast_f(u0) * w4.x + gelu_fast_f(u1) * w4.y;
     }
-    part = block_sum(part, scratch);
+    part = block_sum(part, scratch);   // also orders the reads of `cur` before it is overwritten
     if (threadIdx.x == 0) o[(int64_t)m * B * g.P + bp] = part;
   }
 }
 
-// Backward of the offset-net tail, one pass over H:
+// Backward of the offset-net tail, one pass over H (same staging):
 //   dU = dO * w4 * gelu'(U);  dH[b,pos,c] = dU * wdw[c,k] * gelu'(H[b,pos,c])   (bf16 out)
 // and per-CTA partial sums of the parameter gradients
 //   dwdw[c,k] += dU * gelu(H[pos(p,k)]),  dbdw += dU,  dw4 += dO * gelu(U),  dbf += dH
@@ -89,52 +111,69 @@ static __global__ void __launch_bounds__(512) lam_dw_bwd_tc_kernel(const __nv_bf
                                                                    const float* __restrict__ U, const float* __restrict__ dO,
                                                                    sig_align_params prm, Geo g, int B, int L, int d,
                                                                    __nv_bfloat16* __restrict__ dH, float* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(dw_smem);
   const int m = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int c = threadIdx.x * 2;
-  if (c >= d) return;
+  const bool active = c < d;
+  const __nv_bfloat16* Hm = H + m * hms;
   const float* wdw = prm.off2_w[m];
-  const float2 w4 = *reinterpret_cast<const float2*>(prm.off4_w[m] + c);
+  const int bp0 = chunk * kDwPairs, bp_end = min(B * g.P, bp0 + kDwPairs);
+  dw_stage_window(Hm, stage, g, bp0, L, d);
+  cp_async_commit();
+  float2 w4 = make_float2(0.f, 0.f);
   float wk0[16], wk1[16];
+  if (active) {
+    w4 = *reinterpret_cast<const float2*>(prm.off4_w[m] + c);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    wk0[k] = wdw[c * 16 + k];
-    wk1[k] = wdw[(c + 1) * 16 + k];
+    for (int k = 0; k < 16; ++k) {
+      wk0[k] = wdw[c * 16 + k];
+      wk1[k] = wdw[(c + 1) * 16 + k];
+    }
   }
   float a0[19], a1[19];
 #pragma unroll
   for (int i = 0; i < 19; ++i) a0[i] = a1[i] = 0.f;
-  const int bp_end = min(B * g.P, (chunk + 1) * kDwPairs);
-  for (int bp = chunk * kDwPairs; bp < bp_end; ++bp) {
-    const int b = bp / g.P, p = bp % g.P;
-    const int py = p / g.Wk, px = p % g.Wk;
-    const int64_t ui = ((int64_t)m * B * g.P + bp) * d + c;
-    const float go = dO[(int64_t)m * B * g.P + bp];
-    const float2 u = *reinterpret_cast<const float2*>(U + ui);
-    float gu0, dgu0, gu1, dgu1;
-    gelu_fast(u.x, gu0, dgu0);
-    gelu_fast(u.y, gu1, dgu1);
-    const float du0 = go * w4.x * dgu0, du1 = go * w4.y * dgu1;
-    a0[16] += du0; a1[16] += du1;
-    a0[17] += go * gu0; a1[17] += go * gu1;
+  for (int bp = bp0; bp < bp_end; ++bp) {
+    const __nv_bfloat16* cur = stage + ((bp - bp0) & 1) * 16 * d;
+    if (bp + 1 < bp_end) dw_stage_window(Hm, stage + ((bp + 1 - bp0) & 1) * 16 * d, g, bp + 1, L, d);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (active) {
+      const int b = bp / g.P, p = bp % g.P;
+      const int py = p / g.Wk, px = p % g.Wk;
+      const int64_t ui = ((int64_t)m * B * g.P + bp) * d + c;
+      const float go = dO[(int64_t)m * B * g.P + bp];
+      const float2 u = *reinterpret_cast<const float2*>(U + ui);
+      float gu0, dgu0, gu1, dgu1;
+      gelu_fast(u.x, gu0, dgu0);
+      gelu_fast(u.y, gu1, dgu1);
+      const float du0 = go * w4.x * dgu0, du1 = go * w4.y * dgu1;
+      a0[16] += du0; a1[16] += du1;
+      a0[17] += go * gu0; a1[17] += go * gu1;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
-      const int64_t idx = m * hms + ((int64_t)b * L + l) * d + c;
-      const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(H + idx);
-      const float h0 = __low2float(hv), h1 = __high2float(hv);
-      float gh0, dgh0, gh1, dgh1;   // gelu and gelu' share one exp and one reciprocal per element
-      gelu_fast(h0, gh0, dgh0);
-      gelu_fast(h1, gh1, dgh1);
-      const float dh0 = du0 * wk0[k] * dgh0, dh1 = du1 * wk1[k] * dgh1;
-      *reinterpret_cast<__nv_bfloat162*>(dH + idx) = __floats2bfloat162_rn(dh0, dh1);
-      a0[k] = fmaf(du0, gh0, a0[k]);
-      a1[k] = fmaf(du1, gh1, a1[k]);
-      a0[18] += dh0; a1[18] += dh1;
+      for (int k = 0; k < 16; ++k) {
+        const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
+        const uint32_t hv = *reinterpret_cast<const uint32_t*>(cur + k * d + c);
+        const float h0 = bf16lo_to_f32(hv), h1 = bf16hi_to_f32(hv);
+        float gh0, dgh0, gh1, dgh1;   // gelu and gelu' share one exp and one reciprocal per element
+        gelu_fast(h0, gh0, dgh0);
+        gelu_fast(h1, gh1, dgh1);
+        const float dh0 = du0 * wk0[k] * dgh0, dh1 = du1 * wk1[k] * dgh1;
+        *reinterpret_cast<__nv_bfloat162*>(dH + m * hms + ((int64_t)b * L + l) * d + c) = __floats2bfloat162_rn(dh0, dh1);
+        a0[k] = fmaf(du0, gh0, a0[k]);
+        a1[k] = fmaf(du1, gh1, a1[k]);
+        a0[18] += dh0; a1[18] += dh1;
+      }
     }
+    __syncthreads();   // all reads of `cur` done before the next iteration's prefetch overwrites it
   }
-  float* dst = part + (((int64_t)m * nchunk + chunk) * 19) * d + c;
+  if (active) {
+    float* dst = part + (((int64_t)m * nchunk + chunk) * 19) * d + c;
 #pragma unroll
-  for (int i = 0; i < 19; ++i) *reinterpret_cast<float2*>(dst + (int64_t)i * d) = make_float2(a0[i], a1[i]);
+    for (int i = 0; i < 19; ++i) *reinterpret_cast<float2*>(dst + (int64_t)i * d) = make_float2(a0[i], a1[i]);
+  }
 }
 
 // deterministic reduction of the partials into the parameter gradients.  grid (ceil(d/64), 19, 3), 256 threads:
@@ -587,7 +626,9 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   }
   {
     SIG_PHASE("lam_dwconv_fwd");
-    lam_dw_fwd_tc_kernel<<<dim3((unsigned)ceil_div((int64_t)B * g.P, kDwPairs), 3), (unsigned)ceil_div(d / 2, 32) * 32, 0, s>>>(
+    const size_t dw_smem_bytes = (size_t)2 * 16 * d * sizeof(__nv_bfloat16);
+    cudaFuncSetAttribute(lam_dw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes);
+    lam_dw_fwd_tc_kernel<<<dim3((unsigned)ceil_div((int64_t)B * g.P, kDwPairs), 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s>>>(
         c.H, (int64_t)BL * d, *p, g, B, L, d, c.U, c.o);
     SIG_CHECK_LAUNCH();
   }
@@ -671,8 +712,10 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   {
     SIG_PHASE("lam_dwconv_bwd");
     const int nchunk = (int)ceil_div((int64_t)B * g.P, kDwPairs);
-    lam_dw_bwd_tc_kernel<<<dim3(nchunk, 3), (unsigned)ceil_div(d / 2, 32) * 32, 0, s>>>(c.H, (int64_t)BL * d, c.U, c.dO, *p, g, B, L, d,
-                                                                                      c.dH, c.dwpart);
+    const size_t dw_smem_bytes = (size_t)2 * 16 * d * sizeof(__nv_bfloat16);
+    cudaFuncSetAttribute(lam_dw_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes);
+    lam_dw_bwd_tc_kernel<<<dim3(nchunk, 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s>>>(c.H, (int64_t)BL * d, c.U, c.dO, *p, g,
+                                                                                                  B, L, d, c.dH, c.dwpart);
     SIG_CHECK_LAUNCH();
     lam_dw_param_reduce_kernel<<<dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s>>>(c.dwpart, nchunk, *dp, c.dbf, d);
     SIG_CHECK_LAUNCH();

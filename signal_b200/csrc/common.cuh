@@ -70,6 +70,25 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = raw;
 }
 
+// 4-byte global load the compiler may not sink to its use (an invariant `const __restrict__` load is
+// re-scheduled next to its consumer to save registers, which serialises the memory latency).
+__device__ __forceinline__ uint32_t ld_global_u32_early(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// ---- cp.async (LDGSTS) staging -------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- math -------------------------------------------------------------------
 __device__ __forceinline__ float gelu_f(float x) {  // nn.GELU() erf form
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
