@@ -208,15 +208,10 @@ def run_gpu(args):
     # each backward returns its parameter gradients as views of ONE flat fp32 arena (one for SIM, one
     # for AlignM); autograd adopts those views as .grad, so data parallel needs two all-reduces per step
 
+    from signal_b200 import parallel
+
     def allreduce_grads():
-        bases = {}
-        for p in params:
-            if p.grad is not None:
-                b = p.grad._base if p.grad._base is not None else p.grad
-                bases[id(b)] = b
-        for b in bases.values():
-            dist.all_reduce(b)
-            b.div_(world)
+        parallel.allreduce_param_grads(params, world)
 
     host_sets = []
     for k in range(NSETS):
