@@ -24,6 +24,7 @@ struct GradPtrs3 {
 // =============================================================================================
 // mean over the L tokens: grid (B, 3), thread per channel.  useB.py:92-94
 static __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ Xf, int B, int L, int d, float* __restrict__ mean) {
+  pdl_enter();
   const int b = blockIdx.x, m = blockIdx.y;
   const float* x = Xf + ((int64_t)m * B + b) * L * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -37,6 +38,7 @@ static __global__ void __launch_bounds__(256) pool_kernel(const float* __restric
 // Gram entries ll, vv, aa, va (volume.py:35,42-44).  grid B.
 static __global__ void __launch_bounds__(256) gam_norm_kernel(const float* __restrict__ mean, int B, int d, float* __restrict__ f,
                                                               float* __restrict__ nrm, float* __restrict__ self4) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int b = blockIdx.x;
   float inv[3];
@@ -74,6 +76,7 @@ __device__ __forceinline__ float gram_det(float ll, float vv, float aa, float va
 static __global__ void volume_kernel(const float* __restrict__ ll, const float* __restrict__ vv, const float* __restrict__ aa,
                                      const float* __restrict__ va, const float* __restrict__ lv, const float* __restrict__ la,
                                      int B1, int B2, float* __restrict__ V) {
+  pdl_enter();
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B1 * B2) return;
   const int i = (int)(idx / B2), j = (int)(idx % B2);
@@ -98,6 +101,7 @@ static __global__ void __launch_bounds__(1024) gam_loss_kernel(const float* __re
                                                                float* __restrict__ Wla, float* __restrict__ rowA,
                                                                float* __restrict__ colC, float* __restrict__ loss_out,
                                                                float* __restrict__ dtau_out) {
+  pdl_enter();
   __shared__ float scratch[33];
   const float* ll = self4;
   const float* vv = self4 + B;
@@ -191,6 +195,7 @@ static __global__ void __launch_bounds__(256) gam_finish_kernel(const float* __r
                                                                 const float* __restrict__ rowA, const float* __restrict__ colC,
                                                                 const float* __restrict__ df, int B, int L, int d,
                                                                 float* __restrict__ dmean) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int b = blockIdx.x, m = blockIdx.y;
   const float* fr = f + ((int64_t)0 * B + b) * d;
@@ -235,6 +240,7 @@ __host__ __device__ inline Geo make_geo(int h, int w) {
 static __global__ void __launch_bounds__(256) lam_dw_fwd_kernel(const float* __restrict__ G, const float* __restrict__ wdw,
                                                                 const float* __restrict__ bdw, const float* __restrict__ w4, Geo g,
                                                                 int L, int d, float* __restrict__ U, float* __restrict__ o) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
   const int py = p / g.Wk, px = p % g.Wk;
@@ -292,6 +298,7 @@ __device__ inline Taps make_taps(float o, int p, const Geo& g) {
 // S[b,p,:] = bilinear sample of X[b] at the predicted position.  grid (B*P)
 static __global__ void __launch_bounds__(256) lam_sample_fwd_kernel(const float* __restrict__ X, const float* __restrict__ o, Geo g,
                                                                     int L, int d, float* __restrict__ S) {
+  pdl_enter();
   const int bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
   const Taps t = make_taps(o[bp], p, g);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -305,6 +312,7 @@ static __global__ void __launch_bounds__(256) lam_sample_fwd_kernel(const float*
 
 // pairwise MSE partial sums (useB.py:161-165): grid (B*P), part[bp] = sum_c [(n-r)^2+(t-r)^2+(t-n)^2]
 static __global__ void __launch_bounds__(256) lam_mse_kernel(const float* __restrict__ S, int64_t mstride, int d, float* __restrict__ part) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int64_t bp = blockIdx.x;
   float a = 0.f;
@@ -318,6 +326,7 @@ static __global__ void __launch_bounds__(256) lam_mse_kernel(const float* __rest
 
 // out[0] = scale * sum(part[0..n))   (single CTA, deterministic)
 static __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ part, int n, float scale, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float scratch[33];
   float a = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) a += part[i];
@@ -328,6 +337,7 @@ static __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict
 // dS_m = g * 2/(3N) * (2 S_m - S_m' - S_m'')   (N = B*P*d), all three modalities.  grid (B*P)
 static __global__ void __launch_bounds__(256) lam_mse_bwd_kernel(const float* __restrict__ S, int64_t mstride, int d, float scale,
                                                                  const float* __restrict__ gptr, float* __restrict__ dS) {
+  pdl_enter();
   const int64_t bp = blockIdx.x;
   const float k = scale * (*gptr);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -342,6 +352,7 @@ static __global__ void __launch_bounds__(256) lam_mse_bwd_kernel(const float* __
 static __global__ void __launch_bounds__(256) lam_sample_bwd_kernel(const float* __restrict__ X, const float* __restrict__ o,
                                                                     const float* __restrict__ dS, Geo g, int L, int d,
                                                                     float* __restrict__ dout_o) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
   const Taps t = make_taps(o[bp], p, g);
@@ -364,6 +375,7 @@ static __global__ void __launch_bounds__(256) lam_dw_bwd_kernel(const float* __r
                                                                 const float* __restrict__ dout_o, const float* __restrict__ wdw,
                                                                 const float* __restrict__ w4, Geo g, int L, int d,
                                                                 float* __restrict__ dU, float* __restrict__ dH) {
+  pdl_enter();
   const int bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
   const int py = p / g.Wk, px = p % g.Wk;
   const float go = dout_o[bp];
@@ -385,6 +397,7 @@ static __global__ void __launch_bounds__(256) lam_dw_param_kernel(const float* _
                                                                   const float* __restrict__ dU, const float* __restrict__ dout_o, Geo g,
                                                                   int B, int L, int d, float* __restrict__ dwdw,
                                                                   float* __restrict__ dbdw, float* __restrict__ dw4) {
+  pdl_enter();
   __shared__ float sm[8][32][19];
   const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -429,6 +442,7 @@ static __global__ void __launch_bounds__(128) align_write_kernel(const float* __
                                                                  const float* __restrict__ gam_g, const float* __restrict__ o,
                                                                  const float* __restrict__ dS, Geo g, int B, int L, int d, T* dpatch,
                                                                  int64_t psb, int64_t psl, T* dcls, int64_t csb, int accumulate) {
+  pdl_enter();
   __shared__ float tw[64];
   __shared__ int tp[64];
   __shared__ int ntap;
@@ -485,7 +499,8 @@ static __global__ void __launch_bounds__(128) align_write_kernel(const float* __
 }
 
 // d(contra_temp) = g_gam * dtau_unit
-static __global__ void scale_scalar_kernel(const float* a, const float* g, float* out) { *out = (*a) * (*g); }
+static __global__ void scale_scalar_kernel(const float* a, const float* g, float* out) {
+  pdl_enter(); *out = (*a) * (*g); }
 
 // =============================================================================================
 // ctx layouts
@@ -567,7 +582,7 @@ static int lam_offsets_fwd(const float* X, const sig_align_params* p, int m, con
     gg.act = 1; gg.pre = lm.H;
     SIG_TRY(launch_gemm(gg, s));
   }
-  lam_dw_fwd_kernel<<<B * g.P, 256, 0, s>>>(lm.G, p->off2_w[m], p->off2_b[m], p->off4_w[m], g, L, d, lm.U, lm.o);
+  SIG_LAUNCH((lam_dw_fwd_kernel), B * g.P, 256, 0, s, lm.G, p->off2_w[m], p->off2_b[m], p->off4_w[m], g, L, d, lm.U, lm.o);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -577,9 +592,9 @@ static int lam_offsets_bwd(const float* X, const sig_align_params* p, const sig_
                            const AlignCtx& c, float* dXdense, const Geo& g, int B, int L, int d, cudaStream_t s) {
   const int BL = B * L;
   SIG_PHASE("lam_offsetnet_bwd");
-  lam_dw_bwd_kernel<<<B * g.P, 256, 0, s>>>(lm.H, lm.U, lm.dO, p->off2_w[m], p->off4_w[m], g, L, d, lm.dU, c.dH);
+  SIG_LAUNCH((lam_dw_bwd_kernel), B * g.P, 256, 0, s, lm.H, lm.U, lm.dO, p->off2_w[m], p->off4_w[m], g, L, d, lm.dU, c.dH);
   SIG_CHECK_LAUNCH();
-  lam_dw_param_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(lm.G, lm.U, lm.dU, lm.dO, g, B, L, d, dp->off2_w[m], dp->off2_b[m],
+  SIG_LAUNCH((lam_dw_param_kernel), (unsigned)ceil_div(d, 32), 256, 0, s, lm.G, lm.U, lm.dU, lm.dO, g, B, L, d, dp->off2_w[m], dp->off2_b[m],
                                                                 dp->off4_w[m]);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(c.dH, d, BL, d, dp->off0_b[m], 1.f, s));
@@ -641,16 +656,16 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   // ---- GAM
   {
   SIG_PHASE("gam_fwd");
-  pool_kernel<<<dim3(B, 3), 256, 0, s>>>(c.Xf, B, L, d, c.mean);
+  SIG_LAUNCH((pool_kernel), dim3(B, 3), 256, 0, s, c.Xf, B, L, d, c.mean);
   SIG_CHECK_LAUNCH();
-  gam_norm_kernel<<<B, 256, 0, s>>>(c.mean, B, d, c.f, c.nrm, c.self4);
+  SIG_LAUNCH((gam_norm_kernel), B, 256, 0, s, c.mean, B, d, c.f, c.nrm, c.self4);
   SIG_CHECK_LAUNCH();
   const float* fr = c.f;
   const float* fn = c.f + (size_t)B * d;
   const float* ft = c.f + (size_t)2 * B * d;
   SIG_TRY(launch_gemm(gemm_nt(fr, d, fn, d, c.lv, B, nullptr, B, B, d), s));
   SIG_TRY(launch_gemm(gemm_nt(fr, d, ft, d, c.la, B, nullptr, B, B, d), s));
-  gam_loss_kernel<<<1, 1024, 0, s>>>(c.self4, c.lv, c.la, p->contra_temp, B, c.V, c.rowstat, c.colstat, c.Wlv, c.Wla, c.rowA,
+  SIG_LAUNCH((gam_loss_kernel), 1, 1024, 0, s, c.self4, c.lv, c.la, p->contra_temp, B, c.V, c.rowstat, c.colstat, c.Wlv, c.Wla, c.rowA,
                                      c.colC, losses, c.dtau);
   SIG_CHECK_LAUNCH();
   }
@@ -662,13 +677,13 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
     for (int m = 0; m < 3; ++m) {
       SIG_TRY(lam_offsets_fwd(c.Xf + m * BL * d, p, m, c.mod[m], g, B, L, d, s));
       SIG_PHASE("lam_sample_fwd");
-      lam_sample_fwd_kernel<<<B * g.P, 256, 0, s>>>(c.Xf + m * BL * d, c.mod[m].o, g, L, d, c.S + m * ms);
+      SIG_LAUNCH((lam_sample_fwd_kernel), B * g.P, 256, 0, s, c.Xf + m * BL * d, c.mod[m].o, g, L, d, c.S + m * ms);
       SIG_CHECK_LAUNCH();
     }
     SIG_PHASE("lam_sample_fwd");
-    lam_mse_kernel<<<B * g.P, 256, 0, s>>>(c.S, ms, d, c.part);
+    SIG_LAUNCH((lam_mse_kernel), B * g.P, 256, 0, s, c.S, ms, d, c.part);
     SIG_CHECK_LAUNCH();
-    sum_kernel<<<1, 256, 0, s>>>(c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
+    SIG_LAUNCH((sum_kernel), 1, 256, 0, s, c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
     SIG_CHECK_LAUNCH();
   }
   return 0;
@@ -711,9 +726,9 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
   }
   SIG_TRY(launch_gemm(gemm_tn(c.Wlv, B, fr, d, dfn, d, B, d, B), s));
   SIG_TRY(launch_gemm(gemm_tn(c.Wla, B, fr, d, dft, d, B, d, B), s));
-  gam_finish_kernel<<<dim3(B, 3), 256, 0, s>>>(c.f, c.nrm, c.rowA, c.colC, c.df, B, L, d, c.dmean);
+  SIG_LAUNCH((gam_finish_kernel), dim3(B, 3), 256, 0, s, c.f, c.nrm, c.rowA, c.colC, c.df, B, L, d, c.dmean);
   SIG_CHECK_LAUNCH();
-  scale_scalar_kernel<<<1, 1, 0, s>>>(c.dtau, dlosses, dp->contra_temp);
+  SIG_LAUNCH((scale_scalar_kernel), 1, 1, 0, s, c.dtau, dlosses, dp->contra_temp);
   SIG_CHECK_LAUNCH();
   }
   // ---- LAM
@@ -722,14 +737,14 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
   if (do_lam) {
     {
     SIG_PHASE("lam_sample_bwd");
-    lam_mse_bwd_kernel<<<B * g.P, 256, 0, s>>>(c.S, ms, d, 2.f / (3.f * (float)B * g.P * d), dlosses + 1, c.dS);
+    SIG_LAUNCH((lam_mse_bwd_kernel), B * g.P, 256, 0, s, c.S, ms, d, 2.f / (3.f * (float)B * g.P * d), dlosses + 1, c.dS);
     SIG_CHECK_LAUNCH();
     }
     for (int m = 0; m < 3; ++m) {
       const float* X = c.Xf + m * BL * d;
       {
       SIG_PHASE("lam_sample_bwd");
-      lam_sample_bwd_kernel<<<B * g.P, 256, 0, s>>>(X, c.mod[m].o, c.dS + m * ms, g, L, d, c.mod[m].dO);
+      SIG_LAUNCH((lam_sample_bwd_kernel), B * g.P, 256, 0, s, X, c.mod[m].o, c.dS + m * ms, g, L, d, c.mod[m].dO);
       SIG_CHECK_LAUNCH();
       }
       SIG_TRY(lam_offsets_bwd(X, p, dp, m, c.mod[m], c, c.dXf + m * BL * d, g, B, L, d, s));
@@ -745,12 +760,12 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
     const float* grow = c.dmean + (size_t)m * B * d;
     const unsigned rows = (unsigned)(BL + (zero_cls && dtok->dcls[m] ? B : 0));
     if (tok->dtype == SIG_BF16)
-      align_write_kernel<__nv_bfloat16><<<rows, 128, 0, s>>>(dense, grow, dlosses, o, dS, g, B, L, d,
+      SIG_LAUNCH((align_write_kernel<__nv_bfloat16>), rows, 128, 0, s, dense, grow, dlosses, o, dS, g, B, L, d,
                                                             static_cast<__nv_bfloat16*>(dtok->dpatch[m]), dtok->patch_stride_b[m],
                                                             dtok->patch_stride_l[m], static_cast<__nv_bfloat16*>(dtok->dcls[m]),
                                                             dtok->cls_stride_b[m], dtok->accumulate);
     else
-      align_write_kernel<float><<<rows, 128, 0, s>>>(dense, grow, dlosses, o, dS, g, B, L, d, static_cast<float*>(dtok->dpatch[m]),
+      SIG_LAUNCH((align_write_kernel<float>), rows, 128, 0, s, dense, grow, dlosses, o, dS, g, B, L, d, static_cast<float*>(dtok->dpatch[m]),
                                                     dtok->patch_stride_b[m], dtok->patch_stride_l[m],
                                                     static_cast<float*>(dtok->dcls[m]), dtok->cls_stride_b[m], dtok->accumulate);
     SIG_CHECK_LAUNCH();
@@ -771,6 +786,7 @@ static int one_view_tokens(const void* x, int64_t sb, int64_t sl, int dtype, int
 
 template <typename T>
 static __global__ void convert_one_kernel(const T* __restrict__ x, int64_t sb, int64_t sl, int L, int d, float* __restrict__ Xf) {
+  pdl_enter();
   const int64_t row = blockIdx.x;
   const int b = (int)(row / L), l = (int)(row % L);
   const T* src = x + b * sb + l * sl;
@@ -795,13 +811,13 @@ int das_forward(const void* x, int64_t sb, int64_t sl, int dtype, int B, int h, 
   AlignCtx c = align_ctx(ctx, B, L, d, 1);
   const int threads = d / 8 >= 128 ? 128 : 64;
   if (dtype == SIG_BF16)
-    convert_one_kernel<__nv_bfloat16><<<B * L, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sl, L, d, c.Xf);
+    SIG_LAUNCH((convert_one_kernel<__nv_bfloat16>), B * L, threads, 0, s, static_cast<const __nv_bfloat16*>(x), sb, sl, L, d, c.Xf);
   else
-    convert_one_kernel<float><<<B * L, threads, 0, s>>>(static_cast<const float*>(x), sb, sl, L, d, c.Xf);
+    SIG_LAUNCH((convert_one_kernel<float>), B * L, threads, 0, s, static_cast<const float*>(x), sb, sl, L, d, c.Xf);
   SIG_CHECK_LAUNCH();
   const Geo g = make_geo(h, w);
   SIG_TRY(lam_offsets_fwd(c.Xf, p, m, c.mod[0], g, B, L, d, s));
-  lam_sample_fwd_kernel<<<B * g.P, 256, 0, s>>>(c.Xf, c.mod[0].o, g, L, d, sampled);
+  SIG_LAUNCH((lam_sample_fwd_kernel), B * g.P, 256, 0, s, c.Xf, c.mod[0].o, g, L, d, sampled);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -822,14 +838,14 @@ int das_backward(const void* x, int64_t sb, int64_t sl, int dtype, int B, int h,
   (void)flags;
   AlignCtx c = align_ctx(ctx, B, L, d, 1);
   const Geo g = make_geo(h, w);
-  lam_sample_bwd_kernel<<<B * g.P, 256, 0, s>>>(c.Xf, c.mod[0].o, dsampled, g, L, d, c.mod[0].dO);
+  SIG_LAUNCH((lam_sample_bwd_kernel), B * g.P, 256, 0, s, c.Xf, c.mod[0].o, dsampled, g, L, d, c.mod[0].dO);
   SIG_CHECK_LAUNCH();
   SIG_TRY(lam_offsets_bwd(c.Xf, p, dp, m, c.mod[0], c, c.dXf, g, B, L, d, s));
   if (dtype == SIG_BF16)
-    align_write_kernel<__nv_bfloat16><<<B * L, 128, 0, s>>>(c.dXf, nullptr, nullptr, c.mod[0].o, dsampled, g, B, L, d,
+    SIG_LAUNCH((align_write_kernel<__nv_bfloat16>), B * L, 128, 0, s, c.dXf, nullptr, nullptr, c.mod[0].o, dsampled, g, B, L, d,
                                                            static_cast<__nv_bfloat16*>(dx), sb, sl, nullptr, 0, 0);
   else
-    align_write_kernel<float><<<B * L, 128, 0, s>>>(c.dXf, nullptr, nullptr, c.mod[0].o, dsampled, g, B, L, d, static_cast<float*>(dx),
+    SIG_LAUNCH((align_write_kernel<float>), B * L, 128, 0, s, c.dXf, nullptr, nullptr, c.mod[0].o, dsampled, g, B, L, d, static_cast<float*>(dx),
                                                    sb, sl, nullptr, 0, 0);
   SIG_CHECK_LAUNCH();
   return 0;
@@ -839,6 +855,7 @@ int das_backward(const void* x, int64_t sb, int64_t sl, int dtype, int B, int h,
 // self dots: out[i] = a[i,:] . b[i,:]   grid rows
 static __global__ void __launch_bounds__(128) rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int d,
                                                             float* __restrict__ out) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int64_t i = blockIdx.x;
   float s = 0.f;
@@ -853,6 +870,7 @@ static __global__ void volume_bwd_pair_kernel(const float* __restrict__ ll, cons
                                               const float* __restrict__ va, const float* __restrict__ lv, const float* __restrict__ la,
                                               const float* __restrict__ dvol, int B1, int B2, float* __restrict__ Wlv,
                                               float* __restrict__ Wla, float* __restrict__ E) {
+  pdl_enter();
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t n = (int64_t)B1 * B2;
   if (idx >= n) return;
@@ -872,6 +890,7 @@ static __global__ void volume_bwd_pair_kernel(const float* __restrict__ ll, cons
 static __global__ void __launch_bounds__(128) axpy_rows_kernel(const float* __restrict__ s1, const float* __restrict__ x,
                                                                const float* __restrict__ s2, const float* __restrict__ y, int d,
                                                                float* __restrict__ out) {
+  pdl_enter();
   const int64_t r = blockIdx.x;
   const float a = 2.f * s1[r], b = s2 ? s2[r] : 0.f;
   for (int c = threadIdx.x; c < d; c += blockDim.x) out[r * d + c] += a * x[r * d + c] + (y ? b * y[r * d + c] : 0.f);
@@ -879,6 +898,7 @@ static __global__ void __launch_bounds__(128) axpy_rows_kernel(const float* __re
 
 // rowsum: out[i] = sum_j X[i*N + j]
 static __global__ void __launch_bounds__(128) rowsum_kernel(const float* __restrict__ X, int N, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int64_t i = blockIdx.x;
   float s = 0.f;
@@ -897,15 +917,15 @@ int volume3_forward(const float* l, const float* v, const float* a, int B1, int 
   float* va = aa + B2;
   float* lv = va + B2;
   float* la = lv + (size_t)B1 * B2;
-  rowdot_kernel<<<B1, 128, 0, s>>>(l, l, d, ll);
-  rowdot_kernel<<<B2, 128, 0, s>>>(v, v, d, vv);
-  rowdot_kernel<<<B2, 128, 0, s>>>(a, a, d, aa);
-  rowdot_kernel<<<B2, 128, 0, s>>>(v, a, d, va);
+  SIG_LAUNCH((rowdot_kernel), B1, 128, 0, s, l, l, d, ll);
+  SIG_LAUNCH((rowdot_kernel), B2, 128, 0, s, v, v, d, vv);
+  SIG_LAUNCH((rowdot_kernel), B2, 128, 0, s, a, a, d, aa);
+  SIG_LAUNCH((rowdot_kernel), B2, 128, 0, s, v, a, d, va);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_gemm(gemm_nt(l, d, v, d, lv, B2, nullptr, B1, B2, d), s));
   SIG_TRY(launch_gemm(gemm_nt(l, d, a, d, la, B2, nullptr, B1, B2, d), s));
   const int64_t n = (int64_t)B1 * B2;
-  volume_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(ll, vv, aa, va, lv, la, B1, B2, vol);
+  SIG_LAUNCH((volume_kernel), (unsigned)ceil_div(n, 256), 256, 0, s, ll, vv, aa, va, lv, la, B1, B2, vol);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -924,16 +944,16 @@ int volume3_backward(const float* l, const float* v, const float* a, int B1, int
   float* E = Wla + n;          // 4n
   float* rs = E + 4 * n;       // rowA[B1]
   float* cs = rs + B1;         // colC[3][B2]
-  rowdot_kernel<<<B1, 128, 0, s>>>(l, l, d, ll);
-  rowdot_kernel<<<B2, 128, 0, s>>>(v, v, d, vv);
-  rowdot_kernel<<<B2, 128, 0, s>>>(a, a, d, aa);
-  rowdot_kernel<<<B2, 128, 0, s>>>(v, a, d, va);
+  SIG_LAUNCH((rowdot_kernel), B1, 128, 0, s, l, l, d, ll);
+  SIG_LAUNCH((rowdot_kernel), B2, 128, 0, s, v, v, d, vv);
+  SIG_LAUNCH((rowdot_kernel), B2, 128, 0, s, a, a, d, aa);
+  SIG_LAUNCH((rowdot_kernel), B2, 128, 0, s, v, a, d, va);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_gemm(gemm_nt(l, d, v, d, lv, B2, nullptr, B1, B2, d), s));
   SIG_TRY(launch_gemm(gemm_nt(l, d, a, d, la, B2, nullptr, B1, B2, d), s));
-  volume_bwd_pair_kernel<<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, s>>>(ll, vv, aa, va, lv, la, dvol, B1, B2, Wlv, Wla, E);
+  SIG_LAUNCH((volume_bwd_pair_kernel), (unsigned)ceil_div((int64_t)n, 256), 256, 0, s, ll, vv, aa, va, lv, la, dvol, B1, B2, Wlv, Wla, E);
   SIG_CHECK_LAUNCH();
-  rowsum_kernel<<<B1, 128, 0, s>>>(E, B2, rs);
+  SIG_LAUNCH((rowsum_kernel), B1, 128, 0, s, E, B2, rs);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(E + n, B2, B1, B2, cs, 1.f, s));
   SIG_TRY(launch_colsum(E + 2 * n, B2, B1, B2, cs + B2, 1.f, s));
@@ -945,12 +965,12 @@ int volume3_backward(const float* l, const float* v, const float* a, int B1, int
     gg.accumulate = 1;
     SIG_TRY(launch_gemm(gg, s));
   }
-  axpy_rows_kernel<<<B1, 128, 0, s>>>(rs, l, nullptr, nullptr, d, dl);
+  SIG_LAUNCH((axpy_rows_kernel), B1, 128, 0, s, rs, l, nullptr, nullptr, d, dl);
   // dv = Wlv^T l + 2 Cvv v + Cva a ; da = Wla^T l + 2 Caa a + Cva v
   SIG_TRY(launch_gemm(gemm_tn(Wlv, B2, l, d, dv, d, B2, d, B1), s));
-  axpy_rows_kernel<<<B2, 128, 0, s>>>(cs, v, cs + B2, a, d, dv);
+  SIG_LAUNCH((axpy_rows_kernel), B2, 128, 0, s, cs, v, cs + B2, a, d, dv);
   SIG_TRY(launch_gemm(gemm_tn(Wla, B2, l, d, da, d, B2, d, B1), s));
-  axpy_rows_kernel<<<B2, 128, 0, s>>>(cs + 2 * B2, a, cs + B2, v, d, da);
+  SIG_LAUNCH((axpy_rows_kernel), B2, 128, 0, s, cs + 2 * B2, a, cs + B2, v, d, da);
   SIG_CHECK_LAUNCH();
   return 0;
 }

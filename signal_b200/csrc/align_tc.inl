@@ -6,6 +6,7 @@
 // ---- GAM: mean pool straight from the strided token views.  grid (B, 3), 256 threads -------------
 template <typename T>
 static __global__ void __launch_bounds__(256) pool_tok_kernel(TokPtrs3 tp, int B, int L, int d, float* __restrict__ mean) {
+  pdl_enter();
   __shared__ float red[256 * 8];
   const int b = blockIdx.x, m = blockIdx.y;
   const int tpr = d / 8;                       // threads per token row
@@ -57,6 +58,7 @@ __device__ __forceinline__ void dw_stage_window(const __nv_bfloat16* __restrict_
 static __global__ void __launch_bounds__(512) lam_dw_fwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
                                                                    sig_align_params prm, Geo g, int B, int L, int d,
                                                                    float* __restrict__ U, float* __restrict__ o) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char dw_smem[];
   __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(dw_smem);
   __shared__ float scratch[33];
@@ -111,6 +113,7 @@ static __global__ void __launch_bounds__(512) lam_dw_bwd_tc_kernel(const __nv_bf
                                                                    const float* __restrict__ U, const float* __restrict__ dO,
                                                                    sig_align_params prm, Geo g, int B, int L, int d,
                                                                    __nv_bfloat16* __restrict__ dH, float* __restrict__ part) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char dw_smem[];
   __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(dw_smem);
   const int m = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
@@ -180,6 +183,7 @@ static __global__ void __launch_bounds__(512) lam_dw_bwd_tc_kernel(const __nv_bf
 // 64 channels x 4 chunk lanes
 static __global__ void __launch_bounds__(256) lam_dw_param_reduce_kernel(const float* __restrict__ part, int nchunk,
                                                                          sig_align_param_grads gr, float* __restrict__ dbf, int d) {
+  pdl_enter();
   __shared__ float sm[4][64];
   const int m = blockIdx.z, i = blockIdx.y;
   const int cl = threadIdx.x & 63, r = threadIdx.x >> 6;
@@ -202,6 +206,7 @@ static __global__ void __launch_bounds__(256) lam_dw_param_reduce_kernel(const f
 template <typename T>
 static __global__ void __launch_bounds__(128) lam_sample_fwd_tok_kernel(TokPtrs3 tp, const float* __restrict__ o, Geo g, int B, int d,
                                                                         float* __restrict__ S) {
+  pdl_enter();
   const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
   const Taps t = make_taps(o[(int64_t)m * B * g.P + bp], p, g);
   const T* x = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m];
@@ -224,6 +229,7 @@ template <typename T>
 static __global__ void __launch_bounds__(128) lam_sample_bwd_tok_kernel(TokPtrs3 tp, const float* __restrict__ o,
                                                                         const float* __restrict__ dS, Geo g, int B, int d,
                                                                         float* __restrict__ dO) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int m = blockIdx.y, bp = blockIdx.x, b = bp / g.P, p = bp % g.P;
   const Taps t = make_taps(o[(int64_t)m * B * g.P + bp], p, g);
@@ -258,6 +264,7 @@ static __global__ void __launch_bounds__(128) lam_sample_bwd_tok_kernel(TokPtrs3
 template <typename T>
 static __global__ void __launch_bounds__(128) lam_sparse_add_kernel(GradPtrs3 gp, const float* __restrict__ o,
                                                                     const float* __restrict__ dS, Geo g, int B, int d) {
+  pdl_enter();
   const int m = blockIdx.y, b = blockIdx.x;
   const int c = threadIdx.x * 8;
   if (c >= d) return;
@@ -279,15 +286,67 @@ static __global__ void __launch_bounds__(128) lam_sparse_add_kernel(GradPtrs3 gp
   }
 }
 
-// W[o][m] += u[o] * v[m]   (the bias of proj_q reaches conv_offset[0]'s weight gradient: Q = X Wq^T + bq)
-static __global__ void rank1_add_kernel(float* __restrict__ W, const float* __restrict__ u, const float* __restrict__ v, int d) {
+// dW0[m][o][c] += db'[m][o] * bq[m][c]   (the bias of proj_q reaches conv_offset[0]'s weight gradient: Q = X Wq^T + bq)
+// grid (ceil(d*d/256), 3)
+static __global__ void rank1_add3_kernel(sig_align_param_grads gr, const float* __restrict__ dbf, sig_align_params prm, int d) {
+  pdl_enter();
+  const int m = blockIdx.y;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < (int64_t)d * d) W[i] += u[i / d] * v[i % d];
+  if (i < (int64_t)d * d) gr.off0_w[m][i] += dbf[(int64_t)m * d + i / d] * prm.proj_q_b[m][i % d];
+}
+
+// b'[m] = W0[m] bq[m] + b0[m]   grid (ceil(d/8), 3), one warp per output
+static __global__ void __launch_bounds__(256) lam_fold_bias_kernel(sig_align_params prm, int d, float* __restrict__ bfold) {
+  pdl_enter();
+  const int m = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= d) return;
+  const float* W = prm.off0_w[m] + (int64_t)i * d;
+  const float* x = prm.proj_q_b[m];
+  float a = 0.f;
+  for (int k = lane * 4; k < d; k += 128) {
+    const float4 w = *reinterpret_cast<const float4*>(W + k);
+    const float4 v = *reinterpret_cast<const float4*>(x + k);
+    a += w.x * v.x + w.y * v.y + w.z * v.z + w.w * v.w;
+  }
+  a = warp_sum(a);
+  if (lane == 0) bfold[(int64_t)m * d + i] = a + prm.off0_b[m][i];
+}
+
+// db0[m] = db'[m];  dbq[m] = W0[m]^T db'[m]   grid (ceil(d/32), 3), 1024 threads = 32 outputs x 32 k-lanes
+static __global__ void __launch_bounds__(1024) lam_unfold_bias_kernel(sig_align_params prm, sig_align_param_grads gr,
+                                                                      const float* __restrict__ dbf, int d) {
+  pdl_enter();
+  __shared__ float sm[32][33];
+  const int m = blockIdx.y;
+  const int il = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
+  const float* W = prm.off0_w[m];
+  const float* x = dbf + (int64_t)m * d;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < d) {
+    int k = r;
+    for (; k + 32 < d; k += 64) {
+      a0 = fmaf(W[(int64_t)k * d + i], x[k], a0);
+      a1 = fmaf(W[(int64_t)(k + 32) * d + i], x[k + 32], a1);
+    }
+    for (; k < d; k += 32) a0 = fmaf(W[(int64_t)k * d + i], x[k], a0);
+  }
+  sm[r][il] = a0 + a1;
+  __syncthreads();
+  if (r == 0 && i < d) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) t += sm[q][il];
+    gr.proj_q_b[m][i] = t;
+    gr.off0_b[m][i] = x[i];
+  }
 }
 
 // zero the CLS gradient rows (packed [B,1+L,d] destination).  grid (B, 3)
 template <typename T>
 static __global__ void zero_cls_kernel(GradPtrs3 gp, int d) {
+  pdl_enter();
   const int m = blockIdx.y, b = blockIdx.x;
   if (!gp.dcls[m]) return;
   T* dst = static_cast<T*>(gp.dcls[m]) + b * gp.csb[m];
@@ -405,6 +464,7 @@ static __global__ void __launch_bounds__(256) gam_norm_split_kernel(const float*
                                                                     __nv_bfloat16* __restrict__ fb, __nv_bfloat16* __restrict__ fA,
                                                                     __nv_bfloat16* __restrict__ fB, float* __restrict__ nrm,
                                                                     float* __restrict__ self4) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int b = blockIdx.x;
   float inv[3];
@@ -449,6 +509,7 @@ static __global__ void __launch_bounds__(256) gam_norm_split_kernel(const float*
 static __global__ void __launch_bounds__(128) gam_stats_kernel(const float* __restrict__ self4, const float* __restrict__ lv,
                                                                const float* __restrict__ la, const float* __restrict__ tau_p, int B,
                                                                float* __restrict__ stat, float* __restrict__ lossp) {
+  pdl_enter();
   __shared__ float scratch[33];
   const float* ll = self4;
   const float* vv = self4 + B;
@@ -492,6 +553,7 @@ static __global__ void __launch_bounds__(128) gam_coef_kernel(const float* __res
                                                               float* __restrict__ Wla, __nv_bfloat16* __restrict__ WW,
                                                               float* __restrict__ rowA, float* __restrict__ colC,
                                                               float* __restrict__ dtaup) {
+  pdl_enter();
   __shared__ float scratch[33];
   const float* ll = self4;
   const float* vv = self4 + B;
@@ -549,6 +611,7 @@ static __global__ void __launch_bounds__(128) gam_coef_kernel(const float* __res
 // loss = (0.5/B) * sum lossp[0..2B) ; dtau = sum dtaup[0..B)
 static __global__ void __launch_bounds__(256) gam_final_kernel(const float* __restrict__ lossp, const float* __restrict__ dtaup, int B,
                                                                float* __restrict__ loss, float* __restrict__ dtau) {
+  pdl_enter();
   __shared__ float scratch[33];
   float a = 0.f, t = 0.f;
   for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) a += lossp[i];
@@ -568,9 +631,9 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   const TokPtrs3 tp = tok_ptrs3(tok);
   {
     SIG_PHASE("gam_fwd");
-    pool_tok_kernel<__nv_bfloat16><<<dim3(B, 3), 256, 0, s>>>(tp, B, L, d, c.mean);
+    SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), 256, 0, s, tp, B, L, d, c.mean);
     SIG_CHECK_LAUNCH();
-    gam_norm_split_kernel<<<B, 256, 0, s>>>(c.mean, B, d, c.f, c.fb, c.fA, c.fB, c.nrm, c.self4);
+    SIG_LAUNCH((gam_norm_split_kernel), B, 256, 0, s, c.mean, B, d, c.f, c.fb, c.fA, c.fB, c.nrm, c.self4);
     SIG_CHECK_LAUNCH();
     {  // lv = f_r f_n^T, la = f_r f_t^T  (split-bf16, K = 3d)
       TcGemmDesc t = tc_desc();
@@ -580,11 +643,11 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
       t.C[0] = c.lv; t.C[1] = c.la; t.ldc = B;
       SIG_TRY(tc_gemm(t, s));
     }
-    gam_stats_kernel<<<2 * B, 128, 0, s>>>(c.self4, c.lv, c.la, p->contra_temp, B, c.gstat, c.lossp);
+    SIG_LAUNCH((gam_stats_kernel), 2 * B, 128, 0, s, c.self4, c.lv, c.la, p->contra_temp, B, c.gstat, c.lossp);
     SIG_CHECK_LAUNCH();
-    gam_coef_kernel<<<2 * B, 128, 0, s>>>(c.self4, c.lv, c.la, p->contra_temp, c.gstat, B, (B + 7) / 8 * 8, c.Wlv, c.Wla, c.WW, c.rowA, c.colC, c.dtaup);
+    SIG_LAUNCH((gam_coef_kernel), 2 * B, 128, 0, s, c.self4, c.lv, c.la, p->contra_temp, c.gstat, B, (B + 7) / 8 * 8, c.Wlv, c.Wla, c.WW, c.rowA, c.colC, c.dtaup);
     SIG_CHECK_LAUNCH();
-    gam_final_kernel<<<1, 256, 0, s>>>(c.lossp, c.dtaup, B, losses, c.dtau);
+    SIG_LAUNCH((gam_final_kernel), 1, 256, 0, s, c.lossp, c.dtaup, B, losses, c.dtau);
     SIG_CHECK_LAUNCH();
   }
   if (!do_lam) return 0;
@@ -592,14 +655,16 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   const size_t dd = (size_t)d * d, BL = (size_t)B * L;
   {
     SIG_PHASE("lam_fold_weights");
-    for (int m = 0; m < 3; ++m) {
-      SIG_TRY(cast_f32_to_bf16(p->off0_w[m], c.W0b + m * dd, dd, s));
-      SIG_TRY(cast_f32_to_bf16(p->proj_q_w[m], c.Wqb + m * dd, dd, s));
-      // b' = W0 bq + b0
-      gemv_kernel<<<(unsigned)ceil_div(d, 8), 256, 0, s>>>(p->off0_w[m], d, 1, p->proj_q_b[m], p->off0_b[m], d, d,
-                                                          c.bfold + (size_t)m * d);
-      SIG_CHECK_LAUNCH();
+    {
+      CastJob jobs[6];
+      for (int m = 0; m < 3; ++m) {
+        jobs[2 * m] = {p->off0_w[m], c.W0b + m * dd, (int64_t)dd};
+        jobs[2 * m + 1] = {p->proj_q_w[m], c.Wqb + m * dd, (int64_t)dd};
+      }
+      SIG_TRY(cast_f32_to_bf16_multi(jobs, 6, s));
     }
+    SIG_LAUNCH((lam_fold_bias_kernel), dim3((unsigned)ceil_div(d, 8), 3), 256, 0, s, *p, d, c.bfold);   // b' = W0 bq + b0
+    SIG_CHECK_LAUNCH();
     // W' = W0 Wq  (A = W0 [d_out, d_mid] K-major; B[n = d_in, k = d_mid] = Wq[k][n] -> MN-major)
     TcGemmDesc t = tc_desc();
     t.A = batched(tc_k2d(nullptr, d, d, d), c.W0b, dd);
@@ -628,17 +693,17 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     SIG_PHASE("lam_dwconv_fwd");
     const size_t dw_smem_bytes = (size_t)2 * 16 * d * sizeof(__nv_bfloat16);
     cudaFuncSetAttribute(lam_dw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes);
-    lam_dw_fwd_tc_kernel<<<dim3((unsigned)ceil_div((int64_t)B * g.P, kDwPairs), 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s>>>(
+    SIG_LAUNCH((lam_dw_fwd_tc_kernel), dim3((unsigned)ceil_div((int64_t)B * g.P, kDwPairs), 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s, 
         c.H, (int64_t)BL * d, *p, g, B, L, d, c.U, c.o);
     SIG_CHECK_LAUNCH();
   }
   {
     SIG_PHASE("lam_sample_fwd");
-    lam_sample_fwd_tok_kernel<__nv_bfloat16><<<dim3(B * g.P, 3), (unsigned)ceil_div(d / 8, 32) * 32, 0, s>>>(tp, c.o, g, B, d, c.S);
+    SIG_LAUNCH((lam_sample_fwd_tok_kernel<__nv_bfloat16>), dim3(B * g.P, 3), (unsigned)ceil_div(d / 8, 32) * 32, 0, s, tp, c.o, g, B, d, c.S);
     SIG_CHECK_LAUNCH();
-    lam_mse_kernel<<<B * g.P, 256, 0, s>>>(c.S, (int64_t)B * g.P * d, d, c.part);
+    SIG_LAUNCH((lam_mse_kernel), B * g.P, 256, 0, s, c.S, (int64_t)B * g.P * d, d, c.part);
     SIG_CHECK_LAUNCH();
-    sum_kernel<<<1, 256, 0, s>>>(c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
+    SIG_LAUNCH((sum_kernel), 1, 256, 0, s, c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
     SIG_CHECK_LAUNCH();
   }
   return 0;
@@ -678,13 +743,13 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
       t.C[0] = dfn; t.C[1] = dft; t.ldc = d;
       SIG_TRY(tc_gemm(t, s));
     }
-    gam_finish_kernel<<<dim3(B, 3), 256, 0, s>>>(c.f, c.nrm, c.rowA, c.colC, c.df, B, L, d, c.dmean);
+    SIG_LAUNCH((gam_finish_kernel), dim3(B, 3), 256, 0, s, c.f, c.nrm, c.rowA, c.colC, c.df, B, L, d, c.dmean);
     SIG_CHECK_LAUNCH();
-    scale_scalar_kernel<<<1, 1, 0, s>>>(c.dtau, dlosses, dp->contra_temp);
+    SIG_LAUNCH((scale_scalar_kernel), 1, 1, 0, s, c.dtau, dlosses, dp->contra_temp);
     SIG_CHECK_LAUNCH();
   }
   if (dtok->zero_cls && !dtok->accumulate) {
-    zero_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 64, 0, s>>>(gp, d);
+    SIG_LAUNCH((zero_cls_kernel<__nv_bfloat16>), dim3(B, 3), 64, 0, s, gp, d);
     SIG_CHECK_LAUNCH();
   }
   if (!do_lam) {
@@ -692,7 +757,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_PHASE("align_write");
     const Geo g = make_geo(8, 8);
     for (int m = 0; m < 3; ++m) {
-      align_write_kernel<__nv_bfloat16><<<(unsigned)BL, 128, 0, s>>>(nullptr, c.dmean + (size_t)m * B * d, dlosses, nullptr, nullptr, g,
+      SIG_LAUNCH((align_write_kernel<__nv_bfloat16>), (unsigned)BL, 128, 0, s, nullptr, c.dmean + (size_t)m * B * d, dlosses, nullptr, nullptr, g,
                                                                     B, L, d, static_cast<__nv_bfloat16*>(dtok->dpatch[m]),
                                                                     dtok->patch_stride_b[m], dtok->patch_stride_l[m], nullptr, 0,
                                                                     dtok->accumulate);
@@ -704,9 +769,9 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   const unsigned cthreads = (unsigned)ceil_div(d / 8, 32) * 32;
   {
     SIG_PHASE("lam_sample_bwd");
-    lam_mse_bwd_kernel<<<B * g.P, 256, 0, s>>>(c.S, (int64_t)B * g.P * d, d, 2.f / (3.f * (float)B * g.P * d), dlosses + 1, c.dS);
+    SIG_LAUNCH((lam_mse_bwd_kernel), B * g.P, 256, 0, s, c.S, (int64_t)B * g.P * d, d, 2.f / (3.f * (float)B * g.P * d), dlosses + 1, c.dS);
     SIG_CHECK_LAUNCH();
-    lam_sample_bwd_tok_kernel<__nv_bfloat16><<<dim3(B * g.P, 3), cthreads, 0, s>>>(tp, c.o, c.dS, g, B, d, c.dO);
+    SIG_LAUNCH((lam_sample_bwd_tok_kernel<__nv_bfloat16>), dim3(B * g.P, 3), cthreads, 0, s, tp, c.o, c.dS, g, B, d, c.dO);
     SIG_CHECK_LAUNCH();
   }
   {
@@ -714,10 +779,10 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     const int nchunk = (int)ceil_div((int64_t)B * g.P, kDwPairs);
     const size_t dw_smem_bytes = (size_t)2 * 16 * d * sizeof(__nv_bfloat16);
     cudaFuncSetAttribute(lam_dw_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes);
-    lam_dw_bwd_tc_kernel<<<dim3(nchunk, 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s>>>(c.H, (int64_t)BL * d, c.U, c.dO, *p, g,
+    SIG_LAUNCH((lam_dw_bwd_tc_kernel), dim3(nchunk, 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s, c.H, (int64_t)BL * d, c.U, c.dO, *p, g,
                                                                                                   B, L, d, c.dH, c.dwpart);
     SIG_CHECK_LAUNCH();
-    lam_dw_param_reduce_kernel<<<dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s>>>(c.dwpart, nchunk, *dp, c.dbf, d);
+    SIG_LAUNCH((lam_dw_param_reduce_kernel), dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s, c.dwpart, nchunk, *dp, c.dbf, d);
     SIG_CHECK_LAUNCH();
   }
   {
@@ -737,7 +802,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.accumulate = dtok->accumulate;
     t.bn = (d % 256 == 0) ? 256 : 128;
     SIG_TRY(tc_gemm(t, s));
-    lam_sparse_add_kernel<__nv_bfloat16><<<dim3(B, 3), cthreads, 0, s>>>(gp, c.o, c.dS, g, B, d);
+    SIG_LAUNCH((lam_sparse_add_kernel<__nv_bfloat16>), dim3(B, 3), cthreads, 0, s, gp, c.o, c.dS, g, B, d);
     SIG_CHECK_LAUNCH();
   }
   {
@@ -777,14 +842,10 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
       t.ldc = d;
       SIG_TRY(tc_gemm(t, s));
     }
-    for (int m = 0; m < 3; ++m) {
-      rank1_add_kernel<<<(unsigned)ceil_div((int64_t)dd, 256), 256, 0, s>>>(dp->off0_w[m], c.dbf + (size_t)m * d, p->proj_q_b[m], d);
-      SIG_CHECK_LAUNCH();
-      // db0 = db' ; dbq = W0^T db'
-      cudaMemcpyAsync(dp->off0_b[m], c.dbf + (size_t)m * d, d * sizeof(float), cudaMemcpyDeviceToDevice, s);
-      gemv_t_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(p->off0_w[m], d, c.dbf + (size_t)m * d, d, d, dp->proj_q_b[m]);
-      SIG_CHECK_LAUNCH();
-    }
+    SIG_LAUNCH((rank1_add3_kernel), dim3((unsigned)ceil_div((int64_t)dd, 256), 3), 256, 0, s, *dp, c.dbf, *p, d);
+    SIG_CHECK_LAUNCH();
+    SIG_LAUNCH((lam_unfold_bias_kernel), dim3((unsigned)ceil_div(d, 32), 3), 1024, 0, s, *p, *dp, c.dbf, d);   // db0 = db', dbq = W0^T db'
+    SIG_CHECK_LAUNCH();
   }
   return 0;
 }

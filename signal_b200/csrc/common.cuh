@@ -15,6 +15,10 @@
     if (e__ != cudaSuccess) return (int)e__;       \
   } while (0)
 
+// SIG_LAUNCH((kernel<...>), grid, block, smem_bytes, stream, args...)
+#define SIG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::sig::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, ##__VA_ARGS__)
+
 #define SIG_TRY(expr)            \
   do {                           \
     int rc__ = (expr);           \
@@ -22,6 +26,35 @@
   } while (0)
 
 namespace sig {
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and
+// starts with pdl_enter(): it lets the next kernel of the stream be scheduled early (its launch latency
+// and prologue overlap this kernel) and then waits until the previous kernel has completed and its
+// writes are visible.  Nothing touches global memory before the wait, so stream order is preserved.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+bool pdl_enabled();   // prof.cu: SIG_PDL=0 in the environment turns the launch attribute off
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 constexpr int kHeads = 8;        // useA.py:449
 constexpr int kMaxL = 128;       // patch tokens per modality (make_model.py:67)

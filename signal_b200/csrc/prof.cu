@@ -1,6 +1,7 @@
 #include "prof.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -19,6 +20,14 @@ struct Rec {
 };
 std::vector<Rec> g_recs;
 }  // namespace
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SIG_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 void prof_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -29,6 +29,7 @@ struct TokPtrs {
 
 template <typename T>
 static __global__ void convert_tokens_kernel(TokPtrs tp, int B, int L, int d, float* __restrict__ Xf, float* __restrict__ clsf) {
+  pdl_enter();
   const int m = blockIdx.y;
   const int64_t row = blockIdx.x;  // [0, B*L) patches, [B*L, B*L+B) cls
   const T* src;
@@ -60,9 +61,9 @@ int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s) 
   dim3 grid((unsigned)((int64_t)t->B * t->L + t->B), 3);
   const int threads = t->d / 8 >= 128 ? 128 : 64;
   if (t->dtype == SIG_BF16)
-    convert_tokens_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(tp, t->B, t->L, t->d, Xf, clsf);
+    SIG_LAUNCH((convert_tokens_kernel<__nv_bfloat16>), grid, threads, 0, s, tp, t->B, t->L, t->d, Xf, clsf);
   else
-    convert_tokens_kernel<float><<<grid, threads, 0, s>>>(tp, t->B, t->L, t->d, Xf, clsf);
+    SIG_LAUNCH((convert_tokens_kernel<float>), grid, threads, 0, s, tp, t->B, t->L, t->d, Xf, clsf);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -71,6 +72,7 @@ int convert_tokens(const sig_tokens* t, float* Xf, float* clsf, cudaStream_t s) 
 template <typename T>
 static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ clsf, __nv_bfloat16* __restrict__ clsb,
                                          __nv_bfloat16* __restrict__ clsb2) {
+  pdl_enter();
   const int b = blockIdx.x, m = blockIdx.y;
   const T* src = static_cast<const T*>(tp.cls[m]) + b * tp.csb[m];
   float* dst = clsf + ((int64_t)b * 3 + m) * d;
@@ -89,6 +91,7 @@ static __global__ void gather_cls_kernel(TokPtrs tp, int d, float* __restrict__ 
 // csel[r] = cls[r] . u + s0   grid R, 128 threads
 static __global__ void __launch_bounds__(128) csel_fold_kernel(const float* __restrict__ clsf, const float* __restrict__ u,
                                                                const float* __restrict__ s0, int d, float* __restrict__ csel) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int64_t r = blockIdx.x;
   float a = 0.f;
@@ -99,6 +102,7 @@ static __global__ void __launch_bounds__(128) csel_fold_kernel(const float* __re
 
 // out[n][0:d] = hi(M[n][:]), out[n][d:2d] = lo(M[n][:]);  grid d, 128 threads
 static __global__ void split_hl_kernel(const float* __restrict__ M, int d, __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   const int64_t n = blockIdx.x;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     const float v = M[n * d + c];
@@ -109,6 +113,7 @@ static __global__ void split_hl_kernel(const float* __restrict__ M, int d, __nv_
 }
 
 static __global__ void dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float scratch[33];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(a[i], b[i], s);
@@ -135,6 +140,7 @@ static __global__ void __launch_bounds__(256) sim_scores_tok_kernel(TokPtrs tp, 
                                                                     const float* __restrict__ qtsel, const float* __restrict__ csel,
                                                                     int B, int L, int d, float* __restrict__ sel_logits,
                                                                     float* __restrict__ intra_raw) {
+  pdl_enter();
   extern __shared__ float qv[];  // [4][d]
   const int m = blockIdx.y, b = blockIdx.z;
   for (int i = threadIdx.x; i < 4 * d; i += blockDim.x) {
@@ -178,6 +184,7 @@ static __global__ void __launch_bounds__(256) sim_scores_kernel(const float* __r
                                                                 const float* __restrict__ qtsel, const float* __restrict__ csel,
                                                                 int B, int L, int d, float* __restrict__ sel_logits,
                                                                 float* __restrict__ intra_raw) {
+  pdl_enter();
   extern __shared__ float qv[];  // [4][d]
   const int m = blockIdx.y, b = blockIdx.z;
   for (int i = threadIdx.x; i < 4 * d; i += blockDim.x) {
@@ -285,6 +292,7 @@ static __device__ void select_masks(const float* intra, const float* inter, cons
 static __global__ void __launch_bounds__(256) sim_select_kernel(const float* __restrict__ sel_logits, const float* __restrict__ intra_raw,
                                                                 int B, int L, int d, int which, int k1, int k2, int max_keep,
                                                                 float* __restrict__ masks, float* __restrict__ masks2) {
+  pdl_enter();
   __shared__ float s_inter[3 * 2 * kMaxL], s_intra[3 * kMaxL], s_raw[3 * kMaxL], s_mask[3 * kMaxL];
   __shared__ float s_full[3 * kMaxL];
   __shared__ unsigned char f_inter[3 * 2 * kMaxL], f_intra[3 * kMaxL];
@@ -341,6 +349,7 @@ static __global__ void __launch_bounds__(256) sim_select_kernel(const float* __r
 static __global__ void __launch_bounds__(256) select_from_scores_kernel(const float* __restrict__ intra, const float* __restrict__ inter,
                                                                         const float* __restrict__ raw, int B, int L, int which, int k1,
                                                                         int k2, int max_keep, float* __restrict__ masks) {
+  pdl_enter();
   __shared__ float s_inter[3 * 2 * kMaxL], s_intra[3 * kMaxL], s_raw[3 * kMaxL], s_mask[3 * kMaxL];
   __shared__ unsigned char f_inter[3 * 2 * kMaxL], f_intra[3 * kMaxL];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -363,7 +372,7 @@ static __global__ void __launch_bounds__(256) select_from_scores_kernel(const fl
 
 int select_from_scores(const float* intra, const float* inter, const float* raw, int B, int L, int which, int k1, int k2,
                        int max_keep, float* masks, cudaStream_t s) {
-  select_from_scores_kernel<<<B, 256, 0, s>>>(intra, inter, raw, B, L, which, k1, k2, max_keep, masks);
+  SIG_LAUNCH((select_from_scores_kernel), B, 256, 0, s, intra, inter, raw, B, L, which, k1, k2, max_keep, masks);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -372,6 +381,7 @@ int select_from_scores(const float* intra, const float* inter, const float* raw,
 template <typename T>
 static __global__ void mask_mul_kernel(const float* __restrict__ Xf, const float* __restrict__ masks, int64_t rows, int d,
                                        T* __restrict__ selected) {
+  pdl_enter();
   const int64_t row = blockIdx.x;
   const float mk = masks[row];
   for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
@@ -395,6 +405,7 @@ static __global__ void __launch_bounds__(256) sim_attn_fwd_kernel(const float* _
                                                                   const float* __restrict__ qt, const float* __restrict__ cq, int B,
                                                                   int L, int d, float* __restrict__ xbar, float* __restrict__ amax,
                                                                   float* __restrict__ asum) {
+  pdl_enter();
   extern __shared__ float smem[];
   float* qs = smem;               // [6][d]
   float* lg = qs + 6 * d;         // [6][3L]
@@ -479,6 +490,7 @@ static __global__ void __launch_bounds__(256) sim_attn_bwd_kernel(const float* _
                                                                   const float* __restrict__ xbar, const float* __restrict__ amax,
                                                                   const float* __restrict__ asum, const float* __restrict__ dxbar,
                                                                   int B, int L, int d, float* __restrict__ dqt, float* __restrict__ dXf) {
+  pdl_enter();
   extern __shared__ float smem[];
   const int T3 = 3 * L;
   float* qs = smem;
@@ -602,6 +614,7 @@ struct GradPtrs {
 template <typename T>
 static __global__ void write_token_grads_kernel(GradPtrs gp, const float* __restrict__ dXf, const float* __restrict__ dclsf, int B,
                                                 int L, int d) {
+  pdl_enter();
   const int m = blockIdx.y;
   const int64_t row = blockIdx.x;
   const float* src;
@@ -641,9 +654,9 @@ int write_token_grads(const sig_token_grads* g, int dtype, const float* dXf, con
   dim3 grid((unsigned)((int64_t)B * L + B), 3);
   const int threads = d / 8 >= 128 ? 128 : 64;
   if (dtype == SIG_BF16)
-    write_token_grads_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(gp, dXf, dclsf, B, L, d);
+    SIG_LAUNCH((write_token_grads_kernel<__nv_bfloat16>), grid, threads, 0, s, gp, dXf, dclsf, B, L, d);
   else
-    write_token_grads_kernel<float><<<grid, threads, 0, s>>>(gp, dXf, dclsf, B, L, d);
+    SIG_LAUNCH((write_token_grads_kernel<float>), grid, threads, 0, s, gp, dXf, dclsf, B, L, d);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -651,6 +664,7 @@ int write_token_grads(const sig_token_grads* g, int dtype, const float* dXf, con
 // dcls[m][b] (+)= dclsf[b][m]   grid (B, 3)
 template <typename T>
 static __global__ void write_cls_grads_kernel(GradPtrs gp, const float* __restrict__ dclsf, int d) {
+  pdl_enter();
   const int b = blockIdx.x, m = blockIdx.y;
   if (!gp.dcls[m]) return;
   T* dst = static_cast<T*>(gp.dcls[m]) + b * gp.csb[m];
@@ -669,6 +683,7 @@ static __global__ void write_cls_grads_kernel(GradPtrs gp, const float* __restri
 }
 
 static __global__ void fill_kernel(float* __restrict__ p, float v, int64_t n) {
+  pdl_enter();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -792,7 +807,7 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
     t.M = R; t.N = d; t.K = 2 * d;
     t.C[0] = c.qtsel; t.ldc = d; t.bias[0] = f->v;
     SIG_TRY(tc_gemm(t, s));
-    csel_fold_kernel<<<R, 128, 0, s>>>(c.clsf, f->u, f->s0, d, c.csel);
+    SIG_LAUNCH((csel_fold_kernel), R, 128, 0, s, c.clsf, f->u, f->s0, d, c.csel);
     SIG_CHECK_LAUNCH();
   } else {
     // q = W_q cls + b_q (useA.py:123); qt = W_k^T q; c = q . b_k
@@ -802,12 +817,12 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
   }
   dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
   if (c.tc)
-    sim_scores_tok_kernel<__nv_bfloat16><<<grid, 256, 4 * d * sizeof(float), s>>>(tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
+    SIG_LAUNCH((sim_scores_tok_kernel<__nv_bfloat16>), grid, 256, 4 * d * sizeof(float), s, tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
                                                                                  c.sel_logits, c.intra_raw);
   else
-    sim_scores_kernel<<<grid, 256, 4 * d * sizeof(float), s>>>(c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);
+    SIG_LAUNCH((sim_scores_kernel), grid, 256, 4 * d * sizeof(float), s, c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);
   SIG_CHECK_LAUNCH();
-  sim_select_kernel<<<B, 256, 0, s>>>(c.sel_logits, c.intra_raw, B, L, d, which, k1, k2, max_keep, c.maskf, masks_out);
+  SIG_LAUNCH((sim_select_kernel), B, 256, 0, s, c.sel_logits, c.intra_raw, B, L, d, which, k1, k2, max_keep, c.maskf, masks_out);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -860,7 +875,7 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
   } else {
     const size_t sm = attn_fwd_smem(L, d);
     cudaFuncSetAttribute(sim_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    sim_attn_fwd_kernel<<<dim3(B, 4), 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, B, L, d, c.xbar, c.amax, c.asum);
+    SIG_LAUNCH((sim_attn_fwd_kernel), dim3(B, 4), 256, sm, s, c.Xf, maskf, c.qtatt, c.catt, B, L, d, c.xbar, c.amax, c.asum);
     SIG_CHECK_LAUNCH();
   }
   }
@@ -871,7 +886,7 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
     SIG_TRY(launch_gemm(g, s));
   }
   SIG_TRY(launch_gemm(gemm_nt(c.o, d, p->out_proj_w, d, c.attn, d, p->out_proj_b, R, d, d), s));
-  layernorm_fwd_kernel<float><<<R, 256, 0, s>>>(c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
+  SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
   SIG_CHECK_LAUNCH();
   {
     Gemm g = gemm_nt(c.y1, d, p->ffn0_w, d, c.h1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d);
@@ -879,7 +894,7 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
     SIG_TRY(launch_gemm(g, s));
   }
   SIG_TRY(launch_gemm(gemm_nt(c.h1, 2 * (int64_t)d, p->ffn2_w, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
-  layernorm_fwd_kernel<OutT><<<R, 256, 0, s>>>(c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
+  SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -911,7 +926,7 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
   {
   SIG_PHASE("sim_post_bwd");
   // LN2
-  layernorm_bwd_kernel<InT><<<R, 256, 0, s>>>(dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
+  SIG_LAUNCH((layernorm_bwd_kernel<InT>), R, 256, 0, s, dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln2_w, 1.f, s));
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln2_b, 1.f, s));
@@ -921,7 +936,7 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
   SIG_TRY(launch_gemm(gemm_nn(c.dr2, d, p->ffn2_w, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d), s));
   {
     const int64_t n = (int64_t)R * 2 * d;
-    gelu_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(c.dh1, c.a1, c.dh1, n);  // dh1 := da1
+    SIG_LAUNCH((gelu_bwd_kernel), (unsigned)ceil_div(n, 256), 256, 0, s, c.dh1, c.a1, c.dh1, n);  // dh1 := da1
     SIG_CHECK_LAUNCH();
   }
   SIG_TRY(launch_colsum(c.dh1, 2 * (int64_t)d, R, 2 * d, g->ffn0_b, 1.f, s));
@@ -932,7 +947,7 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
     SIG_TRY(launch_gemm(gg, s));
   }
   // LN1
-  layernorm_bwd_kernel<float><<<R, 256, 0, s>>>(c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
+  SIG_LAUNCH((layernorm_bwd_kernel<float>), R, 256, 0, s, c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln1_w, 1.f, s));
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln1_b, 1.f, s));
@@ -960,7 +975,7 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
   } else {
     const size_t sm = attn_bwd_smem(L, d);
     cudaFuncSetAttribute(sim_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    sim_attn_bwd_kernel<<<B, 256, sm, s>>>(c.Xf, maskf, c.qtatt, c.catt, c.xbar, c.amax, c.asum, c.dxbar, B, L, d, c.dqt, c.dXf);
+    SIG_LAUNCH((sim_attn_bwd_kernel), B, 256, sm, s, c.Xf, maskf, c.qtatt, c.catt, c.xbar, c.amax, c.asum, c.dxbar, B, L, d, c.dqt, c.dXf);
     SIG_CHECK_LAUNCH();
   }
   }
@@ -998,13 +1013,13 @@ static int check_sim_params(const sig_sim_params* p, bool need_sel, bool need_at
 int sim_fold_selection(const sig_sim_params* p, int d, void* m_hl, float* v, float* u, float* s0, float* ws, cudaStream_t s) {
   // M[n][k] = sum_j W_k[j][n] W_q[j][k]
   SIG_TRY(launch_gemm(gemm_tn(p->sel_wk, d, p->sel_wq, d, ws, d, d, d, d), s));
-  split_hl_kernel<<<d, 128, 0, s>>>(ws, d, static_cast<__nv_bfloat16*>(m_hl));
+  SIG_LAUNCH((split_hl_kernel), d, 128, 0, s, ws, d, static_cast<__nv_bfloat16*>(m_hl));
   SIG_CHECK_LAUNCH();
-  gemv_t_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(p->sel_wk, d, p->sel_bq, d, d, v);   // v = W_k^T b_q
+  SIG_LAUNCH((gemv_t_kernel), (unsigned)ceil_div(d, 32), 1024, 0, s, p->sel_wk, d, p->sel_bq, d, d, v);   // v = W_k^T b_q
   SIG_CHECK_LAUNCH();
-  gemv_t_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, s>>>(p->sel_wq, d, p->sel_bk, d, d, u);   // u = W_q^T b_k
+  SIG_LAUNCH((gemv_t_kernel), (unsigned)ceil_div(d, 32), 1024, 0, s, p->sel_wq, d, p->sel_bk, d, d, u);   // u = W_q^T b_k
   SIG_CHECK_LAUNCH();
-  dot_kernel<<<1, 256, 0, s>>>(p->sel_bq, p->sel_bk, d, s0);
+  SIG_LAUNCH((dot_kernel), 1, 256, 0, s, p->sel_bq, p->sel_bk, d, s0);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -1022,7 +1037,7 @@ int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, 
   SimCtx c = sim_ctx(ctx, B, L, d, tcp);
   if (tcp) {
     SIG_PHASE("convert_tokens");
-    gather_cls_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(tok_ptrs(tok), d, c.clsf, c.clsb, c.clsb2);
+    SIG_LAUNCH((gather_cls_kernel<__nv_bfloat16>), dim3(B, 3), 96, 0, s, tok_ptrs(tok), d, c.clsf, c.clsb, c.clsb2);
     SIG_CHECK_LAUNCH();
   } else {
     SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));
@@ -1035,7 +1050,7 @@ int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, 
     cudaMemcpyAsync(c.maskf, ext_masks, (size_t)3 * B * L * sizeof(float), cudaMemcpyDeviceToDevice, s);
     maskf = c.maskf;
   } else if (tcp) {
-    fill_kernel<<<(unsigned)ceil_div((int64_t)3 * B * L, 256), 256, 0, s>>>(c.maskf, 1.f, (int64_t)3 * B * L);
+    SIG_LAUNCH((fill_kernel), (unsigned)ceil_div((int64_t)3 * B * L, 256), 256, 0, s, c.maskf, 1.f, (int64_t)3 * B * L);
     SIG_CHECK_LAUNCH();
     maskf = c.maskf;
   }
@@ -1071,7 +1086,7 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
       gp.psb[m] = dtok->patch_stride_b[m]; gp.psl[m] = dtok->patch_stride_l[m]; gp.csb[m] = dtok->cls_stride_b[m];
     }
     gp.accumulate = dtok->accumulate;
-    write_cls_grads_kernel<__nv_bfloat16><<<dim3(B, 3), 96, 0, s>>>(gp, c.dr1, d);
+    SIG_LAUNCH((write_cls_grads_kernel<__nv_bfloat16>), dim3(B, 3), 96, 0, s, gp, c.dr1, d);
     SIG_CHECK_LAUNCH();
     return 0;
   }
@@ -1093,9 +1108,9 @@ int sim_select(const sig_tokens* tok, const sig_sim_params* p, int which, int k1
     const int64_t rows = (int64_t)3 * B * L;
     const int threads = d / 8 >= 128 ? 128 : 64;
     if (tok->dtype == SIG_BF16)
-      mask_mul_kernel<__nv_bfloat16><<<(unsigned)rows, threads, 0, s>>>(c.Xf, c.maskf, rows, d, static_cast<__nv_bfloat16*>(selected));
+      SIG_LAUNCH((mask_mul_kernel<__nv_bfloat16>), (unsigned)rows, threads, 0, s, c.Xf, c.maskf, rows, d, static_cast<__nv_bfloat16*>(selected));
     else
-      mask_mul_kernel<float><<<(unsigned)rows, threads, 0, s>>>(c.Xf, c.maskf, rows, d, static_cast<float*>(selected));
+      SIG_LAUNCH((mask_mul_kernel<float>), (unsigned)rows, threads, 0, s, c.Xf, c.maskf, rows, d, static_cast<float*>(selected));
     SIG_CHECK_LAUNCH();
   }
   return 0;
@@ -1105,6 +1120,7 @@ int sim_select(const sig_tokens* tok, const sig_sim_params* p, int which, int k1
 template <typename T>
 static __global__ void mask_mul_bwd_kernel(const T* __restrict__ dsel, const float* __restrict__ masks, GradPtrs gp, int B, int L,
                                            int d) {
+  pdl_enter();
   const int m = blockIdx.y;
   const int64_t row = blockIdx.x;
   const int b = (int)(row / L), l = (int)(row % L);
@@ -1141,9 +1157,9 @@ int mask_mul_bwd(const void* dselected, const float* masks, int dtype, int B, in
   dim3 grid((unsigned)((int64_t)B * L), 3);
   const int threads = d / 8 >= 128 ? 128 : 64;
   if (dtype == SIG_BF16)
-    mask_mul_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(dselected), masks, gp, B, L, d);
+    SIG_LAUNCH((mask_mul_bwd_kernel<__nv_bfloat16>), grid, threads, 0, s, static_cast<const __nv_bfloat16*>(dselected), masks, gp, B, L, d);
   else
-    mask_mul_bwd_kernel<float><<<grid, threads, 0, s>>>(static_cast<const float*>(dselected), masks, gp, B, L, d);
+    SIG_LAUNCH((mask_mul_bwd_kernel<float>), grid, threads, 0, s, static_cast<const float*>(dselected), masks, gp, B, L, d);
   SIG_CHECK_LAUNCH();
   return 0;
 }

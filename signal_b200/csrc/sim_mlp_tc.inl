@@ -40,6 +40,7 @@ static void per_head(TcOperand& o, const __nv_bfloat16* base, int64_t stride) {
 // c[(b,q),h] = scale * q_h . b_k^h   grid R, 256 threads (one warp per head)
 static __global__ void __launch_bounds__(256) catt_kernel(const float* __restrict__ qatt, const float* __restrict__ bk, int d, float scale,
                                                           float* __restrict__ catt) {
+  pdl_enter();
   const int64_t row = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, hd = d / kHeads;
   float a = 0.f;
@@ -50,6 +51,7 @@ static __global__ void __launch_bounds__(256) catt_kernel(const float* __restric
 
 // da = dh * gelu'(a) in place (fp32) + bf16 shadow
 static __global__ void gelu_bwd_shadow_kernel(float* dh, const float* __restrict__ a, __nv_bfloat16* __restrict__ shadow, int64_t n) {
+  pdl_enter();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) {
     const float v = dh[i] * gelu_grad_f(a[i]);
@@ -59,12 +61,10 @@ static __global__ void gelu_bwd_shadow_kernel(float* dh, const float* __restrict
 }
 
 static int cast_sim_weights(const SimCtx& c, const sig_sim_params* p, int d, cudaStream_t s) {
-  const size_t dd = (size_t)d * d;
-  SIG_TRY(cast_f32_to_bf16(p->in_proj_w, c.Wb, 3 * dd, s));
-  SIG_TRY(cast_f32_to_bf16(p->out_proj_w, c.Wb + 3 * dd, dd, s));
-  SIG_TRY(cast_f32_to_bf16(p->ffn0_w, c.Wb + 4 * dd, 2 * dd, s));
-  SIG_TRY(cast_f32_to_bf16(p->ffn2_w, c.Wb + 6 * dd, 2 * dd, s));
-  return 0;
+  const int64_t dd = (int64_t)d * d;
+  const CastJob jobs[4] = {{p->in_proj_w, c.Wb, 3 * dd}, {p->out_proj_w, c.Wb + 3 * dd, dd}, {p->ffn0_w, c.Wb + 4 * dd, 2 * dd},
+                           {p->ffn2_w, c.Wb + 6 * dd, 2 * dd}};
+  return cast_f32_to_bf16_multi(jobs, 4, s);
 }
 
 static int attn_prep_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, cudaStream_t s) {
@@ -87,7 +87,7 @@ static int attn_prep_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
     for (int h = 0; h < kHeads; ++h) t.C[h] = c.qtatt + (size_t)h * d;
     SIG_TRY(tc_gemm(t, s));
   }
-  catt_kernel<<<R, 256, 0, s>>>(c.qatt, p->in_proj_b + d, d, scale, c.catt);
+  SIG_LAUNCH((catt_kernel), R, 256, 0, s, c.qatt, p->in_proj_b + d, d, scale, c.catt);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -115,7 +115,7 @@ static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
     SIG_TRY(tc_gemm(t, s));
   }
   SIG_TRY(tc_gemm(lin_nt(c.ob, d, wob, d, c.attn, d, p->out_proj_b, R, d, d), s));
-  layernorm_fwd_kernel<float><<<R, 256, 0, s>>>(c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
+  SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
   SIG_CHECK_LAUNCH();
   SIG_TRY(cast_f32_to_bf16(c.y1, c.y1b, (int64_t)R * d, s));
   {
@@ -124,7 +124,7 @@ static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
     SIG_TRY(tc_gemm(t, s));
   }
   SIG_TRY(tc_gemm(lin_nt(c.h1b, 2 * (int64_t)d, w2b, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
-  layernorm_fwd_kernel<OutT><<<R, 256, 0, s>>>(c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
+  SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -139,8 +139,9 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   const __nv_bfloat16* w1b = c.Wb + 4 * dd;
   const __nv_bfloat16* w2b = c.Wb + 6 * dd;
   float* dwv = g->in_proj_w + 2 * dd;
-  SIG_TRY(cast_sim_weights(c, p, d, s));   // backward may run long after forward: do not rely on the forward copy
-  layernorm_bwd_kernel<InT><<<R, 256, 0, s>>>(dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
+  // the bf16 weight shadows written by the forward call are reused: autograd's version check on the
+  // saved parameters rules out an in-place update between forward and backward
+  SIG_LAUNCH((layernorm_bwd_kernel<InT>), R, 256, 0, s, dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln2_w, 1.f, s));
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln2_b, 1.f, s));
@@ -150,7 +151,7 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   SIG_TRY(tc_gemm(lin_nn(c.dr2b, d, w2b, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d), s));              // dh1 = dr2 W2
   {
     const int64_t n = (int64_t)R * 2 * d;
-    gelu_bwd_shadow_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(c.dh1, c.a1, c.da1b, n);
+    SIG_LAUNCH((gelu_bwd_shadow_kernel), (unsigned)ceil_div(n, 256), 256, 0, s, c.dh1, c.a1, c.da1b, n);
     SIG_CHECK_LAUNCH();
   }
   SIG_TRY(launch_colsum(c.dh1, 2 * (int64_t)d, R, 2 * d, g->ffn0_b, 1.f, s));
@@ -160,7 +161,7 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     t.accumulate = 1;
     SIG_TRY(tc_gemm(t, s));
   }
-  layernorm_bwd_kernel<float><<<R, 256, 0, s>>>(c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
+  SIG_LAUNCH((layernorm_bwd_kernel<float>), R, 256, 0, s, c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln1_w, 1.f, s));
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln1_b, 1.f, s));

@@ -201,6 +201,7 @@ struct DxProblem {
 // ------------------------------------------------------------------------------------------------
 // DXQT[b][32 + e][:] = bf16(qt[b][e][:]) (e < 24), zero rows elsewhere in [32, 64).  grid (B, 32)
 static __global__ void build_qt_kernel(const float* __restrict__ qt, __nv_bfloat16* __restrict__ DXQT, int d) {
+  pdl_enter();
   const int b = blockIdx.x, e = blockIdx.y;
   __nv_bfloat16* dst = DXQT + ((int64_t)b * 64 + 32 + e) * d;
   for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) {
@@ -213,6 +214,7 @@ static __global__ void build_qt_kernel(const float* __restrict__ qt, __nv_bfloat
 // DXQT[b][e][:] = bf16(dxbar[b][e][:]) (e < 24), zero rows in [24, 32); delta[b][e] = dxbar_e . xbar_e.  grid (B, 32)
 static __global__ void __launch_bounds__(128) build_dx_kernel(const float* __restrict__ dxbar, const float* __restrict__ xbar,
                                                               __nv_bfloat16* __restrict__ DXQT, float* __restrict__ delta, int d) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int b = blockIdx.x, e = blockIdx.y;
   __nv_bfloat16* dst = DXQT + ((int64_t)b * 64 + e) * d;
@@ -236,6 +238,7 @@ static __global__ void __launch_bounds__(128) build_dx_kernel(const float* __res
 // both layouts (token-major [384][32] and query-major [32][384], bf16).  grid B, 256 threads, dyn smem 384*33 floats
 static __global__ void __launch_bounds__(256) sim_softmax_kernel(const float* __restrict__ S32, const float* __restrict__ maskf, int B,
                                                                  int L, __nv_bfloat16* __restrict__ Ptok, __nv_bfloat16* __restrict__ PT) {
+  pdl_enter();
   extern __shared__ float sm[];   // [384][33]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float* src = S32 + (int64_t)b * 384 * 32;
@@ -295,7 +298,7 @@ size_t sim_tc_softmax_smem() { return (size_t)384 * 33 * sizeof(float); }
 
 int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s) {
   const int B = tok->B, d = tok->d, L = tok->L;
-  build_qt_kernel<<<dim3(B, 32), 96, 0, s>>>(k.qtatt, k.DXQT, d);
+  SIG_LAUNCH((build_qt_kernel), dim3(B, 32), 96, 0, s, k.qtatt, k.DXQT, d);
   SIG_CHECK_LAUNCH();
   {
     RowsParams p{};
@@ -311,7 +314,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
       cudaFuncSetAttribute(sim_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_tc_softmax_smem());
       attr = true;
     }
-    sim_softmax_kernel<<<B, 256, sim_tc_softmax_smem(), s>>>(k.S32, k.maskf, B, L, k.Ptok, k.PT);
+    SIG_LAUNCH((sim_softmax_kernel), B, 256, sim_tc_softmax_smem(), s, k.S32, k.maskf, B, L, k.Ptok, k.PT);
     SIG_CHECK_LAUNCH();
   }
   {
@@ -326,7 +329,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
 
 int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token_grads* dtok, cudaStream_t s) {
   const int B = tok->B, d = tok->d, L = tok->L;
-  build_dx_kernel<<<dim3(B, 32), 96, 0, s>>>(k.dxbar, k.xbar, k.DXQT, k.delta, d);
+  SIG_LAUNCH((build_dx_kernel), dim3(B, 32), 96, 0, s, k.dxbar, k.xbar, k.DXQT, k.delta, d);
   SIG_CHECK_LAUNCH();
   {
     RowsParams p{};

@@ -51,6 +51,7 @@ inline Gemm gemm_tn(const float* A, int64_t lda, const float* Bm, int64_t ldb, f
 constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16;
 
 static __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
+  pdl_enter();
   __shared__ float As[kGemmBK][kGemmBM + 4];
   __shared__ float Bs[kGemmBK][kGemmBN + 4];
   const int tid = threadIdx.x;
@@ -149,31 +150,40 @@ inline int launch_gemm(const Gemm& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
   dim3 grid((unsigned)ceil_div(g.N, kGemmBN), (unsigned)ceil_div(g.M, kGemmBM),
             (unsigned)(g.ksplit > 1 ? g.ksplit : g.batch));
-  gemm_simt_kernel<<<grid, 256, 0, s>>>(g);
+  SIG_LAUNCH((gemm_simt_kernel), grid, 256, 0, s, g);
   SIG_CHECK_LAUNCH();
   return 0;
 }
 
-// out[n] = sum_m X[m*ldx + n] (deterministic; 32 columns x 8 row lanes per CTA)
-static __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N,
-                                                            float* __restrict__ out, float scale) {
-  __shared__ float sm[8][33];
+// out[n] = scale * sum_m X[m*ldx + n] (deterministic; 32 columns x 32 row lanes per CTA, 4 loads in flight per thread)
+static __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ X, int64_t ldx, int M, int N,
+                                                             float* __restrict__ out, float scale) {
+  pdl_enter();
+  __shared__ float sm[32][33];
   const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + c;
-  float acc = 0.f;
-  if (n < N)
-    for (int m = r; m < M; m += 8) acc += X[m * ldx + n];
-  sm[r][c] = acc;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (n < N) {
+    int m = r;
+    for (; m + 96 < M; m += 128) {
+      a0 += X[(int64_t)m * ldx + n];
+      a1 += X[(int64_t)(m + 32) * ldx + n];
+      a2 += X[(int64_t)(m + 64) * ldx + n];
+      a3 += X[(int64_t)(m + 96) * ldx + n];
+    }
+    for (; m < M; m += 32) a0 += X[(int64_t)m * ldx + n];
+  }
+  sm[r][c] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (r == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][c];
+    for (int i = 0; i < 32; ++i) t += sm[i][c];
     out[n] = t * scale;
   }
 }
 inline int launch_colsum(const float* X, int64_t ldx, int M, int N, float* out, float scale, cudaStream_t s) {
-  colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, s>>>(X, ldx, M, N, out, scale);
+  SIG_LAUNCH((colsum_kernel), (unsigned)ceil_div(N, 32), 1024, 0, s, X, ldx, M, N, out, scale);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -185,6 +195,7 @@ static __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* 
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    int d, float* __restrict__ sum_out, float* __restrict__ mean,
                                                                    float* __restrict__ rstd, OutT* __restrict__ y) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
   const float* xr = x + row * d;
@@ -217,6 +228,7 @@ static __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const InT* __
                                                                    const float* __restrict__ rstd, const float* __restrict__ extra,
                                                                    int d, float* __restrict__ dx, float* __restrict__ dyx,
                                                                    float* __restrict__ dyf) {
+  pdl_enter();
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
   const float mu = mean[row], rs = rstd[row];
@@ -242,13 +254,15 @@ static __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const InT* __
 }
 
 // da = dh * gelu'(a)
-static __global__ void gelu_bwd_kernel(const float* dh, const float* __restrict__ a, float* da, int64_t n) {  // in-place safe
+static __global__ void gelu_bwd_kernel(const float* dh, const float* __restrict__ a, float* da, int64_t n) {
+  pdl_enter();  // in-place safe
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) da[i] = dh[i] * gelu_grad_f(a[i]);
 }
 
 // y[i] = a[i] + b[i]
 static __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+  pdl_enter();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) y[i] = a[i] + b[i];
 }
@@ -257,6 +271,7 @@ static __global__ void add_kernel(const float* __restrict__ a, const float* __re
 static __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ W, int64_t ws_i, int64_t ws_k,
                                                           const float* __restrict__ x, const float* __restrict__ add, int n, int kdim,
                                                           float* __restrict__ y) {
+  pdl_enter();
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n) return;
   float a = 0.f;
@@ -265,24 +280,32 @@ static __global__ void __launch_bounds__(256) gemv_kernel(const float* __restric
   if (lane == 0) y[i] = a + (add ? add[i] : 0.f);
 }
 
-// y[i] = sum_k W[k*ld + i] x[k]  (W^T x with coalesced row reads).  grid ceil(n/32), 256 threads = 32 outputs x 8 k-lanes
-static __global__ void __launch_bounds__(256) gemv_t_kernel(const float* __restrict__ W, int64_t ld, const float* __restrict__ x, int n,
-                                                            int kdim, float* __restrict__ y) {
-  __shared__ float sm[8][33];
+// y[i] = sum_k W[k*ld + i] x[k]  (W^T x with coalesced row reads).  grid ceil(n/32), 1024 threads = 32 outputs x 32 k-lanes
+static __global__ void __launch_bounds__(1024) gemv_t_kernel(const float* __restrict__ W, int64_t ld, const float* __restrict__ x, int n,
+                                                             int kdim, float* __restrict__ y) {
+  pdl_enter();
+  __shared__ float sm[32][33];
   const int il = threadIdx.x & 31, r = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + il;
-  float a = 0.f;
-  if (i < n)
-    for (int k = r; k < kdim; k += 8) a = fmaf(W[k * ld + i], x[k], a);
-  sm[r][il] = a;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (i < n) {
+    int k = r;
+    for (; k + 96 < kdim; k += 128) {
+      a0 = fmaf(W[(int64_t)k * ld + i], x[k], a0);
+      a1 = fmaf(W[(int64_t)(k + 32) * ld + i], x[k + 32], a1);
+      a2 = fmaf(W[(int64_t)(k + 64) * ld + i], x[k + 64], a2);
+      a3 = fmaf(W[(int64_t)(k + 96) * ld + i], x[k + 96], a3);
+    }
+    for (; k < kdim; k += 32) a0 = fmaf(W[(int64_t)k * ld + i], x[k], a0);
+  }
+  sm[r][il] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (r == 0 && i < n) {
     float t = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += sm[q][il];
+    for (int q = 0; q < 32; ++q) t += sm[q][il];
     y[i] = t;
   }
 }
-
 
 }  // namespace sig

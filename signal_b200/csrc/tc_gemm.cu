@@ -274,6 +274,7 @@ int tc_gemm(const TcGemmDesc& g, cudaStream_t s) {
 
 // ---- bf16 helpers ---------------------------------------------------------------------------------
 static __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_enter();
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -289,12 +290,49 @@ static __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bflo
 
 int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s) {
   if (n <= 0) return 0;
-  cast_bf16_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(src, dst, n);
+  SIG_LAUNCH((cast_bf16_kernel), (unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s, src, dst, n);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+struct CastJobs {
+  CastJob j[8];
+};
+static __global__ void cast_bf16_multi_kernel(CastJobs jobs) {
+  pdl_enter();
+  const CastJob jb = jobs.j[blockIdx.y];
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < jb.n; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < jb.n) {
+      const float4 v = *reinterpret_cast<const float4*>(jb.src + i);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(jb.dst + i) = o;
+    } else {
+      for (int64_t q = i; q < jb.n; ++q) jb.dst[q] = __float2bfloat16_rn(jb.src[q]);
+    }
+  }
+}
+
+int cast_f32_to_bf16_multi(const CastJob* jobs, int n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (n > 8) return SIG_ERR_SHAPE;
+  CastJobs js{};
+  int64_t mx = 0;
+  for (int i = 0; i < n; ++i) {
+    js.j[i] = jobs[i];
+    mx = jobs[i].n > mx ? jobs[i].n : mx;
+  }
+  int64_t blocks = ceil_div(ceil_div(mx, 4), 256);
+  if (blocks > 1184) blocks = 1184;
+  SIG_LAUNCH((cast_bf16_multi_kernel), dim3((unsigned)blocks, (unsigned)n), 256, 0, s, js);
   SIG_CHECK_LAUNCH();
   return 0;
 }
 
 static __global__ void transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols) {
+  pdl_enter();
   __shared__ float t[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -310,7 +348,7 @@ static __global__ void transpose_bf16_kernel(const float* __restrict__ src, __nv
 
 int transpose_f32_to_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
-  transpose_bf16_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, rows, cols);
+  SIG_LAUNCH((transpose_bf16_kernel), grid, dim3(32, 8), 0, s, src, dst, rows, cols);
   SIG_CHECK_LAUNCH();
   return 0;
 }

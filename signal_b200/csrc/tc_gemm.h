@@ -69,6 +69,13 @@ int tc_gemm(const TcGemmDesc& g, cudaStream_t s);
 
 // bf16 helpers used around the GEMMs
 int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
+// several fp32 -> bf16 casts in one launch (n <= 8 jobs)
+struct CastJob {
+  const float* src;
+  __nv_bfloat16* dst;
+  int64_t n;
+};
+int cast_f32_to_bf16_multi(const CastJob* jobs, int n, cudaStream_t s);
 // dst[c][r] = bf16(src[r][c]) for a row-major [rows, cols] fp32 matrix
 int transpose_f32_to_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, cudaStream_t s);
 

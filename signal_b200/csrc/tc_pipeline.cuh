@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_units = Problem::num_units(p);
 
+  pdl_launch_dependents();   // PDL: the next kernel may be scheduled; it waits for us in its own pdl_wait()
   if (warp == 0 && lane == 0) Problem::prefetch(p);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // setup (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
@@ -163,7 +165,7 @@ int launch(const typename Problem::Params& p, int units, cudaStream_t s) {
   }
   if (units <= 0) return 0;
   const int grid = units < num_sms() ? units : num_sms();
-  pipeline_kernel<BN, Problem><<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(p);
+  SIG_LAUNCH((pipeline_kernel<BN, Problem>), grid, kThreads, Cfg<BN>::kSmemBytes, s, p);
   SIG_CHECK_LAUNCH();
   return 0;
 }
