@@ -222,11 +222,16 @@ def run_gpu(args):
     wg = torch.tensor(W_GAM, device=dev)
     wl = torch.tensor(W_LAM, device=dev)
 
+    head = M.FusionHead(sim, al) if args.fused else None
+
     def fwd_bwd(toks):
         patches = [t[:, 1:] for t in toks]
         cls = [t[:, 0] for t in toks]
-        out = sim(*patches, *cls)
-        gam, lam = al(*patches, stage="together_CLS_Patch")
+        if head is not None:     # one call: AlignM on a side stream next to SIM, one token-gradient writer
+            out, gam, lam = head(*patches, *cls, stage="together_CLS_Patch")
+        else:                    # the reference's two consecutive module calls (make_model.py:191,205)
+            out = sim(*patches, *cls)
+            gam, lam = al(*patches, stage="together_CLS_Patch")
         torch.autograd.backward([out, gam, lam], [cot, wg, wl])
         return out, gam, lam
 
@@ -362,7 +367,7 @@ def run_gpu(args):
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(d), "global_batch": B * world, "parallelism": f"dp{world}",
-                       "launch": "cuda_graph_replay" if args.graph else "eager", "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
+                       "launch": "cuda_graph_replay" if args.graph else "eager", "api": "FusionHead(SIM, AlignM)" if args.fused else "SIM(...); AlignM(...)", "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
                        "grad_allreduce": "NCCL all-reduce of the two flat head-gradient arenas (SIM, AlignM) per step" if world > 1 else "n/a"},
             "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
@@ -385,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager module calls instead of CUDA-graph replays")
+    ap.add_argument("--no-fused", dest="fused", action="store_false",
+                    help="call SIM and AlignM one after the other instead of through signal_b200.FusionHead")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

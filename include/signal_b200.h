@@ -75,6 +75,11 @@ typedef struct sig_token_grads {
   int64_t cls_stride_b[3];
   int32_t accumulate;
   int32_t zero_cls;              /* AlignM: also write zeros to dcls rows when dcls != NULL */
+  /* Optional cross-stream ordering when SIM and AlignM backward run concurrently on two streams and
+   * share one gradient map (cudaEvent_t, may be NULL): the call makes its stream wait on `wait_event`
+   * before its first write to dpatch/dcls and records `done_event` after its last one. */
+  void* wait_event;
+  void* done_event;
 } sig_token_grads;
 
 /* Optional cache of the frozen token_selection parameters folded together (they never receive a

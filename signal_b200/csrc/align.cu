@@ -752,6 +752,7 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
   }
   // ---- single writer per modality
   SIG_PHASE("align_write");
+  if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
   const bool zero_cls = dtok->zero_cls != 0;
   for (int m = 0; m < 3; ++m) {
     const float* dense = do_lam ? c.dXf + m * BL * d : nullptr;
@@ -770,6 +771,7 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
                                                     static_cast<float*>(dtok->dcls[m]), dtok->cls_stride_b[m], dtok->accumulate);
     SIG_CHECK_LAUNCH();
   }
+  if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
   return 0;
 }
 

@@ -748,6 +748,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_LAUNCH((scale_scalar_kernel), 1, 1, 0, s, c.dtau, dlosses, dp->contra_temp);
     SIG_CHECK_LAUNCH();
   }
+  if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
   if (dtok->zero_cls && !dtok->accumulate) {
     SIG_LAUNCH((zero_cls_kernel<__nv_bfloat16>), dim3(B, 3), 64, 0, s, gp, d);
     SIG_CHECK_LAUNCH();
@@ -763,6 +764,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
                                                                     dtok->accumulate);
       SIG_CHECK_LAUNCH();
     }
+    if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
     return 0;
   }
   const Geo g = make_geo(h, w);
@@ -804,6 +806,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_TRY(tc_gemm(t, s));
     SIG_LAUNCH((lam_sparse_add_kernel<__nv_bfloat16>), dim3(B, 3), cthreads, 0, s, gp, c.o, c.dS, g, B, d);
     SIG_CHECK_LAUNCH();
+    if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
   }
   {
     SIG_PHASE("lam_offsetnet_bwd_dw");

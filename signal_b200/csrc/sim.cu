@@ -1088,9 +1088,13 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
     gp.accumulate = dtok->accumulate;
     SIG_LAUNCH((write_cls_grads_kernel<__nv_bfloat16>), dim3(B, 3), 96, 0, s, gp, c.dr1, d);
     SIG_CHECK_LAUNCH();
+    if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
     return 0;
   }
-  return write_token_grads(dtok, tok->dtype, c.dXf, c.dr1, B, L, d, s);
+  if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
+  SIG_TRY(write_token_grads(dtok, tok->dtype, c.dXf, c.dr1, B, L, d, s));
+  if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
+  return 0;
 }
 
 int sim_select(const sig_tokens* tok, const sig_sim_params* p, int which, int k1, int k2, int max_keep, float* masks,

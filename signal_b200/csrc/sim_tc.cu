@@ -339,6 +339,7 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
     p.Ptok = k.Ptok; p.delta = k.delta; p.PdS = k.PdS; p.dST = k.dST;
     SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s)));
   }
+  if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
   {
     DxParams p{};
     SIG_TRY(tc::make_map_2d(k.PdS, (int64_t)B * 384, 64, 64, 128, &p.ta));

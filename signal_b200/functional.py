@@ -384,3 +384,91 @@ class VolumeFunction(torch.autograd.Function):
                                          dv.data_ptr(), da.data_ptr(), ws.data_ptr(), nbytes, dev.index, L_.stream_ptr(dev)),
                      "sig_volume3_bwd")
         return dl.to(ctx.dtypes[0]), dv.to(ctx.dtypes[1]), da.to(ctx.dtypes[2])
+
+
+# ------------------------------------------------------------------------------------------
+# Whole head: SIM and AlignM of one step as ONE autograd node
+# ------------------------------------------------------------------------------------------
+class HeadFunction(torch.autograd.Function):
+    """Select_Interactive_Module.forward + AlignmentM.forward on the same three [B,1+L,d] token maps.
+
+    The two modules are independent until their gradients meet in the token maps, so AlignM runs on a
+    side stream concurrently with SIM (forward and backward), and the backward writes ONE gradient
+    map per modality: AlignM's kernels overwrite it, SIM's token-gradient GEMM accumulates on top
+    (ordered by a CUDA event).  tensors: 3 token maps, 16 SIM parameters, 22 AlignM parameters and,
+    optionally, the 4 tensors of the folded-selection cache.
+    """
+
+    @staticmethod
+    def forward(ctx, h: int, w: int, do_lam: bool, k1: int, k2: int, max_keep: int, flags: int, side, event, *tensors):
+        toks, sp, ap, fold = tensors[:3], tensors[3:19], tensors[19:41], tensors[41:]
+        lib = L_.load()
+        patches, cls = _split_tokens(True, toks)
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        dt = L_.dtype_enum(patches[0])
+        tok = L_.tokens_struct(patches, cls)
+        tok_a = L_.tokens_struct(patches, None)
+        sprm = L_.sim_params_struct(sp, fold if len(fold) == 4 else None)
+        mods = [ap[1 + 7 * m: 8 + 7 * m] for m in range(3)]
+        for t in ap:
+            L_._f32c(t)
+        aprm = L_.align_params_struct(ap[0], mods)
+        out = torch.empty(B, 3 * d, dtype=patches[0].dtype, device=dev)
+        masks = torch.empty(3, B, L, dtype=torch.float32, device=dev)
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        nb_s = L_.ctx_bytes(L_.CTX_SIM, B, L, d, dt, flags)
+        nb_a = L_.ctx_bytes(L_.CTX_ALIGN, B, L, d, dt, flags)
+        buf_s = torch.empty(nb_s, dtype=torch.uint8, device=dev)
+        buf_a = torch.empty(nb_a, dtype=torch.uint8, device=dev)
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            side.wait_stream(main)
+            L_.check(lib.sig_align_fwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), losses.data_ptr(), buf_a.data_ptr(), nb_a,
+                                       flags, dev.index, side.cuda_stream), "sig_align_fwd")
+            L_.check(lib.sig_sim_fwd(C.byref(tok), C.byref(sprm), k1, k2, max_keep, out.data_ptr(), masks.data_ptr(),
+                                     buf_s.data_ptr(), nb_s, flags, dev.index, main.cuda_stream), "sig_sim_fwd")
+            main.wait_stream(side)
+        ctx.save_for_backward(*toks, *sp, *ap, buf_s, buf_a)
+        ctx.cfg = (h, w, do_lam, flags, side, event, len(fold))
+        ctx.mark_non_differentiable(masks)
+        return out, masks, losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, dout, _dmasks, dgam, dlam):
+        h, w, do_lam, flags, side, event, nfold = ctx.cfg
+        saved = ctx.saved_tensors
+        toks, sp, ap, buf_s, buf_a = saved[:3], saved[3:19], saved[19:41], saved[41], saved[42]
+        lib = L_.load()
+        patches, cls = _split_tokens(True, toks)
+        B, L, d = patches[0].shape
+        dev = patches[0].device
+        z = torch.zeros((), dtype=torch.float32, device=dev)
+        dl = torch.stack([z if dgam is None else dgam.float(), z if dlam is None else dlam.float()]).contiguous()
+        dout = (torch.zeros(B, 3 * d, dtype=patches[0].dtype, device=dev) if dout is None
+                else dout.to(patches[0].dtype).contiguous())
+        dtoks = [torch.empty_like(t) for t in toks]
+        dpatch, dcls = [t[:, 1:] for t in dtoks], [t[:, 0] for t in dtoks]
+        _, pg_s = _arena(_SIM_GRAD_SHAPES(d), dev)
+        flat_a, pg_a = _arena(_align_grad_shapes(d), dev)
+        if not do_lam:
+            flat_a.zero_()
+        tok = L_.tokens_struct(patches, cls)
+        tok_a = L_.tokens_struct(patches, None)
+        sprm = L_.sim_params_struct(sp)
+        mods = [ap[1 + 7 * m: 8 + 7 * m] for m in range(3)]
+        aprm = L_.align_params_struct(ap[0], mods)
+        gs_s = L_.sim_grads_struct(pg_s)
+        gs_a = L_.align_params_struct(pg_a[0], [pg_a[1 + 7 * m: 8 + 7 * m] for m in range(3)], cls=L_.SigAlignParamGrads)
+        evh = event.cuda_event
+        tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=False, zero_cls=True, done_event=evh)   # AlignM overwrites ...
+        tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=True, wait_event=evh)                   # ... SIM adds on top
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            side.wait_stream(main)
+            L_.check(lib.sig_align_bwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg_a), C.byref(gs_a),
+                                       buf_a.data_ptr(), buf_a.numel(), flags, dev.index, side.cuda_stream), "sig_align_bwd")
+            L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(sprm), dout.data_ptr(), C.byref(tg_s), C.byref(gs_s), buf_s.data_ptr(),
+                                     buf_s.numel(), flags, dev.index, main.cuda_stream), "sig_sim_bwd")
+            main.wait_stream(side)
+        return (None,) * 9 + tuple(dtoks) + (None,) * 4 + tuple(pg_s) + tuple(pg_a) + (None,) * nfold

@@ -30,7 +30,8 @@ class SigTokens(C.Structure):
 
 class SigTokenGrads(C.Structure):
     _fields_ = [("dpatch", _VP3), ("dcls", _VP3), ("patch_stride_b", _I64x3), ("patch_stride_l", _I64x3),
-                ("cls_stride_b", _I64x3), ("accumulate", C.c_int32), ("zero_cls", C.c_int32)]
+                ("cls_stride_b", _I64x3), ("accumulate", C.c_int32), ("zero_cls", C.c_int32),
+                ("wait_event", C.c_void_p), ("done_event", C.c_void_p)]
 
 
 SIM_PARAM_FIELDS = ["sel_wq", "sel_bq", "sel_wk", "sel_bk", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b",
@@ -169,7 +170,8 @@ def tokens_struct(patches: Sequence[torch.Tensor], cls: Optional[Sequence[torch.
 
 
 def token_grads_struct(dpatch: Sequence[torch.Tensor], dcls: Optional[Sequence[torch.Tensor]],
-                       accumulate: bool = False, zero_cls: bool = False) -> SigTokenGrads:
+                       accumulate: bool = False, zero_cls: bool = False, wait_event: Optional[int] = None,
+                       done_event: Optional[int] = None) -> SigTokenGrads:
     g = SigTokenGrads()
     for m in range(3):
         g.dpatch[m] = dpatch[m].data_ptr()
@@ -180,6 +182,8 @@ def token_grads_struct(dpatch: Sequence[torch.Tensor], dcls: Optional[Sequence[t
             g.cls_stride_b[m] = dcls[m].stride(0)
     g.accumulate = int(accumulate)
     g.zero_cls = int(zero_cls)
+    g.wait_event = wait_event
+    g.done_event = done_event
     return g
 
 

@@ -20,7 +20,7 @@ import torch.nn as nn
 from . import functional as F_
 
 __all__ = ["TokenSelection", "ModalInteractive", "LayerNorm", "Select_Interactive_Module", "AlignmentM", "DA_sample",
-           "volume_computation3"]
+           "volume_computation3", "FusionHead"]
 
 
 def _packed_base(patch: torch.Tensor, glob: torch.Tensor):
@@ -261,3 +261,53 @@ class AlignmentM(nn.Module):
 def volume_computation3(language, video, audio):
     """utils/volume.py:14-62 -> [B1,B2] fp32."""
     return F_.VolumeFunction.apply(language, video, audio)
+
+
+class FusionHead:
+    """SIM + AlignM of one training step as a single call.
+
+    ``head = FusionHead(model.SIM, model.AlignM)`` holds references to the two drop-in modules (it owns
+    no parameters, so checkpoints are unchanged) and replaces the two consecutive calls of
+    make_model.py:191,205::
+
+        vars_total = self.SIM(rgb_patch, ni_patch, ti_patch, RGB_global, NI_global, TI_global)
+        loss_area, patch_loss = self.AlignM(rgb_patch, ni_patch, ti_patch, stage=...)
+
+    by ``vars_total, loss_area, patch_loss = head(rgb_patch, ..., TI_global, stage=...)``.  AlignM then runs
+    on a side stream next to SIM, and the backward writes one token-gradient map per modality.
+    Falls back to the two module calls when the six inputs are not views of three [B,1+L,d] maps.
+    """
+
+    def __init__(self, sim: "Select_Interactive_Module", align: "AlignmentM"):
+        self.sim, self.align = sim, align
+        self._side = {}
+
+    def _stream(self, dev):
+        st = self._side.get(dev)
+        if st is None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))       # materialise the underlying cudaEvent_t
+            st = (torch.cuda.Stream(dev), ev)
+            self._side[dev] = st
+        return st
+
+    def __call__(self, rgb_patch, ni_patch, ti_patch, rgb_global, ni_global, ti_global, stage="together_CLS_Patch"):
+        sim, al = self.sim, self.align
+        ts, mi = sim.token_selection, sim.modal_interactive
+        bases = [_packed_base(p, g) for p, g in ((rgb_patch, rgb_global), (ni_patch, ni_global), (ti_patch, ti_global))]
+        hooked = ts._forward_hooks or ts._forward_pre_hooks or mi._forward_hooks or mi._forward_pre_hooks
+        patched = "Cls_Align" in al.__dict__ or "patch_Align" in al.__dict__
+        if any(b is None for b in bases) or hooked or patched or not rgb_patch.is_cuda:
+            out = sim(rgb_patch, ni_patch, ti_patch, rgb_global, ni_global, ti_global)
+            res = al(rgb_patch, ni_patch, ti_patch, stage=stage)
+            return (out, res, None) if stage == "CLS" else (out, res[0], res[1])
+        L = rgb_patch.size(1)
+        side, ev = self._stream(rgb_patch.device)
+        params = [p.detach() for p in ts._sel_params()] + mi._attn_params() + al._params()
+        flags = sim.flags | al.flags
+        if rgb_patch.dtype == torch.bfloat16 and not (flags & 1):
+            params = params + list(ts._selection_fold())
+        out, masks, gam, lam = F_.HeadFunction.apply(al.h, al.w, stage != "CLS", ts.k1, ts.k2, ts._max_keep(L), flags, side, ev,
+                                                     *bases, *params)
+        ts.last_masks = {"RGB": masks[0].unsqueeze(-1), "NI": masks[1].unsqueeze(-1), "TI": masks[2].unsqueeze(-1)}
+        return (out, gam, None) if stage == "CLS" else (out, gam, lam)

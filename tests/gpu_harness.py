@@ -16,7 +16,7 @@ def build_modules(c, sim_p, al_p, device="cuda"):
     return sim.to(device), al.to(device)
 
 
-def cuda_record(c, dtype=torch.float32, packed=True, flags=0, sim_p=None, al_p=None, toks=None, cot=None):
+def cuda_record(c, dtype=torch.float32, packed=True, flags=0, sim_p=None, al_p=None, toks=None, cot=None, fused=False):
     if sim_p is None:
         sim_p, al_p, toks, cot = gu.case_inputs(c)
     sim, al = build_modules(c, sim_p, al_p)
@@ -26,9 +26,12 @@ def cuda_record(c, dtype=torch.float32, packed=True, flags=0, sim_p=None, al_p=N
     cot = cot.to("cuda")
     patches = [t[:, 1:] for t in toks]
     cls = [t[:, 0] for t in toks]
-    out = sim(*patches, *cls)
+    if fused:
+        out, gam, lam = M.FusionHead(sim, al)(*patches, *cls, stage="together_CLS_Patch")
+    else:
+        out = sim(*patches, *cls)
+        gam, lam = al(*patches, stage="together_CLS_Patch")
     masks = sim.token_selection.last_masks
-    gam, lam = al(*patches, stage="together_CLS_Patch")
     rec = {
         "sim_out": out.detach().float().cpu().numpy(),
         "masks": np.stack([masks[k][..., 0].cpu().numpy().astype(np.uint8) for k in ("RGB", "NI", "TI")]),

@@ -120,3 +120,27 @@ def test_bf16_full_batch_b128_matches_oracle():
     flips = int((got["masks"] != ref["masks"]).sum())
     assert flips <= 4, f"{flips} mask flips at B=128 bf16"
     h.compare_records(got, ref, BF16_TOL, check_masks=False, label="B128 d768 bf16", lam_flip_robust=True)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("name", ["rgbnt201_d512", "vehicle_d512"])
+def test_fusion_head_matches_the_two_modules(name, dtype, tol):
+    """FusionHead (AlignM on a side stream, one token-gradient writer) vs calling SIM and AlignM separately."""
+    h = _harness()
+    c = BF16_CASES[name]
+    sim_p, al_p, toks, cot = _bf16_inputs(c)
+    toks = [t.to(dtype) for t in toks]
+    a = h.cuda_record(c, dtype, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot, fused=True)
+    b = h.cuda_record(c, dtype, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot, fused=False)
+    h.compare_records(a, b, tol, check_masks=True, label=name + " fused-vs-separate")
+    # all three objectives at once: the shared gradient map must hold the SUM of the three contributions
+    import gpu_harness
+    from signal_b200 import modules as M
+    sim, al = gpu_harness.build_modules(c, sim_p, al_p)
+    tk = [t.to("cuda", dtype).requires_grad_(True) for t in toks]
+    out, gam, lam = M.FusionHead(sim, al)(*[t[:, 1:] for t in tk], *[t[:, 0] for t in tk])
+    torch.autograd.backward([out, gam, lam], [cot.to("cuda", dtype), torch.tensor(0.2, device="cuda"), torch.tensor(0.2, device="cuda")])
+    for m in range(3):
+        want = a["dtok_full_sim"][m] + 0.2 * a["dtok_full_gam"][m] + 0.2 * a["dtok_full_lam"][m]
+        got = tk[m].grad.float().cpu()
+        assert float((got - want).norm() / want.norm()) < (2e-2 if dtype == torch.bfloat16 else 1e-5)
