@@ -687,6 +687,7 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     }
     t.ldc = d; t.out_bf16 = 1;
     t.bn = (d % 256 == 0) ? 256 : 128;
+    t.mt = 1;   // (mt = 2, 256 x 256 units, measured slower: the single TMEM buffer serialises the epilogue)
     SIG_TRY(tc_gemm(t, s));
   }
   {
@@ -803,6 +804,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.c_stride_b = dtok->patch_stride_b[0]; t.c_stride_l = dtok->patch_stride_l[0];
     t.accumulate = dtok->accumulate;
     t.bn = (d % 256 == 0) ? 256 : 128;
+    t.mt = 1;   // (mt = 2, 256 x 256 units, measured slower: the single TMEM buffer serialises the epilogue)
     SIG_TRY(tc_gemm(t, s));
     SIG_LAUNCH((lam_sparse_add_kernel<__nv_bfloat16>), dim3(B, 3), cthreads, 0, s, gp, c.o, c.dS, g, B, d);
     SIG_CHECK_LAUNCH();
@@ -818,7 +820,9 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.M = d; t.N = d; t.K = (int)BL; t.batch = 3;
     for (int m = 0; m < 3; ++m) t.C[m] = c.dWf + m * dd;
     t.ldc = d;
-    const int tiles = (int)(ceil_div(d, 128) * ceil_div(d, 128)) * 3;
+    t.bn = 128;
+    t.mt = 1;
+    const int tiles = (int)(ceil_div(d, 128 * t.mt) * ceil_div(d, t.bn)) * 3;
     int ks = (2 * 148 + tiles - 1) / tiles;
     if (ks < 1) ks = 1;
     t.ksplit = ks;

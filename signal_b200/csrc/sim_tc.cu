@@ -53,7 +53,7 @@ struct RowsProblem {
     tc::load_kmajor_tok(&p.ta[z], sa, bar, kb * BK, b, 1);
     tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, b * 64 + p.b_row_off);
   }
-  __device__ static void epilogue(const Params& p, int unit, uint32_t tmem_acc, int q, int lane) {
+  __device__ static void epilogue(const Params& p, int unit, int /*mt*/, uint32_t tmem_acc, int q, int lane) {
     const int b = unit / 3, z = unit % 3;
     const int l = q * 32 + lane;
     const int j = z * 128 + l;
@@ -124,7 +124,7 @@ struct ColsProblem {
     tc::load_mnmajor_tok(&p.ta[kb >> 1], sa, bar, c0, (kb & 1) * 64, b, 128);
     tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, b * 32);
   }
-  __device__ static void epilogue(const Params& p, int unit, uint32_t tmem_acc, int q, int lane) {
+  __device__ static void epilogue(const Params& p, int unit, int /*mt*/, uint32_t tmem_acc, int q, int lane) {
     const int mt = (p.d + 127) / 128;
     const int b = unit / mt, c = (unit % mt) * 128 + q * 32 + lane;
     uint32_t r[32];
@@ -166,7 +166,7 @@ struct DxProblem {
     tc::load_kmajor_2d(&p.ta, sa, bar, 0, b * 384 + z * 128);
     tc::load_mnmajor_2d(&p.tb, sb, bar, n0, b * 64, BN);
   }
-  __device__ static void epilogue(const Params& p, int unit, uint32_t tmem_acc, int q, int lane) {
+  __device__ static void epilogue(const Params& p, int unit, int /*mt*/, uint32_t tmem_acc, int q, int lane) {
     const int nt = (p.d + BN - 1) / BN;
     const int n0 = (unit % nt) * BN, bz = unit / nt, b = bz / 3, z = bz % 3;
     const int l = q * 32 + lane;
@@ -306,7 +306,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
     SIG_TRY(tc::make_map_2d(k.DXQT, (int64_t)B * 64, d, d, 32, &p.tb));
     p.B = B; p.d = d; p.L = L; p.b_row_off = 32; p.mode = 0;
     p.maskf = k.maskf; p.catt = k.catt; p.S32 = k.S32;
-    SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s)));
+    SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s, d / 64)));
   }
   {
     static bool attr = false;
@@ -322,7 +322,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
     SIG_TRY(make_tok_maps(tok, 64, p.ta));
     SIG_TRY(tc::make_map_2d(k.PT, (int64_t)B * 32, 384, 384, 32, &p.tb));
     p.B = B; p.d = d; p.out = k.xbar;
-    SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s)));
+    SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s, 6)));
   }
   return 0;
 }
@@ -337,7 +337,7 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
     SIG_TRY(tc::make_map_2d(k.DXQT, (int64_t)B * 64, d, d, 32, &p.tb));
     p.B = B; p.d = d; p.L = L; p.b_row_off = 0; p.mode = 1;
     p.Ptok = k.Ptok; p.delta = k.delta; p.PdS = k.PdS; p.dST = k.dST;
-    SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s)));
+    SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s, d / 64)));
   }
   if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
   {
@@ -351,15 +351,15 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
       p.psl[z] = dtok->patch_stride_l[z];
     }
     p.accumulate = dtok->accumulate;
-    if (d % 256 == 0) SIG_TRY((tc::launch<256, DxProblem<256>>(p, 3 * B * (d / 256), s)));
-    else SIG_TRY((tc::launch<128, DxProblem<128>>(p, 3 * B * (int)ceil_div(d, 128), s)));
+    if (d % 256 == 0) SIG_TRY((tc::launch<256, DxProblem<256>>(p, 3 * B * (d / 256), s, 1)));
+    else SIG_TRY((tc::launch<128, DxProblem<128>>(p, 3 * B * (int)ceil_div(d, 128), s, 1)));
   }
   {
     ColsParams p{};
     SIG_TRY(make_tok_maps(tok, 64, p.ta));
     SIG_TRY(tc::make_map_2d(k.dST, (int64_t)B * 32, 384, 384, 32, &p.tb));
     p.B = B; p.d = d; p.out = k.dqt;
-    SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s)));
+    SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s, 6)));
   }
   return 0;
 }

@@ -3,6 +3,7 @@
 // operands are described by TMA tensor maps so strided token views are consumed in place.
 #include "tc_gemm.h"
 
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_pipeline.cuh"
@@ -55,6 +56,14 @@ int make_map_tok(const void* ptr, int64_t B, int64_t d, int64_t stride_b, int64_
   return encode(const_cast<void*>(ptr), 3, gdim, gstr, box, out);
 }
 
+int stage_override() {
+  static const int v = [] {
+    const char* e = getenv("SIG_TC_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -94,7 +103,7 @@ struct TcKernelParams {
   float* pre[8];
 };
 
-template <int BN, bool AMN, bool BMN>
+template <int BN, bool AMN, bool BMN, int MT = 1>
 struct GemmProblem {
   using Params = TcKernelParams;
   static constexpr int kAMn = AMN, kBMn = BMN;
@@ -114,7 +123,7 @@ struct GemmProblem {
     const int ks = r % p.ksplit;
     r /= p.ksplit;
     n0 = (r % p.tiles_n) * BN;
-    m0 = (r / p.tiles_n) * BM;
+    m0 = (r / p.tiles_n) * BM * MT;
     kb0 = ks * per;
     kb1 = min(p.kblocks, kb0 + per);
   }
@@ -132,12 +141,14 @@ struct GemmProblem {
   __device__ static void load(const Params& p, int unit, int kb, uint8_t* sa, uint8_t* sb, uint64_t* bar) {
     int z, m0, n0, kb0, kb1;
     decode(p, unit, z, m0, n0, kb0, kb1);
-    load_one(&p.ta[z], p.a_mode, sa, bar, m0, kb, BM);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) load_one(&p.ta[z], p.a_mode, sa + mt * tc::kATileBytes, bar, m0 + mt * BM, kb, BM);
     load_one(&p.tb[z], p.b_mode, sb, bar, n0, kb, BN);
   }
-  __device__ static void epilogue(const Params& p, int unit, uint32_t tmem_acc, int q, int lane) {
+  __device__ static void epilogue(const Params& p, int unit, int mt, uint32_t tmem_acc, int q, int lane) {
     int z, m0, n0, kb0, kb1;
     decode(p, unit, z, m0, n0, kb0, kb1);
+    m0 += mt * BM;
       const int row = m0 + q * 32 + lane;
       const float* bias = p.bias[z];
       const long long row_off = p.c_tok ? (long long)(row >> 7) * p.c_stride_b + (long long)(row & 127) * p.c_stride_l
@@ -158,30 +169,71 @@ struct GemmProblem {
           const bool full_cols = col0 + 32 <= p.N;
           if (p.ksplit > 1) {
             float* dst = static_cast<float*>(p.C[z]) + row_off + col0;
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+            if (full_cols && vec_ok) {   // 16-byte vector reductions (red.global.add.v4.f32)
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                             "f"(v[j + 3])
+                             : "memory");
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+            }
           } else {
             if (bias) {
+              if (full_cols) {   // unpredicated 16-byte loads, all issued before the first use
+                float4 b4[8];
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] += bias[col0 + j];
+                for (int j = 0; j < 8; ++j) b4[j] = *reinterpret_cast<const float4*>(bias + col0 + 4 * j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] += b4[j].x; v[4 * j + 1] += b4[j].y; v[4 * j + 2] += b4[j].z; v[4 * j + 3] += b4[j].w;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) v[j] += bias[col0 + j];
+              }
             }
             if (p.pre[z]) {
               float* pd = p.pre[z] + (long long)row * p.ldc + col0;
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) pd[j] = v[j];
+              if (full_cols && vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(pd + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) pd[j] = v[j];
+              }
             }
             if (p.act == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
             }
             if (rvec) {
+              if (full_cols) {
+                float4 r4[8];
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] = fmaf(rscale, rvec[col0 + j], v[j]);
+                for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(rvec + col0 + 4 * j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] = fmaf(rscale, r4[j].x, v[4 * j]); v[4 * j + 1] = fmaf(rscale, r4[j].y, v[4 * j + 1]);
+                  v[4 * j + 2] = fmaf(rscale, r4[j].z, v[4 * j + 2]); v[4 * j + 3] = fmaf(rscale, r4[j].w, v[4 * j + 3]);
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) v[j] = fmaf(rscale, rvec[col0 + j], v[j]);
+              }
             }
             if (p.C2[z]) {
               __nv_bfloat16* d2 = static_cast<__nv_bfloat16*>(p.C2[z]) + (long long)row * p.ldc2 + col0;
+              if (full_cols && (p.ldc2 % 8) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  float t[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) t[i] = v[j + i];
+                  store8(d2 + j, t);
+                }
+              } else
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) d2[j] = __float2bfloat16_rn(v[j]);
             }
@@ -228,7 +280,7 @@ struct GemmProblem {
   }
 };
 
-template <int BN>
+template <int BN, int MT>
 int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
   TcKernelParams p{};
   auto mk = [&](const TcOperand& o, int z, int extent, CUtensorMap* out) -> int {
@@ -251,16 +303,17 @@ int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
   p.ldc = g.ldc; p.out_bf16 = g.out_bf16; p.alpha = g.alpha; p.act = g.act; p.ksplit = g.ksplit < 1 ? 1 : g.ksplit;
   p.c_tok = g.c_tok; p.c_stride_b = g.c_stride_b; p.c_stride_l = g.c_stride_l;
   p.rowvec_scale = g.rowvec_scale; p.accumulate = g.accumulate; p.ldc2 = g.ldc2;
-  p.tiles_m = (int)ceil_div(g.M, BM);
+  p.tiles_m = (int)ceil_div(g.M, BM * MT);
   p.tiles_n = (int)ceil_div(g.N, BN);
   p.kblocks = (int)ceil_div(g.K, BK);
   if (p.ksplit > p.kblocks) p.ksplit = p.kblocks;
   const int units = p.tiles_m * p.tiles_n * p.ksplit * p.batch;
   const bool amn = g.A.mode >= TC_MN2D, bmn = g.B.mode >= TC_MN2D;
-  if (amn && bmn) return tc::launch<BN, GemmProblem<BN, true, true>>(p, units, s);
-  if (amn) return tc::launch<BN, GemmProblem<BN, true, false>>(p, units, s);
-  if (bmn) return tc::launch<BN, GemmProblem<BN, false, true>>(p, units, s);
-  return tc::launch<BN, GemmProblem<BN, false, false>>(p, units, s);
+  const int kpu = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  if (amn && bmn) return tc::launch<BN, GemmProblem<BN, true, true, MT>, MT>(p, units, s, kpu);
+  if (amn) return tc::launch<BN, GemmProblem<BN, true, false, MT>, MT>(p, units, s, kpu);
+  if (bmn) return tc::launch<BN, GemmProblem<BN, false, true, MT>, MT>(p, units, s, kpu);
+  return tc::launch<BN, GemmProblem<BN, false, false, MT>, MT>(p, units, s, kpu);
 }
 
 }  // namespace
@@ -268,8 +321,9 @@ int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
 int tc_gemm(const TcGemmDesc& g, cudaStream_t s) {
   if (g.M < 1 || g.N < 1 || g.K < 1 || g.batch < 1 || g.batch > 8) return SIG_ERR_SHAPE;
   if (g.ksplit > 1 && (g.out_bf16 || g.act)) return SIG_ERR_SHAPE;
-  if (g.bn == 256) return launch_gemm_bn<256>(g, s);
-  return launch_gemm_bn<128>(g, s);
+  if (g.bn == 256 && g.mt == 2) return launch_gemm_bn<256, 2>(g, s);
+  if (g.bn == 256) return launch_gemm_bn<256, 1>(g, s);
+  return launch_gemm_bn<128, 1>(g, s);
 }
 
 // ---- bf16 helpers ---------------------------------------------------------------------------------

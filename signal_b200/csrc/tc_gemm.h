@@ -34,6 +34,7 @@ struct TcGemmDesc {
   int act;                  // 0 none, 1 GELU
   int ksplit;               // > 1: fp32 atomic accumulation into a pre-zeroed C (no bias / act / bf16)
   int bn;                   // 128 or 256 (N tile)
+  int mt;                   // 1 or 2 (with bn == 256): 128-row M tiles per work unit sharing one B tile
   // token-strided output: row = (b, l) with l in [0,128): element (row, n) at C + b*c_stride_b + l*c_stride_l + n
   int c_tok;
   int64_t c_stride_b, c_stride_l;
@@ -48,7 +49,7 @@ struct TcGemmDesc {
 
 inline TcGemmDesc tc_desc() {
   TcGemmDesc g{};
-  g.batch = 1; g.alpha = 1.f; g.ksplit = 1; g.bn = 128;
+  g.batch = 1; g.alpha = 1.f; g.ksplit = 1; g.bn = 128; g.mt = 1;
   return g;
 }
 inline TcOperand tc_k2d(const void* p, int64_t rows, int64_t k, int64_t ld) {

@@ -19,15 +19,22 @@ namespace tc {
 
 constexpr int BM = 128, BK = 64;
 constexpr int kThreads = 256;
-constexpr int kABytes = BM * BK * 2;
+constexpr int kATileBytes = BM * BK * 2;
 
-template <int BN>
+// MT = number of 128-row M tiles a CTA computes against ONE B tile (MT = 2: a 256 x BN output per
+// unit; the B operand is fetched once for both, which raises the FLOPs per byte pulled from L2 --
+// these GEMMs are bound by the ~8.7 TB/s L2 -> SM operand stream, not by the tensor pipe).
+template <int BN, int MT = 1>
 struct Cfg {
+  static constexpr int kABytes = MT * kATileBytes;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN <= 32 ? 8 : (BN <= 128 ? 6 : 4);
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kStages = (220 * 1024) / kStageBytes > 8 ? 8 : (220 * 1024) / kStageBytes;
+  static constexpr int kAccCols = MT * BN;                              // fp32 accumulator columns of one unit
+  static constexpr int kAccBufs = 2 * kAccCols <= 512 ? 2 : 1;          // double buffered when TMEM allows
+  static constexpr int kTmemCols = kAccBufs * kAccCols < 32 ? 32 : kAccBufs * kAccCols;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 + 256; }
 };
 
 // Loads one operand tile of `extent` M/N-rows for k-block starting at element k0.
@@ -46,16 +53,16 @@ __device__ __forceinline__ void load_mnmajor_tok(const CUtensorMap* tm, uint8_t*
   for (int j = 0; j < extent / 64; ++j) ptx::tma_load_3d(dst + j * 64 * BK * 2, tm, bar, mn0 + 64 * j, l0, sample);
 }
 
-template <int BN, class Problem>
-__global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_constant__ typename Problem::Params p) {
-  using C = Cfg<BN>;
+template <int BN, int MT, class Problem>
+__global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_constant__ typename Problem::Params p, const int nstages) {
+  using C = Cfg<BN, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // 1024 B aligned (128B-swizzle atoms)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nstages * C::kStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + C::kStages;
-  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* empty = bars + nstages;
+  uint64_t* tmem_full = bars + 2 * nstages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -65,11 +72,11 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
   pdl_launch_dependents();   // PDL: the next kernel may be scheduled; it waits for us in its own pdl_wait()
   if (warp == 0 && lane == 0) Problem::prefetch(p);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < nstages; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C::kAccBufs; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 128);
     }
@@ -89,11 +96,11 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
       int kb0, kb1;
       Problem::krange(p, unit, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const uint32_t stage = it % C::kStages, ph = (it / C::kStages) & 1;
+        const uint32_t stage = it % nstages, ph = (it / nstages) & 1;
         ptx::mbar_wait(&empty[stage], ph ^ 1);
         ptx::mbar_expect_tx(&full[stage], C::kStageBytes);
         uint8_t* sa = smem + stage * C::kStageBytes;
-        Problem::load(p, unit, kb, sa, sa + kABytes, &full[stage]);
+        Problem::load(p, unit, kb, sa, sa + C::kABytes, &full[stage]);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -108,21 +115,24 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++tcount) {
       int kb0, kb1;
       Problem::krange(p, unit, kb0, kb1);
-      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const uint32_t acc = tcount % C::kAccBufs, aph = (tcount / C::kAccBufs) & 1;
       ptx::mbar_wait(&tmem_empty[acc], aph ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const uint32_t stage = it % C::kStages, ph = (it / C::kStages) & 1;
+        const uint32_t stage = it % nstages, ph = (it / nstages) & 1;
         ptx::mbar_wait(&full[stage], ph);
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(smem + stage * C::kStageBytes);
-        const uint32_t b_addr = a_addr + kABytes;
+        const uint32_t b_addr = a_addr + C::kABytes;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = ptx::make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024);
           const uint64_t db = ptx::make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024);
-          ptx::umma_bf16(d_tmem, da, db, idesc, kb > kb0 || k > 0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = ptx::make_smem_desc(a_addr + mt * kATileBytes + k * a_kstep, a_lbo, 1024);
+            ptx::umma_bf16(d_tmem + mt * BN, da, db, idesc, kb > kb0 || k > 0);
+          }
         }
         ptx::umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
       }
@@ -133,10 +143,12 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
     const int q = warp & 3;
     uint32_t tcount = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++tcount) {
-      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const uint32_t acc = tcount % C::kAccBufs, aph = (tcount / C::kAccBufs) & 1;
       ptx::mbar_wait(&tmem_full[acc], aph);
       ptx::tc_fence_after();
-      Problem::epilogue(p, unit, tmem_base + acc * BN + ((uint32_t)(q * 32) << 16), q, lane);
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt)
+        Problem::epilogue(p, unit, mt, tmem_base + acc * C::kAccCols + mt * BN + ((uint32_t)(q * 32) << 16), q, lane);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
@@ -156,16 +168,24 @@ int make_map_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box
 int make_map_tok(const void* ptr, int64_t B, int64_t d, int64_t stride_b, int64_t stride_l, int box_rows, CUtensorMap* out);
 int num_sms();
 
-template <int BN, class Problem>
-int launch(const typename Problem::Params& p, int units, cudaStream_t s) {
+int stage_override();   // SIG_TC_STAGES in the environment (tuning aid), 0 = automatic
+
+// kblocks_per_unit: K-blocks one work unit runs through; short K loops get a shallower ring (less
+// shared memory to carve out, fewer barriers to initialise) -- it only needs to cover the load latency.
+template <int BN, class Problem, int MT = 1>
+int launch(const typename Problem::Params& p, int units, cudaStream_t s, int kblocks_per_unit = 1 << 20) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(pipeline_kernel<BN, Problem>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    cudaFuncSetAttribute(pipeline_kernel<BN, MT, Problem>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::kSmemBytes);
     attr_set = true;
   }
   if (units <= 0) return 0;
   const int grid = units < num_sms() ? units : num_sms();
-  SIG_LAUNCH((pipeline_kernel<BN, Problem>), grid, kThreads, Cfg<BN>::kSmemBytes, s, p);
+  int stages = Cfg<BN, MT>::kStages;
+  const int per_cta = kblocks_per_unit * (int)ceil_div(units, grid);
+  if (per_cta < stages) stages = per_cta < 2 ? 2 : per_cta;
+  if (stage_override() > 0 && stage_override() < stages) stages = stage_override();
+  SIG_LAUNCH((pipeline_kernel<BN, MT, Problem>), grid, kThreads, (Cfg<BN, MT>::smem_bytes(stages)), s, p, stages);
   SIG_CHECK_LAUNCH();
   return 0;
 }

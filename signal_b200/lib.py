@@ -282,7 +282,7 @@ def debug_gemm_bf16(A, a_mode, B, b_mode, M, N, K, out_bf16=False, bias=None, al
     dev = A.device
     csb = csl = 0
     if out is None:
-        out = torch.zeros(M, N, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        out = (torch.zeros if ksplit > 1 else torch.empty)(M, N, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
     else:
         csb, csl = out.stride(0), out.stride(1)
         out_bf16 = out.dtype == torch.bfloat16

@@ -108,3 +108,22 @@ def test_weight_grad_many_units_splitk():
     dH = _rand((Bs * 128, d), 16)
     out = lib.debug_gemm_bf16(dH, 2, X, 3, d, d, Bs * 128, ksplit=3)
     _check(out, dH.float().T @ X.float().reshape(-1, d))
+
+
+def test_256x256_units_share_the_b_tile():
+    """bn=512 selects 256 x 256 work units (two M tiles against one B tile, single TMEM buffer)."""
+    from signal_b200 import lib
+    Bs, d = 37, 768          # odd sample count: the second M tile of the last unit is out of bounds
+    tok = _rand((Bs, 129, d), 21)
+    W = _rand((d, d), 22)
+    A = tok[:, 1:]
+    bias = torch.randn(d, device="cuda")
+    out = lib.debug_gemm_bf16(A, 1, W, 0, Bs * 128, d, d, bn=512, out_bf16=True, bias=bias)
+    _check(out, A.float().reshape(-1, d) @ W.float().T + bias, 6e-3)
+    dH = _rand((Bs * 128, d), 23)
+    dst = torch.full((Bs, 129, d), 3.0, dtype=torch.bfloat16, device="cuda")
+    lib.debug_gemm_bf16(dH, 0, W, 2, Bs * 128, d, d, bn=512, out=dst[:, 1:])
+    _check(dst[:, 1:], (dH.float() @ W.float()).reshape(Bs, 128, d), 6e-3)
+    assert bool((dst[:, 0] == 3.0).all())
+    out = lib.debug_gemm_bf16(dH, 2, A, 3, d, d, Bs * 128, ksplit=5, bn=512)
+    _check(out, dH.float().T @ A.float().reshape(-1, d))
