@@ -629,6 +629,13 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);
+  // GAM (pool -> Gram grid -> loss) is independent of LAM: run it on the side stream
+  const Fork fk = do_lam ? get_fork(FORK_ALIGN_FWD) : Fork();
+  cudaStream_t smain = s;
+  if (fk.ok()) {
+    fk.fork(smain);
+    s = fk.side;
+  }
   {
     SIG_PHASE("gam_fwd");
     SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), 256, 0, s, tp, B, L, d, c.mean);
@@ -650,6 +657,7 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     SIG_LAUNCH((gam_final_kernel), 1, 256, 0, s, c.lossp, c.dtaup, B, losses, c.dtau);
     SIG_CHECK_LAUNCH();
   }
+  s = smain;
   if (!do_lam) return 0;
   const Geo g = make_geo(h, w);
   const size_t dd = (size_t)d * d, BL = (size_t)B * L;
@@ -707,6 +715,7 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     SIG_LAUNCH((sum_kernel), 1, 256, 0, s, c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
     SIG_CHECK_LAUNCH();
   }
+  if (fk.ok()) fk.join(smain);
   return 0;
 }
 
@@ -717,6 +726,12 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   const TokPtrs3 tp = tok_ptrs3(tok);
   const GradPtrs3 gp = grad_ptrs3(dtok);
   const size_t dd = (size_t)d * d, BL = (size_t)B * L;
+  const Fork fkb = do_lam ? get_fork(FORK_ALIGN_BWD) : Fork();
+  cudaStream_t smain = s;
+  if (fkb.ok()) {
+    fkb.fork(smain);
+    s = fkb.side;
+  }
   {
     SIG_PHASE("gam_bwd");
     const float* fr = c.f;
@@ -749,6 +764,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_LAUNCH((scale_scalar_kernel), 1, 1, 0, s, c.dtau, dlosses, dp->contra_temp);
     SIG_CHECK_LAUNCH();
   }
+  s = smain;
   if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
   if (dtok->zero_cls && !dtok->accumulate) {
     SIG_LAUNCH((zero_cls_kernel<__nv_bfloat16>), dim3(B, 3), 64, 0, s, gp, d);
@@ -788,6 +804,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_LAUNCH((lam_dw_param_reduce_kernel), dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s, c.dwpart, nchunk, *dp, c.dbf, d);
     SIG_CHECK_LAUNCH();
   }
+  if (fkb.ok()) fkb.join(smain);   // the dX epilogue adds the GAM rows (dmean)
   {
     SIG_PHASE("lam_offsetnet_bwd_dx");
     // d(patches) = dH W' + g_gam * dmean  -> written once, in the token dtype, at the token strides
@@ -820,7 +837,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.M = d; t.N = d; t.K = (int)BL; t.batch = 3;
     for (int m = 0; m < 3; ++m) t.C[m] = c.dWf + m * dd;
     t.ldc = d;
-    t.bn = 128;
+    t.bn = (d % 256 == 0) ? 256 : 128;
     t.mt = 1;
     const int tiles = (int)(ceil_div(d, 128 * t.mt) * ceil_div(d, t.bn)) * 3;
     int ks = (2 * 148 + tiles - 1) / tiles;

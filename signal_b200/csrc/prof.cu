@@ -21,6 +21,31 @@ struct Rec {
 std::vector<Rec> g_recs;
 }  // namespace
 
+Fork get_fork(int slot) {
+  static std::mutex mu;
+  static Fork forks[8][FORK_SLOTS];
+  static const bool enabled = [] {
+    const char* e = getenv("SIG_FORK");
+    return !(e && e[0] == '0');
+  }();
+  Fork none;
+  if (!enabled || slot < 0 || slot >= FORK_SLOTS) return none;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 8) return none;
+  std::lock_guard<std::mutex> lk(mu);
+  Fork& f = forks[dev][slot];
+  if (!f.side) {
+    cudaStream_t st = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return none;
+    if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess)
+      return none;
+    f.side = st; f.ev_fork = a; f.ev_join = b;
+  }
+  return f;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("SIG_PDL");

@@ -15,3 +15,26 @@ struct ProfScope {
 }  // namespace sig
 
 #define SIG_PHASE(name) ::sig::ProfScope prof_scope__(name, s)
+
+namespace sig {
+// Internal side streams: independent sub-chains of one entry point (e.g. the GAM grid next to the LAM
+// GEMMs, weight-gradient GEMMs next to the activation-gradient chain) are enqueued on a library-owned
+// non-blocking stream, forked from and joined back into the caller's stream with events, so the call
+// is still ordered on `stream` as a whole and stays CUDA-graph capturable (the fork/join becomes
+// parallel branches of the graph).  One stream + two events per slot, created once per device.
+enum ForkSlot { FORK_SIM_FWD = 0, FORK_SIM_BWD = 1, FORK_ALIGN_FWD = 2, FORK_ALIGN_BWD = 3, FORK_SLOTS = 4 };
+struct Fork {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool ok() const { return side != nullptr; }
+  void fork(cudaStream_t main) const {   // side continues from main's current position
+    cudaEventRecord(ev_fork, main);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+  }
+  void join(cudaStream_t main) const {   // main waits for everything enqueued on side
+    cudaEventRecord(ev_join, side);
+    cudaStreamWaitEvent(main, ev_join, 0);
+  }
+};
+Fork get_fork(int slot);   // returns a disabled Fork (ok() == false) when SIG_FORK=0
+}  // namespace sig

@@ -832,7 +832,7 @@ static size_t attn_bwd_smem(int L, int d) { return (size_t)(12 * d + 12 * 3 * L 
 
 template <typename OutT>
 static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_sim_params* p, const float* maskf, int B, int L,
-                             int d, OutT* out, cudaStream_t s) {
+                             int d, OutT* out, const Fork& sel_fork, cudaStream_t s) {
   const int R = 3 * B, hd = d / kHeads;
   const float scale = 1.0f / sqrtf((float)hd);
   const float* wq = p->in_proj_w;
@@ -846,6 +846,7 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
       SIG_PHASE("sim_attn_prep");
       SIG_TRY(attn_prep_tc(c, p, B, d, s));
     }
+    if (sel_fork.ok()) sel_fork.join(s);   // the token kernels need the selection masks
     {
       SIG_PHASE("sim_attn_tokens_fwd");
       SIG_TRY(sim_tc_tokens_fwd(tok, tc_bufs(c, maskf), s));
@@ -912,16 +913,17 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
   float* dwk = g->in_proj_w + (size_t)d * d;
   float* dwv = g->in_proj_w + (size_t)2 * d * d;
   if (c.tc) {
+    const Fork fk = get_fork(FORK_SIM_BWD);   // weight-gradient GEMMs; joined by sim_backward
     {
       SIG_PHASE("sim_post_bwd");
-      SIG_TRY((attn_post_bwd_tc<InT>(c, p, B, d, dout, g, s)));
+      SIG_TRY((attn_post_bwd_tc<InT>(c, p, B, d, dout, g, fk, s)));
     }
     {
       SIG_PHASE("sim_attn_tokens_bwd");
       SIG_TRY(sim_tc_tokens_bwd(tok, tc_bufs(c, maskf), dtok, s));
     }
     SIG_PHASE("sim_attn_prep_bwd");
-    return attn_prep_bwd_tc(c, p, B, d, g, s);
+    return attn_prep_bwd_tc(c, p, B, d, g, fk, s);
   }
   {
   SIG_PHASE("sim_post_bwd");
@@ -1043,8 +1045,12 @@ int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, 
     SIG_TRY(convert_tokens(tok, c.Xf, c.clsf, s));
   }
   const float* maskf = nullptr;
+  Fork sel_fork;
   if (do_select) {
-    SIG_TRY(run_selection(c, tok, p, B, L, d, 3, k1, k2, max_keep, masks_out, s));
+    // the selection chain (scores -> softmax -> rank-select) is independent of the attention prep
+    if (tcp) sel_fork = get_fork(FORK_SIM_FWD);
+    if (sel_fork.ok()) sel_fork.fork(s);
+    SIG_TRY(run_selection(c, tok, p, B, L, d, 3, k1, k2, max_keep, masks_out, sel_fork.ok() ? sel_fork.side : s));
     maskf = c.maskf;
   } else if (ext_masks) {
     cudaMemcpyAsync(c.maskf, ext_masks, (size_t)3 * B * L * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -1055,8 +1061,8 @@ int sim_forward(const sig_tokens* tok, const sig_sim_params* p, bool do_select, 
     maskf = c.maskf;
   }
   if (tok->dtype == SIG_BF16)
-    return run_attention_fwd<__nv_bfloat16>(c, tok, p, maskf, B, L, d, static_cast<__nv_bfloat16*>(out), s);
-  return run_attention_fwd<float>(c, tok, p, maskf, B, L, d, static_cast<float*>(out), s);
+    return run_attention_fwd<__nv_bfloat16>(c, tok, p, maskf, B, L, d, static_cast<__nv_bfloat16*>(out), sel_fork, s);
+  return run_attention_fwd<float>(c, tok, p, maskf, B, L, d, static_cast<float*>(out), sel_fork, s);
 }
 
 int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks, const void* dout, const sig_token_grads* dtok,
@@ -1089,6 +1095,10 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
     SIG_LAUNCH((write_cls_grads_kernel<__nv_bfloat16>), dim3(B, 3), 96, 0, s, gp, c.dr1, d);
     SIG_CHECK_LAUNCH();
     if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
+    {
+      const Fork fk = get_fork(FORK_SIM_BWD);
+      if (fk.ok()) fk.join(s);   // weight-gradient GEMMs enqueued on the side stream
+    }
     return 0;
   }
   if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);

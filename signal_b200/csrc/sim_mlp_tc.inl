@@ -129,9 +129,17 @@ static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
   return 0;
 }
 
+// Weight-gradient GEMMs only read bf16 shadows that are never rewritten inside the call, so they run on
+// the side stream `fk` next to the activation-gradient chain (forked after their operands exist).
+static int side_gemm(const Fork& fk, cudaStream_t s, const TcGemmDesc& t) {
+  if (!fk.ok()) return tc_gemm(t, s);
+  fk.fork(s);
+  return tc_gemm(t, fk.side);
+}
+
 template <typename InT>
 static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, const InT* dout, const sig_sim_param_grads* g,
-                            cudaStream_t s) {
+                            const Fork& fk, cudaStream_t s) {
   const int R = 3 * B, hd = d / kHeads;
   const size_t dd = (size_t)d * d;
   const __nv_bfloat16* wvb = c.Wb + 2 * dd;
@@ -147,7 +155,7 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln2_b, 1.f, s));
   SIG_TRY(launch_colsum(c.dr2, d, R, d, g->ffn2_b, 1.f, s));
   SIG_TRY(cast_f32_to_bf16(c.dr2, c.dr2b, (int64_t)R * d, s));
-  SIG_TRY(tc_gemm(lin_tn(c.dr2b, d, c.h1b, 2 * (int64_t)d, g->ffn2_w, 2 * (int64_t)d, d, 2 * d, R), s));       // dW2 = dr2^T h1
+  SIG_TRY(side_gemm(fk, s, lin_tn(c.dr2b, d, c.h1b, 2 * (int64_t)d, g->ffn2_w, 2 * (int64_t)d, d, 2 * d, R)));   // dW2 = dr2^T h1
   SIG_TRY(tc_gemm(lin_nn(c.dr2b, d, w2b, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d), s));              // dh1 = dr2 W2
   {
     const int64_t n = (int64_t)R * 2 * d;
@@ -155,7 +163,7 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     SIG_CHECK_LAUNCH();
   }
   SIG_TRY(launch_colsum(c.dh1, 2 * (int64_t)d, R, 2 * d, g->ffn0_b, 1.f, s));
-  SIG_TRY(tc_gemm(lin_tn(c.da1b, 2 * (int64_t)d, c.y1b, d, g->ffn0_w, d, 2 * d, d, R), s));                     // dW1 = da1^T y1
+  SIG_TRY(side_gemm(fk, s, lin_tn(c.da1b, 2 * (int64_t)d, c.y1b, d, g->ffn0_w, d, 2 * d, d, R)));                 // dW1 = da1^T y1
   {  // dy1 = dr2 + da1 W1
     TcGemmDesc t = lin_nn(c.da1b, 2 * (int64_t)d, w1b, d, c.dr2, d, R, d, 2 * d);
     t.accumulate = 1;
@@ -167,7 +175,7 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln1_b, 1.f, s));
   SIG_TRY(launch_colsum(c.dr1, d, R, d, g->out_proj_b, 1.f, s));
   SIG_TRY(cast_f32_to_bf16(c.dr1, c.dr1b, (int64_t)R * d, s));
-  SIG_TRY(tc_gemm(lin_tn(c.dr1b, d, c.ob, d, g->out_proj_w, d, d, d, R), s));                                    // dWo = dr1^T o
+  SIG_TRY(side_gemm(fk, s, lin_tn(c.dr1b, d, c.ob, d, g->out_proj_w, d, d, d, R)));                                // dWo = dr1^T o
   {  // do = dr1 Wo
     TcGemmDesc t = lin_nn(c.dr1b, d, wob, d, c.dob, d, R, d, d);
     t.C2[0] = c.dobb; t.ldc2 = d;
@@ -180,7 +188,7 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     per_head(t.A, c.dobb, hd);
     per_head(t.B, c.xbarb, d);
     for (int h = 0; h < kHeads; ++h) t.C[h] = dwv + (size_t)h * hd * d;
-    SIG_TRY(tc_gemm(t, s));
+    SIG_TRY(side_gemm(fk, s, t));
   }
   {  // dxbar_h = do_h W_v^h
     TcGemmDesc t = lin_nn(c.dobb, d, wvb, d, c.dxbar, 8 * (int64_t)d, R, d, hd);
@@ -193,7 +201,8 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   return 0;
 }
 
-static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, const sig_sim_param_grads* g, cudaStream_t s) {
+static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, const sig_sim_param_grads* g, const Fork& fk,
+                            cudaStream_t s) {
   const int R = 3 * B, hd = d / kHeads;
   const float scale = 1.0f / sqrtf((float)hd);
   const size_t dd = (size_t)d * d;
@@ -219,11 +228,11 @@ static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     per_head(t.A, c.qattb, hd);
     per_head(t.B, c.dqtb, d);
     for (int h = 0; h < kHeads; ++h) t.C[h] = dwk + (size_t)h * hd * d;
-    SIG_TRY(tc_gemm(t, s));
+    SIG_TRY(side_gemm(fk, s, t));
   }
   cudaMemsetAsync(g->in_proj_b + d, 0, d * sizeof(float), s);  // key bias: softmax shift invariance => exactly 0
   SIG_TRY(launch_colsum(c.dqatt, d, R, d, g->in_proj_b, 1.f, s));
-  SIG_TRY(tc_gemm(lin_tn(c.dqattb, d, c.clsb, d, dwq, d, d, d, R), s));                                           // dWq = dq^T cls
+  SIG_TRY(side_gemm(fk, s, lin_tn(c.dqattb, d, c.clsb, d, dwq, d, d, d, R)));                                       // dWq = dq^T cls
   {  // dcls = dr1 (residual) + dq W_q
     TcGemmDesc t = lin_nn(c.dqattb, d, wqb, d, c.dr1, d, R, d, d);
     t.accumulate = 1;
