@@ -236,6 +236,10 @@ int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const 
                         int64_t c_stride_b, int64_t c_stride_l, const float* rowvec, const float* rowvec_scale,
                         int accumulate, int device, void* stream);
 
+/* Debug aid: with SIG_TC_STAMPS=1 in the environment, CTA 0 of every tcgen05 pipeline launch records
+ * clock64() at nine points of its life (tc_pipeline.cuh); this copies the 16-slot stamp array out. */
+int sig_debug_tc_stamps(long long* out16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,174 +3,197 @@
 // linear maps proj_q -> conv_offset[0] folded into one (DAS.py:129,136: no non-linearity between
 // them), everything else is HBM-bound SIMT code with 16-byte accesses.
 
-// ---- GAM: mean pool straight from the strided token views.  grid (B, 3), 256 threads -------------
+// ---- GAM: mean pool straight from the strided token views.  grid (B, 3), 4 * d/8 threads -----------
+// Four row groups per CTA; a thread owns 8 channels (16 B) and keeps 8 row loads in flight.
+// dyn smem: [4][d] floats.  Algorithmic traffic: the tokens, read once.
+constexpr int kPoolGroups = 4, kPoolUnroll = 8;
 template <typename T>
-static __global__ void __launch_bounds__(256) pool_tok_kernel(TokPtrs3 tp, int B, int L, int d, float* __restrict__ mean) {
+static __global__ void __launch_bounds__(512) pool_tok_kernel(TokPtrs3 tp, int B, int L, int d, float* __restrict__ mean) {
   pdl_enter();
-  __shared__ float red[256 * 8];
+  extern __shared__ __align__(16) float pool_red[];   // [kPoolGroups][d]
   const int b = blockIdx.x, m = blockIdx.y;
   const int tpr = d / 8;                       // threads per token row
-  const int ngrp = blockDim.x / tpr;           // row groups working in parallel
   const int grp = threadIdx.x / tpr, c = (threadIdx.x % tpr) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (grp < ngrp) {
-    const T* x = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m];
-    for (int l = grp; l < L; l += ngrp) {
-      float v[8];
-      load8(x + l * tp.psl[m] + c, v);
+  if (grp < kPoolGroups) {
+    const T* x = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m] + c;
+    for (int l0 = grp; l0 < L; l0 += kPoolGroups * kPoolUnroll) {
+      float v[kPoolUnroll][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      for (int u = 0; u < kPoolUnroll; ++u) {
+        const int l = l0 + u * kPoolGroups;
+        if (l < L) load8(x + l * tp.psl[m], v[u]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kPoolUnroll; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
     }
+    store8(pool_red + grp * d + c, acc);
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
   __syncthreads();
-  if (grp == 0) {
-    for (int g2 = 1; g2 < ngrp; ++g2)
+  const float inv = 1.f / L;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += red[(g2 * tpr + threadIdx.x) * 8 + i];
-    const float inv = 1.f / L;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= inv;
-    store8(mean + ((int64_t)m * B + b) * d + c, acc);
+    for (int g2 = 0; g2 < kPoolGroups; ++g2) t += pool_red[g2 * d + i];
+    mean[((int64_t)m * B + b) * d + i] = t * inv;
   }
 }
 
 // ---- LAM: depthwise 4x4/s4 conv + GELU + 1x1 -> offset logit, from the bf16 pre-activation H ------
-// A CTA walks kDwPairs sample points; the 16 window rows of H of the next point ([16][d] bf16) are
-// staged into shared memory with cp.async while the current point is being processed (double buffer).
-// Thread t owns channels 2t, 2t+1; its 2 x 16 depthwise taps stay in registers.
-constexpr int kDwPairs = 8;
-
-__device__ __forceinline__ void dw_stage_window(const __nv_bfloat16* __restrict__ Hm, __nv_bfloat16* buf, const Geo& g, int bp, int L,
-                                                int d) {
-  const int b = bp / g.P, p = bp % g.P;
-  const int py = p / g.Wk, px = p % g.Wk;
-  const int cpr = d / 8;                               // 16-byte chunks per row
-  for (int i = threadIdx.x; i < 16 * cpr; i += blockDim.x) {
-    const int k = i / cpr, ch = i % cpr;
-    const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
-    cp_async_16(buf + k * d + ch * 8, Hm + ((int64_t)b * L + l) * d + ch * 8);
-  }
+// Streaming kernels, no shared-memory staging: thread t owns channels 2t, 2t+1 and reads its 16
+// window taps of a sample point as 16 independent 4-byte loads (a warp covers one 128-byte line per
+// tap, every sector fully used), so each thread keeps 16-32 loads in flight and the loop over the
+// CTA's points needs no block-level synchronisation.  Algorithmic traffic: H read once (fwd);
+// H read + dH written once (bwd).
+constexpr int kDwFwdMaxPts = 16;   // sample points per CTA, forward (upper bound: size of the reduction scratch)
+// Points per CTA such that the grid (chunks x 3 modalities) is one full wave of 2 CTAs per SM.
+static int dw_pts_per_cta(int64_t BP, int max_pts) {
+  const int slots = 2 * tc_num_sms() / 3;
+  int pts = (int)ceil_div(BP, slots > 0 ? slots : 1);
+  if (pts < 1) pts = 1;
+  return max_pts > 0 && pts > max_pts ? max_pts : pts;
 }
 
-// grid (ceil(B*P / kDwPairs), 3), d/2 threads, dyn smem 2*16*d bf16.  U saved (fp32) for backward.
-static __global__ void __launch_bounds__(512) lam_dw_fwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
-                                                                   sig_align_params prm, Geo g, int B, int L, int d,
-                                                                   float* __restrict__ U, float* __restrict__ o) {
-  pdl_enter();
-  extern __shared__ __align__(16) unsigned char dw_smem[];
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(dw_smem);
-  __shared__ float scratch[33];
-  const int m = blockIdx.y, chunk = blockIdx.x;
+__device__ __forceinline__ void dw_load_window(const __nv_bfloat16* __restrict__ base, int w, int d, bool active, uint32_t (&hv)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    hv[k] = active ? ld_global_u32_early(base + (int64_t)((k >> 2) * w + (k & 3)) * d) : 0u;
+}
+
+// grid (ceil(B*P / pts), 3), d/2 threads (rounded up to a warp).  U saved (fp32) for backward.
+// <D, W> = compile-time channel count / grid width (0 = runtime) so tap offsets become immediates.
+template <int D, int W>
+static __global__ void __launch_bounds__(384, 2) lam_dw_fwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
+                                                                      sig_align_params prm, Geo g, int B, int L, int d_rt,
+                                                                      int pts, float* __restrict__ U, float* __restrict__ o) {
+  pdl_launch_dependents();
+  const int d = D ? D : d_rt;
+  if (W) g.w = W;
+  __shared__ float red[kDwFwdMaxPts][16];
+  const int m = blockIdx.y;
   const int c = threadIdx.x * 2;
   const bool active = c < d;
-  const __nv_bfloat16* Hm = H + m * hms;
-  const float* wdw = prm.off2_w[m];
-  const int bp0 = chunk * kDwPairs, bp_end = min(B * g.P, bp0 + kDwPairs);
-  dw_stage_window(Hm, stage, g, bp0, L, d);
-  cp_async_commit();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // parameters are not produced by the preceding kernels: fetch them before the dependency wait
   float wk0[16], wk1[16];
   float2 w4 = make_float2(0.f, 0.f), bd = make_float2(0.f, 0.f);
   if (active) {
+    const float4* wp = reinterpret_cast<const float4*>(prm.off2_w[m] + (int64_t)c * 16);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      wk0[k] = wdw[c * 16 + k];
-      wk1[k] = wdw[(c + 1) * 16 + k];
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = wp[q], b4 = wp[4 + q];
+      wk0[4 * q] = a.x; wk0[4 * q + 1] = a.y; wk0[4 * q + 2] = a.z; wk0[4 * q + 3] = a.w;
+      wk1[4 * q] = b4.x; wk1[4 * q + 1] = b4.y; wk1[4 * q + 2] = b4.z; wk1[4 * q + 3] = b4.w;
     }
     w4 = *reinterpret_cast<const float2*>(prm.off4_w[m] + c);
     bd = *reinterpret_cast<const float2*>(prm.off2_b[m] + c);
   }
-  for (int bp = bp0; bp < bp_end; ++bp) {
-    const __nv_bfloat16* cur = stage + ((bp - bp0) & 1) * 16 * d;
-    if (bp + 1 < bp_end) dw_stage_window(Hm, stage + ((bp + 1 - bp0) & 1) * 16 * d, g, bp + 1, L, d);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+  pdl_wait();
+  const __nv_bfloat16* Hm = H + m * hms;
+  const int bp0 = blockIdx.x * pts, npts = min(pts, B * g.P - bp0);
+#pragma unroll 2
+  for (int i = 0; i < npts; ++i) {
+    const int bp = bp0 + i, b = bp / g.P, p = bp % g.P;
+    const int py = p / g.Wk, px = p % g.Wk;
+    uint32_t hv[16];
+    dw_load_window(Hm + ((int64_t)b * L + (4 * py) * g.w + 4 * px) * d + c, g.w, d, active, hv);
+    float u0 = bd.x, u1 = bd.y;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      u0 = fmaf(gelu_tanh_f(bf16lo_to_f32(hv[k])), wk0[k], u0);
+      u1 = fmaf(gelu_tanh_f(bf16hi_to_f32(hv[k])), wk1[k], u1);
+    }
     float part = 0.f;
     if (active) {
-      float u0 = bd.x, u1 = bd.y;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const uint32_t hv = *reinterpret_cast<const uint32_t*>(cur + k * d + c);
-        u0 = fmaf(gelu_fast_f(bf16lo_to_f32(hv)), wk0[k], u0);
-        u1 = fmaf(gelu_fast_f(bf16hi_to_f32(hv)), wk1[k], u1);
-      }
       *reinterpret_cast<float2*>(U + ((int64_t)m * B * g.P + bp) * d + c) = make_float2(u0, u1);
       part = gelu_fast_f(u0) * w4.x + gelu_fast_f(u1) * w4.y;
     }
-    part = block_sum(part, scratch);   // also orders the reads of `cur` before it is overwritten
-    if (threadIdx.x == 0) o[(int64_t)m * B * g.P + bp] = part;
+    part = warp_sum(part);
+    if (lane == 0) red[i][warp] = part;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < npts) {   // fixed summation order: deterministic
+    float t = 0.f;
+    for (int q = 0; q < nw; ++q) t += red[threadIdx.x][q];
+    o[(int64_t)m * B * g.P + bp0 + threadIdx.x] = t;
   }
 }
 
-// Backward of the offset-net tail, one pass over H (same staging):
+// Backward of the offset-net tail, one pass over H:
 //   dU = dO * w4 * gelu'(U);  dH[b,pos,c] = dU * wdw[c,k] * gelu'(H[b,pos,c])   (bf16 out)
 // and per-CTA partial sums of the parameter gradients
 //   dwdw[c,k] += dU * gelu(H[pos(p,k)]),  dbdw += dU,  dw4 += dO * gelu(U),  dbf += dH
-// grid (ceil(B*P / kDwPairs), 3), d/2 threads (2 channels each).  part: [3][nchunk][19][d]
-static __global__ void __launch_bounds__(512) lam_dw_bwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
-                                                                   const float* __restrict__ U, const float* __restrict__ dO,
-                                                                   sig_align_params prm, Geo g, int B, int L, int d,
-                                                                   __nv_bfloat16* __restrict__ dH, float* __restrict__ part) {
-  pdl_enter();
+// grid (ceil(B*P / pts), 3), d/2 threads (2 channels each); the depthwise taps live in shared
+// memory as [k][c] (conflict-free 8-byte reads) so two CTAs fit the register file of an SM.
+// part: [3][nchunk][19][d]
+template <int D, int W>
+static __global__ void __launch_bounds__(384, 2) lam_dw_bwd_tc_kernel(const __nv_bfloat16* __restrict__ H, int64_t hms,
+                                                                      const float* __restrict__ U, const float* __restrict__ dO,
+                                                                      sig_align_params prm, Geo g, int B, int L, int d_rt,
+                                                                      int pts, __nv_bfloat16* __restrict__ dH, float* __restrict__ part) {
+  pdl_launch_dependents();
+  const int d = D ? D : d_rt;
+  if (W) g.w = W;
   extern __shared__ __align__(16) unsigned char dw_smem[];
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(dw_smem);
+  float* wT = reinterpret_cast<float*>(dw_smem);   // [16][d]
   const int m = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int c = threadIdx.x * 2;
   const bool active = c < d;
-  const __nv_bfloat16* Hm = H + m * hms;
-  const float* wdw = prm.off2_w[m];
-  const int bp0 = chunk * kDwPairs, bp_end = min(B * g.P, bp0 + kDwPairs);
-  dw_stage_window(Hm, stage, g, bp0, L, d);
-  cp_async_commit();
   float2 w4 = make_float2(0.f, 0.f);
-  float wk0[16], wk1[16];
   if (active) {
     w4 = *reinterpret_cast<const float2*>(prm.off4_w[m] + c);
+    const float4* wp = reinterpret_cast<const float4*>(prm.off2_w[m] + (int64_t)c * 16);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      wk0[k] = wdw[c * 16 + k];
-      wk1[k] = wdw[(c + 1) * 16 + k];
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = wp[q], b4 = wp[4 + q];
+      *reinterpret_cast<float2*>(wT + (4 * q) * d + c) = make_float2(a.x, b4.x);
+      *reinterpret_cast<float2*>(wT + (4 * q + 1) * d + c) = make_float2(a.y, b4.y);
+      *reinterpret_cast<float2*>(wT + (4 * q + 2) * d + c) = make_float2(a.z, b4.z);
+      *reinterpret_cast<float2*>(wT + (4 * q + 3) * d + c) = make_float2(a.w, b4.w);
     }
   }
+  // (each thread reads back only the taps it wrote itself: no barrier needed)
+  pdl_wait();
+  const __nv_bfloat16* Hm = H + m * hms;
+  __nv_bfloat16* dHm = dH + m * hms;
+  const int bp0 = chunk * pts, bp_end = min(B * g.P, bp0 + pts);
   float a0[19], a1[19];
 #pragma unroll
   for (int i = 0; i < 19; ++i) a0[i] = a1[i] = 0.f;
   for (int bp = bp0; bp < bp_end; ++bp) {
-    const __nv_bfloat16* cur = stage + ((bp - bp0) & 1) * 16 * d;
-    if (bp + 1 < bp_end) dw_stage_window(Hm, stage + ((bp + 1 - bp0) & 1) * 16 * d, g, bp + 1, L, d);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+    const int b = bp / g.P, p = bp % g.P;
+    const int py = p / g.Wk, px = p % g.Wk;
+    const int64_t off = ((int64_t)b * L + (4 * py) * g.w + 4 * px) * d + c;
+    uint32_t hv[16];
+    dw_load_window(Hm + off, g.w, d, active, hv);
     if (active) {
-      const int b = bp / g.P, p = bp % g.P;
-      const int py = p / g.Wk, px = p % g.Wk;
-      const int64_t ui = ((int64_t)m * B * g.P + bp) * d + c;
       const float go = dO[(int64_t)m * B * g.P + bp];
-      const float2 u = *reinterpret_cast<const float2*>(U + ui);
+      const float2 u = *reinterpret_cast<const float2*>(U + ((int64_t)m * B * g.P + bp) * d + c);
       float gu0, dgu0, gu1, dgu1;
       gelu_fast(u.x, gu0, dgu0);
       gelu_fast(u.y, gu1, dgu1);
       const float du0 = go * w4.x * dgu0, du1 = go * w4.y * dgu1;
       a0[16] += du0; a1[16] += du1;
-      a0[17] += go * gu0; a1[17] += go * gu1;
+      a0[17] = fmaf(go, gu0, a0[17]); a1[17] = fmaf(go, gu1, a1[17]);
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const int l = (4 * py + (k >> 2)) * g.w + 4 * px + (k & 3);
-        const uint32_t hv = *reinterpret_cast<const uint32_t*>(cur + k * d + c);
-        const float h0 = bf16lo_to_f32(hv), h1 = bf16hi_to_f32(hv);
-        float gh0, dgh0, gh1, dgh1;   // gelu and gelu' share one exp and one reciprocal per element
-        gelu_fast(h0, gh0, dgh0);
-        gelu_fast(h1, gh1, dgh1);
-        const float dh0 = du0 * wk0[k] * dgh0, dh1 = du1 * wk1[k] * dgh1;
-        *reinterpret_cast<__nv_bfloat162*>(dH + m * hms + ((int64_t)b * L + l) * d + c) = __floats2bfloat162_rn(dh0, dh1);
+        const float2 wk = *reinterpret_cast<const float2*>(wT + k * d + c);
+        float gh0, dgh0, gh1, dgh1;   // gelu and gelu' share one tanh per element
+        gelu_tanh(bf16lo_to_f32(hv[k]), gh0, dgh0);
+        gelu_tanh(bf16hi_to_f32(hv[k]), gh1, dgh1);
+        const float dh0 = du0 * wk.x * dgh0, dh1 = du1 * wk.y * dgh1;
+        *reinterpret_cast<__nv_bfloat162*>(dHm + off + (int64_t)((k >> 2) * g.w + (k & 3)) * d) = __floats2bfloat162_rn(dh0, dh1);
         a0[k] = fmaf(du0, gh0, a0[k]);
         a1[k] = fmaf(du1, gh1, a1[k]);
         a0[18] += dh0; a1[18] += dh1;
       }
     }
-    __syncthreads();   // all reads of `cur` done before the next iteration's prefetch overwrites it
   }
   if (active) {
     float* dst = part + (((int64_t)m * nchunk + chunk) * 19) * d + c;
@@ -405,7 +428,7 @@ static AlignTcCtx align_tc_ctx(void* base, int B, int L, int d) {
   c.H = a.take<__nv_bfloat16>(3 * BL * d);
   c.dH = a.take<__nv_bfloat16>(3 * BL * d);
   c.U = a.take<float>(3 * (size_t)B * P * d);
-  c.dwpart = a.take<float>(3 * (size_t)ceil_div((int64_t)B * P, kDwPairs) * 19 * d);
+  c.dwpart = a.take<float>(3 * (size_t)ceil_div((int64_t)B * P, dw_pts_per_cta((int64_t)B * P, 0)) * 19 * d);
   c.o = a.take<float>(3 * (size_t)B * P);
   c.dO = a.take<float>(3 * (size_t)B * P);
   c.S = a.take<float>(3 * (size_t)B * P * d);
@@ -447,7 +470,7 @@ static TcOperand batched(TcOperand o, const void* base, size_t stride_elems) { r
 
 static bool tc_path_ok(const sig_tokens* t, unsigned flags) {
   if (flags & SIG_FLAG_FORCE_SIMT) return false;
-  if (t->dtype != SIG_BF16 || t->L != 128) return false;
+  if (t->dtype != SIG_BF16 || t->L != 128 || t->d > 768) return false;   // (the LAM depthwise kernels run d/2 <= 384 threads)
   // one 3-D tensor-map geometry for the three modalities
   for (int m = 1; m < 3; ++m)
     if (t->patch_stride_b[m] != t->patch_stride_b[0] || t->patch_stride_l[m] != t->patch_stride_l[0]) return false;
@@ -638,7 +661,7 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   }
   {
     SIG_PHASE("gam_fwd");
-    SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), 256, 0, s, tp, B, L, d, c.mean);
+    SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), (unsigned)ceil_div(kPoolGroups * (d / 8), 32) * 32, (size_t)kPoolGroups * d * sizeof(float), s, tp, B, L, d, c.mean);
     SIG_CHECK_LAUNCH();
     SIG_LAUNCH((gam_norm_split_kernel), B, 256, 0, s, c.mean, B, d, c.f, c.fb, c.fA, c.fB, c.nrm, c.self4);
     SIG_CHECK_LAUNCH();
@@ -700,10 +723,16 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   }
   {
     SIG_PHASE("lam_dwconv_fwd");
-    const size_t dw_smem_bytes = (size_t)2 * 16 * d * sizeof(__nv_bfloat16);
-    cudaFuncSetAttribute(lam_dw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes);
-    SIG_LAUNCH((lam_dw_fwd_tc_kernel), dim3((unsigned)ceil_div((int64_t)B * g.P, kDwPairs), 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s, 
-        c.H, (int64_t)BL * d, *p, g, B, L, d, c.U, c.o);
+    const int pts = dw_pts_per_cta((int64_t)B * g.P, kDwFwdMaxPts);
+    const dim3 grid((unsigned)ceil_div((int64_t)B * g.P, pts), 3);
+    const unsigned thr = (unsigned)ceil_div(d / 2, 32) * 32;
+#define SIG_DW_FWD(D, W) SIG_LAUNCH((lam_dw_fwd_tc_kernel<D, W>), grid, thr, 0, s, c.H, (int64_t)BL * d, *p, g, B, L, d, pts, c.U, c.o)
+    if (d == 768 && w == 8) SIG_DW_FWD(768, 8);
+    else if (d == 768 && w == 16) SIG_DW_FWD(768, 16);
+    else if (d == 512 && w == 8) SIG_DW_FWD(512, 8);
+    else if (d == 512 && w == 16) SIG_DW_FWD(512, 16);
+    else SIG_DW_FWD(0, 0);
+#undef SIG_DW_FWD
     SIG_CHECK_LAUNCH();
   }
   {
@@ -795,11 +824,19 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   }
   {
     SIG_PHASE("lam_dwconv_bwd");
-    const int nchunk = (int)ceil_div((int64_t)B * g.P, kDwPairs);
-    const size_t dw_smem_bytes = (size_t)2 * 16 * d * sizeof(__nv_bfloat16);
-    cudaFuncSetAttribute(lam_dw_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes);
-    SIG_LAUNCH((lam_dw_bwd_tc_kernel), dim3(nchunk, 3), (unsigned)ceil_div(d / 2, 32) * 32, dw_smem_bytes, s, c.H, (int64_t)BL * d, c.U, c.dO, *p, g,
-                                                                                                  B, L, d, c.dH, c.dwpart);
+    const int pts = dw_pts_per_cta((int64_t)B * g.P, 0);
+    const int nchunk = (int)ceil_div((int64_t)B * g.P, pts);
+    const size_t dw_smem_bytes = (size_t)16 * d * sizeof(float);
+    const unsigned thr = (unsigned)ceil_div(d / 2, 32) * 32;
+#define SIG_DW_BWD(D, W)                                                                                                    \
+  SIG_LAUNCH((lam_dw_bwd_tc_kernel<D, W>), dim3(nchunk, 3), thr, dw_smem_bytes, s, c.H, (int64_t)BL * d, c.U, c.dO, *p, g, B, L, d, \
+             pts, c.dH, c.dwpart)
+    if (d == 768 && w == 8) SIG_DW_BWD(768, 8);
+    else if (d == 768 && w == 16) SIG_DW_BWD(768, 16);
+    else if (d == 512 && w == 8) SIG_DW_BWD(512, 8);
+    else if (d == 512 && w == 16) SIG_DW_BWD(512, 16);
+    else SIG_DW_BWD(0, 0);
+#undef SIG_DW_BWD
     SIG_CHECK_LAUNCH();
     SIG_LAUNCH((lam_dw_param_reduce_kernel), dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s, c.dwpart, nchunk, *dp, c.dbf, d);
     SIG_CHECK_LAUNCH();

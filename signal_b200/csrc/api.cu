@@ -185,4 +185,6 @@ int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const 
   return sig::tc_gemm(g, (cudaStream_t)stream);
 }
 
+int sig_debug_tc_stamps(long long* out16) { return sig::tc_read_stamps(out16); }
+
 }  // extern "C"

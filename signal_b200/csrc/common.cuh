@@ -103,6 +103,20 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = raw;
 }
 
+// 4 consecutive bf16 channels (8 B).
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+  v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 raw;
+  raw.x = *reinterpret_cast<const uint32_t*>(&a);
+  raw.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = raw;
+}
+
 // 4-byte global load the compiler may not sink to its use (an invariant `const __restrict__` load is
 // re-scheduled next to its consumer to save registers, which serialises the memory latency).
 __device__ __forceinline__ uint32_t ld_global_u32_early(const void* p) {
@@ -151,6 +165,28 @@ __device__ __forceinline__ float gelu_fast_f(float x) {
   float g, dg;
   gelu_fast(x, g, dg);
   return g;
+}
+
+// tanh-form GELU value + derivative for the HBM-bound LAM depthwise kernels of the bf16 path, where the
+// erf form above is the bottleneck (issue slots, not memory).  One MUFU.TANH and 7 FP32 ops per element.
+// |gelu_tanh - gelu_erf| <= 5e-4 absolute (at |x| ~ 2), below the 4e-3 rounding step of the bf16
+// pre-activation it is applied to.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(x2, 0.0356774081f, 0.7978845608f));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ void gelu_tanh(float x, float& g, float& dg) {
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(x2, 0.0356774081f, 0.7978845608f));
+  const float cdf = fmaf(0.5f, t, 0.5f);
+  g = x * cdf;
+  dg = fmaf(0.5f * x * fmaf(-t, t, 1.0f), fmaf(x2, 0.1070322243f, 0.7978845608f), cdf);
 }
 
 // ---- reductions ---------------------------------------------------------------

@@ -134,47 +134,64 @@ static TokPtrs tok_ptrs(const sig_tokens* t) {
 // selection scores
 // ---------------------------------------------------------------------------------------------
 // Same four dot products per token as sim_scores_kernel, reading the strided token views in place.
-// grid (ceil(L/32), 3, B), 256 threads: 8 warps x 4 tokens, 8 channels per lane per step (16 B loads).
+// grid (3, B), 256 threads: one CTA per (modality, sample) stages its four query vectors once, then
+// each warp streams 4 token rows at a time (8 channels = 16 B per lane per row and column step, all
+// row loads of a step issued before the first FMA) -- one pass over the tokens, T*s bytes per sample.
+constexpr int kScoreRows = 4;
 template <typename T>
 static __global__ void __launch_bounds__(256) sim_scores_tok_kernel(TokPtrs tp, const float* __restrict__ clsf,
                                                                     const float* __restrict__ qtsel, const float* __restrict__ csel,
                                                                     int B, int L, int d, float* __restrict__ sel_logits,
                                                                     float* __restrict__ intra_raw) {
   pdl_enter();
-  extern __shared__ float qv[];  // [4][d]
-  const int m = blockIdx.y, b = blockIdx.z;
-  for (int i = threadIdx.x; i < 4 * d; i += blockDim.x) {
+  extern __shared__ __align__(16) float qv[];  // [4][d]
+  const int m = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x * 4; i < 4 * d; i += blockDim.x * 4) {
     const int r = i / d, c = i % d;
-    qv[i] = r < 3 ? qtsel[((int64_t)b * 3 + r) * d + c] : clsf[((int64_t)b * 3 + m) * d + c];
+    const float* src = r < 3 ? qtsel + ((int64_t)b * 3 + r) * d + c : clsf + ((int64_t)b * 3 + m) * d + c;
+    *reinterpret_cast<float4*>(qv + i) = *reinterpret_cast<const float4*>(src);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float inv = rsqrtf((float)d);
+  const float cs0 = csel[b * 3 + 0], cs1 = csel[b * 3 + 1], cs2 = csel[b * 3 + 2];
   const T* xb = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m];
-  for (int i = 0; i < 4; ++i) {
-    const int l = blockIdx.x * 32 + w * 4 + i;
-    if (l >= L) break;
-    const T* x = xb + l * tp.psl[m];
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int l0 = w * kScoreRows; l0 < L; l0 += nw * kScoreRows) {
+    float a[kScoreRows][4];
+#pragma unroll
+    for (int i = 0; i < kScoreRows; ++i) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
     for (int c = lane * 8; c < d; c += 256) {
-      float xv[8];
-      load8(x + c, xv);
+      float xv[kScoreRows][8];
+#pragma unroll
+      for (int i = 0; i < kScoreRows; ++i) {
+        const int l = min(l0 + i, L - 1);
+        load8(xb + l * tp.psl[m] + c, xv[i]);
+      }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         float qq[8];
         load8(qv + r * d + c, qq);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) a[r] = fmaf(xv[t], qq[t], a[r]);
+        for (int i = 0; i < kScoreRows; ++i)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) a[i][r] = fmaf(xv[i][t], qq[t], a[i][r]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) a[r] = warp_sum(a[r]);
-    if (lane == 0) {
+    for (int i = 0; i < kScoreRows; ++i)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[i][r] = warp_sum(a[i][r]);
+    if (lane < kScoreRows && l0 + lane < L) {
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kScoreRows; ++i)
+        if (lane == i) { v0 = a[i][0]; v1 = a[i][1]; v2 = a[i][2]; v3 = a[i][3]; }
+      const int l = l0 + lane;
       const int64_t base = (int64_t)b * 3 * 3 * L + (int64_t)m * L + l;
-      sel_logits[base] = (a[0] + csel[b * 3 + 0]) * inv;
-      sel_logits[base + 3 * L] = (a[1] + csel[b * 3 + 1]) * inv;
-      sel_logits[base + 6 * L] = (a[2] + csel[b * 3 + 2]) * inv;
-      intra_raw[((int64_t)b * 3 + m) * L + l] = a[3];
+      sel_logits[base] = (v0 + cs0) * inv;
+      sel_logits[base + 3 * L] = (v1 + cs1) * inv;
+      sel_logits[base + 6 * L] = (v2 + cs2) * inv;
+      intra_raw[((int64_t)b * 3 + m) * L + l] = v3;
     }
   }
 }
@@ -817,7 +834,7 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
   }
   dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
   if (c.tc)
-    SIG_LAUNCH((sim_scores_tok_kernel<__nv_bfloat16>), grid, 256, 4 * d * sizeof(float), s, tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
+    SIG_LAUNCH((sim_scores_tok_kernel<__nv_bfloat16>), dim3(3, (unsigned)B), 256, 4 * d * sizeof(float), s, tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
                                                                                  c.sel_logits, c.intra_raw);
   else
     SIG_LAUNCH((sim_scores_kernel), grid, 256, 4 * d * sizeof(float), s, c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);

@@ -47,14 +47,25 @@ struct RowsProblem {
     ptx::prefetch_tmap(&p.tb);
   }
   __device__ static int num_units(const Params& p) { return 3 * p.B; }
-  __device__ static void krange(const Params& p, int, int& kb0, int& kb1) { kb0 = 0; kb1 = p.d / BK; }
-  __device__ static void load(const Params& p, int unit, int kb, uint8_t* sa, uint8_t* sb, uint64_t* bar) {
-    const int b = unit / 3, z = unit % 3;
-    tc::load_kmajor_tok(&p.ta[z], sa, bar, kb * BK, b, 1);
-    tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, b * 64 + p.b_row_off);
+  struct Unit {
+    int b, z, kb0, kb1;
+  };
+  __device__ static Unit unit_info(const Params& p, int unit) {
+    Unit u;
+    u.b = unit / 3; u.z = unit - 3 * u.b; u.kb0 = 0; u.kb1 = p.d / BK;
+    return u;
   }
-  __device__ static void epilogue(const Params& p, int unit, int /*mt*/, uint32_t tmem_acc, int q, int lane) {
-    const int b = unit / 3, z = unit % 3;
+  __device__ static void load_a(const Params& p, const Unit& u, int kb, uint8_t* sa, uint64_t* bar) {
+    tc::load_kmajor_tok(&p.ta[u.z], sa, bar, kb * BK, u.b, 1);
+  }
+  __device__ static void load_b(const Params& p, const Unit& u, int kb, uint8_t* sb, uint64_t* bar) {
+    tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, u.b * 64 + p.b_row_off);
+  }
+  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int lane, float* /*scratch*/,
+                                  uint64_t* acc_bar, uint32_t acc_phase, long long* /*stamps*/) {
+    ptx::mbar_wait(acc_bar, acc_phase);
+    ptx::tc_fence_after();
+    const int b = u.b, z = u.z;
     const int l = q * 32 + lane;
     const int j = z * 128 + l;
     uint32_t r[32];
@@ -117,16 +128,26 @@ struct ColsProblem {
     ptx::prefetch_tmap(&p.tb);
   }
   __device__ static int num_units(const Params& p) { return p.B * ((p.d + 127) / 128); }
-  __device__ static void krange(const Params&, int, int& kb0, int& kb1) { kb0 = 0; kb1 = 6; }
-  __device__ static void load(const Params& p, int unit, int kb, uint8_t* sa, uint8_t* sb, uint64_t* bar) {
+  struct Unit {
+    int b, c0, kb0, kb1;
+  };
+  __device__ static Unit unit_info(const Params& p, int unit) {
+    Unit u;
     const int mt = (p.d + 127) / 128;
-    const int b = unit / mt, c0 = (unit % mt) * 128;
-    tc::load_mnmajor_tok(&p.ta[kb >> 1], sa, bar, c0, (kb & 1) * 64, b, 128);
-    tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, b * 32);
+    u.b = unit / mt; u.c0 = (unit - u.b * mt) * 128; u.kb0 = 0; u.kb1 = 6;
+    return u;
   }
-  __device__ static void epilogue(const Params& p, int unit, int /*mt*/, uint32_t tmem_acc, int q, int lane) {
-    const int mt = (p.d + 127) / 128;
-    const int b = unit / mt, c = (unit % mt) * 128 + q * 32 + lane;
+  __device__ static void load_a(const Params& p, const Unit& u, int kb, uint8_t* sa, uint64_t* bar) {
+    tc::load_mnmajor_tok(&p.ta[kb >> 1], sa, bar, u.c0, (kb & 1) * 64, u.b, 128);
+  }
+  __device__ static void load_b(const Params& p, const Unit& u, int kb, uint8_t* sb, uint64_t* bar) {
+    tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, u.b * 32);
+  }
+  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int lane, float* /*scratch*/,
+                                  uint64_t* acc_bar, uint32_t acc_phase, long long* /*stamps*/) {
+    ptx::mbar_wait(acc_bar, acc_phase);
+    ptx::tc_fence_after();
+    const int b = u.b, c = u.c0 + q * 32 + lane;
     uint32_t r[32];
     ptx::tmem_ld32(tmem_acc, r);
     ptx::tmem_ld_wait();
@@ -159,37 +180,78 @@ struct DxProblem {
     ptx::prefetch_tmap(&p.tb);
   }
   __device__ static int num_units(const Params& p) { return 3 * p.B * ((p.d + BN - 1) / BN); }
-  __device__ static void krange(const Params&, int, int& kb0, int& kb1) { kb0 = 0; kb1 = 1; }
-  __device__ static void load(const Params& p, int unit, int, uint8_t* sa, uint8_t* sb, uint64_t* bar) {
+  struct Unit {
+    int b, z, n0, kb0, kb1;
+  };
+  __device__ static Unit unit_info(const Params& p, int unit) {
+    Unit u;
     const int nt = (p.d + BN - 1) / BN;
-    const int n0 = (unit % nt) * BN, bz = unit / nt, b = bz / 3, z = bz % 3;
-    tc::load_kmajor_2d(&p.ta, sa, bar, 0, b * 384 + z * 128);
-    tc::load_mnmajor_2d(&p.tb, sb, bar, n0, b * 64, BN);
+    const int bz = unit / nt;
+    u.n0 = (unit - bz * nt) * BN; u.b = bz / 3; u.z = bz - 3 * u.b; u.kb0 = 0; u.kb1 = 1;
+    return u;
   }
-  __device__ static void epilogue(const Params& p, int unit, int /*mt*/, uint32_t tmem_acc, int q, int lane) {
-    const int nt = (p.d + BN - 1) / BN;
-    const int n0 = (unit % nt) * BN, bz = unit / nt, b = bz / 3, z = bz % 3;
-    const int l = q * 32 + lane;
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.dpatch[z]) + b * p.psb[z] + l * p.psl[z];
+  __device__ static void load_a(const Params& p, const Unit& u, int, uint8_t* sa, uint64_t* bar) {
+    tc::load_kmajor_2d(&p.ta, sa, bar, 0, u.b * 384 + u.z * 128);
+  }
+  __device__ static void load_b(const Params& p, const Unit& u, int, uint8_t* sb, uint64_t* bar) {
+    tc::load_mnmajor_2d(&p.tb, sb, bar, u.n0, u.b * 64, BN);
+  }
+  // one k-block per unit: the epilogue IS the kernel.  Each 32 x 32 block goes through the transpose
+  // tile so that the read-modify-write of the gradient map is 4 rows x 64 contiguous bytes per warp
+  // instruction, with all 8 old-value loads of a chunk issued before the first add.
+  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int lane, float* scratch,
+                                  uint64_t* acc_bar, uint32_t acc_phase, long long* /*stamps*/) {
+    const int n0 = u.n0, z = u.z;
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const int l0 = q * 32 + sub;                                   // this lane's token row in step i is l0 + 4 i
+    const long long step = 4 * p.psl[z];
+    __nv_bfloat16* const base = static_cast<__nv_bfloat16*>(p.dpatch[z]) + u.b * p.psb[z] + l0 * p.psl[z];
+    const int nrows = p.L - l0;
+    const int accumulate = p.accumulate;
+    bool waited = false;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      const int col = n0 + c * 32 + c4;
+      if (n0 + c * 32 >= p.d) break;   // warp-uniform
+      const bool colok = col + 3 < p.d;   // d is a multiple of 8 on this path
+      __nv_bfloat16* const dst = base + col;
+      uint2 old[8];                      // old values (zeros when overwriting): requested first, they overlap the TMEM read
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        old[i] = (accumulate && 4 * i < nrows && colok) ? *reinterpret_cast<const uint2*>(dst + i * step) : make_uint2(0u, 0u);
+      if (!waited) {                     // first chunk: its old-value loads are already in flight
+        ptx::mbar_wait(acc_bar, acc_phase);
+        ptx::tc_fence_after();
+        waited = true;
+      }
       uint32_t r[32];
       ptx::tmem_ld32(tmem_acc + c * 32, r);
       ptx::tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      if (l < p.L && col0 < p.d) {
+      {
+        float v[32];
 #pragma unroll
-        for (int jj = 0; jj < 32; jj += 8) {
-          float t[8];
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        __syncwarp();
+        tc::epi_put_row(scratch, lane, v);
+        __syncwarp();
+      }
+      if (p.L == 128 && n0 + c * 32 + 32 <= p.d) {   // warp-uniform: whole 32 x 32 block in range -> branch-free stores
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = __uint_as_float(r[jj + i]);
-          if (p.accumulate) {
-            float o[8];
-            load8(dst + col0 + jj, o);
+        for (int i = 0; i < 8; ++i) {
+          const float4 t4 = tc::epi_get(scratch, lane, i);
+          float t[4] = {t4.x, t4.y, t4.z, t4.w};
+          t[0] += __uint_as_float(old[i].x << 16); t[1] += __uint_as_float(old[i].x & 0xffff0000u);
+          t[2] += __uint_as_float(old[i].y << 16); t[3] += __uint_as_float(old[i].y & 0xffff0000u);
+          store4(dst + i * step, t);
+        }
+      } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] += o[i];
-          }
-          store8(dst + col0 + jj, t);
+        for (int i = 0; i < 8; ++i) {
+          const float4 t4 = tc::epi_get(scratch, lane, i);
+          float t[4] = {t4.x, t4.y, t4.z, t4.w};
+          t[0] += __uint_as_float(old[i].x << 16); t[1] += __uint_as_float(old[i].x & 0xffff0000u);
+          t[2] += __uint_as_float(old[i].y << 16); t[3] += __uint_as_float(old[i].y & 0xffff0000u);
+          if (4 * i < nrows && colok) store4(dst + i * step, t);
         }
       }
     }

@@ -80,4 +80,7 @@ int cast_f32_to_bf16_multi(const CastJob* jobs, int n, cudaStream_t s);
 // dst[c][r] = bf16(src[r][c]) for a row-major [rows, cols] fp32 matrix
 int transpose_f32_to_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, cudaStream_t s);
 
+int tc_read_stamps(long long* out16);   // SIG_TC_STAMPS=1 debug aid (tc_pipeline.cuh)
+int tc_num_sms();   // multiprocessor count of the current device (cached)
+
 }  // namespace sig
