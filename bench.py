@@ -209,9 +209,11 @@ def run_gpu(args):
     # for AlignM); autograd adopts those views as .grad, so data parallel needs two all-reduces per step
 
     from signal_b200 import parallel
+    ncoll = [0]     # collectives issued by the last step
 
     def allreduce_grads():
-        parallel.allreduce_param_grads(params, world)
+        if args.allreduce and not overlap:
+            ncoll[0] = parallel.allreduce_param_grads(params, world)
 
     host_sets = []
     for k in range(NSETS):
@@ -223,6 +225,12 @@ def run_gpu(args):
     wl = torch.tensor(W_LAM, device=dev)
 
     head = M.FusionHead(sim, al) if args.fused else None
+    overlap = head is not None and world > 1 and args.allreduce and args.overlap
+    if overlap:   # each module's arena is all-reduced inside the backward, on the stream that produced it
+        def _sync(flat):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        head.grad_sync = _sync
+        ncoll[0] = 2
 
     def fwd_bwd(toks):
         patches = [t[:, 1:] for t in toks]
@@ -251,7 +259,6 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    eager_step = step
     for i in range(max(args.warmup, 3)):
         step(i)
     sync_all()
@@ -269,13 +276,16 @@ def run_gpu(args):
             lb = lib.launch_count()
             with torch.cuda.graph(g):
                 fwd_bwd(dev_sets[k])
-                if world > 1:
+                if world > 1 and args.allreduce_in_graph:
                     allreduce_grads()
             graph_launches = lib.launch_count() - lb
-            graphs.append(g)
+            graphs.append((g, parallel.grad_arenas(params)))
 
         def step(i):
-            graphs[i % NSETS].replay()
+            g, arenas = graphs[i % NSETS]
+            g.replay()
+            if world > 1 and not args.allreduce_in_graph and args.allreduce and not overlap:
+                ncoll[0] = parallel.allreduce_arenas(arenas, world)
 
         for i in range(max(args.warmup, 3)):
             step(i)
@@ -330,9 +340,16 @@ def run_gpu(args):
     roof, phases = None, None
     if rank == 0:
         prof_steps = 5
+        if head is not None:
+            head.grad_sync = None            # rank-local pass: no collectives
         lib.profile_enable(True)
-        for i in range(prof_steps):
-            eager_step(i)
+        for i in range(prof_steps):          # local work only: the other ranks are not in this pass (no collective)
+            toks = dev_sets[i % NSETS]
+            for t in toks:
+                t.grad = None
+            for p_ in params:
+                p_.grad = None
+            fwd_bwd(toks)
         torch.cuda.synchronize()
         lib.profile_enable(False)
         prof = lib.profile_collect()
@@ -368,7 +385,9 @@ def run_gpu(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(d), "global_batch": B * world, "parallelism": f"dp{world}",
                        "launch": "cuda_graph_replay" if args.graph else "eager", "api": "FusionHead(SIM, AlignM)" if args.fused else "SIM(...); AlignM(...)", "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
-                       "grad_allreduce": "NCCL all-reduce of the two flat head-gradient arenas (SIM, AlignM) per step" if world > 1 else "n/a"},
+                       "grad_allreduce": (f"NCCL all-reduce (avg) of the flat head-gradient arenas, {ncoll[0]} collectives per step, "
+                                          + ("issued inside the backward on the producing stream (FusionHead.grad_sync), " if overlap else "after the backward, ")
+                                          + ("captured in the step graph" if args.graph and (args.allreduce_in_graph or overlap) else "eager")) if world > 1 else "n/a"},
             "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -378,7 +397,11 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured graphs hold NCCL work: drop them before the communicator, and do not let a slow
+        # communicator teardown keep the launcher waiting after the result line is out
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
@@ -390,6 +413,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager module calls instead of CUDA-graph replays")
+    ap.add_argument("--allreduce-eager", dest="allreduce_in_graph", action="store_false",
+                    help="(diagnostic) issue the NCCL all-reduce after each graph replay instead of capturing it in the step graph")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false",
+                    help="(diagnostic) all-reduce after the backward instead of inside it (FusionHead.grad_sync)")
+    ap.add_argument("--no-allreduce", dest="allreduce", action="store_false", help="(diagnostic) skip the gradient all-reduce at N>1")
     ap.add_argument("--no-fused", dest="fused", action="store_false",
                     help="call SIM and AlignM one after the other instead of through signal_b200.FusionHead")
     args = ap.parse_args()

@@ -430,7 +430,7 @@ class HeadFunction(torch.autograd.Function):
                                      buf_s.data_ptr(), nb_s, flags, dev.index, main.cuda_stream), "sig_sim_fwd")
             main.wait_stream(side)
         ctx.save_for_backward(*toks, *sp, *ap, buf_s, buf_a)
-        ctx.cfg = (h, w, do_lam, flags, side, event, len(fold))
+        ctx.cfg = (h, w, do_lam, flags, side, event, len(fold))   # event: (torch.cuda.Event, grad_sync or None)
         ctx.mark_non_differentiable(masks)
         return out, masks, losses[0], losses[1]
 
@@ -449,7 +449,7 @@ class HeadFunction(torch.autograd.Function):
                 else dout.to(patches[0].dtype).contiguous())
         dtoks = [torch.empty_like(t) for t in toks]
         dpatch, dcls = [t[:, 1:] for t in dtoks], [t[:, 0] for t in dtoks]
-        _, pg_s = _arena(_SIM_GRAD_SHAPES(d), dev)
+        flat_s, pg_s = _arena(_SIM_GRAD_SHAPES(d), dev)
         flat_a, pg_a = _arena(_align_grad_shapes(d), dev)
         if not do_lam:
             flat_a.zero_()
@@ -460,6 +460,7 @@ class HeadFunction(torch.autograd.Function):
         aprm = L_.align_params_struct(ap[0], mods)
         gs_s = L_.sim_grads_struct(pg_s)
         gs_a = L_.align_params_struct(pg_a[0], [pg_a[1 + 7 * m: 8 + 7 * m] for m in range(3)], cls=L_.SigAlignParamGrads)
+        event, grad_sync = event
         evh = event.cuda_event
         tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=False, zero_cls=True, done_event=evh)   # AlignM overwrites ...
         tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=True, wait_event=evh)                   # ... SIM adds on top
@@ -468,7 +469,12 @@ class HeadFunction(torch.autograd.Function):
             side.wait_stream(main)
             L_.check(lib.sig_align_bwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg_a), C.byref(gs_a),
                                        buf_a.data_ptr(), buf_a.numel(), flags, dev.index, side.cuda_stream), "sig_align_bwd")
+            if grad_sync is not None:    # data parallel: each arena's exchange starts on the stream that produced it,
+                with torch.cuda.stream(side):   # so AlignM's all-reduce overlaps what is left of SIM's backward (and vice versa)
+                    grad_sync(flat_a)
             L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(sprm), dout.data_ptr(), C.byref(tg_s), C.byref(gs_s), buf_s.data_ptr(),
                                      buf_s.numel(), flags, dev.index, main.cuda_stream), "sig_sim_bwd")
+            if grad_sync is not None:
+                grad_sync(flat_s)
             main.wait_stream(side)
         return (None,) * 9 + tuple(dtoks) + (None,) * 4 + tuple(pg_s) + tuple(pg_a) + (None,) * nfold

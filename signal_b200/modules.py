@@ -278,9 +278,14 @@ class FusionHead:
     Falls back to the two module calls when the six inputs are not views of three [B,1+L,d] maps.
     """
 
-    def __init__(self, sim: "Select_Interactive_Module", align: "AlignmentM"):
+    def __init__(self, sim: "Select_Interactive_Module", align: "AlignmentM", grad_sync=None):
         self.sim, self.align = sim, align
         self._side = {}
+        # Data parallel (one process per GPU): ``grad_sync(flat)`` is called inside the backward, once per
+        # module, with that module's flat fp32 parameter-gradient arena, on the stream that produced it --
+        # e.g. ``lambda a: dist.all_reduce(a, op=dist.ReduceOp.AVG)``.  The gradients that reach ``.grad``
+        # are then already averaged and the exchange of one module overlaps the other's backward.
+        self.grad_sync = grad_sync
 
     def _stream(self, dev):
         st = self._side.get(dev)
@@ -307,7 +312,7 @@ class FusionHead:
         flags = sim.flags | al.flags
         if rgb_patch.dtype == torch.bfloat16 and not (flags & 1):
             params = params + list(ts._selection_fold())
-        out, masks, gam, lam = F_.HeadFunction.apply(al.h, al.w, stage != "CLS", ts.k1, ts.k2, ts._max_keep(L), flags, side, ev,
-                                                     *bases, *params)
+        out, masks, gam, lam = F_.HeadFunction.apply(al.h, al.w, stage != "CLS", ts.k1, ts.k2, ts._max_keep(L), flags, side,
+                                                     (ev, self.grad_sync), *bases, *params)
         ts.last_masks = {"RGB": masks[0].unsqueeze(-1), "NI": masks[1].unsqueeze(-1), "TI": masks[2].unsqueeze(-1)}
         return (out, gam, None) if stage == "CLS" else (out, gam, lam)

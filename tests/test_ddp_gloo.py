@@ -25,16 +25,32 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     shapes = [(6, 4), (6,), (), (3, 1, 2, 2)]
     params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes] + [torch.nn.Parameter(torch.zeros(5))]
-    flat_a, views_a = _arena(shapes[:2], "cpu")
-    flat_b, views_b = _arena(shapes[2:], "cpu")
-    flat_a.fill_(float(rank + 1))
-    flat_b.fill_(float(10 * (rank + 1)))
-    for p, v in zip(params, views_a + views_b):
-        p.grad = v
+    class _Views(torch.autograd.Function):   # gradients reach .grad the way the library's backward delivers them
+        @staticmethod
+        def forward(ctx, *ps):
+            return sum(p.sum() for p in ps)
+
+        @staticmethod
+        def backward(ctx, g):   # like functional.*.backward: views of flat arenas that only the engine keeps alive
+            flat_a, views_a = _arena(shapes[:2], "cpu")
+            flat_b, views_b = _arena(shapes[2:], "cpu")
+            flat_a.fill_(float(rank + 1))
+            flat_b.fill_(float(10 * (rank + 1)))
+            return tuple(views_a + views_b)
+
+    _Views.apply(*params[:4]).backward()
+    assert all(p.grad._base is None for p in params[:4])   # detached by the engine, storage still shared
+    assert params[0].grad.untyped_storage().data_ptr() == params[1].grad.untyped_storage().data_ptr()
     # params[4] has no gradient (like token_selection.W_q/W_k/W_v)
     n = parallel.allreduce_param_grads(params, world)
     ok = n == 2 and all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5)) for p in params[:2]) and \
         all(torch.allclose(p.grad, torch.full_like(p.grad, 15.0)) for p in params[2:4]) and params[4].grad is None
+    # gradients that are NOT arena views (six separate tensors): coalesced into one bucket collective
+    loose = [torch.nn.Parameter(torch.zeros(3)) for _ in range(6)]
+    for p in loose:
+        p.grad = torch.full((3,), float(rank + 1))
+    n2 = parallel.allreduce_param_grads(loose, world)
+    ok = ok and n2 == 1 and all(torch.allclose(p.grad, torch.full((3,), 1.5)) for p in loose)
     sl = parallel.shard_batch(256, rank, world)
     ok = ok and (sl.start, sl.stop) == (rank * 128, rank * 128 + 128)
     q.put((rank, bool(ok)))
