@@ -235,6 +235,14 @@ def run_gpu(args):
     def fwd_bwd(toks):
         patches = [t[:, 1:] for t in toks]
         cls = [t[:, 0] for t in toks]
+        if args.only == "sim":   # (diagnostic) one module only
+            out = sim(*patches, *cls)
+            torch.autograd.backward([out], [cot])
+            return out, wg, wl
+        if args.only == "align":
+            gam, lam = al(*patches, stage="together_CLS_Patch")
+            torch.autograd.backward([gam, lam], [wg, wl])
+            return cot, gam, lam
         if head is not None:     # one call: AlignM on a side stream next to SIM, one token-gradient writer
             out, gam, lam = head(*patches, *cls, stage="together_CLS_Patch")
         else:                    # the reference's two consecutive module calls (make_model.py:191,205)
@@ -480,6 +488,7 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager module calls instead of CUDA-graph replays")
     ap.add_argument("--allreduce-eager", dest="allreduce_in_graph", action="store_false",
                     help="(diagnostic) issue the NCCL all-reduce after each graph replay instead of capturing it in the step graph")
+    ap.add_argument("--only", default="", choices=["", "sim", "align"], help="(diagnostic) time one module's fwd+bwd only")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="(diagnostic) all-reduce after the backward instead of inside it (FusionHead.grad_sync)")
     ap.add_argument("--no-allreduce", dest="allreduce", action="store_false", help="(diagnostic) skip the gradient all-reduce at N>1")

@@ -838,7 +838,24 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     else SIG_DW_BWD(0, 0);
 #undef SIG_DW_BWD
     SIG_CHECK_LAUNCH();
+  }
+  // Everything below that is not on the dH -> dX / dW' path runs on a second side stream: the partial-sum
+  // reduction and the bias un-fold (they only need the partials), later the sparse bilinear part of
+  // d(patches) (after the dX GEMM) and one of the two un-fold GEMMs.
+  const Fork fk2 = get_fork(FORK_ALIGN_BWD2);
+  cudaStream_t s2 = s;
+  if (fk2.ok()) {
+    fk2.fork(s);
+    s2 = fk2.side;
+  }
+  {
+    cudaStream_t s = s2;
+    SIG_PHASE("lam_dwconv_param_grads");
+    const int pts = dw_pts_per_cta((int64_t)B * g.P, 0);
+    const int nchunk = (int)ceil_div((int64_t)B * g.P, pts);
     SIG_LAUNCH((lam_dw_param_reduce_kernel), dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s, c.dwpart, nchunk, *dp, c.dbf, d);
+    SIG_CHECK_LAUNCH();
+    SIG_LAUNCH((lam_unfold_bias_kernel), dim3((unsigned)ceil_div(d, 32), 3), 1024, 0, s, *p, *dp, c.dbf, d);   // db0 = db', dbq = W0^T db'
     SIG_CHECK_LAUNCH();
   }
   if (fkb.ok()) fkb.join(smain);   // the dX epilogue adds the GAM rows (dmean)
@@ -860,6 +877,11 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.bn = (d % 256 == 0) ? 256 : 128;
     t.mt = 1;   // (mt = 2, 256 x 256 units, measured slower: the single TMEM buffer serialises the epilogue)
     SIG_TRY(tc_gemm(t, s));
+  }
+  {
+    if (fk2.ok()) fk2.fork(s);   // after the dX GEMM
+    cudaStream_t s = s2;
+    SIG_PHASE("lam_sparse_dx");
     SIG_LAUNCH((lam_sparse_add_kernel<__nv_bfloat16>), dim3(B, 3), cthreads, 0, s, gp, c.o, c.dS, g, B, d);
     SIG_CHECK_LAUNCH();
     if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
@@ -885,6 +907,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   {
     SIG_PHASE("lam_unfold_grads");
     SIG_TRY(cast_f32_to_bf16(c.dWf, c.dWfb, 3 * dd, s));
+    if (fk2.ok()) fk2.fork(s);
     {  // dWq[d_mid, d_in] = W0^T dW'  : A[m = d_mid, k = d_out] = W0[k][m] (MN-major), B[n = d_in, k = d_out] = dW'[k][n] (MN-major)
       TcGemmDesc t = tc_desc();
       t.A = batched(tc_mn2d(nullptr, d, d, d), c.W0b, dd);
@@ -892,7 +915,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
       t.M = d; t.N = d; t.K = d; t.batch = 3;
       for (int m = 0; m < 3; ++m) t.C[m] = dp->proj_q_w[m];
       t.ldc = d;
-      SIG_TRY(tc_gemm(t, s));
+      SIG_TRY(tc_gemm(t, s2));   // next to dW0 on the side stream
     }
     {  // dW0[d_out, d_mid] = dW' Wq^T : A = dW' [d_out, d_in] K-major, B = Wq [d_mid, d_in] K-major
       TcGemmDesc t = tc_desc();
@@ -903,9 +926,8 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
       t.ldc = d;
       SIG_TRY(tc_gemm(t, s));
     }
+    if (fk2.ok()) fk2.join(s);   // dbf (reduced on the side stream) feeds the rank-1 term; also the end-of-call join
     SIG_LAUNCH((rank1_add3_kernel), dim3((unsigned)ceil_div((int64_t)dd, 256), 3), 256, 0, s, *dp, c.dbf, *p, d);
-    SIG_CHECK_LAUNCH();
-    SIG_LAUNCH((lam_unfold_bias_kernel), dim3((unsigned)ceil_div(d, 32), 3), 1024, 0, s, *p, *dp, c.dbf, d);   // db0 = db', dbq = W0^T db'
     SIG_CHECK_LAUNCH();
   }
   return 0;

@@ -22,7 +22,7 @@ namespace sig {
 // non-blocking stream, forked from and joined back into the caller's stream with events, so the call
 // is still ordered on `stream` as a whole and stays CUDA-graph capturable (the fork/join becomes
 // parallel branches of the graph).  One stream + two events per slot, created once per device.
-enum ForkSlot { FORK_SIM_FWD = 0, FORK_SIM_BWD = 1, FORK_ALIGN_FWD = 2, FORK_ALIGN_BWD = 3, FORK_SLOTS = 4 };
+enum ForkSlot { FORK_SIM_FWD = 0, FORK_SIM_BWD = 1, FORK_ALIGN_FWD = 2, FORK_ALIGN_BWD = 3, FORK_ALIGN_BWD2 = 4, FORK_SLOTS = 5 };
 struct Fork {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

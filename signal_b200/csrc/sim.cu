@@ -803,6 +803,7 @@ static SimTcBufs tc_bufs(const SimCtx& c, const float* maskf) {
   SimTcBufs k{};
   k.maskf = maskf; k.qtatt = c.qtatt; k.catt = c.catt; k.DXQT = c.DXQT; k.S32 = c.S32; k.Ptok = c.Ptok; k.PT = c.PT;
   k.xbar = c.xbar; k.dxbar = c.dxbar; k.delta = c.delta; k.PdS = c.PdS; k.dST = c.dST; k.dqt = c.dqt;
+  k.xbarb = c.xbarb; k.dqtb = c.dqtb;
   return k;
 }
 
@@ -904,7 +905,7 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
     SIG_TRY(launch_gemm(g, s));
   }
   SIG_TRY(launch_gemm(gemm_nt(c.o, d, p->out_proj_w, d, c.attn, d, p->out_proj_b, R, d, d), s));
-  SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
+  SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1, (__nv_bfloat16*)nullptr);
   SIG_CHECK_LAUNCH();
   {
     Gemm g = gemm_nt(c.y1, d, p->ffn0_w, d, c.h1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d);
@@ -912,7 +913,7 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
     SIG_TRY(launch_gemm(g, s));
   }
   SIG_TRY(launch_gemm(gemm_nt(c.h1, 2 * (int64_t)d, p->ffn2_w, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
-  SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
+  SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out, (__nv_bfloat16*)nullptr);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -945,7 +946,7 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
   {
   SIG_PHASE("sim_post_bwd");
   // LN2
-  SIG_LAUNCH((layernorm_bwd_kernel<InT>), R, 256, 0, s, dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
+  SIG_LAUNCH((layernorm_bwd_kernel<InT>), R, 256, 0, s, dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf, (__nv_bfloat16*)nullptr);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln2_w, 1.f, s));
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln2_b, 1.f, s));
@@ -966,7 +967,7 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
     SIG_TRY(launch_gemm(gg, s));
   }
   // LN1
-  SIG_LAUNCH((layernorm_bwd_kernel<float>), R, 256, 0, s, c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
+  SIG_LAUNCH((layernorm_bwd_kernel<float>), R, 256, 0, s, c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf, (__nv_bfloat16*)nullptr);
   SIG_CHECK_LAUNCH();
   SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln1_w, 1.f, s));
   SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln1_b, 1.f, s));

@@ -100,7 +100,7 @@ static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
   const __nv_bfloat16* wob = c.Wb + 3 * dd;
   const __nv_bfloat16* w1b = c.Wb + 4 * dd;
   const __nv_bfloat16* w2b = c.Wb + 6 * dd;
-  SIG_TRY(cast_f32_to_bf16(c.xbar, c.xbarb, (int64_t)R * 8 * d, s));
+  // (xbarb, the bf16 shadow of xbar, was written by the pooling kernel's epilogue)
   {  // o_h = W_v^h xbar_h + b_v^h
     TcGemmDesc t = lin_nt(c.xbarb, 8 * (int64_t)d, wvb, d, c.o, d, nullptr, R, hd, d);
     t.batch = kHeads;
@@ -115,16 +115,15 @@ static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
     SIG_TRY(tc_gemm(t, s));
   }
   SIG_TRY(tc_gemm(lin_nt(c.ob, d, wob, d, c.attn, d, p->out_proj_b, R, d, d), s));
-  SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1);
+  SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1, c.y1b);
   SIG_CHECK_LAUNCH();
-  SIG_TRY(cast_f32_to_bf16(c.y1, c.y1b, (int64_t)R * d, s));
   {
     TcGemmDesc t = lin_nt(c.y1b, d, w1b, d, c.h1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d);
     t.act = 1; t.pre[0] = c.a1; t.C2[0] = c.h1b; t.ldc2 = 2 * (int64_t)d;
     SIG_TRY(tc_gemm(t, s));
   }
   SIG_TRY(tc_gemm(lin_nt(c.h1b, 2 * (int64_t)d, w2b, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
-  SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out);
+  SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out, (__nv_bfloat16*)nullptr);
   SIG_CHECK_LAUNCH();
   return 0;
 }
@@ -135,6 +134,13 @@ static int side_gemm(const Fork& fk, cudaStream_t s, const TcGemmDesc& t) {
   if (!fk.ok()) return tc_gemm(t, s);
   fk.fork(s);
   return tc_gemm(t, fk.side);
+}
+
+// Column sums of buffers that are not written again inside the call: next to the weight-gradient GEMMs.
+static int side_colsum(const Fork& fk, cudaStream_t s, const float* X, int64_t ldx, int M, int N, float* out) {
+  if (!fk.ok()) return launch_colsum(X, ldx, M, N, out, 1.f, s);
+  fk.fork(s);
+  return launch_colsum(X, ldx, M, N, out, 1.f, fk.side);
 }
 
 template <typename InT>
@@ -149,12 +155,11 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   float* dwv = g->in_proj_w + 2 * dd;
   // the bf16 weight shadows written by the forward call are reused: autograd's version check on the
   // saved parameters rules out an in-place update between forward and backward
-  SIG_LAUNCH((layernorm_bwd_kernel<InT>), R, 256, 0, s, dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf);
+  SIG_LAUNCH((layernorm_bwd_kernel<InT>), R, 256, 0, s, dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf, c.dr2b);
   SIG_CHECK_LAUNCH();
-  SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln2_w, 1.f, s));
-  SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln2_b, 1.f, s));
-  SIG_TRY(launch_colsum(c.dr2, d, R, d, g->ffn2_b, 1.f, s));
-  SIG_TRY(cast_f32_to_bf16(c.dr2, c.dr2b, (int64_t)R * d, s));
+  // (the three column sums read buffers that are rewritten further down this stream -- dyx/dyf by the second
+  //  LayerNorm backward, dr2 by the accumulating GEMM -- so they stay on it, as ONE launch)
+  SIG_TRY(launch_colsum3(c.dyx, g->ln2_w, c.dyf, g->ln2_b, c.dr2, g->ffn2_b, d, R, d, s));
   SIG_TRY(side_gemm(fk, s, lin_tn(c.dr2b, d, c.h1b, 2 * (int64_t)d, g->ffn2_w, 2 * (int64_t)d, d, 2 * d, R)));   // dW2 = dr2^T h1
   SIG_TRY(tc_gemm(lin_nn(c.dr2b, d, w2b, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d), s));              // dh1 = dr2 W2
   {
@@ -162,26 +167,23 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     SIG_LAUNCH((gelu_bwd_shadow_kernel), (unsigned)ceil_div(n, 256), 256, 0, s, c.dh1, c.a1, c.da1b, n);
     SIG_CHECK_LAUNCH();
   }
-  SIG_TRY(launch_colsum(c.dh1, 2 * (int64_t)d, R, 2 * d, g->ffn0_b, 1.f, s));
+  SIG_TRY(side_colsum(fk, s, c.dh1, 2 * (int64_t)d, R, 2 * d, g->ffn0_b));   // dh1 is not written again
   SIG_TRY(side_gemm(fk, s, lin_tn(c.da1b, 2 * (int64_t)d, c.y1b, d, g->ffn0_w, d, 2 * d, d, R)));                 // dW1 = da1^T y1
   {  // dy1 = dr2 + da1 W1
     TcGemmDesc t = lin_nn(c.da1b, 2 * (int64_t)d, w1b, d, c.dr2, d, R, d, 2 * d);
     t.accumulate = 1;
     SIG_TRY(tc_gemm(t, s));
   }
-  SIG_LAUNCH((layernorm_bwd_kernel<float>), R, 256, 0, s, c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf);
+  SIG_LAUNCH((layernorm_bwd_kernel<float>), R, 256, 0, s, c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf, c.dr1b);
   SIG_CHECK_LAUNCH();
-  SIG_TRY(launch_colsum(c.dyx, d, R, d, g->ln1_w, 1.f, s));
-  SIG_TRY(launch_colsum(c.dyf, d, R, d, g->ln1_b, 1.f, s));
-  SIG_TRY(launch_colsum(c.dr1, d, R, d, g->out_proj_b, 1.f, s));
-  SIG_TRY(cast_f32_to_bf16(c.dr1, c.dr1b, (int64_t)R * d, s));
+  SIG_TRY(launch_colsum3(c.dyx, g->ln1_w, c.dyf, g->ln1_b, c.dr1, g->out_proj_b, d, R, d, s));   // (dr1 is accumulated into later)
   SIG_TRY(side_gemm(fk, s, lin_tn(c.dr1b, d, c.ob, d, g->out_proj_w, d, d, d, R)));                                // dWo = dr1^T o
   {  // do = dr1 Wo
     TcGemmDesc t = lin_nn(c.dr1b, d, wob, d, c.dob, d, R, d, d);
     t.C2[0] = c.dobb; t.ldc2 = d;
     SIG_TRY(tc_gemm(t, s));
   }
-  SIG_TRY(launch_colsum(c.dob, d, R, d, g->in_proj_b + 2 * d, 1.f, s));
+  SIG_TRY(side_colsum(fk, s, c.dob, d, R, d, g->in_proj_b + 2 * d));
   {  // dW_v^h = do_h^T xbar_h
     TcGemmDesc t = lin_tn(c.dobb, d, c.xbarb, 8 * (int64_t)d, dwv, d, hd, d, R);
     t.batch = kHeads;
@@ -210,7 +212,7 @@ static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   const __nv_bfloat16* wkb = c.Wb + dd;
   float* dwq = g->in_proj_w;
   float* dwk = g->in_proj_w + dd;
-  SIG_TRY(cast_f32_to_bf16(c.dqt, c.dqtb, (int64_t)R * 8 * d, s));
+  // (dqtb, the bf16 shadow of dqt, was written by the token kernel's epilogue)
   {  // dq_h = scale * dqt_h W_k^hT
     TcGemmDesc t = lin_nt(c.dqtb, 8 * (int64_t)d, wkb, d, c.dqatt, d, nullptr, R, hd, d);
     t.batch = kHeads; t.alpha = scale; t.ldc2 = d;
@@ -230,8 +232,14 @@ static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     for (int h = 0; h < kHeads; ++h) t.C[h] = dwk + (size_t)h * hd * d;
     SIG_TRY(side_gemm(fk, s, t));
   }
-  cudaMemsetAsync(g->in_proj_b + d, 0, d * sizeof(float), s);  // key bias: softmax shift invariance => exactly 0
-  SIG_TRY(launch_colsum(c.dqatt, d, R, d, g->in_proj_b, 1.f, s));
+  if (fk.ok()) {
+    fk.fork(s);
+    cudaMemsetAsync(g->in_proj_b + d, 0, d * sizeof(float), fk.side);  // key bias: softmax shift invariance => exactly 0
+    SIG_TRY(launch_colsum(c.dqatt, d, R, d, g->in_proj_b, 1.f, fk.side));
+  } else {
+    cudaMemsetAsync(g->in_proj_b + d, 0, d * sizeof(float), s);
+    SIG_TRY(launch_colsum(c.dqatt, d, R, d, g->in_proj_b, 1.f, s));
+  }
   SIG_TRY(side_gemm(fk, s, lin_tn(c.dqattb, d, c.clsb, d, dwq, d, d, d, R)));                                       // dWq = dq^T cls
   {  // dcls = dr1 (residual) + dq W_q
     TcGemmDesc t = lin_nn(c.dqattb, d, wqb, d, c.dr1, d, R, d, d);

@@ -118,6 +118,7 @@ struct ColsParams {
   CUtensorMap tb;      // W_all [B*32, 384], box [32 x 64]
   int B, d;
   float* out;          // [B][24][d]
+  __nv_bfloat16* out_b;   // same layout: bf16 shadow feeding the next GEMM (may be null)
 };
 
 struct ColsProblem {
@@ -155,6 +156,11 @@ struct ColsProblem {
     float* dst = p.out + (int64_t)b * 24 * p.d + c;
 #pragma unroll
     for (int e = 0; e < 24; ++e) dst[(int64_t)e * p.d] = __uint_as_float(r[e]);
+    if (p.out_b) {
+      __nv_bfloat16* db = p.out_b + (int64_t)b * 24 * p.d + c;
+#pragma unroll
+      for (int e = 0; e < 24; ++e) db[(int64_t)e * p.d] = __float2bfloat16_rn(__uint_as_float(r[e]));
+    }
   }
 };
 
@@ -383,7 +389,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
     ColsParams p{};
     SIG_TRY(make_tok_maps(tok, 64, p.ta));
     SIG_TRY(tc::make_map_2d(k.PT, (int64_t)B * 32, 384, 384, 32, &p.tb));
-    p.B = B; p.d = d; p.out = k.xbar;
+    p.B = B; p.d = d; p.out = k.xbar; p.out_b = k.xbarb;
     SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s, 6)));
   }
   return 0;
@@ -420,7 +426,7 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
     ColsParams p{};
     SIG_TRY(make_tok_maps(tok, 64, p.ta));
     SIG_TRY(tc::make_map_2d(k.dST, (int64_t)B * 32, 384, 384, 32, &p.tb));
-    p.B = B; p.d = d; p.out = k.dqt;
+    p.B = B; p.d = d; p.out = k.dqt; p.out_b = k.dqtb;
     SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s, 6)));
   }
   return 0;

@@ -13,11 +13,13 @@ struct SimTcBufs {
   __nv_bfloat16* Ptok;       // [B][384][32] P~ = softmax * mask
   __nv_bfloat16* PT;         // [B][32][384] P~ transposed
   float* xbar;               // [B][24][d]
+  __nv_bfloat16* xbarb;      // bf16 shadow of xbar (written with it)
   const float* dxbar;        // [B][24][d]
   float* delta;              // [B][32]
   __nv_bfloat16* PdS;        // [B][384][64] [P~ | dS~]
   __nv_bfloat16* dST;        // [B][32][384] dS~ transposed
   float* dqt;                // [B][24][d]
+  __nv_bfloat16* dqtb;       // bf16 shadow of dqt (written with it)
 };
 
 int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s);

@@ -182,6 +182,45 @@ static __global__ void __launch_bounds__(1024) colsum_kernel(const float* __rest
     out[n] = t * scale;
   }
 }
+// Up to four column sums of same-shaped matrices in one launch (grid.y = job).
+struct ColsumJobs {
+  const float* X[4];
+  float* out[4];
+};
+static __global__ void __launch_bounds__(1024) colsum_multi_kernel(ColsumJobs jobs, int64_t ldx, int M, int N) {
+  pdl_enter();
+  __shared__ float sm[32][33];
+  const float* __restrict__ X = jobs.X[blockIdx.y];
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (n < N) {
+    int m = r;
+    for (; m + 96 < M; m += 128) {
+      a0 += X[(int64_t)m * ldx + n];
+      a1 += X[(int64_t)(m + 32) * ldx + n];
+      a2 += X[(int64_t)(m + 64) * ldx + n];
+      a3 += X[(int64_t)(m + 96) * ldx + n];
+    }
+    for (; m < M; m += 32) a0 += X[(int64_t)m * ldx + n];
+  }
+  sm[r][c] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (r == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += sm[i][c];
+    jobs.out[blockIdx.y][n] = t;
+  }
+}
+inline int launch_colsum3(const float* X0, float* o0, const float* X1, float* o1, const float* X2, float* o2, int64_t ldx, int M, int N,
+                          cudaStream_t s) {
+  ColsumJobs j{};
+  j.X[0] = X0; j.out[0] = o0; j.X[1] = X1; j.out[1] = o1; j.X[2] = X2; j.out[2] = o2;
+  SIG_LAUNCH((colsum_multi_kernel), dim3((unsigned)ceil_div(N, 32), 3), 1024, 0, s, j, ldx, M, N);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
 inline int launch_colsum(const float* X, int64_t ldx, int M, int N, float* out, float scale, cudaStream_t s) {
   SIG_LAUNCH((colsum_kernel), (unsigned)ceil_div(N, 32), 1024, 0, s, X, ldx, M, N, out, scale);
   SIG_CHECK_LAUNCH();
@@ -194,7 +233,8 @@ template <typename OutT>
 static __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    int d, float* __restrict__ sum_out, float* __restrict__ mean,
-                                                                   float* __restrict__ rstd, OutT* __restrict__ y) {
+                                                                   float* __restrict__ rstd, OutT* __restrict__ y,
+                                                                   __nv_bfloat16* __restrict__ y_shadow) {
   pdl_enter();
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
@@ -212,7 +252,9 @@ static __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* 
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     const float t = xr[c] + (rr ? rr[c] : 0.f);
     if (sum_out) sum_out[row * d + c] = t;
-    y[row * d + c] = from_f32<OutT>((t - mu) * rs * gamma[c] + beta[c]);
+    const float yv = (t - mu) * rs * gamma[c] + beta[c];
+    y[row * d + c] = from_f32<OutT>(yv);
+    if (y_shadow) y_shadow[row * d + c] = __float2bfloat16_rn(yv);   // operand of the next tcgen05 GEMM
   }
   if (threadIdx.x == 0) {
     mean[row] = mu;
@@ -227,7 +269,7 @@ static __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const InT* __
                                                                    const float* __restrict__ gamma, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ extra,
                                                                    int d, float* __restrict__ dx, float* __restrict__ dyx,
-                                                                   float* __restrict__ dyf) {
+                                                                   float* __restrict__ dyf, __nv_bfloat16* __restrict__ dx_shadow) {
   pdl_enter();
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
@@ -248,6 +290,7 @@ static __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const InT* __
     float v = rs * (g - s1 - xh * s2);
     if (extra) v += extra[row * d + c];
     dx[row * d + c] = v;
+    if (dx_shadow) dx_shadow[row * d + c] = __float2bfloat16_rn(v);
     dyx[row * d + c] = dyv * xh;
     dyf[row * d + c] = dyv;
   }

@@ -70,6 +70,15 @@ int read_stamps(long long* out16) {
   return cudaMemcpy(out16, stamps_ptr(), sizeof(long long) * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
+int sm_reserve() {
+  static const int v = [] {
+    const char* e = getenv("SIG_TC_RESERVE");
+    int r = e ? atoi(e) : 0;
+    return r < 0 ? 0 : (r > 64 ? 64 : r);
+  }();
+  return v;
+}
+
 int stage_override() {
   static const int v = [] {
     const char* e = getenv("SIG_TC_STAGES");

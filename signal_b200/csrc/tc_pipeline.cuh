@@ -221,6 +221,7 @@ int make_map_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box
 int make_map_tok(const void* ptr, int64_t B, int64_t d, int64_t stride_b, int64_t stride_l, int box_rows, CUtensorMap* out);
 int num_sms();
 
+int sm_reserve();       // SIG_TC_RESERVE in the environment: SMs a persistent launch leaves free
 int stage_override();   // SIG_TC_STAGES in the environment (tuning aid), 0 = automatic
 
 // kblocks_per_unit: K-blocks one work unit runs through; short K loops get a shallower ring (less
@@ -233,7 +234,10 @@ int launch(const typename Problem::Params& p, int units, cudaStream_t s, int kbl
     attr_set = true;
   }
   if (units <= 0) return 0;
-  const int grid = units < num_sms() ? units : num_sms();
+  // Kernels with at least one unit per SM are persistent and would hold every SM for their whole run; leaving a
+  // few SMs free (SIG_TC_RESERVE, default in tc_gemm.cu) lets the short kernels of a concurrent stream -- the other
+  // module's dependency chain -- keep moving.  These kernels are bound by the L2 operand stream, not by SM count.
+  const int grid = units < num_sms() ? units : num_sms() - sm_reserve();
   int stages = Cfg<BN, MT>::kStages;
   const int per_cta = kblocks_per_unit * (int)ceil_div(units, grid);
   if (per_cta < stages) stages = per_cta < 2 ? 2 : per_cta;
