@@ -77,7 +77,9 @@ typedef struct sig_token_grads {
   int32_t zero_cls;              /* AlignM: also write zeros to dcls rows when dcls != NULL */
   /* Optional cross-stream ordering when SIM and AlignM backward run concurrently on two streams and
    * share one gradient map (cudaEvent_t, may be NULL): the call makes its stream wait on `wait_event`
-   * before its first write to dpatch/dcls and records `done_event` after its last one. */
+   * before its first write to dpatch and records `done_event` after its last write to dpatch (the CLS
+   * rows are only ever written by SIM; AlignM zero-fills them only when accumulate == 0).  The call
+   * that records must be issued before the call that waits. */
   void* wait_event;
   void* done_event;
 } sig_token_grads;
@@ -225,6 +227,9 @@ unsigned long long sig_debug_launch_count(void);
  * names_buf receives '\n'-separated phase names; ms[i]/counts[i] the summed time and scope count. */
 int sig_profile_enable(int on);
 int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);
+/* Time line of the recorded scopes ("name start_us end_us" lines, relative to the earliest start); with
+ * SIG_PROF_CAPTURE=1 scopes are also recorded during stream capture, so a graph replay can be laid out. */
+int sig_profile_timeline(char* buf, size_t bytes);
 
 /* Unit-test seam for the tcgen05 GEMM core: C = alpha * A . B^T (+bias) (GELU if act), bf16 operands.
  * mode: 0 row-major [rows,K]; 1 token view [B,128,d] with rows=(b,l), K=d; 2 row-major [K,cols];

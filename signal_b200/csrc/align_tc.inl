@@ -794,7 +794,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_CHECK_LAUNCH();
   }
   s = smain;
-  if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
+  if (!do_lam && dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
   if (dtok->zero_cls && !dtok->accumulate) {
     SIG_LAUNCH((zero_cls_kernel<__nv_bfloat16>), dim3(B, 3), 64, 0, s, gp, d);
     SIG_CHECK_LAUNCH();
@@ -858,10 +858,57 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_LAUNCH((lam_unfold_bias_kernel), dim3((unsigned)ceil_div(d, 32), 3), 1024, 0, s, *p, *dp, c.dbf, d);   // db0 = db', dbq = W0^T db'
     SIG_CHECK_LAUNCH();
   }
+  {
+    SIG_PHASE("lam_offsetnet_bwd_dw");
+    // dW' = dH^T X  (both operands MN-major: K = all B*L positions), split-K with fp32 atomics.  First: it
+    // only needs dH, and its un-fold chain then runs on the side stream under the dX GEMM.
+    cudaMemsetAsync(c.dWf, 0, 3 * dd * sizeof(float), s);
+    TcGemmDesc t = tc_desc();
+    t.A = batched(tc_mn2d(nullptr, (int64_t)BL, d, d), c.dH, BL * d);
+    t.B = tok_operand(tok, TC_MNTOK);
+    t.M = d; t.N = d; t.K = (int)BL; t.batch = 3;
+    for (int m = 0; m < 3; ++m) t.C[m] = c.dWf + m * dd;
+    t.ldc = d;
+    t.bn = (d % 256 == 0) ? 256 : 128;
+    t.mt = 1;
+    const int tiles = (int)(ceil_div(d, 128 * t.mt) * ceil_div(d, t.bn)) * 3;
+    int ks = (2 * 148 + tiles - 1) / tiles;
+    if (ks < 1) ks = 1;
+    t.ksplit = ks;
+    SIG_TRY(tc_gemm(t, s));
+  }
+  {
+    if (fk2.ok()) fk2.fork(s);   // after the dW' GEMM
+    cudaStream_t s = s2;
+    SIG_PHASE("lam_unfold_grads");
+    SIG_TRY(cast_f32_to_bf16(c.dWf, c.dWfb, 3 * dd, s));
+    {  // dWq[d_mid, d_in] = W0^T dW'  : A[m = d_mid, k = d_out] = W0[k][m] (MN-major), B[n = d_in, k = d_out] = dW'[k][n] (MN-major)
+      TcGemmDesc t = tc_desc();
+      t.A = batched(tc_mn2d(nullptr, d, d, d), c.W0b, dd);
+      t.B = batched(tc_mn2d(nullptr, d, d, d), c.dWfb, dd);
+      t.M = d; t.N = d; t.K = d; t.batch = 3;
+      for (int m = 0; m < 3; ++m) t.C[m] = dp->proj_q_w[m];
+      t.ldc = d;
+      SIG_TRY(tc_gemm(t, s));
+    }
+    {  // dW0[d_out, d_mid] = dW' Wq^T : A = dW' [d_out, d_in] K-major, B = Wq [d_mid, d_in] K-major
+      TcGemmDesc t = tc_desc();
+      t.A = batched(tc_k2d(nullptr, d, d, d), c.dWfb, dd);
+      t.B = batched(tc_k2d(nullptr, d, d, d), c.Wqb, dd);
+      t.M = d; t.N = d; t.K = d; t.batch = 3;
+      for (int m = 0; m < 3; ++m) t.C[m] = dp->off0_w[m];
+      t.ldc = d;
+      SIG_TRY(tc_gemm(t, s));
+    }
+    // (dbf was reduced earlier on this same side stream)
+    SIG_LAUNCH((rank1_add3_kernel), dim3((unsigned)ceil_div((int64_t)dd, 256), 3), 256, 0, s, *dp, c.dbf, *p, d);
+    SIG_CHECK_LAUNCH();
+  }
   if (fkb.ok()) fkb.join(smain);   // the dX epilogue adds the GAM rows (dmean)
+  if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);   // first write to the shared gradient map
   {
     SIG_PHASE("lam_offsetnet_bwd_dx");
-    // d(patches) = dH W' + g_gam * dmean  -> written once, in the token dtype, at the token strides
+    // d(patches) (+)= dH W' + g_gam * dmean  -> in the token dtype, at the token strides
     TcGemmDesc t = tc_desc();
     t.A = batched(tc_k2d(nullptr, (int64_t)BL, d, d), c.dH, BL * d);
     t.B = batched(tc_mn2d(nullptr, d, d, d), c.Wfb, dd);
@@ -879,56 +926,11 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_TRY(tc_gemm(t, s));
   }
   {
-    if (fk2.ok()) fk2.fork(s);   // after the dX GEMM
-    cudaStream_t s = s2;
     SIG_PHASE("lam_sparse_dx");
     SIG_LAUNCH((lam_sparse_add_kernel<__nv_bfloat16>), dim3(B, 3), cthreads, 0, s, gp, c.o, c.dS, g, B, d);
     SIG_CHECK_LAUNCH();
     if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
   }
-  {
-    SIG_PHASE("lam_offsetnet_bwd_dw");
-    // dW' = dH^T X  (both operands MN-major: K = all B*L positions), split-K with fp32 atomics
-    cudaMemsetAsync(c.dWf, 0, 3 * dd * sizeof(float), s);
-    TcGemmDesc t = tc_desc();
-    t.A = batched(tc_mn2d(nullptr, (int64_t)BL, d, d), c.dH, BL * d);
-    t.B = tok_operand(tok, TC_MNTOK);
-    t.M = d; t.N = d; t.K = (int)BL; t.batch = 3;
-    for (int m = 0; m < 3; ++m) t.C[m] = c.dWf + m * dd;
-    t.ldc = d;
-    t.bn = (d % 256 == 0) ? 256 : 128;
-    t.mt = 1;
-    const int tiles = (int)(ceil_div(d, 128 * t.mt) * ceil_div(d, t.bn)) * 3;
-    int ks = (2 * 148 + tiles - 1) / tiles;
-    if (ks < 1) ks = 1;
-    t.ksplit = ks;
-    SIG_TRY(tc_gemm(t, s));
-  }
-  {
-    SIG_PHASE("lam_unfold_grads");
-    SIG_TRY(cast_f32_to_bf16(c.dWf, c.dWfb, 3 * dd, s));
-    if (fk2.ok()) fk2.fork(s);
-    {  // dWq[d_mid, d_in] = W0^T dW'  : A[m = d_mid, k = d_out] = W0[k][m] (MN-major), B[n = d_in, k = d_out] = dW'[k][n] (MN-major)
-      TcGemmDesc t = tc_desc();
-      t.A = batched(tc_mn2d(nullptr, d, d, d), c.W0b, dd);
-      t.B = batched(tc_mn2d(nullptr, d, d, d), c.dWfb, dd);
-      t.M = d; t.N = d; t.K = d; t.batch = 3;
-      for (int m = 0; m < 3; ++m) t.C[m] = dp->proj_q_w[m];
-      t.ldc = d;
-      SIG_TRY(tc_gemm(t, s2));   // next to dW0 on the side stream
-    }
-    {  // dW0[d_out, d_mid] = dW' Wq^T : A = dW' [d_out, d_in] K-major, B = Wq [d_mid, d_in] K-major
-      TcGemmDesc t = tc_desc();
-      t.A = batched(tc_k2d(nullptr, d, d, d), c.dWfb, dd);
-      t.B = batched(tc_k2d(nullptr, d, d, d), c.Wqb, dd);
-      t.M = d; t.N = d; t.K = d; t.batch = 3;
-      for (int m = 0; m < 3; ++m) t.C[m] = dp->off0_w[m];
-      t.ldc = d;
-      SIG_TRY(tc_gemm(t, s));
-    }
-    if (fk2.ok()) fk2.join(s);   // dbf (reduced on the side stream) feeds the rank-1 term; also the end-of-call join
-    SIG_LAUNCH((rank1_add3_kernel), dim3((unsigned)ceil_div((int64_t)dd, 256), 3), 256, 0, s, *dp, c.dbf, *p, d);
-    SIG_CHECK_LAUNCH();
-  }
+  if (fk2.ok()) fk2.join(s);
   return 0;
 }

@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -56,15 +57,24 @@ bool pdl_enabled() {
 
 void prof_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-ProfScope::ProfScope(const char* name, cudaStream_t stream) : idx(-1), s(stream) {
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : idx(-1), s(stream), capturing(false) {
   if (!g_enabled.load(std::memory_order_relaxed)) return;
+  // SIG_PROF_CAPTURE=1: also record inside stream capture (the events become event-record nodes of the graph,
+  // so a replay can be laid out on a time line with sig_profile_timeline)
+  static const bool in_capture = [] {
+    const char* e = getenv("SIG_PROF_CAPTURE");
+    return e && e[0] == '1';
+  }();
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) return;
+  if (st != cudaStreamCaptureStatusNone && !in_capture) return;
   Rec r;
   r.name = name;
   if (cudaEventCreate(&r.a) != cudaSuccess) return;
   if (cudaEventCreate(&r.b) != cudaSuccess) { cudaEventDestroy(r.a); return; }
-  cudaEventRecord(r.a, stream);
+  capturing = st != cudaStreamCaptureStatusNone;
+  if (capturing) cudaEventRecordWithFlags(r.a, stream, cudaEventRecordExternal);   // a node the host can time after a replay
+  else cudaEventRecord(r.a, stream);
   std::lock_guard<std::mutex> lk(g_mu);
   g_recs.push_back(r);
   idx = (int)g_recs.size() - 1;
@@ -73,7 +83,10 @@ ProfScope::ProfScope(const char* name, cudaStream_t stream) : idx(-1), s(stream)
 ProfScope::~ProfScope() {
   if (idx < 0) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  if (idx < (int)g_recs.size()) cudaEventRecord(g_recs[idx].b, s);
+  if (idx < (int)g_recs.size()) {
+    if (capturing) cudaEventRecordWithFlags(g_recs[idx].b, s, cudaEventRecordExternal);
+    else cudaEventRecord(g_recs[idx].b, s);
+  }
 }
 }  // namespace sig
 
@@ -84,6 +97,36 @@ unsigned long long sig_debug_launch_count(void) { return sig::g_launches.load();
 int sig_profile_enable(int on) {
   sig::g_enabled.store(on ? 1 : 0);
   return 0;
+}
+
+// Time line of the recorded scopes: "name start_us end_us\n" per scope, relative to the earliest start.
+// Does not clear the record (a captured graph keeps using the events); returns the number of scopes written.
+int sig_profile_timeline(char* buf, size_t bytes) {
+  std::lock_guard<std::mutex> lk(sig::g_mu);
+  if (sig::g_recs.empty() || !buf || !bytes) return 0;
+  std::string out;
+  int n = 0;
+  cudaEvent_t ref = nullptr;
+  float best = 0.f;
+  for (auto& r : sig::g_recs) {   // earliest start = the one no other start precedes
+    if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+    if (!ref) { ref = r.a; continue; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ref, r.a) == cudaSuccess && t < best) { ref = r.a; best = 0.f; }
+  }
+  if (!ref) return 0;
+  for (auto& r : sig::g_recs) {
+    float t0 = 0.f, t1 = 0.f;
+    if (cudaEventElapsedTime(&t0, ref, r.a) != cudaSuccess || cudaEventElapsedTime(&t1, ref, r.b) != cudaSuccess) continue;
+    char line[160];
+    snprintf(line, sizeof line, "%s %.1f %.1f\n", r.name.c_str(), t0 * 1e3f, t1 * 1e3f);
+    if (out.size() + strlen(line) + 1 > bytes) break;
+    out += line;
+    ++n;
+  }
+  std::strncpy(buf, out.c_str(), bytes - 1);
+  buf[bytes - 1] = 0;
+  return n;
 }
 
 // Synchronises the recorded events, writes up to `max` aggregated phases ('\n'-separated names

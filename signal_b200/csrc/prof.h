@@ -9,6 +9,7 @@ void prof_count_launch();
 struct ProfScope {
   int idx;
   cudaStream_t s;
+  bool capturing;
   ProfScope(const char* name, cudaStream_t stream);
   ~ProfScope();
 };

@@ -1112,7 +1112,7 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
     gp.accumulate = dtok->accumulate;
     SIG_LAUNCH((write_cls_grads_kernel<__nv_bfloat16>), dim3(B, 3), 96, 0, s, gp, c.dr1, d);
     SIG_CHECK_LAUNCH();
-    if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
+    // (done_event was recorded right after the token-gradient kernel, sim_tc_tokens_bwd)
     {
       const Fork fk = get_fork(FORK_SIM_BWD);
       if (fk.ok()) fk.join(s);   // weight-gradient GEMMs enqueued on the side stream

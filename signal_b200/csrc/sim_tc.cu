@@ -421,6 +421,8 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
     p.accumulate = dtok->accumulate;
     if (d % 256 == 0) SIG_TRY((tc::launch<256, DxProblem<256>>(p, 3 * B * (d / 256), s, 1)));
     else SIG_TRY((tc::launch<128, DxProblem<128>>(p, 3 * B * (int)ceil_div(d, 128), s, 1)));
+    // the patch rows of the shared gradient map are complete (the CLS rows belong to SIM alone)
+    if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
   }
   {
     ColsParams p{};

@@ -394,7 +394,7 @@ class HeadFunction(torch.autograd.Function):
 
     The two modules are independent until their gradients meet in the token maps, so AlignM runs on a
     side stream concurrently with SIM (forward and backward), and the backward writes ONE gradient
-    map per modality: AlignM's kernels overwrite it, SIM's token-gradient GEMM accumulates on top
+    map per modality: SIM's token-gradient kernel overwrites it, AlignM's dX GEMM accumulates on top
     (ordered by a CUDA event).  tensors: 3 token maps, 16 SIM parameters, 22 AlignM parameters and,
     optionally, the 4 tensors of the folded-selection cache.
     """
@@ -462,19 +462,22 @@ class HeadFunction(torch.autograd.Function):
         gs_a = L_.align_params_struct(pg_a[0], [pg_a[1 + 7 * m: 8 + 7 * m] for m in range(3)], cls=L_.SigAlignParamGrads)
         event, grad_sync = event
         evh = event.cuda_event
-        tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=False, zero_cls=True, done_event=evh)   # AlignM overwrites ...
-        tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=True, wait_event=evh)                   # ... SIM adds on top
+        # SIM's token-gradient kernel overwrites the shared map (it has no long GEMM in front of it and finishes
+        # first); AlignM's dX GEMM, which can run its weight-gradient GEMM while it waits, adds on top
+        tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=False, done_event=evh)
+        tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=True, zero_cls=False, wait_event=evh)
         main = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):
             side.wait_stream(main)
-            L_.check(lib.sig_align_bwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg_a), C.byref(gs_a),
-                                       buf_a.data_ptr(), buf_a.numel(), flags, dev.index, side.cuda_stream), "sig_align_bwd")
-            if grad_sync is not None:    # data parallel: each arena's exchange starts on the stream that produced it,
-                with torch.cuda.stream(side):   # so AlignM's all-reduce overlaps what is left of SIM's backward (and vice versa)
-                    grad_sync(flat_a)
+            # (SIM first: its call records the event AlignM's call waits on)
             L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(sprm), dout.data_ptr(), C.byref(tg_s), C.byref(gs_s), buf_s.data_ptr(),
                                      buf_s.numel(), flags, dev.index, main.cuda_stream), "sig_sim_bwd")
+            if grad_sync is not None:    # data parallel: each arena's exchange starts on the stream that produced it,
+                grad_sync(flat_s)        # so one module's all-reduce overlaps what is left of the other's backward
+            L_.check(lib.sig_align_bwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg_a), C.byref(gs_a),
+                                       buf_a.data_ptr(), buf_a.numel(), flags, dev.index, side.cuda_stream), "sig_align_bwd")
             if grad_sync is not None:
-                grad_sync(flat_s)
+                with torch.cuda.stream(side):
+                    grad_sync(flat_a)
             main.wait_stream(side)
         return (None,) * 9 + tuple(dtoks) + (None,) * 4 + tuple(pg_s) + tuple(pg_a) + (None,) * nfold

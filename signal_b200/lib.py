@@ -70,7 +70,7 @@ EXPORTS = [
     "sig_sim_fwd", "sig_sim_bwd", "sig_sim_fold_selection", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
-    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps",
+    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     lib.sig_volume3_fwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, sz, i, vp]
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
     lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
+    lib.sig_profile_timeline.argtypes = [C.c_char_p, sz]
     lib.sig_debug_tc_stamps.argtypes = [P(C.c_longlong)]
     lib.sig_debug_launch_count.restype = C.c_ulonglong
     lib.sig_profile_enable.argtypes = [i]

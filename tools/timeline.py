@@ -1,0 +1,51 @@
+"""Time line of ONE CUDA-graph replay of the fused step (SIG_PROF_CAPTURE=1 python tools/timeline.py):
+the library's phase scopes are recorded as event nodes inside the captured graph."""
+import os, sys
+os.environ.setdefault("SIG_PROF_CAPTURE", "1")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import torch
+from signal_b200 import lib, modules as M, synthetic as syn
+L_ = lib.load()
+d, B = 768, 128
+dev = torch.device("cuda", 0)
+sim = M.Select_Interactive_Module(d, k=80); al = M.AlignmentM(d, 16, 8)
+sim.load_state_dict(syn.make_params(syn.sim_param_shapes(d), 1234)); al.load_state_dict(syn.make_params(syn.align_param_shapes(d), 1235))
+sim, al = sim.to(dev), al.to(dev)
+params = list(sim.parameters()) + list(al.parameters())
+toks = [t.to(dev).requires_grad_(True) for t in syn.make_tokens(B, d, seed=1, dtype=torch.bfloat16)]
+cot = syn.make_cotangent(B, d).to(dev, torch.bfloat16)
+wg = torch.tensor(0.2, device=dev); wl = torch.tensor(0.2, device=dev)
+head = M.FusionHead(sim, al)
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+def fwd_bwd():
+    patches = [t[:, 1:] for t in toks]; cls = [t[:, 0] for t in toks]
+    if only == "sim":
+        out = sim(*patches, *cls); torch.autograd.backward([out], [cot])
+    elif only == "align":
+        gam, lam = al(*patches, stage="together_CLS_Patch"); torch.autograd.backward([gam, lam], [wg, wl])
+    else:
+        out, gam, lam = head(*patches, *cls, stage="together_CLS_Patch")
+        torch.autograd.backward([out, gam, lam], [cot, wg, wl])
+for _ in range(3):
+    for t in toks: t.grad = None
+    for p in params: p.grad = None
+    fwd_bwd()
+torch.cuda.synchronize()
+for t in toks: t.grad = None
+for p in params: p.grad = None
+g = torch.cuda.CUDAGraph()
+lib.profile_enable(True)
+with torch.cuda.graph(g):
+    fwd_bwd()
+lib.profile_enable(False)
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+buf = C.create_string_buffer(1 << 16)
+n = L_.sig_profile_timeline(buf, len(buf))
+rows = [l.split() for l in buf.value.decode().strip().splitlines()]
+rows = sorted(((r[0], float(r[1]), float(r[2])) for r in rows), key=lambda r: r[1])
+print(f"{n} scopes; step spans {max(r[2] for r in rows):.1f} us")
+for name, a, b in rows:
+    print(f"{a:8.1f} {b:8.1f} {b - a:7.1f}  {name}")
