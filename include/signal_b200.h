@@ -82,6 +82,17 @@ typedef struct sig_token_grads {
    * that records must be issued before the call that waits. */
   void* wait_event;
   void* done_event;
+  /* Optional fusion of SIM's token gradient into AlignM's dX GEMM (bf16 tensor-core path, both modules on the
+   * same three [B,1+L,d] maps).  SIM's d(patches) is a K = 64 product [P~ | dS~] . [dxbar ; qt] per sample;
+   * instead of writing it (and AlignM re-reading it to add its own part) the two operands are handed to
+   * AlignM, whose dX GEMM appends them as one more k-block.
+   *   in SIM's struct:   fuse_skip_dx = 1 -> sig_sim_bwd prepares the operands in its ctx, does not touch dpatch,
+   *                      and records done_event once they are complete;
+   *   in AlignM's struct: fuse_pds / fuse_dxqt = the operand pointers (sig_sim_dx_operands) -> added to dpatch. */
+  int32_t fuse_skip_dx;
+  int32_t reserved_;
+  const void* fuse_pds;
+  const void* fuse_dxqt;
 } sig_token_grads;
 
 /* Optional cache of the frozen token_selection parameters folded together (they never receive a
@@ -225,6 +236,11 @@ int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int 
 unsigned long long sig_debug_launch_count(void);
 /* per-phase CUDA-event timing: enable, run, then collect (synchronises the recorded events).
  * names_buf receives '\n'-separated phase names; ms[i]/counts[i] the summed time and scope count. */
+/* Device pointers, inside a SIM ctx buffer of the bf16 tensor-core path, of the two operands of SIM's token
+ * gradient ([B][384][64] and [B*64][d], bf16) -- see sig_token_grads.fuse_*.  Returns SIG_ERR_DTYPE when
+ * this (dtype, L, flags) combination does not run on that path. */
+int sig_sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flags, void** pds, void** dxqt);
+
 int sig_profile_enable(int on);
 int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);
 /* Time line of the recorded scopes ("name start_us end_us" lines, relative to the earliest start); with

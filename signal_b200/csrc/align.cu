@@ -704,8 +704,10 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
     for (int m = 1; m < 3; ++m)
       if (dtok->patch_stride_b[m] != dtok->patch_stride_b[0] || dtok->patch_stride_l[m] != dtok->patch_stride_l[0])
         return SIG_ERR_SHAPE;
+    if (dtok->fuse_pds && !do_lam) return SIG_ERR_SHAPE;   // the fused operands ride on the LAM dX GEMM
     return align_backward_tc(tok, p, h, w, do_lam, dlosses, dtok, dp, ctx, s);
   }
+  if (dtok->fuse_pds) return SIG_ERR_SHAPE;   // only the tensor-core path can take SIM's operands
   if (ctx_bytes < align_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
   AlignCtx c = align_ctx(ctx, B, L, d, 3);
   const size_t BL = (size_t)B * L;

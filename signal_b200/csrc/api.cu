@@ -185,6 +185,10 @@ int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const 
   return sig::tc_gemm(g, (cudaStream_t)stream);
 }
 
+int sig_sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flags, void** pds, void** dxqt) {
+  return sig::sim_dx_operands(ctx, B, L, d, dtype, flags, pds, dxqt);
+}
+
 int sig_debug_tc_stamps(long long* out16) { return sig::tc_read_stamps(out16); }
 
 }  // extern "C"

@@ -1125,6 +1125,15 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
   return 0;
 }
 
+int sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flags, void** pds, void** dxqt) {
+  if (!ctx || !pds || !dxqt) return SIG_ERR_NULL;
+  if (!sim_tc_ok(dtype, L, flags)) return SIG_ERR_DTYPE;
+  const SimCtx c = sim_ctx(ctx, B, L, d, true);
+  *pds = c.PdS;
+  *dxqt = c.DXQT;
+  return 0;
+}
+
 int sim_select(const sig_tokens* tok, const sig_sim_params* p, int which, int k1, int k2, int max_keep, float* masks,
                void* selected, void* ctx, size_t ctx_bytes, cudaStream_t s) {
   SIG_TRY(check_tokens(tok, true));

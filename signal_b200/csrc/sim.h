@@ -17,6 +17,7 @@ int sim_select(const sig_tokens* tok, const sig_sim_params* p, int which, int k1
                void* selected, void* ctx, size_t ctx_bytes, cudaStream_t s);
 int select_from_scores(const float* intra, const float* inter, const float* raw, int B, int L, int which, int k1, int k2,
                        int max_keep, float* masks, cudaStream_t s);
+int sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flags, void** pds, void** dxqt);
 int mask_mul_bwd(const void* dselected, const float* masks, int dtype, int B, int L, int d, const sig_token_grads* g,
                  cudaStream_t s);
 }  // namespace sig

@@ -407,8 +407,11 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
     p.Ptok = k.Ptok; p.delta = k.delta; p.PdS = k.PdS; p.dST = k.dST;
     SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s, d / 64)));
   }
-  if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
-  {
+  if (dtok->fuse_skip_dx) {
+    // AlignM's dX GEMM consumes [P~ | dS~] (PdS) and [dxbar ; qt] (DXQT) as one more k-block: they are complete here
+    if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
+  } else {
+    if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
     DxParams p{};
     SIG_TRY(tc::make_map_2d(k.PdS, (int64_t)B * 384, 64, 64, 128, &p.ta));
     SIG_TRY(tc::make_map_2d(k.DXQT, (int64_t)B * 64, d, d, 64, &p.tb));

@@ -79,6 +79,15 @@ int sm_reserve() {
   return v;
 }
 
+int make_map_3d(const void* ptr, int64_t cols, int64_t rows, int64_t nb, int64_t stride_row, int64_t stride_b, int box_rows,
+                CUtensorMap* out) {
+  if ((stride_row * 2) % 16 || (stride_b * 2) % 16) return SIG_ERR_ALIGN;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nb};
+  cuuint64_t gstr[2] = {(cuuint64_t)stride_row * 2, (cuuint64_t)stride_b * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  return encode(const_cast<void*>(ptr), 3, gdim, gstr, box, out);
+}
+
 int stage_override() {
   static const int v = [] {
     const char* e = getenv("SIG_TC_STAGES");
@@ -124,6 +133,8 @@ struct TcKernelParams {
   void* C2[8];
   long long ldc2;
   float* pre[8];
+  int extra;              // 1: one more k-block (index kblocks) from the per-sample operands tax / tbx
+  CUtensorMap tax, tbx;
 };
 
 template <int BN, bool AMN, bool BMN, int MT = 1>
@@ -135,6 +146,10 @@ struct GemmProblem {
     for (int z = 0; z < p.batch; ++z) {
       ptx::prefetch_tmap(&p.ta[z]);
       ptx::prefetch_tmap(&p.tb[z]);
+    }
+    if (p.extra) {
+      ptx::prefetch_tmap(&p.tax);
+      ptx::prefetch_tmap(&p.tbx);
     }
   }
   __device__ static int num_units(const Params& p) { return p.tiles_m * p.tiles_n * p.ksplit * p.batch; }
@@ -153,7 +168,7 @@ struct GemmProblem {
     u.n0 = (r - tm * p.tiles_n) * BN;
     u.m0 = tm * BM * MT;
     u.kb0 = ks * per;
-    u.kb1 = min(p.kblocks, u.kb0 + per);
+    u.kb1 = min(p.kblocks, u.kb0 + per) + p.extra;   // (extra implies ksplit == 1)
     return u;
   }
   template <bool kMn>   // the operand's major-ness is a compile-time property: one runtime test (2-D vs token view) remains
@@ -168,10 +183,18 @@ struct GemmProblem {
     }
   }
   __device__ static void load_a(const Params& p, const Unit& u, int kb, uint8_t* sa, uint64_t* bar) {
+    if (kb == p.kblocks) {   // the per-sample extra block: rows z*128.. of sample m0/128
+      ptx::tma_load_3d(sa, &p.tax, bar, 0, u.z * 128, u.m0 >> 7);
+      return;
+    }
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) load_one<AMN>(&p.ta[u.z], p.a_mode, sa + mt * tc::kATileBytes, bar, u.m0 + mt * BM, kb, BM);
   }
   __device__ static void load_b(const Params& p, const Unit& u, int kb, uint8_t* sb, uint64_t* bar) {
+    if (kb == p.kblocks) {
+      tc::load_mnmajor_2d(&p.tbx, sb, bar, u.n0, (u.m0 >> 7) * 64, BN);
+      return;
+    }
     load_one<BMN>(&p.tb[u.z], p.b_mode, sb, bar, u.n0, kb, BN);
   }
 
@@ -383,7 +406,13 @@ int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
   if (p.ksplit > p.kblocks) p.ksplit = p.kblocks;
   const int units = p.tiles_m * p.tiles_n * p.ksplit * p.batch;
   const bool amn = g.A.mode >= TC_MN2D, bmn = g.B.mode >= TC_MN2D;
-  const int kpu = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  if (g.xa || g.xb) {
+    if (!g.xa || !g.xb || g.xB < 1 || amn || !bmn || MT != 1 || p.ksplit != 1 || g.M != g.xB * 128 || g.batch > 3) return SIG_ERR_SHAPE;
+    SIG_TRY(tc::make_map_3d(g.xa, 64, 384, g.xB, 64, 384 * 64, 128, &p.tax));
+    SIG_TRY(tc::make_map_2d(g.xb, (int64_t)g.xB * 64, g.N, g.N, 64, &p.tbx));
+    p.extra = 1;
+  }
+  const int kpu = (p.kblocks + p.ksplit - 1) / p.ksplit + p.extra;
   if (amn && bmn) return tc::launch<BN, GemmProblem<BN, true, true, MT>, MT>(p, units, s, kpu);
   if (amn) return tc::launch<BN, GemmProblem<BN, true, false, MT>, MT>(p, units, s, kpu);
   if (bmn) return tc::launch<BN, GemmProblem<BN, false, true, MT>, MT>(p, units, s, kpu);

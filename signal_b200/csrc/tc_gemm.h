@@ -45,6 +45,13 @@ struct TcGemmDesc {
   void* C2[8];              // optional bf16 copy of the stored value (row pitch ldc2)
   int64_t ldc2;
   float* pre[8];            // optional fp32 copy of the value before the activation (row pitch ldc)
+  // Optional extra 64-wide K block appended to the contraction, with PER-SAMPLE operands (M tile = one sample,
+  // batch entry z = modality): C[z][(b,l), n] += sum_k xa[b][z*128 + l][k] * xb[b*64 + k][n].
+  //   xa: [xB][384][64] bf16 (K-major rows), xb: [xB*64][N] bf16 (read MN-major).
+  // Requires A K-major (2-D), B MN-major, ksplit == 1, mt == 1.  (SIM's token gradient inside AlignM's dX GEMM.)
+  const void* xa;
+  const void* xb;
+  int xB;
 };
 
 inline TcGemmDesc tc_desc() {

@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
 // [box_rows x 64].  Token view: [B, 128, d] with element strides, box [1 x box_rows x 64].
 int make_map_2d(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out);
 int make_map_tok(const void* ptr, int64_t B, int64_t d, int64_t stride_b, int64_t stride_l, int box_rows, CUtensorMap* out);
+int make_map_3d(const void* ptr, int64_t cols, int64_t rows, int64_t nb, int64_t stride_row, int64_t stride_b, int box_rows,
+                CUtensorMap* out);   // [nb][rows][cols], box [1 x box_rows x 64]
 int num_sms();
 
 int sm_reserve();       // SIG_TC_RESERVE in the environment: SMs a persistent launch leaves free

@@ -8,6 +8,8 @@ then write one [B,1+L,d] gradient per modality directly (no per-view zero-fill +
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
@@ -464,8 +466,17 @@ class HeadFunction(torch.autograd.Function):
         evh = event.cuda_event
         # SIM's token-gradient kernel overwrites the shared map (it has no long GEMM in front of it and finishes
         # first); AlignM's dX GEMM, which can run its weight-gradient GEMM while it waits, adds on top
-        tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=False, done_event=evh)
-        tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=True, zero_cls=False, wait_event=evh)
+        fuse = None
+        if do_lam and L == 128 and d <= 768 and os.environ.get("SIG_FUSE_DX", "1") != "0":   # (AlignM's tensor-core path limits)
+            fuse = L_.sim_dx_operands(buf_s, B, L, d, L_.dtype_enum(patches[0]), flags)
+        if fuse is not None:
+            # bf16 tensor-core path: SIM hands the two operands of its token gradient to AlignM, whose dX GEMM
+            # appends them as one more k-block and writes the shared map once (no SIM write, no read-back)
+            tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=False, done_event=evh, fuse_skip_dx=True)
+            tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=False, zero_cls=False, wait_event=evh, fuse_ops=fuse)
+        else:
+            tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=False, done_event=evh)
+            tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=True, zero_cls=False, wait_event=evh)
         main = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):
             side.wait_stream(main)

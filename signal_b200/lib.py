@@ -31,7 +31,8 @@ class SigTokens(C.Structure):
 class SigTokenGrads(C.Structure):
     _fields_ = [("dpatch", _VP3), ("dcls", _VP3), ("patch_stride_b", _I64x3), ("patch_stride_l", _I64x3),
                 ("cls_stride_b", _I64x3), ("accumulate", C.c_int32), ("zero_cls", C.c_int32),
-                ("wait_event", C.c_void_p), ("done_event", C.c_void_p)]
+                ("wait_event", C.c_void_p), ("done_event", C.c_void_p),
+                ("fuse_skip_dx", C.c_int32), ("reserved_", C.c_int32), ("fuse_pds", C.c_void_p), ("fuse_dxqt", C.c_void_p)]
 
 
 SIM_PARAM_FIELDS = ["sel_wq", "sel_bq", "sel_wk", "sel_bk", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b",
@@ -70,7 +71,7 @@ EXPORTS = [
     "sig_sim_fwd", "sig_sim_bwd", "sig_sim_fold_selection", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
-    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline",
+    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_sim_dx_operands",
 ]
 
 
@@ -109,6 +110,7 @@ def load():
     lib.sig_volume3_fwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, sz, i, vp]
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
     lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
+    lib.sig_sim_dx_operands.argtypes = [vp, i, i, i, i, u, P(vp), P(vp)]
     lib.sig_profile_timeline.argtypes = [C.c_char_p, sz]
     lib.sig_debug_tc_stamps.argtypes = [P(C.c_longlong)]
     lib.sig_debug_launch_count.restype = C.c_ulonglong
@@ -173,7 +175,7 @@ def tokens_struct(patches: Sequence[torch.Tensor], cls: Optional[Sequence[torch.
 
 def token_grads_struct(dpatch: Sequence[torch.Tensor], dcls: Optional[Sequence[torch.Tensor]],
                        accumulate: bool = False, zero_cls: bool = False, wait_event: Optional[int] = None,
-                       done_event: Optional[int] = None) -> SigTokenGrads:
+                       done_event: Optional[int] = None, fuse_skip_dx: bool = False, fuse_ops=None) -> SigTokenGrads:
     g = SigTokenGrads()
     for m in range(3):
         g.dpatch[m] = dpatch[m].data_ptr()
@@ -186,7 +188,18 @@ def token_grads_struct(dpatch: Sequence[torch.Tensor], dcls: Optional[Sequence[t
     g.zero_cls = int(zero_cls)
     g.wait_event = wait_event
     g.done_event = done_event
+    g.fuse_skip_dx = int(fuse_skip_dx)
+    if fuse_ops is not None:
+        g.fuse_pds, g.fuse_dxqt = fuse_ops
     return g
+
+
+def sim_dx_operands(ctx_buf: torch.Tensor, B: int, L: int, d: int, dtype: int, flags: int):
+    """(pds, dxqt) device pointers inside a SIM ctx buffer, or None when this configuration does not run on
+    the bf16 tensor-core path (see sig_token_grads.fuse_* in include/signal_b200.h)."""
+    a, b = C.c_void_p(), C.c_void_p()
+    rc = load().sig_sim_dx_operands(ctx_buf.data_ptr(), B, L, d, dtype, flags, C.byref(a), C.byref(b))
+    return (a.value, b.value) if rc == 0 else None
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
