@@ -156,22 +156,37 @@ class ClockSampler:
 # algorithmic work per phase (per step of B samples); DESIGN.md states the derivation
 # ---------------------------------------------------------------------------------------------
 def phase_work(B, d, s=2):
-    """Algorithmic work per step of the bf16 path, as implemented.
-    T*s = bytes of one sample's patch tokens; the folded offset net is ONE d x d GEMM per modality."""
+    """Algorithmic work per launch of the bf16 path, as implemented: {phase: (bound, work, kernel)}.
+    T*s = bytes of one sample's patch tokens; the folded offset net is ONE d x d GEMM per modality.  Every phase
+    listed here brackets exactly one kernel launch."""
     T = 3 * L * d            # token elements per sample
     gemm = 3 * 2 * L * d * d * B                                   # folded 1x1 conv, three modalities
     return {
-        # phase: (bound, work)   bytes for hbm, flops for tensor
-        "lam_offsetnet_fwd": ("tensor", gemm),                     # H = X W'^T
-        "lam_offsetnet_bwd_dx": ("tensor", gemm),                  # dX = dH W'
-        "lam_offsetnet_bwd_dw": ("tensor", gemm),                  # dW' = dH^T X
-        "lam_dwconv_fwd": ("hbm", B * T * s),                      # read H
-        "lam_dwconv_bwd": ("hbm", 2 * B * T * s),                  # read H, write dH
-        "sim_select": ("hbm", B * T * s),                          # one pass over the tokens
-        "sim_attn_tokens_fwd": ("hbm", 2 * B * T * s),             # logits pass + pooling pass
-        "sim_attn_tokens_bwd": ("hbm", 3 * B * T * s),             # dP pass + dQ pass + d(patches) write
-        "gam_fwd": ("hbm", B * T * s),                             # mean pool
+        # phase: (bound, work [bytes for hbm, flops for tensor], kernel)
+        "lam_offsetnet_fwd": ("tensor", gemm, "pipeline_kernel<256,GemmProblem<256,K,K>>  H = X W'^T + b'"),
+        "lam_offsetnet_bwd_dx": ("tensor", gemm, "pipeline_kernel<256,GemmProblem<256,K,MN>>  dX = dH W' (+GAM rows)"),
+        "lam_offsetnet_bwd_dw": ("tensor", gemm, "pipeline_kernel<256,GemmProblem<256,MN,MN>>  dW' = dH^T X (split-K)"),
+        "lam_dwconv_fwd": ("hbm", B * T * s, "lam_dw_fwd_tc_kernel  (read H)"),
+        "lam_dwconv_bwd": ("hbm", 2 * B * T * s, "lam_dw_bwd_tc_kernel  (read H, write dH)"),
+        "sim_scores": ("hbm", B * T * s, "sim_scores_tok_kernel  (one pass over the tokens)"),
+        "gam_pool": ("hbm", B * T * s, "pool_tok_kernel  (one pass over the tokens)"),
+        "sim_attn_logits_fwd": ("hbm", B * T * s, "pipeline_kernel<32,RowsProblem>  (one pass over the tokens)"),
+        "sim_attn_pool_fwd": ("hbm", B * T * s, "pipeline_kernel<32,ColsProblem>  (one pass over the tokens)"),
+        "sim_attn_dlogits_bwd": ("hbm", B * T * s, "pipeline_kernel<32,RowsProblem>  (one pass over the tokens)"),
+        "sim_attn_dx_bwd": ("hbm", B * T * s, "pipeline_kernel<256,DxProblem>  (write d(patches); fused into the dX GEMM under FusionHead)"),
+        "sim_attn_dq_bwd": ("hbm", B * T * s, "pipeline_kernel<32,ColsProblem>  (one pass over the tokens)"),
     }
+
+
+def ncu_traffic():
+    """{phase: dram bytes read + written per launch} from the committed ncu --set full summary (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("per_launch_dram_bytes", {})
+        except Exception:
+            return {}
+    return {}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -406,39 +421,65 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = B * world * e2e_steps / (float(t.item()) * 1e-3)
 
-    # ---- profiled pass (rank 0): per-phase CUDA-event times -> roofline of the dominant phase
-    roof, phases = None, None
+    # ---- profiled pass (rank 0): CUDA events recorded by the library around each phase, on the stream that runs
+    # it, with the two modules called one after the other (no cross-module overlap) -> per-kernel rooflines.
+    roof, phases, kernels = None, None, None
     if rank == 0:
-        prof_steps = 5
+        prof_steps = 10
         if head is not None:
             head.grad_sync = None            # rank-local pass: no collectives
+
+        def seq_step(toks):
+            patches = [t[:, 1:] for t in toks]
+            cls = [t[:, 0] for t in toks]
+            out = sim(*patches, *cls)
+            gam, lam = al(*patches, stage="together_CLS_Patch")
+            torch.autograd.backward([out, gam, lam], [cot, wg, wl])
+
+        for i in range(2):
+            seq_step(dev_sets[i % NSETS])
+        torch.cuda.synchronize()
         lib.profile_enable(True)
-        for i in range(prof_steps):          # local work only: the other ranks are not in this pass (no collective)
+        for i in range(prof_steps):          # local work only: the other ranks are not in this pass
             toks = dev_sets[i % NSETS]
             for t in toks:
                 t.grad = None
             for p_ in params:
                 p_.grad = None
-            fwd_bwd(toks)
+            seq_step(toks)
         torch.cuda.synchronize()
         lib.profile_enable(False)
         prof = lib.profile_collect()
         pk = peaks()
         work = phase_work(B, d)
         phases = {k: round(v[0] / prof_steps * 1e3, 1) for k, v in prof.items()}   # us per step
-        tot = sum(phases.values())
-        known = {k: v for k, v in phases.items() if k in work}
-        dom = max(known, key=known.get) if known else None
-        if dom:
-            bound, w = work[dom]
-            sec = phases[dom] * 1e-6
+        traffic = ncu_traffic()
+        kernels = {}
+        for k, (bound, w, kname) in work.items():
+            if k not in phases or phases[k] <= 0:
+                continue
+            sec = phases[k] * 1e-6
             if bound == "hbm":
                 ach, peak, unit = w / sec / 1e9, pk["hbm"], "GB/s"
             else:
                 ach, peak, unit = w / sec / 1e12, pk["tensor"], "TFLOP/s"
-            roof = {"kernel": dom, "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": pk["src"],
-                    "share_of_step": round(phases[dom] / tot, 3) if tot else None}
+            kernels[k] = {"kernel": kname, "bound": bound, "us": phases[k], "achieved": round(ach, 1), "peak": peak, "unit": unit,
+                          "frac": round(ach / peak, 4), "traffic": traffic.get(k)}
+        # dominant kernel of the step: the tcgen05 GEMM of the LAM offset net (three launches per step: H = X W'^T,
+        # dX = dH W', dW' = dH^T X -- one template, one algorithmic work figure)
+        gem = [kernels[k] for k in ("lam_offsetnet_fwd", "lam_offsetnet_bwd_dx", "lam_offsetnet_bwd_dw") if k in kernels]
+        if gem:
+            us = sum(g["us"] for g in gem) / len(gem)
+            w = work["lam_offsetnet_fwd"][1]
+            ach = w / (us * 1e-6) / 1e12
+            tr = [g["traffic"] for g in gem if g["traffic"]]
+            roof = {"kernel": "tc::pipeline_kernel<256,1,GemmProblem<256,...>> (LAM offset-net GEMMs: H = X W'^T, dX = dH W', dW' = dH^T X)",
+                    "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tensor"], "unit": "TFLOP/s", "frac": round(ach / pk["tensor"], 4),
+                    "traffic": round(sum(tr) / len(tr)) if tr else None, "peak_source": pk["src"] + " (sustained cuBLAS bf16; burst %.0f)" % pk["tensor_burst"],
+                    "launches_per_step": len(gem), "avg_launch_us": round(us, 1),
+                    "algorithmic_flops_per_launch": w, "share_of_step": round(sum(g["us"] for g in gem) / (ms_step * 1e3), 3),
+                    "how": "CUDA events around each launch on its stream, modules run back to back (eager), mean of %d steps; "
+                           "traffic = dram bytes read+written per launch from profiles/ (ncu --set full)" % prof_steps}
     if world > 1:
         dist.barrier()
 
@@ -465,6 +506,7 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "kernels": kernels,
             "phases_us": phases,
             "cpu_baseline": cpu,
         }

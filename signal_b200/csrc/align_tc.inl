@@ -661,8 +661,11 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   }
   {
     SIG_PHASE("gam_fwd");
-    SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), (unsigned)ceil_div(kPoolGroups * (d / 8), 32) * 32, (size_t)kPoolGroups * d * sizeof(float), s, tp, B, L, d, c.mean);
-    SIG_CHECK_LAUNCH();
+    {
+      SIG_PHASE("gam_pool");
+      SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), (unsigned)ceil_div(kPoolGroups * (d / 8), 32) * 32, (size_t)kPoolGroups * d * sizeof(float), s, tp, B, L, d, c.mean);
+      SIG_CHECK_LAUNCH();
+    }
     SIG_LAUNCH((gam_norm_split_kernel), B, 256, 0, s, c.mean, B, d, c.f, c.fb, c.fA, c.fB, c.nrm, c.self4);
     SIG_CHECK_LAUNCH();
     {  // lv = f_r f_n^T, la = f_r f_t^T  (split-bf16, K = 3d)
@@ -859,10 +862,10 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_CHECK_LAUNCH();
   }
   {
-    SIG_PHASE("lam_offsetnet_bwd_dw");
     // dW' = dH^T X  (both operands MN-major: K = all B*L positions), split-K with fp32 atomics.  First: it
     // only needs dH, and its un-fold chain then runs on the side stream under the dX GEMM.
     cudaMemsetAsync(c.dWf, 0, 3 * dd * sizeof(float), s);
+    SIG_PHASE("lam_offsetnet_bwd_dw");
     TcGemmDesc t = tc_desc();
     t.A = batched(tc_mn2d(nullptr, (int64_t)BL, d, d), c.dH, BL * d);
     t.B = tok_operand(tok, TC_MNTOK);

@@ -305,8 +305,9 @@ static __device__ void select_masks(const float* intra, const float* inter, cons
   }
 }
 
-// grid B, 256 threads.  Softmax the logits into the reference-defined scores, then rank-select.
-static __global__ void __launch_bounds__(256) sim_select_kernel(const float* __restrict__ sel_logits, const float* __restrict__ intra_raw,
+// grid B, 1024 threads (one CTA per sample: latency-bound, so as many threads as a CTA can have -- one
+// rank count per thread).  Softmax the logits into the reference-defined scores, then rank-select.
+static __global__ void __launch_bounds__(1024) sim_select_kernel(const float* __restrict__ sel_logits, const float* __restrict__ intra_raw,
                                                                 int B, int L, int d, int which, int k1, int k2, int max_keep,
                                                                 float* __restrict__ masks, float* __restrict__ masks2) {
   pdl_enter();
@@ -834,13 +835,14 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
     SIG_TRY(launch_gemm(gemm_nt(c.qsel, d, p->sel_bk, d, c.csel, 1, nullptr, R, 1, d), s));
   }
   dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
-  if (c.tc)
+  if (c.tc) {
+    SIG_PHASE("sim_scores");
     SIG_LAUNCH((sim_scores_tok_kernel<__nv_bfloat16>), dim3(3, (unsigned)B), 256, 4 * d * sizeof(float), s, tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
                                                                                  c.sel_logits, c.intra_raw);
-  else
+  } else
     SIG_LAUNCH((sim_scores_kernel), grid, 256, 4 * d * sizeof(float), s, c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);
   SIG_CHECK_LAUNCH();
-  SIG_LAUNCH((sim_select_kernel), B, 256, 0, s, c.sel_logits, c.intra_raw, B, L, d, which, k1, k2, max_keep, c.maskf, masks_out);
+  SIG_LAUNCH((sim_select_kernel), B, 1024, 0, s, c.sel_logits, c.intra_raw, B, L, d, which, k1, k2, max_keep, c.maskf, masks_out);
   SIG_CHECK_LAUNCH();
   return 0;
 }

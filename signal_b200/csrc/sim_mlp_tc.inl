@@ -49,6 +49,17 @@ static __global__ void __launch_bounds__(256) catt_kernel(const float* __restric
   if (lane == 0) catt[row * 8 + h] = a * scale;
 }
 
+// shadow = bf16(gelu(a)), 4 elements per thread (n is a multiple of 4: rows of 2d)
+static __global__ void gelu_shadow_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ shadow, int64_t n) {
+  pdl_enter();
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(a + i);
+    const float t[4] = {gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w)};
+    store4(shadow + i, t);
+  }
+}
+
 // da = dh * gelu'(a) in place (fp32) + bf16 shadow
 static __global__ void gelu_bwd_shadow_kernel(float* dh, const float* __restrict__ a, __nv_bfloat16* __restrict__ shadow, int64_t n) {
   pdl_enter();
@@ -118,9 +129,13 @@ static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
   SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1, c.y1b);
   SIG_CHECK_LAUNCH();
   {
-    TcGemmDesc t = lin_nt(c.y1b, d, w1b, d, c.h1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d);
-    t.act = 1; t.pre[0] = c.a1; t.C2[0] = c.h1b; t.ldc2 = 2 * (int64_t)d;
-    SIG_TRY(tc_gemm(t, s));
+    // a1 = y1 W1^T + b1 (fp32, kept for the backward), then h1 = gelu(a1) as the bf16 operand of the next GEMM.
+    // The activation is a separate full-grid elementwise launch: inside the GEMM it would run on the four
+    // epilogue warps of 36 CTAs (erf on one warp per scheduler), which measured 3x the GEMM itself.
+    SIG_TRY(tc_gemm(lin_nt(c.y1b, d, w1b, d, c.a1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d), s));
+    const int64_t n = (int64_t)R * 2 * d;
+    SIG_LAUNCH((gelu_shadow_kernel), (unsigned)ceil_div(n, 4 * 256), 256, 0, s, c.a1, c.h1b, n);
+    SIG_CHECK_LAUNCH();
   }
   SIG_TRY(tc_gemm(lin_nt(c.h1b, 2 * (int64_t)d, w2b, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
   SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out, (__nv_bfloat16*)nullptr);

@@ -12,6 +12,7 @@
 // (A, B, C, E) or K = 64 (D) and ride along for free.
 #include "sim_tc.h"
 
+#include "prof.h"
 #include "tc_pipeline.cuh"
 
 namespace sig {
@@ -303,8 +304,9 @@ static __global__ void __launch_bounds__(128) build_dx_kernel(const float* __res
 }
 
 // softmax over the 384 tokens for each of the 24 effective queries of sample b; writes P~ = P * mask in
-// both layouts (token-major [384][32] and query-major [32][384], bf16).  grid B, 256 threads, dyn smem 384*33 floats
-static __global__ void __launch_bounds__(256) sim_softmax_kernel(const float* __restrict__ S32, const float* __restrict__ maskf, int B,
+// both layouts (token-major [384][32] and query-major [32][384], bf16).  grid B, 1024 threads (one warp per
+// query row: the kernel is one CTA per sample, i.e. latency-bound, so it wants every warp it can get), dyn smem 384*33 floats
+static __global__ void __launch_bounds__(1024) sim_softmax_kernel(const float* __restrict__ S32, const float* __restrict__ maskf, int B,
                                                                  int L, __nv_bfloat16* __restrict__ Ptok, __nv_bfloat16* __restrict__ PT) {
   pdl_enter();
   extern __shared__ float sm[];   // [384][33]
@@ -312,7 +314,7 @@ static __global__ void __launch_bounds__(256) sim_softmax_kernel(const float* __
   const float* src = S32 + (int64_t)b * 384 * 32;
   for (int i = tid; i < 384 * 32; i += blockDim.x) sm[(i >> 5) * 33 + (i & 31)] = src[i];
   __syncthreads();
-  for (int e = w; e < 32; e += 8) {
+  for (int e = w; e < 32; e += (int)(blockDim.x >> 5)) {   // one warp per query row
     __nv_bfloat16* prow = PT + ((int64_t)b * 32 + e) * 384;
     if (e >= 24) {
       for (int j = lane; j < 384; j += 32) {
@@ -374,6 +376,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
     SIG_TRY(tc::make_map_2d(k.DXQT, (int64_t)B * 64, d, d, 32, &p.tb));
     p.B = B; p.d = d; p.L = L; p.b_row_off = 32; p.mode = 0;
     p.maskf = k.maskf; p.catt = k.catt; p.S32 = k.S32;
+    SIG_PHASE("sim_attn_logits_fwd");
     SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s, d / 64)));
   }
   {
@@ -382,7 +385,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
       cudaFuncSetAttribute(sim_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_tc_softmax_smem());
       attr = true;
     }
-    SIG_LAUNCH((sim_softmax_kernel), B, 256, sim_tc_softmax_smem(), s, k.S32, k.maskf, B, L, k.Ptok, k.PT);
+    SIG_LAUNCH((sim_softmax_kernel), B, 1024, sim_tc_softmax_smem(), s, k.S32, k.maskf, B, L, k.Ptok, k.PT);
     SIG_CHECK_LAUNCH();
   }
   {
@@ -390,6 +393,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
     SIG_TRY(make_tok_maps(tok, 64, p.ta));
     SIG_TRY(tc::make_map_2d(k.PT, (int64_t)B * 32, 384, 384, 32, &p.tb));
     p.B = B; p.d = d; p.out = k.xbar; p.out_b = k.xbarb;
+    SIG_PHASE("sim_attn_pool_fwd");
     SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s, 6)));
   }
   return 0;
@@ -405,6 +409,7 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
     SIG_TRY(tc::make_map_2d(k.DXQT, (int64_t)B * 64, d, d, 32, &p.tb));
     p.B = B; p.d = d; p.L = L; p.b_row_off = 0; p.mode = 1;
     p.Ptok = k.Ptok; p.delta = k.delta; p.PdS = k.PdS; p.dST = k.dST;
+    SIG_PHASE("sim_attn_dlogits_bwd");
     SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s, d / 64)));
   }
   if (dtok->fuse_skip_dx) {
@@ -422,6 +427,7 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
       p.psl[z] = dtok->patch_stride_l[z];
     }
     p.accumulate = dtok->accumulate;
+    SIG_PHASE("sim_attn_dx_bwd");
     if (d % 256 == 0) SIG_TRY((tc::launch<256, DxProblem<256>>(p, 3 * B * (d / 256), s, 1)));
     else SIG_TRY((tc::launch<128, DxProblem<128>>(p, 3 * B * (int)ceil_div(d, 128), s, 1)));
     // the patch rows of the shared gradient map are complete (the CLS rows belong to SIM alone)
@@ -432,6 +438,7 @@ int sim_tc_tokens_bwd(const sig_tokens* tok, const SimTcBufs& k, const sig_token
     SIG_TRY(make_tok_maps(tok, 64, p.ta));
     SIG_TRY(tc::make_map_2d(k.dST, (int64_t)B * 32, 384, 384, 32, &p.tb));
     p.B = B; p.d = d; p.out = k.dqt; p.out_b = k.dqtb;
+    SIG_PHASE("sim_attn_dq_bwd");
     SIG_TRY((tc::launch<32, ColsProblem>(p, B * (int)ceil_div(d, 128), s, 6)));
   }
   return 0;
