@@ -424,13 +424,18 @@ class HeadFunction(torch.autograd.Function):
         buf_s = torch.empty(nb_s, dtype=torch.uint8, device=dev)
         buf_a = torch.empty(nb_a, dtype=torch.uint8, device=dev)
         main = torch.cuda.current_stream(dev)
+        hi = event[2] if len(event) > 2 and event[2] is not None else main    # SIM's (high-priority) stream
         with torch.cuda.device(dev):
             side.wait_stream(main)
+            if hi is not main:
+                hi.wait_stream(main)
+            L_.check(lib.sig_sim_fwd(C.byref(tok), C.byref(sprm), k1, k2, max_keep, out.data_ptr(), masks.data_ptr(),
+                                     buf_s.data_ptr(), nb_s, flags, dev.index, hi.cuda_stream), "sig_sim_fwd")
             L_.check(lib.sig_align_fwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), losses.data_ptr(), buf_a.data_ptr(), nb_a,
                                        flags, dev.index, side.cuda_stream), "sig_align_fwd")
-            L_.check(lib.sig_sim_fwd(C.byref(tok), C.byref(sprm), k1, k2, max_keep, out.data_ptr(), masks.data_ptr(),
-                                     buf_s.data_ptr(), nb_s, flags, dev.index, main.cuda_stream), "sig_sim_fwd")
             main.wait_stream(side)
+            if hi is not main:
+                main.wait_stream(hi)
         ctx.save_for_backward(*toks, *sp, *ap, buf_s, buf_a)
         ctx.cfg = (h, w, do_lam, flags, side, event, len(fold))   # event: (torch.cuda.Event, grad_sync or None)
         ctx.mark_non_differentiable(masks)
@@ -462,7 +467,8 @@ class HeadFunction(torch.autograd.Function):
         aprm = L_.align_params_struct(ap[0], mods)
         gs_s = L_.sim_grads_struct(pg_s)
         gs_a = L_.align_params_struct(pg_a[0], [pg_a[1 + 7 * m: 8 + 7 * m] for m in range(3)], cls=L_.SigAlignParamGrads)
-        event, grad_sync = event
+        hi = event[2] if len(event) > 2 else None
+        event, grad_sync = event[0], event[1]
         evh = event.cuda_event
         # SIM's token-gradient kernel overwrites the shared map (it has no long GEMM in front of it and finishes
         # first); AlignM's dX GEMM, which can run its weight-gradient GEMM while it waits, adds on top
@@ -478,17 +484,24 @@ class HeadFunction(torch.autograd.Function):
             tg_s = L_.token_grads_struct(dpatch, dcls, accumulate=False, done_event=evh)
             tg_a = L_.token_grads_struct(dpatch, dcls, accumulate=True, zero_cls=False, wait_event=evh)
         main = torch.cuda.current_stream(dev)
+        if hi is None:
+            hi = main
         with torch.cuda.device(dev):
             side.wait_stream(main)
+            if hi is not main:
+                hi.wait_stream(main)
             # (SIM first: its call records the event AlignM's call waits on)
             L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(sprm), dout.data_ptr(), C.byref(tg_s), C.byref(gs_s), buf_s.data_ptr(),
-                                     buf_s.numel(), flags, dev.index, main.cuda_stream), "sig_sim_bwd")
+                                     buf_s.numel(), flags, dev.index, hi.cuda_stream), "sig_sim_bwd")
             if grad_sync is not None:    # data parallel: each arena's exchange starts on the stream that produced it,
-                grad_sync(flat_s)        # so one module's all-reduce overlaps what is left of the other's backward
+                with torch.cuda.stream(hi):   # so one module's all-reduce overlaps what is left of the other's backward
+                    grad_sync(flat_s)
             L_.check(lib.sig_align_bwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg_a), C.byref(gs_a),
                                        buf_a.data_ptr(), buf_a.numel(), flags, dev.index, side.cuda_stream), "sig_align_bwd")
             if grad_sync is not None:
                 with torch.cuda.stream(side):
                     grad_sync(flat_a)
             main.wait_stream(side)
+            if hi is not main:
+                main.wait_stream(hi)
         return (None,) * 9 + tuple(dtoks) + (None,) * 4 + tuple(pg_s) + tuple(pg_a) + (None,) * nfold

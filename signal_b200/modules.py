@@ -14,6 +14,8 @@ identical); their forward is never called -- all arithmetic runs in libsignal_b2
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -292,7 +294,9 @@ class FusionHead:
         if st is None:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))       # materialise the underlying cudaEvent_t
-            st = (torch.cuda.Stream(dev), ev)
+            # SIG_PRIO=1 (experiment, off by default -- measured slower): SIM on a high-priority stream
+            hi = torch.cuda.Stream(dev, priority=-1) if os.environ.get("SIG_PRIO", "0") == "1" else None
+            st = (torch.cuda.Stream(dev), ev, hi)
             self._side[dev] = st
         return st
 
@@ -307,12 +311,12 @@ class FusionHead:
             res = al(rgb_patch, ni_patch, ti_patch, stage=stage)
             return (out, res, None) if stage == "CLS" else (out, res[0], res[1])
         L = rgb_patch.size(1)
-        side, ev = self._stream(rgb_patch.device)
+        side, ev, hi = self._stream(rgb_patch.device)
         params = [p.detach() for p in ts._sel_params()] + mi._attn_params() + al._params()
         flags = sim.flags | al.flags
         if rgb_patch.dtype == torch.bfloat16 and not (flags & 1):
             params = params + list(ts._selection_fold())
         out, masks, gam, lam = F_.HeadFunction.apply(al.h, al.w, stage != "CLS", ts.k1, ts.k2, ts._max_keep(L), flags, side,
-                                                     (ev, self.grad_sync), *bases, *params)
+                                                     (ev, self.grad_sync, hi), *bases, *params)
         ts.last_masks = {"RGB": masks[0].unsqueeze(-1), "NI": masks[1].unsqueeze(-1), "TI": masks[2].unsqueeze(-1)}
         return (out, gam, None) if stage == "CLS" else (out, gam, lam)
