@@ -3,35 +3,49 @@
 // linear maps proj_q -> conv_offset[0] folded into one (DAS.py:129,136: no non-linearity between
 // them), everything else is HBM-bound SIMT code with 16-byte accesses.
 
-// ---- GAM: mean pool straight from the strided token views.  grid (B, 3), 4 * d/8 threads -----------
-// Four row groups per CTA; a thread owns 8 channels (16 B) and keeps 8 row loads in flight.
-// dyn smem: [4][d] floats.  Algorithmic traffic: the tokens, read once.
-constexpr int kPoolGroups = 4, kPoolUnroll = 8;
+// ---- GAM: mean pool straight from the strided token views.  grid (B, 3), 8 * d/8 threads -----------
+// Eight row groups per CTA; a thread owns 8 channels (16 B) of 16 rows and requests ALL of them before the first
+// add: one memory round trip per CTA, ~200 KB in flight per SM, and CTAs retire/start continuously (2.6 waves),
+// which keeps HBM busy -- a looped version with the same bytes per thread ran its rounds in lock step at 40 %.
+// dyn smem: [8][d] floats.  Algorithmic traffic: the tokens, read once.
+constexpr int kPoolGroups = 8;
 template <typename T>
-static __global__ void __launch_bounds__(512) pool_tok_kernel(TokPtrs3 tp, int B, int L, int d, float* __restrict__ mean) {
+static __global__ void __launch_bounds__(768) pool_tok_kernel(TokPtrs3 tp, int B, int L, int d, float* __restrict__ mean) {
   pdl_enter();
   extern __shared__ __align__(16) float pool_red[];   // [kPoolGroups][d]
   const int b = blockIdx.x, m = blockIdx.y;
   const int tpr = d / 8;                       // threads per token row
   const int grp = threadIdx.x / tpr, c = (threadIdx.x % tpr) * 8;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  constexpr int kRows = kMaxL / kPoolGroups;   // 16 rows per thread
   if (grp < kPoolGroups) {
     const T* x = static_cast<const T*>(tp.patch[m]) + b * tp.psb[m] + c;
-    for (int l0 = grp; l0 < L; l0 += kPoolGroups * kPoolUnroll) {
-      float v[kPoolUnroll][8];
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (sizeof(T) == 2) {
+      uint4 raw[kRows];                        // 64 registers of raw bf16: converted only while summing
 #pragma unroll
-      for (int u = 0; u < kPoolUnroll; ++u) {
-        const int l = l0 + u * kPoolGroups;
-        if (l < L) load8(x + l * tp.psl[m], v[u]);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-        }
+      for (int u = 0; u < kRows; ++u) {
+        const int l = grp + u * kPoolGroups;
+        raw[u] = l < L ? *reinterpret_cast<const uint4*>(x + l * tp.psl[m]) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < kPoolUnroll; ++u)
+      for (int u = 0; u < kRows; ++u) {
+        const uint32_t wv[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
+        for (int t = 0; t < 4; ++t) {
+          acc[2 * t] += __uint_as_float(wv[t] << 16);
+          acc[2 * t + 1] += __uint_as_float(wv[t] & 0xffff0000u);
+        }
+      }
+    } else {
+      for (int u = 0; u < kRows; ++u) {
+        const int l = grp + u * kPoolGroups;
+        if (l < L) {
+          float v[8];
+          load8(x + l * tp.psl[m], v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+      }
     }
     store8(pool_red + grp * d + c, acc);
   }
