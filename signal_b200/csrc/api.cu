@@ -179,7 +179,8 @@ int sig_debug_gemm_bf16(const void* A, int a_mode, const int64_t* a_geom, const 
   fill(g.A, A, a_mode, a_geom);
   fill(g.B, B, b_mode, b_geom);
   g.M = M; g.N = N; g.K = K; g.C[0] = C; g.ldc = ldc; g.out_bf16 = out_bf16; g.bias[0] = bias; g.alpha = alpha;
-  g.act = act; g.ksplit = ksplit; g.bn = bn == 512 ? 256 : bn; g.mt = bn == 512 ? 2 : 1;   // bn = 512: 256 x 256 units
+  g.act = act; g.ksplit = ksplit; g.bn = (bn == 512 || bn == 1024) ? 256 : bn; g.mt = bn == 512 ? 2 : 1;   // bn = 512: 256 x 256 units
+  g.pair = bn == 1024;                                                                           // bn = 1024: 256 x 256 units on CTA pairs
   if (c_stride_b) { g.c_tok = 1; g.c_stride_b = c_stride_b; g.c_stride_l = c_stride_l; }
   g.rowvec[0] = rowvec; g.rowvec_scale = rowvec_scale; g.accumulate = accumulate;
   return sig::tc_gemm(g, (cudaStream_t)stream);

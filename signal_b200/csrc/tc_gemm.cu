@@ -377,6 +377,208 @@ struct GemmProblem {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the large GEMMs: a cluster of two CTAs computes a 256 x BN unit.
+// Each CTA stages ITS 128 rows of A and HALF of the B tile (BN/2 rows); the leader's MMA thread issues
+// M = 256 instructions that read both halves, so the bytes a SM pulls per k-block drop from 48 KB to 32 KB
+// at BN = 256 -- the single-CTA kernel is bound by exactly that L2 -> SM stream.  Same ring / TMEM double
+// buffering / epilogue as tc::pipeline_kernel; differences: both CTAs' TMA transactions land on the LEADER's
+// full barrier, MMA completion is multicast to both CTAs' barriers, and the non-leader's epilogue threads
+// release the accumulator with a remote arrive on the leader's tmem_empty barrier.
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool AMN, bool BMN>
+__global__ void __launch_bounds__(tc::kThreads, 1) pair_gemm_kernel(const __grid_constant__ TcKernelParams p, const int nstages) {
+  using P1 = GemmProblem<BN, AMN, BMN, 1>;
+  using P2 = GemmProblem<BN, AMN, BMN, 2>;   // unit decode with 256-row M tiles
+  constexpr int kABytes = tc::kATileBytes, kBBytes = (BN / 2) * BK * 2, kStageBytes = kABytes + kBBytes;
+  constexpr int kAccCols = BN, kAccBufs = 2 * BN <= 512 ? 2 : 1, kTmemCols = kAccBufs * BN < 32 ? 32 : kAccBufs * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nstages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + nstages;
+  uint64_t* tmem_full = bars + 2 * nstages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_scratch = reinterpret_cast<float*>(smem + nstages * kStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_units = P2::num_units(p);
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) P1::prefetch(p);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < nstages; ++i) {
+      ptx::mbar_init(&full[i], 2);      // the leader's two producers (A, B) arm it for BOTH CTAs' bytes
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kAccBufs; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 256);   // 128 epilogue threads of each CTA (leader's barrier is the one waited on)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_2sm<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                  // barriers of both CTAs initialised before any remote arrive / transaction
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if ((warp == 0 || warp == 3) && lane == 0) {
+    // ================= TMA producers (both CTAs): warp 0 = this CTA's 128 rows of A, warp 3 = its half of B =================
+    const bool is_a = warp == 0;
+    uint32_t stage = 0, ph = 0;
+    for (int unit = pair; unit < total_units; unit += npairs) {
+      const typename P2::Unit u = P2::unit_info(p, unit);
+      const int m0 = u.m0 + (int)rank * BM;
+      const int n0 = u.n0 + (int)rank * (BN / 2);
+      const CUtensorMap* tm = is_a ? &p.ta[u.z] : &p.tb[u.z];
+      const int mode = is_a ? p.a_mode : p.b_mode;
+      const int mn0 = is_a ? m0 : n0;
+      constexpr int kExtent = 128;        // rows of A / rows of this CTA's half of B (BN = 256)
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
+        ptx::mbar_wait(&empty[stage], ph ^ 1);
+        const uint32_t lbar = ptx::mapa_u32(&full[stage], 0);
+        if (leader) ptx::mbar_expect_tx(&full[stage], 2u * (is_a ? (uint32_t)kABytes : (uint32_t)kBBytes));
+        uint8_t* dst = smem + stage * kStageBytes + (is_a ? 0 : kABytes);
+        const int k0 = kb * BK;
+        if (mode == TC_K2D) ptx::tma_load_2d_2sm(dst, tm, lbar, k0, mn0);
+        else if (mode == TC_KTOK) ptx::tma_load_3d_2sm(dst, tm, lbar, k0, 0, mn0 >> 7);
+        else if (mode == TC_MN2D) {
+#pragma unroll
+          for (int j = 0; j < kExtent / 64; ++j) ptx::tma_load_2d_2sm(dst + j * 64 * BK * 2, tm, lbar, mn0 + 64 * j, k0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kExtent / 64; ++j) ptx::tma_load_3d_2sm(dst + j * 64 * BK * 2, tm, lbar, mn0 + 64 * j, k0 & 127, k0 >> 7);
+        }
+        if (++stage == (uint32_t)nstages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ================= MMA issuer (leader CTA only) =================
+    const uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN, AMN, BMN);
+    constexpr uint32_t a_lbo = AMN ? 64 * 128 : 16, b_lbo = BMN ? 64 * 128 : 16;
+    constexpr uint32_t a_kstep = AMN ? 16 * 128 : 32, b_kstep = BMN ? 16 * 128 : 32;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint64_t da0 = ptx::make_smem_desc(smem_base, a_lbo, 1024);
+    const uint64_t db0 = ptx::make_smem_desc(smem_base + kABytes, b_lbo, 1024);
+    uint32_t stage = 0, ph = 0, acc = 0, aph = 0;
+    for (int unit = pair; unit < total_units; unit += npairs) {
+      const typename P2::Unit u = P2::unit_info(p, unit);
+      ptx::mbar_wait(&tmem_empty[acc], aph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
+        ptx::mbar_wait(&full[stage], ph);
+        ptx::tc_fence_after();
+        const uint64_t soff = (uint64_t)((stage * (uint32_t)kStageBytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          ptx::umma_bf16_2sm(d_tmem, da0 + soff + (uint64_t)((k * a_kstep) >> 4), db0 + soff + (uint64_t)((k * b_kstep) >> 4), idesc,
+                             kb > u.kb0 || k > 0);
+        ptx::umma_commit_2sm(&empty[stage]);      // frees the stage in both CTAs
+        if (++stage == (uint32_t)nstages) { stage = 0; ph ^= 1; }
+      }
+      ptx::umma_commit_2sm(&tmem_full[acc]);      // accumulator complete, both CTAs
+      if (++acc == (uint32_t)kAccBufs) { acc = 0; aph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs, each its own 128 accumulator rows) =================
+    const int q = warp & 3;
+    uint32_t acc = 0, aph = 0;
+    for (int unit = pair; unit < total_units; unit += npairs) {
+      typename P2::Unit u2 = P2::unit_info(p, unit);
+      typename P1::Unit u;
+      u.z = u2.z; u.m0 = u2.m0 + (int)rank * BM; u.n0 = u2.n0; u.kb0 = u2.kb0; u.kb1 = u2.kb1;
+      P1::epilogue(p, u, 0, tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16), q, lane, epi_scratch + q * 32 * tc::kEpiLd,
+                   &tmem_full[acc], aph, nullptr);
+      ptx::tc_fence_before();
+      if (leader) ptx::mbar_arrive(&tmem_empty[acc]);
+      else ptx::mbar_arrive_cluster(ptx::mapa_u32(&tmem_empty[acc], 0));
+      if (++acc == (uint32_t)kAccBufs) { acc = 0; aph ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                  // nobody tears down while the peer may still touch this CTA's smem / TMEM
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm<kTmemCols>(tmem_base);
+  }
+}
+
+template <bool AMN, bool BMN>
+static int launch_pair(const TcKernelParams& p, int units, int kpu, cudaStream_t s) {
+  constexpr int BN = 256;
+  constexpr int kStageBytes = tc::kATileBytes + (BN / 2) * BK * 2;
+  auto kernel = pair_gemm_kernel<BN, AMN, BMN>;
+  int stages = (220 * 1024 - tc::kEpiBytes) / kStageBytes;
+  if (stages > 8) stages = 8;
+  const int max_smem = stages * kStageBytes + 1024 + 256 + tc::kEpiBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    attr_set = true;
+  }
+  if (units <= 0) return 0;
+  const int npairs_max = tc::num_sms() / 2;
+  const int npairs = units < npairs_max ? units : npairs_max;
+  const int per_cta = kpu * (int)ceil_div(units, npairs);
+  if (per_cta < stages) stages = per_cta < 2 ? 2 : per_cta;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = stages * kStageBytes + 1024 + 256 + tc::kEpiBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, p, stages);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+// g.pair: 256 x 256 units on CTA pairs.  A: K-major token view or MN-major 2-D; B: K-major 2-D or MN-major (2-D / token view).
+static int launch_gemm_pair(const TcGemmDesc& g, cudaStream_t s) {
+  if (g.bn != 256 || g.mt != 1 || g.xa || g.xb) return SIG_ERR_SHAPE;
+  TcKernelParams p{};
+  auto mk = [&](const TcOperand& o, int z, CUtensorMap* out) -> int {   // every box is 128 M/N-rows (K-major) or 64 x 64 (MN-major)
+    if (o.mode == TC_K2D) return tc::make_map_2d(o.ptr[z], o.rows, o.cols, o.ld, 128, out);
+    if (o.mode == TC_MN2D) return tc::make_map_2d(o.ptr[z], o.rows, o.cols, o.ld, 64, out);
+    return tc::make_map_tok(o.ptr[z], o.rows, o.cols, o.stride_b, o.stride_l, o.mode == TC_KTOK ? 128 : 64, out);
+  };
+  for (int z = 0; z < g.batch; ++z) {
+    SIG_TRY(mk(g.A, z, &p.ta[z]));
+    SIG_TRY(mk(g.B, z, &p.tb[z]));
+    p.C[z] = g.C[z]; p.bias[z] = g.bias[z]; p.rowvec[z] = g.rowvec[z]; p.C2[z] = g.C2[z]; p.pre[z] = g.pre[z];
+    if (!g.C[z]) return SIG_ERR_NULL;
+  }
+  p.a_mode = g.A.mode; p.b_mode = g.B.mode;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
+  p.ldc = g.ldc; p.out_bf16 = g.out_bf16; p.alpha = g.alpha; p.act = g.act; p.ksplit = g.ksplit < 1 ? 1 : g.ksplit;
+  p.c_tok = g.c_tok; p.c_stride_b = g.c_stride_b; p.c_stride_l = g.c_stride_l;
+  p.rowvec_scale = g.rowvec_scale; p.accumulate = g.accumulate; p.ldc2 = g.ldc2;
+  p.tiles_m = (int)ceil_div(g.M, 2 * BM);
+  p.tiles_n = (int)ceil_div(g.N, 256);
+  p.kblocks = (int)ceil_div(g.K, BK);
+  if (p.ksplit > p.kblocks) p.ksplit = p.kblocks;
+  const int units = p.tiles_m * p.tiles_n * p.ksplit * p.batch;
+  const int kpu = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  const bool amn = g.A.mode >= TC_MN2D, bmn = g.B.mode >= TC_MN2D;
+  if (amn && bmn) return launch_pair<true, true>(p, units, kpu, s);
+  if (amn) return launch_pair<true, false>(p, units, kpu, s);
+  if (bmn) return launch_pair<false, true>(p, units, kpu, s);
+  return launch_pair<false, false>(p, units, kpu, s);
+}
+
 template <int BN, int MT>
 int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
   TcKernelParams p{};
@@ -427,6 +629,7 @@ int tc_read_stamps(long long* out16) { return tc::read_stamps(out16); }
 int tc_gemm(const TcGemmDesc& g, cudaStream_t s) {
   if (g.M < 1 || g.N < 1 || g.K < 1 || g.batch < 1 || g.batch > 8) return SIG_ERR_SHAPE;
   if (g.ksplit > 1 && (g.out_bf16 || g.act)) return SIG_ERR_SHAPE;
+  if (g.pair) return launch_gemm_pair(g, s);
   if (g.bn == 256 && g.mt == 2) return launch_gemm_bn<256, 2>(g, s);
   if (g.bn == 256) return launch_gemm_bn<256, 1>(g, s);
   return launch_gemm_bn<128, 1>(g, s);

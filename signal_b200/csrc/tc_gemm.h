@@ -35,6 +35,7 @@ struct TcGemmDesc {
   int ksplit;               // > 1: fp32 atomic accumulation into a pre-zeroed C (no bias / act / bf16)
   int bn;                   // 128 or 256 (N tile)
   int mt;                   // 1 or 2 (with bn == 256): 128-row M tiles per work unit sharing one B tile
+  int pair;                 // 1 (with bn == 256, mt == 1): 256 x 256 units on CTA pairs (cta_group::2), see tc_gemm.cu
   // token-strided output: row = (b, l) with l in [0,128): element (row, n) at C + b*c_stride_b + l*c_stride_l + n
   int c_tok;
   int64_t c_stride_b, c_stride_l;

@@ -127,3 +127,28 @@ def test_256x256_units_share_the_b_tile():
     assert bool((dst[:, 0] == 3.0).all())
     out = lib.debug_gemm_bf16(dH, 2, A, 3, d, d, Bs * 128, ksplit=5, bn=512)
     _check(out, dH.float().T @ A.float().reshape(-1, d))
+
+
+def test_cta_pair_units():
+    """bn=1024 selects 256 x 256 units on CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of
+    the B tile.  Same three GEMM shapes as the LAM offset net; an odd sample count leaves the second CTA's rows
+    of the last unit out of bounds."""
+    from signal_b200 import lib
+    Bs, d = 37, 768
+    tok = _rand((Bs, 129, d), 31)
+    W = _rand((d, d), 32)
+    A = tok[:, 1:]
+    bias = torch.randn(d, device="cuda")
+    out = lib.debug_gemm_bf16(A, 1, W, 0, Bs * 128, d, d, bn=1024, out_bf16=True, bias=bias)       # H = X W^T + b
+    _check(out, A.float().reshape(-1, d) @ W.float().T + bias, 6e-3)
+    dH = _rand((Bs * 128, d), 33)
+    dst = torch.full((Bs, 129, d), 3.0, dtype=torch.bfloat16, device="cuda")
+    lib.debug_gemm_bf16(dH, 0, W, 2, Bs * 128, d, d, bn=1024, out=dst[:, 1:])                        # dX = dH W
+    _check(dst[:, 1:], (dH.float() @ W.float()).reshape(Bs, 128, d), 6e-3)
+    assert bool((dst[:, 0] == 3.0).all())
+    out = lib.debug_gemm_bf16(dH, 2, A, 3, d, d, Bs * 128, ksplit=5, bn=1024)                         # dW = dH^T X
+    _check(out, dH.float().T @ A.float().reshape(-1, d))
+    M, N, K = 1024, 512, 768                                                                          # plain 2-D operands
+    A2, B2 = _rand((M, K), 34), _rand((N, K), 35)
+    out = lib.debug_gemm_bf16(A2, 0, B2, 0, M, N, K, bn=1024)
+    _check(out, A2.float() @ B2.float().T)

@@ -45,12 +45,12 @@ tok = rnd(Bs, 129, d)
 X = tok[:, 1:]
 W = rnd(d, d)
 dH = rnd(Bs * 128, d)
-for bn in (128, 256, 512):
+for bn in (128, 256, 512, 1024):
     t = timeit(lambda: lib.debug_gemm_bf16(X, 1, W, 0, Bs * 128, d, d, bn=bn, out_bf16=True))
     print(f"LAM fwd  bn={bn}: {t:7.2f} us  {2*Bs*128*d*d/t/1e6:8.1f} TFLOP/s")
     t = timeit(lambda: lib.debug_gemm_bf16(dH, 0, W, 2, Bs * 128, d, d, bn=bn, out_bf16=True))
     print(f"LAM dX   bn={bn}: {t:7.2f} us  {2*Bs*128*d*d/t/1e6:8.1f} TFLOP/s")
-for bn, ks in ((128, 4), (128, 8), (256, 8), (512, 11), (512, 16), (512, 33)):
+for bn, ks in ((128, 4), (128, 8), (256, 8), (512, 11), (512, 16), (512, 33), (1024, 8), (1024, 16), (1024, 33)):
     t = timeit(lambda: lib.debug_gemm_bf16(dH, 2, X, 3, d, d, Bs * 128, ksplit=ks, bn=bn))
     print(f"LAM dW   bn={bn} ksplit={ks}: {t:7.2f} us  {2*Bs*128*d*d/t/1e6:8.1f} TFLOP/s")
 print("stages override:", os.environ.get("SIG_TC_STAGES"), " PDL:", os.environ.get("SIG_PDL"))
