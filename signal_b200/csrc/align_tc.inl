@@ -736,6 +736,7 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     t.ldc = d; t.out_bf16 = 1;
     t.bn = (d % 256 == 0) ? 256 : 128;
     t.mt = 1;   // (mt = 2, 256 x 256 units, measured slower: the single TMEM buffer serialises the epilogue)
+    t.pair = t.bn == 256 && tc_pair_enabled();   // 256 x 256 units on CTA pairs (cta_group::2): 5 % faster
     SIG_TRY(tc_gemm(t, s));
   }
   {
@@ -888,8 +889,10 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.ldc = d;
     t.bn = (d % 256 == 0) ? 256 : 128;
     t.mt = 1;
-    const int tiles = (int)(ceil_div(d, 128 * t.mt) * ceil_div(d, t.bn)) * 3;
-    int ks = (2 * 148 + tiles - 1) / tiles;
+    t.pair = t.bn == 256 && tc_pair_enabled();
+    const int tiles = (int)(ceil_div(d, t.pair ? 256 : 128 * t.mt) * ceil_div(d, t.bn)) * 3;
+    const int workers = t.pair ? tc_num_sms() / 2 : tc_num_sms();
+    int ks = (2 * workers + tiles - 1) / tiles;   // about two split-K units per CTA (pair)
     if (ks < 1) ks = 1;
     t.ksplit = ks;
     SIG_TRY(tc_gemm(t, s));

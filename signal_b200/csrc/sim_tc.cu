@@ -62,10 +62,11 @@ struct RowsProblem {
   __device__ static void load_b(const Params& p, const Unit& u, int kb, uint8_t* sb, uint64_t* bar) {
     tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, u.b * 64 + p.b_row_off);
   }
-  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int lane, float* /*scratch*/,
+  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int half, int lane, float* /*scratch*/,
                                   uint64_t* acc_bar, uint32_t acc_phase, long long* /*stamps*/) {
-    ptx::mbar_wait(acc_bar, acc_phase);
+    ptx::mbar_wait(acc_bar, acc_phase);   // (also the idle half: its arrival on tmem_empty must not run a phase ahead)
     ptx::tc_fence_after();
+    if (half) return;   // a single 32-column chunk: the second set of epilogue warps has nothing to do
     const int b = u.b, z = u.z;
     const int l = q * 32 + lane;
     const int j = z * 128 + l;
@@ -145,10 +146,11 @@ struct ColsProblem {
   __device__ static void load_b(const Params& p, const Unit& u, int kb, uint8_t* sb, uint64_t* bar) {
     tc::load_kmajor_2d(&p.tb, sb, bar, kb * BK, u.b * 32);
   }
-  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int lane, float* /*scratch*/,
+  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int half, int lane, float* /*scratch*/,
                                   uint64_t* acc_bar, uint32_t acc_phase, long long* /*stamps*/) {
-    ptx::mbar_wait(acc_bar, acc_phase);
+    ptx::mbar_wait(acc_bar, acc_phase);   // (also the idle half: its arrival on tmem_empty must not run a phase ahead)
     ptx::tc_fence_after();
+    if (half) return;   // a single 32-column chunk: the second set of epilogue warps has nothing to do
     const int b = u.b, c = u.c0 + q * 32 + lane;
     uint32_t r[32];
     ptx::tmem_ld32(tmem_acc, r);
@@ -206,7 +208,7 @@ struct DxProblem {
   // one k-block per unit: the epilogue IS the kernel.  Each 32 x 32 block goes through the transpose
   // tile so that the read-modify-write of the gradient map is 4 rows x 64 contiguous bytes per warp
   // instruction, with all 8 old-value loads of a chunk issued before the first add.
-  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int lane, float* scratch,
+  __device__ static void epilogue(const Params& p, const Unit& u, int /*mt*/, uint32_t tmem_acc, int q, int half, int lane, float* scratch,
                                   uint64_t* acc_bar, uint32_t acc_phase, long long* /*stamps*/) {
     const int n0 = u.n0, z = u.z;
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
@@ -216,8 +218,9 @@ struct DxProblem {
     const int nrows = p.L - l0;
     const int accumulate = p.accumulate;
     bool waited = false;
+    constexpr int kChunks = BN / 32 / 2;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half * kChunks; c < (half + 1) * kChunks; ++c) {
       const int col = n0 + c * 32 + c4;
       if (n0 + c * 32 >= p.d) break;   // warp-uniform
       const bool colok = col + 3 < p.d;   // d is a multiple of 8 on this path

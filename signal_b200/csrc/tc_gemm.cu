@@ -244,7 +244,7 @@ struct GemmProblem {
       }
     }
   }
-  __device__ static void epilogue(const Params& p, const Unit& u, int mt, uint32_t tmem_acc, int q, int lane, float* scratch,
+  __device__ static void epilogue(const Params& p, const Unit& u, int mt, uint32_t tmem_acc, int q, int half, int lane, float* scratch,
                                   uint64_t* acc_bar, uint32_t acc_phase, long long* stamps) {
 #define EPI_STAMP(i) do { if (stamps) stamps[i] = clock64(); } while (0)
     const int z = u.z, n0 = u.n0;
@@ -284,32 +284,34 @@ struct GemmProblem {
       }
       return t;
     };
-    float4 cv = colv_at(0);                          // requested before the accumulator is waited for
+    constexpr int kChunks = BN / 32 / 2;             // this warp's share: chunks [c_lo, c_lo + kChunks)
+    const int c_lo = half * kChunks;
+    float4 cv = colv_at(c_lo);                       // requested before the accumulator is waited for
     EPI_STAMP(9);
     ptx::mbar_wait(acc_bar, acc_phase);              // accumulator complete
     ptx::tc_fence_after();
     EPI_STAMP(10);
     if (u.kb1 <= u.kb0) return;
     uint32_t r[32];
-    ptx::tmem_ld32(tmem_acc, r);                     // the read of chunk c+1 is issued as soon as chunk c is in `v`
+    ptx::tmem_ld32(tmem_acc + c_lo * 32, r);         // the read of chunk c+1 is issued as soon as chunk c is in `v`
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_lo; c < c_lo + kChunks; ++c) {
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;                        // warp-uniform
       const int col = col0 + c4;
       ptx::tmem_ld_wait();
-      if (c == 0) EPI_STAMP(11);
+      if (c == c_lo) EPI_STAMP(11);
       {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
-        if (c + 1 < BN / 32) ptx::tmem_ld32(tmem_acc + (c + 1) * 32, r);   // in flight during this chunk's stores
+        if (c + 1 < c_lo + kChunks) ptx::tmem_ld32(tmem_acc + (c + 1) * 32, r);   // in flight during this chunk's stores
         __syncwarp();                                // the previous chunk's tile reads are done
         tc::epi_put_row(scratch, lane, v);
         __syncwarp();
       }
-      const float4 cvn = (c + 1 < BN / 32) ? colv_at(c + 1) : cv;   // next chunk's column vector: a chunk ahead
-      if (c == 0) EPI_STAMP(12);
+      const float4 cvn = (c + 1 < c_lo + kChunks) ? colv_at(c + 1) : cv;   // next chunk's column vector: a chunk ahead
+      if (c == c_lo) EPI_STAMP(12);
       if (fast_unit && col0 + 32 <= p.N) {
         if (red) {
           float* dst = static_cast<float*>(p.C[z]) + off0 + col;
@@ -368,8 +370,8 @@ struct GemmProblem {
         }
       }
       cv = cvn;
-      if (c == 0) EPI_STAMP(13);
-      if (c == 1) EPI_STAMP(14);
+      if (c == c_lo) EPI_STAMP(13);
+      if (c == c_lo + 1) EPI_STAMP(14);
     }
     EPI_STAMP(15);
 #undef EPI_STAMP
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) pair_gemm_kernel(const __grid
     }
     for (int i = 0; i < kAccBufs; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 256);   // 128 epilogue threads of each CTA (leader's barrier is the one waited on)
+      ptx::mbar_init(&tmem_empty[i], 2 * 32 * tc::kEpiWarps);   // the epilogue threads of both CTAs (the leader's barrier is the one waited on)
     }
     ptx::fence_barrier_init();
   }
@@ -495,8 +497,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) pair_gemm_kernel(const __grid
       typename P2::Unit u2 = P2::unit_info(p, unit);
       typename P1::Unit u;
       u.z = u2.z; u.m0 = u2.m0 + (int)rank * BM; u.n0 = u2.n0; u.kb0 = u2.kb0; u.kb1 = u2.kb1;
-      P1::epilogue(p, u, 0, tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16), q, lane, epi_scratch + q * 32 * tc::kEpiLd,
-                   &tmem_full[acc], aph, nullptr);
+      P1::epilogue(p, u, 0, tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16), q, (warp - 4) >> 2, lane,
+                   epi_scratch + (warp - 4) * 32 * tc::kEpiLd, &tmem_full[acc], aph, nullptr);
       ptx::tc_fence_before();
       if (leader) ptx::mbar_arrive(&tmem_empty[acc]);
       else ptx::mbar_arrive_cluster(ptx::mapa_u32(&tmem_empty[acc], 0));
@@ -624,6 +626,13 @@ int launch_gemm_bn(const TcGemmDesc& g, cudaStream_t s) {
 }  // namespace
 
 int tc_num_sms() { return tc::num_sms(); }
+bool tc_pair_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SIG_TC_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 int tc_read_stamps(long long* out16) { return tc::read_stamps(out16); }
 
 int tc_gemm(const TcGemmDesc& g, cudaStream_t s) {

@@ -89,6 +89,7 @@ int cast_f32_to_bf16_multi(const CastJob* jobs, int n, cudaStream_t s);
 int transpose_f32_to_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, cudaStream_t s);
 
 int tc_read_stamps(long long* out16);   // SIG_TC_STAMPS=1 debug aid (tc_pipeline.cuh)
+bool tc_pair_enabled();   // SIG_TC_PAIR=0 in the environment keeps the large GEMMs on the single-CTA kernel
 int tc_num_sms();   // multiprocessor count of the current device (cached)
 
 }  // namespace sig

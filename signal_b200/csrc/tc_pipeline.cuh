@@ -3,7 +3,9 @@
 //   warp 0, 3 : TMA producers (A / B operand; cp.async.bulk.tensor -> 128B-swizzled shared-memory ring, mbarrier complete_tx)
 //   warp 1 : MMA issuer    (one thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM, tcgen05.commit)
 //   warp 2 : TMEM allocator
-//   warps 4-7 : epilogue   (tcgen05.ld of the accumulator, problem-specific math, global stores)
+//   warps 4-11 : epilogue  (tcgen05.ld of the accumulator, problem-specific math, global stores); warp w reads TMEM lane
+//                quadrant w % 4, warps 4-7 the first half of the accumulator columns, warps 8-11 the second half (the
+//                epilogue is instruction-latency bound: twice the warps, twice the rate)
 //
 // Persistent: CTA i processes work units i, i+grid, ...; the smem ring and the two TMEM accumulator
 // buffers run continuously across units, so the epilogue of unit n overlaps the MMAs of unit n+1.
@@ -19,14 +21,15 @@ namespace sig {
 namespace tc {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant: each takes half of the accumulator columns
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kATileBytes = BM * BK * 2;
 // Epilogue transpose scratch: one [32 rows][kEpiLd floats] tile per epilogue warp.  tcgen05.ld hands a
 // thread one accumulator ROW (32 consecutive columns); stored from there a warp store touches 32
 // different lines.  Staged through this tile a warp instead writes 4 rows x 128 contiguous bytes per
 // instruction (kEpiLd = 36 keeps 16-byte alignment and is bank-conflict free both ways).
 constexpr int kEpiLd = 36;
-constexpr int kEpiBytes = 4 * 32 * kEpiLd * 4;
+constexpr int kEpiBytes = kEpiWarps * 32 * kEpiLd * 4;
 
 // MT = number of 128-row M tiles a CTA computes against ONE B tile (MT = 2: a 256 x BN output per
 // unit; the B operand is fetched once for both, which raises the FLOPs per byte pulled from L2 --
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
     }
     for (int i = 0; i < C::kAccBufs; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 128);
+      ptx::mbar_init(&tmem_empty[i], 32 * kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -195,8 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_cons
       //  requested everything that does not depend on it)
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt)
-        Problem::epilogue(p, u, mt, tmem_base + acc * C::kAccCols + mt * BN + ((uint32_t)(q * 32) << 16), q, lane,
-                          epi_scratch + q * 32 * kEpiLd, &tmem_full[acc], aph,
+        Problem::epilogue(p, u, mt, tmem_base + acc * C::kAccCols + mt * BN + ((uint32_t)(q * 32) << 16), q, (warp - 4) >> 2, lane,
+                          epi_scratch + (warp - 4) * 32 * kEpiLd, &tmem_full[acc], aph,
                           (first && threadIdx.x == 128 && blockIdx.x == 0) ? stamps : nullptr);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
