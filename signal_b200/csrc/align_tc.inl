@@ -941,11 +941,12 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.out_bf16 = 1; t.c_tok = 1;
     t.c_stride_b = dtok->patch_stride_b[0]; t.c_stride_l = dtok->patch_stride_l[0];
     t.accumulate = dtok->accumulate;
-    if (dtok->fuse_pds && dtok->fuse_dxqt) {   // + SIM's token gradient as a 13th k-block (sig_token_grads.fuse_*)
+    if (dtok->fuse_pds && dtok->fuse_dxqt) {   // + SIM's token gradient as extra k-block(s) (sig_token_grads.fuse_*)
       t.xa = dtok->fuse_pds; t.xb = dtok->fuse_dxqt; t.xB = B;
     }
     t.bn = (d % 256 == 0) ? 256 : 128;
     t.mt = 1;   // (mt = 2, 256 x 256 units, measured slower: the single TMEM buffer serialises the epilogue)
+    t.pair = t.bn == 256 && tc_pair_enabled() && (!t.xa || (B % 2) == 0);   // (a pair covers two samples)
     SIG_TRY(tc_gemm(t, s));
   }
   {

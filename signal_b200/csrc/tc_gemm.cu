@@ -449,6 +449,17 @@ __global__ void __launch_bounds__(tc::kThreads, 1) pair_gemm_kernel(const __grid
         if (leader) ptx::mbar_expect_tx(&full[stage], 2u * (is_a ? (uint32_t)kABytes : (uint32_t)kBBytes));
         uint8_t* dst = smem + stage * kStageBytes + (is_a ? 0 : kABytes);
         const int k0 = kb * BK;
+        if (kb >= p.kblocks) {
+          // per-sample extra blocks (TcGemmDesc::xa/xb): the pair covers samples b0 = m0/128 and b0 + 1, whose
+          // B operands differ, so block e = 0/1 contracts sample b0 + e only: the OTHER CTA's A tile is all zeros
+          // (a box past the last sample: TMA zero-fills it)
+          const int e = kb - p.kblocks, b = (u.m0 >> 7) + e;
+          if (is_a) ptx::tma_load_3d_2sm(dst, &p.tax, lbar, 0, (int)rank == e ? u.z * 128 : 0, (int)rank == e ? b : p.M);
+          else {
+#pragma unroll
+            for (int j = 0; j < kExtent / 64; ++j) ptx::tma_load_2d_2sm(dst + j * 64 * BK * 2, &p.tbx, lbar, n0 + 64 * j, b * 64);
+          }
+        } else
         if (mode == TC_K2D) ptx::tma_load_2d_2sm(dst, tm, lbar, k0, mn0);
         else if (mode == TC_KTOK) ptx::tma_load_3d_2sm(dst, tm, lbar, k0, 0, mn0 >> 7);
         else if (mode == TC_MN2D) {
@@ -550,7 +561,7 @@ static int launch_pair(const TcKernelParams& p, int units, int kpu, cudaStream_t
 
 // g.pair: 256 x 256 units on CTA pairs.  A: K-major token view or MN-major 2-D; B: K-major 2-D or MN-major (2-D / token view).
 static int launch_gemm_pair(const TcGemmDesc& g, cudaStream_t s) {
-  if (g.bn != 256 || g.mt != 1 || g.xa || g.xb) return SIG_ERR_SHAPE;
+  if (g.bn != 256 || g.mt != 1) return SIG_ERR_SHAPE;
   TcKernelParams p{};
   auto mk = [&](const TcOperand& o, int z, CUtensorMap* out) -> int {   // every box is 128 M/N-rows (K-major) or 64 x 64 (MN-major)
     if (o.mode == TC_K2D) return tc::make_map_2d(o.ptr[z], o.rows, o.cols, o.ld, 128, out);
@@ -573,8 +584,14 @@ static int launch_gemm_pair(const TcGemmDesc& g, cudaStream_t s) {
   p.kblocks = (int)ceil_div(g.K, BK);
   if (p.ksplit > p.kblocks) p.ksplit = p.kblocks;
   const int units = p.tiles_m * p.tiles_n * p.ksplit * p.batch;
-  const int kpu = (p.kblocks + p.ksplit - 1) / p.ksplit;
   const bool amn = g.A.mode >= TC_MN2D, bmn = g.B.mode >= TC_MN2D;
+  if (g.xa || g.xb) {   // two extra k-blocks per unit (one per sample of the pair)
+    if (!g.xa || !g.xb || g.xB < 2 || (g.xB & 1) || amn || !bmn || p.ksplit != 1 || g.M != g.xB * 128 || g.batch > 3) return SIG_ERR_SHAPE;
+    SIG_TRY(tc::make_map_3d(g.xa, 64, 384, g.xB, 64, 384 * 64, 128, &p.tax));
+    SIG_TRY(tc::make_map_2d(g.xb, (int64_t)g.xB * 64, g.N, g.N, 64, &p.tbx));
+    p.extra = 2;
+  }
+  const int kpu = (p.kblocks + p.ksplit - 1) / p.ksplit + p.extra;
   if (amn && bmn) return launch_pair<true, true>(p, units, kpu, s);
   if (amn) return launch_pair<true, false>(p, units, kpu, s);
   if (bmn) return launch_pair<false, true>(p, units, kpu, s);
