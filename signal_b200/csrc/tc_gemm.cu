@@ -538,7 +538,7 @@ static int launch_pair(const TcKernelParams& p, int units, int kpu, cudaStream_t
     attr_set = true;
   }
   if (units <= 0) return 0;
-  const int npairs_max = tc::num_sms() / 2;
+  const int npairs_max = (tc::num_sms() - tc::sm_reserve()) / 2;
   const int npairs = units < npairs_max ? units : npairs_max;
   const int per_cta = kpu * (int)ceil_div(units, npairs);
   if (per_cta < stages) stages = per_cta < 2 ? 2 : per_cta;
