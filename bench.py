@@ -205,7 +205,13 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if os.environ.get("SIG_NCCL_PRIO", "1") != "0":
+            # the gradient exchange runs next to GPU-filling kernels: NCCL's CTAs must be dispatched as soon as an
+            # SM has room, not after the compute kernels launched before them have drained
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     if rank == 0:
         entry.build()
     if world > 1:
@@ -241,11 +247,16 @@ def run_gpu(args):
 
     head = M.FusionHead(sim, al) if args.fused else None
     overlap = head is not None and world > 1 and args.allreduce and args.overlap
-    if overlap:   # each module's arena is all-reduced inside the backward, on the stream that produced it
+    if overlap:   # pieces of the gradient arenas are all-reduced inside the backward as soon as they are final
+        nsync = [0]
+
+        skip = int(os.environ.get("SIG_SYNC_SKIP", "0"))   # (diagnostic bit mask: leave out piece 0/1/2 of the exchange)
+
         def _sync(flat):
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            nsync[0] += 1
+            if not (skip >> (nsync[0] - 1)) & 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         head.grad_sync = _sync
-        ncoll[0] = 2
 
     def fwd_bwd(toks):
         patches = [t[:, 1:] for t in toks]
@@ -263,7 +274,11 @@ def run_gpu(args):
         else:                    # the reference's two consecutive module calls (make_model.py:191,205)
             out = sim(*patches, *cls)
             gam, lam = al(*patches, stage="together_CLS_Patch")
+        if overlap:
+            nsync[0] = 0
         torch.autograd.backward([out, gam, lam], [cot, wg, wl])
+        if overlap:
+            ncoll[0] = nsync[0]
         return out, gam, lam
 
     def step(i):
@@ -497,7 +512,7 @@ def run_gpu(args):
             "config": {"workload": workload_name(d), "global_batch": B * world, "parallelism": f"dp{world}",
                        "launch": "cuda_graph_replay" if args.graph else "eager", "api": "FusionHead(SIM, AlignM)" if args.fused else "SIM(...); AlignM(...)", "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
                        "grad_allreduce": (f"NCCL all-reduce (avg) of the flat head-gradient arenas, {ncoll[0]} collectives per step, "
-                                          + ("issued inside the backward on the producing stream (FusionHead.grad_sync), " if overlap else "after the backward, ")
+                                          + ("issued inside the backward on a communication stream as each piece becomes final (FusionHead.grad_sync), " if overlap else "after the backward, ")
                                           + ("captured in the step graph" if args.graph and (args.allreduce_in_graph or overlap) else "eager")) if world > 1 else "n/a"},
             "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "how": "pinned host tokens, H2D of step i+1 on a copy stream under step i's compute (2 staging buffers), "

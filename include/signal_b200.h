@@ -130,6 +130,11 @@ typedef struct sig_sim_param_grads {
   float* ffn2_w; float* ffn2_b;
   float* ln1_w; float* ln1_b;
   float* ln2_w; float* ln2_b;
+  /* Optional (cudaEvent_t, may be NULL): recorded by sig_sim_bwd once every gradient above is final EXCEPT
+   * in_proj_w rows [0, 2d) (W_q, W_k) and in_proj_b, which need the token-side backward first.  A data-parallel
+   * caller starts the exchange of the early part on another stream while the rest of the backward runs
+   * (FusionHead.grad_sync).  On the fp32 SIMT path it is recorded at the end of the call. */
+  void* early_event;
 } sig_sim_param_grads;
 
 /* AlignmentM parameters (modeling/AddModule/useB.py:44-74, DAS.py:30-72), index = modality r,n,t */
@@ -147,6 +152,9 @@ typedef struct sig_align_param_grads {           /* overwritten */
   float* off0_w[3];   float* off0_b[3];
   float* off2_w[3];   float* off2_b[3];
   float* off4_w[3];
+  /* Optional (cudaEvent_t, may be NULL): recorded by sig_align_bwd once ALL gradients above are final; on the
+   * tensor-core path that is before the d(patches) GEMM runs, so the exchange of this arena overlaps it. */
+  void* done_event;
 } sig_align_param_grads;
 
 /* ---- library info ------------------------------------------------------ */
@@ -246,6 +254,10 @@ int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* cou
 /* Time line of the recorded scopes ("name start_us end_us" lines, relative to the earliest start); with
  * SIG_PROF_CAPTURE=1 scopes are also recorded during stream capture, so a graph replay can be laid out. */
 int sig_profile_timeline(char* buf, size_t bytes);
+/* A caller-side scope on the same time line (e.g. around a collective issued between two library calls):
+ * begin returns a handle for sig_profile_scope_end, or NULL when the profiler is off. */
+void* sig_profile_scope_begin(const char* name, void* stream);
+void sig_profile_scope_end(void* scope);
 
 /* Unit-test seam for the tcgen05 GEMM core: C = alpha * A . B^T (+bias) (GELU if act), bf16 operands.
  * mode: 0 row-major [rows,K]; 1 token view [B,128,d] with rows=(b,l), K=d; 2 row-major [K,cols];

@@ -774,6 +774,7 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
     SIG_CHECK_LAUNCH();
   }
   if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
+  if (dp->done_event) cudaEventRecord((cudaEvent_t)dp->done_event, s);
   return 0;
 }
 

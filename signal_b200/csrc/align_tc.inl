@@ -829,6 +829,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
       SIG_CHECK_LAUNCH();
     }
     if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
+    if (dp->done_event) cudaEventRecord((cudaEvent_t)dp->done_event, s);
     return 0;
   }
   const Geo g = make_geo(h, w);
@@ -925,6 +926,15 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_CHECK_LAUNCH();
   }
   if (fkb.ok()) fkb.join(smain);   // the dX epilogue adds the GAM rows (dmean)
+  if (dp->done_event) {
+    // all parameter gradients are enqueued (LAM's on s2, contra_temp's joined into s just above): the caller's
+    // exchange of this arena can run under the dX GEMM
+    if (fk2.ok()) {
+      cudaEventRecord(fk2.ev_join, s);         // (ev_join is re-recorded by the final join below)
+      cudaStreamWaitEvent(s2, fk2.ev_join, 0);
+    }
+    cudaEventRecord((cudaEvent_t)dp->done_event, s2);
+  }
   if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);   // first write to the shared gradient map
   {
     SIG_PHASE("lam_offsetnet_bwd_dx");

@@ -108,6 +108,15 @@ int sig_profile_enable(int on) {
   return 0;
 }
 
+// A caller-side scope on the same time line (e.g. around a collective the caller issues between two library
+// calls): begin returns a handle for sig_profile_scope_end, or NULL when the profiler is off.
+void* sig_profile_scope_begin(const char* name, void* stream) {
+  if (!sig::g_enabled.load(std::memory_order_relaxed) || !name) return nullptr;
+  return new sig::ProfScope(name, static_cast<cudaStream_t>(stream));
+}
+
+void sig_profile_scope_end(void* scope) { delete static_cast<sig::ProfScope*>(scope); }
+
 // Time line of the recorded scopes: "name start_us end_us\n" per scope, relative to the earliest start.
 // Does not clear the record (a captured graph keeps using the events); returns the number of scopes written.
 int sig_profile_timeline(char* buf, size_t bytes) {

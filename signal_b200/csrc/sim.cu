@@ -1124,6 +1124,7 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
   if (dtok->wait_event) cudaStreamWaitEvent(s, (cudaEvent_t)dtok->wait_event, 0);
   SIG_TRY(write_token_grads(dtok, tok->dtype, c.dXf, c.dr1, B, L, d, s));
   if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
+  if (dp->early_event) cudaEventRecord((cudaEvent_t)dp->early_event, s);   // (SIMT path: no early part)
   return 0;
 }
 

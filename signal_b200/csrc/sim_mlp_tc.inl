@@ -207,6 +207,9 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     for (int h = 0; h < kHeads; ++h) t.C[h] = dwv + (size_t)h * hd * d;
     SIG_TRY(side_gemm(fk, s, t));
   }
+  // every parameter gradient except W_q, W_k and in_proj_b is now enqueued: on the side stream, which has
+  // waited for this stream's column sums (sig_sim_param_grads.early_event)
+  if (g->early_event) cudaEventRecord((cudaEvent_t)g->early_event, fk.ok() ? fk.side : s);
   {  // dxbar_h = do_h W_v^h
     TcGemmDesc t = lin_nn(c.dobb, d, wvb, d, c.dxbar, 8 * (int64_t)d, R, d, hd);
     t.batch = kHeads;

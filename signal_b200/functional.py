@@ -37,6 +37,38 @@ def _arena(shapes, device) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     return flat, _carve(flat, shapes)
 
 
+def _head_arena(d: int, device):
+    """ONE flat arena for the gradients of both modules, ``[AlignM | SIM late part | SIM early part]``, so that a
+    data-parallel exchange needs two collectives: ``flat[cut:]`` as soon as SIM's early gradients are final and
+    ``flat[:cut]`` (AlignM's arena + W_q/W_k/in_proj_bias) once the token-side backward is through.
+    Returns (flat, SIM grads, AlignM grads, cut)."""
+    sshapes, ashapes = _SIM_GRAD_SHAPES(d), _align_grad_shapes(d)
+    order = [1, 0] + list(range(2, len(sshapes)))
+    flat, views = _arena(ashapes + [sshapes[i] for i in order], device)
+    pg_a, sv = views[:len(ashapes)], views[len(ashapes):]
+    pg_s = [None] * len(sshapes)
+    for i, v in zip(order, sv):
+        pg_s[i] = v
+    n_a = sum(((int(torch.Size(x).numel()) + 3) // 4 * 4) for x in ashapes)
+    cut = n_a + (3 * d + 3) // 4 * 4 + 2 * d * d
+    return flat, pg_s, pg_a, cut
+
+
+def _sim_arena(d: int, device):
+    """SIM's parameter-gradient arena laid out so that the gradients which are final LAST (in_proj_bias and
+    in_proj_weight rows [0, 2d) = W_q, W_k: they need the token-side backward) are one contiguous prefix
+    ``flat[:split]``; everything in ``flat[split:]`` is final when sig_sim_param_grads.early_event fires.
+    Returns (flat, grads in SIM_GRAD_FIELDS order, split)."""
+    shapes = _SIM_GRAD_SHAPES(d)
+    order = [1, 0] + list(range(2, len(shapes)))          # in_proj_b first, then in_proj_w, then the rest
+    flat, views = _arena([shapes[i] for i in order], device)
+    pg = [None] * len(shapes)
+    for i, v in zip(order, views):
+        pg[i] = v
+    split = (3 * d + 3) // 4 * 4 + 2 * d * d
+    return flat, pg, split
+
+
 def _split_tokens(packed: bool, toks: Sequence[torch.Tensor]):
     if packed:
         for t in toks:
@@ -456,10 +488,18 @@ class HeadFunction(torch.autograd.Function):
                 else dout.to(patches[0].dtype).contiguous())
         dtoks = [torch.empty_like(t) for t in toks]
         dpatch, dcls = [t[:, 1:] for t in dtoks], [t[:, 0] for t in dtoks]
-        flat_s, pg_s = _arena(_SIM_GRAD_SHAPES(d), dev)
-        flat_a, pg_a = _arena(_align_grad_shapes(d), dev)
-        if not do_lam:
-            flat_a.zero_()
+        sync = event[3] if len(event) > 3 else None     # (comm stream, early event, AlignM event, pieces) of FusionHead
+        if event[1] is None:
+            sync = None
+        if sync is not None and sync[3] == 2:
+            flat_h, pg_s, pg_a, cut_h = _head_arena(d, dev)
+            if not do_lam:
+                flat_h[:cut_h].zero_()
+        else:
+            flat_s, pg_s, split_s = _sim_arena(d, dev)
+            flat_a, pg_a = _arena(_align_grad_shapes(d), dev)
+            if not do_lam:
+                flat_a.zero_()
         tok = L_.tokens_struct(patches, cls)
         tok_a = L_.tokens_struct(patches, None)
         sprm = L_.sim_params_struct(sp)
@@ -469,6 +509,9 @@ class HeadFunction(torch.autograd.Function):
         gs_a = L_.align_params_struct(pg_a[0], [pg_a[1 + 7 * m: 8 + 7 * m] for m in range(3)], cls=L_.SigAlignParamGrads)
         hi = event[2] if len(event) > 2 else None
         event, grad_sync = event[0], event[1]
+        if sync is not None:
+            gs_s.early_event = sync[1].cuda_event
+            gs_a.done_event = sync[2].cuda_event
         evh = event.cuda_event
         # SIM's token-gradient kernel overwrites the shared map (it has no long GEMM in front of it and finishes
         # first); AlignM's dX GEMM, which can run its weight-gradient GEMM while it waits, adds on top
@@ -493,12 +536,32 @@ class HeadFunction(torch.autograd.Function):
             # (SIM first: its call records the event AlignM's call waits on)
             L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(sprm), dout.data_ptr(), C.byref(tg_s), C.byref(gs_s), buf_s.data_ptr(),
                                      buf_s.numel(), flags, dev.index, hi.cuda_stream), "sig_sim_bwd")
-            if grad_sync is not None:    # data parallel: each arena's exchange starts on the stream that produced it,
-                with torch.cuda.stream(hi):   # so one module's all-reduce overlaps what is left of the other's backward
+            # Data parallel: the exchange runs on a communication stream in pieces, each started by the event the
+            # library records when that piece is final -- SIM's early part (FFN, out_proj, norms, W_v: ready before
+            # the token-side backward), then AlignM's arena (ready before its dX GEMM) and SIM's W_q/W_k part, as one
+            # collective (default: a collective costs ~25 us + 2.2 us/MB at N = 2) or as two (SIG_SYNC_CHUNKS=3)
+            if sync is not None:
+                comm = sync[0]
+                with torch.cuda.stream(comm):
+                    comm.wait_event(sync[1])
+                    grad_sync(flat_h[cut_h:] if sync[3] == 2 else flat_s[split_s:])
+            elif grad_sync is not None:
+                with torch.cuda.stream(hi):
                     grad_sync(flat_s)
             L_.check(lib.sig_align_bwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg_a), C.byref(gs_a),
                                        buf_a.data_ptr(), buf_a.numel(), flags, dev.index, side.cuda_stream), "sig_align_bwd")
-            if grad_sync is not None:
+            if sync is not None:
+                with torch.cuda.stream(comm):
+                    comm.wait_event(sync[2])
+                    if sync[3] == 2:      # AlignM's arena and SIM's late part are adjacent: one collective
+                        comm.wait_stream(hi)
+                        grad_sync(flat_h[:cut_h])
+                    else:
+                        grad_sync(flat_a)
+                        comm.wait_stream(hi)
+                        grad_sync(flat_s[:split_s])
+                main.wait_stream(comm)
+            elif grad_sync is not None:
                 with torch.cuda.stream(side):
                     grad_sync(flat_a)
             main.wait_stream(side)

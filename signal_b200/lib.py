@@ -49,7 +49,7 @@ class SigSimParams(C.Structure):
 
 
 class SigSimParamGrads(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in SIM_GRAD_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in SIM_GRAD_FIELDS] + [("early_event", C.c_void_p)]
 
 
 ALIGN_MOD_FIELDS = ["proj_q_w", "proj_q_b", "off0_w", "off0_b", "off2_w", "off2_b", "off4_w"]
@@ -60,7 +60,7 @@ class SigAlignParams(C.Structure):
 
 
 class SigAlignParamGrads(C.Structure):
-    _fields_ = [("contra_temp", C.c_void_p)] + [(n, _VP3) for n in ALIGN_MOD_FIELDS]
+    _fields_ = [("contra_temp", C.c_void_p)] + [(n, _VP3) for n in ALIGN_MOD_FIELDS] + [("done_event", C.c_void_p)]
 
 
 _lib = None
@@ -71,7 +71,7 @@ EXPORTS = [
     "sig_sim_fwd", "sig_sim_bwd", "sig_sim_fold_selection", "sig_sim_select_fwd", "sig_sim_select_from_scores", "sig_mask_mul_bwd",
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
-    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_sim_dx_operands",
+    "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_profile_scope_begin", "sig_profile_scope_end", "sig_sim_dx_operands",
 ]
 
 
@@ -112,6 +112,10 @@ def load():
     lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
     lib.sig_sim_dx_operands.argtypes = [vp, i, i, i, i, u, P(vp), P(vp)]
     lib.sig_profile_timeline.argtypes = [C.c_char_p, sz]
+    lib.sig_profile_scope_begin.restype = vp
+    lib.sig_profile_scope_begin.argtypes = [C.c_char_p, vp]
+    lib.sig_profile_scope_end.restype = None
+    lib.sig_profile_scope_end.argtypes = [vp]
     lib.sig_debug_tc_stamps.argtypes = [P(C.c_longlong)]
     lib.sig_debug_launch_count.restype = C.c_ulonglong
     lib.sig_profile_enable.argtypes = [i]

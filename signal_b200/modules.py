@@ -283,10 +283,11 @@ class FusionHead:
     def __init__(self, sim: "Select_Interactive_Module", align: "AlignmentM", grad_sync=None):
         self.sim, self.align = sim, align
         self._side = {}
-        # Data parallel (one process per GPU): ``grad_sync(flat)`` is called inside the backward, once per
-        # module, with that module's flat fp32 parameter-gradient arena, on the stream that produced it --
-        # e.g. ``lambda a: dist.all_reduce(a, op=dist.ReduceOp.AVG)``.  The gradients that reach ``.grad``
-        # are then already averaged and the exchange of one module overlaps the other's backward.
+        # Data parallel (one process per GPU): ``grad_sync(flat)`` is called inside the backward with contiguous
+        # pieces of the flat fp32 parameter-gradient arena (two per step: SIM's early part, then AlignM's gradients
+        # + SIM's W_q/W_k part), on a communication stream that waits for the event the library records when
+        # that piece is final -- e.g. ``lambda a: dist.all_reduce(a, op=dist.ReduceOp.AVG)``.  The gradients
+        # that reach ``.grad`` are then already averaged and the exchange overlaps the rest of the backward.
         self.grad_sync = grad_sync
 
     def _stream(self, dev):
@@ -296,7 +297,16 @@ class FusionHead:
             ev.record(torch.cuda.current_stream(dev))       # materialise the underlying cudaEvent_t
             # SIG_PRIO=1 (experiment, off by default -- measured slower): SIM on a high-priority stream
             hi = torch.cuda.Stream(dev, priority=-1) if os.environ.get("SIG_PRIO", "0") == "1" else None
-            st = (torch.cuda.Stream(dev), ev, hi)
+            # data parallel: a communication stream and the two events the library records when a piece of the
+            # parameter gradients is final (sig_sim_param_grads.early_event, sig_align_param_grads.done_event)
+            sync = [torch.cuda.Stream(dev), torch.cuda.Event(), torch.cuda.Event()]
+            for e in sync[1:]:
+                e.record(torch.cuda.current_stream(dev))
+            # SIG_SYNC_CHUNKS (diagnostic): 2 = default; 3 = AlignM's arena and SIM's late part as two collectives;
+            # 0 = one exchange per module after its backward
+            pieces = int(os.environ.get("SIG_SYNC_CHUNKS", "2"))
+            sync = None if pieces == 0 else sync + [2 if pieces == 2 else 3]
+            st = (torch.cuda.Stream(dev), ev, hi, sync)
             self._side[dev] = st
         return st
 
@@ -311,12 +321,12 @@ class FusionHead:
             res = al(rgb_patch, ni_patch, ti_patch, stage=stage)
             return (out, res, None) if stage == "CLS" else (out, res[0], res[1])
         L = rgb_patch.size(1)
-        side, ev, hi = self._stream(rgb_patch.device)
+        side, ev, hi, sync = self._stream(rgb_patch.device)
         params = [p.detach() for p in ts._sel_params()] + mi._attn_params() + al._params()
         flags = sim.flags | al.flags
         if rgb_patch.dtype == torch.bfloat16 and not (flags & 1):
             params = params + list(ts._selection_fold())
         out, masks, gam, lam = F_.HeadFunction.apply(al.h, al.w, stage != "CLS", ts.k1, ts.k2, ts._max_keep(L), flags, side,
-                                                     (ev, self.grad_sync, hi), *bases, *params)
+                                                     (ev, self.grad_sync, hi, sync), *bases, *params)
         ts.last_masks = {"RGB": masks[0].unsqueeze(-1), "NI": masks[1].unsqueeze(-1), "TI": masks[2].unsqueeze(-1)}
         return (out, gam, None) if stage == "CLS" else (out, gam, lam)

@@ -144,3 +144,51 @@ def test_fusion_head_matches_the_two_modules(name, dtype, tol):
         want = a["dtok_full_sim"][m] + 0.2 * a["dtok_full_gam"][m] + 0.2 * a["dtok_full_lam"][m]
         got = tk[m].grad.float().cpu()
         assert float((got - want).norm() / want.norm()) < (2e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fusion_head_grad_sync_pieces(dtype):
+    """FusionHead.grad_sync (the data-parallel exchange hook) is called with contiguous pieces of the two
+    gradient arenas on a communication stream, each after the event the library records when that piece is
+    final (sig_sim_param_grads.early_event, sig_align_param_grads.done_event).  A hook that doubles its piece in
+    place must therefore yield exactly 2x the gradients of a run without it, and the pieces must tile both
+    arenas once -- a piece handed over before its producer finished would come back undoubled."""
+    _harness()
+    import gpu_harness
+    from signal_b200 import modules as M
+    from signal_b200 import parallel
+    c = BF16_CASES["rgbnt201_d512"]
+    sim_p, al_p, toks, cot = _bf16_inputs(c)
+
+    def run(hook):
+        sim, al = gpu_harness.build_modules(c, sim_p, al_p)
+        head = M.FusionHead(sim, al, grad_sync=hook)
+        tk = [t.to("cuda", dtype).requires_grad_(True) for t in toks]
+        for _ in range(3):      # repeated steps re-use the same events and streams
+            for p in list(sim.parameters()) + list(al.parameters()):
+                p.grad = None
+            out, gam, lam = head(*[t[:, 1:] for t in tk], *[t[:, 0] for t in tk])
+            torch.autograd.backward([out, gam, lam], [cot.to("cuda", dtype), torch.tensor(0.2, device="cuda"), torch.tensor(0.2, device="cuda")])
+        torch.cuda.synchronize()
+        params = list(sim.named_parameters()) + list(al.named_parameters())
+        return {n: p.grad.clone() for n, p in params if p.grad is not None}, parallel.grad_arenas(p for _, p in params)
+
+    pieces = []
+
+    def hook(flat):
+        pieces.append((flat.data_ptr(), flat.numel()))
+        flat.mul_(2.0)
+
+    base, _ = run(None)
+    got, arenas = run(hook)
+    assert len(pieces) == 6 and len(arenas) == 1          # two pieces per step, one arena for both modules
+    total = sum(n for _, n in pieces[-2:])
+    assert total == sum(a.numel() for a in arenas)
+    assert base.keys() == got.keys()
+    # not bit-equal: the split-K weight-gradient GEMM adds its partial tiles with fp32 atomics, and on the bf16 path
+    # the un-fold GEMMs read a bf16 rounding of that sum; an undoubled piece would be off by 0.5
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    errs = {n: float((got[n] - 2.0 * base[n]).norm()) / (float(base[n].norm()) + 1e-30) for n in base}
+    bad = {n: e for n, e in errs.items() if not e <= tol}
+    assert not bad, bad
