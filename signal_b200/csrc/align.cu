@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "sim.h"
 #include "simt_ops.cuh"
+#include "stream_ring.cuh"
+#include "tok_ring.cuh"
 #include "tc_gemm.h"
 
 namespace sig {

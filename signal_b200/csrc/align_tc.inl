@@ -216,6 +216,8 @@ static __global__ void __launch_bounds__(384, 2) lam_dw_bwd_tc_kernel(const __nv
   }
 }
 
+#include "lam_dw_ring.inl"
+
 // deterministic reduction of the partials into the parameter gradients.  grid (ceil(d/64), 19, 3), 256 threads:
 // 64 channels x 4 chunk lanes
 static __global__ void __launch_bounds__(256) lam_dw_param_reduce_kernel(const float* __restrict__ part, int nchunk,
@@ -675,7 +677,25 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   }
   {
     SIG_PHASE("gam_fwd");
-    {
+    const bool rows_contig = tok->patch_stride_l[0] == d && tok->patch_stride_l[1] == d && tok->patch_stride_l[2] == d;
+    if (tok_ring_enabled() && L == kMaxL && (d == 512 || d == 768) && rows_contig) {
+      SIG_PHASE("gam_pool");   // streaming ring: 4 x 48 KB in flight per SM (tok_ring.cuh)
+      TokSrc3 src;
+      for (int m = 0; m < 3; ++m) { src.patch[m] = tok->patch[m]; src.psb[m] = tok->patch_stride_b[m]; }
+      const int n_items = 3 * B * (kMaxL / 32);
+      const int ctas = n_items < tc_num_sms() ? n_items : tc_num_sms();
+      cudaMemsetAsync(c.mean, 0, (size_t)3 * B * d * sizeof(float), s);   // groups split between two CTAs are added atomically
+      if (d == 768) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(pool_ring_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_ring_smem<768>()); attr = true; }
+        SIG_LAUNCH((pool_ring_kernel<768>), ctas, TokRing<768>::kThreads, pool_ring_smem<768>(), s, src, B, n_items, c.mean);
+      } else {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(pool_ring_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_ring_smem<512>()); attr = true; }
+        SIG_LAUNCH((pool_ring_kernel<512>), ctas, TokRing<512>::kThreads, pool_ring_smem<512>(), s, src, B, n_items, c.mean);
+      }
+      SIG_CHECK_LAUNCH();
+    } else {
       SIG_PHASE("gam_pool");
       SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), (unsigned)ceil_div(kPoolGroups * (d / 8), 32) * 32, (size_t)kPoolGroups * d * sizeof(float), s, tp, B, L, d, c.mean);
       SIG_CHECK_LAUNCH();
@@ -739,7 +759,13 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     t.pair = t.bn == 256 && tc_pair_enabled();   // 256 x 256 units on CTA pairs (cta_group::2): 5 % faster
     SIG_TRY(tc_gemm(t, s));
   }
-  {
+  if (dw_ring_ok(L, h, w, d)) {
+    SIG_PHASE("lam_dwconv_fwd");
+    if (d == 768 && w == 8) SIG_TRY((launch_dw_fwd_ring<768, 8>(c.H, *p, B, h, c.U, c.o, s)));
+    else if (d == 768) SIG_TRY((launch_dw_fwd_ring<768, 16>(c.H, *p, B, h, c.U, c.o, s)));
+    else if (w == 8) SIG_TRY((launch_dw_fwd_ring<512, 8>(c.H, *p, B, h, c.U, c.o, s)));
+    else SIG_TRY((launch_dw_fwd_ring<512, 16>(c.H, *p, B, h, c.U, c.o, s)));
+  } else {
     SIG_PHASE("lam_dwconv_fwd");
     const int pts = dw_pts_per_cta((int64_t)B * g.P, kDwFwdMaxPts);
     const dim3 grid((unsigned)ceil_div((int64_t)B * g.P, pts), 3);
@@ -841,7 +867,14 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_LAUNCH((lam_sample_bwd_tok_kernel<__nv_bfloat16>), dim3(B * g.P, 3), cthreads, 0, s, tp, c.o, c.dS, g, B, d, c.dO);
     SIG_CHECK_LAUNCH();
   }
-  {
+  const bool dw_ring = dw_ring_ok(L, h, w, d);
+  if (dw_ring) {
+    SIG_PHASE("lam_dwconv_bwd");
+    if (d == 768 && w == 8) SIG_TRY((launch_dw_bwd_ring<768, 8>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+    else if (d == 768) SIG_TRY((launch_dw_bwd_ring<768, 16>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+    else if (w == 8) SIG_TRY((launch_dw_bwd_ring<512, 8>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+    else SIG_TRY((launch_dw_bwd_ring<512, 16>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+  } else {
     SIG_PHASE("lam_dwconv_bwd");
     const int pts = dw_pts_per_cta((int64_t)B * g.P, 0);
     const int nchunk = (int)ceil_div((int64_t)B * g.P, pts);
@@ -871,7 +904,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     cudaStream_t s = s2;
     SIG_PHASE("lam_dwconv_param_grads");
     const int pts = dw_pts_per_cta((int64_t)B * g.P, 0);
-    const int nchunk = (int)ceil_div((int64_t)B * g.P, pts);
+    const int nchunk = dw_ring ? dw_ring_ctas_per_mod(B, h) : (int)ceil_div((int64_t)B * g.P, pts);
     SIG_LAUNCH((lam_dw_param_reduce_kernel), dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s, c.dwpart, nchunk, *dp, c.dbf, d);
     SIG_CHECK_LAUNCH();
     SIG_LAUNCH((lam_unfold_bias_kernel), dim3((unsigned)ceil_div(d, 32), 3), 1024, 0, s, *p, *dp, c.dbf, d);   // db0 = db', dbq = W0^T db'

@@ -15,6 +15,7 @@
 #include "sim_tc.h"
 #include "simt_ops.cuh"
 #include "tc_gemm.h"
+#include "tok_ring.cuh"
 
 namespace sig {
 
@@ -835,7 +836,25 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
     SIG_TRY(launch_gemm(gemm_nt(c.qsel, d, p->sel_bk, d, c.csel, 1, nullptr, R, 1, d), s));
   }
   dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
-  if (c.tc) {
+  const bool rows_contig = tok->patch_stride_l[0] == d && tok->patch_stride_l[1] == d && tok->patch_stride_l[2] == d;
+  if (c.tc && tok_ring_enabled() && L == kMaxL && (d == 512 || d == 768) && rows_contig) {
+    SIG_PHASE("sim_scores");   // streaming ring: 4 x 48 KB in flight per SM (tok_ring.cuh)
+    TokSrc3 src;
+    for (int m = 0; m < 3; ++m) { src.patch[m] = tok->patch[m]; src.psb[m] = tok->patch_stride_b[m]; }
+    const int n_items = 3 * B * (kMaxL / 32);
+    const int ctas = n_items < tc_num_sms() ? n_items : tc_num_sms();
+    if (d == 768) {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(sim_scores_ring_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_scores_ring_smem<768>()); attr = true; }
+      SIG_LAUNCH((sim_scores_ring_kernel<768>), ctas, TokRing<768>::kThreads, sim_scores_ring_smem<768>(), s, src, c.clsf, c.qtsel, c.csel, B, n_items,
+                 c.sel_logits, c.intra_raw);
+    } else {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(sim_scores_ring_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_scores_ring_smem<512>()); attr = true; }
+      SIG_LAUNCH((sim_scores_ring_kernel<512>), ctas, TokRing<512>::kThreads, sim_scores_ring_smem<512>(), s, src, c.clsf, c.qtsel, c.csel, B, n_items,
+                 c.sel_logits, c.intra_raw);
+    }
+  } else if (c.tc) {
     SIG_PHASE("sim_scores");
     SIG_LAUNCH((sim_scores_tok_kernel<__nv_bfloat16>), dim3(3, (unsigned)B), 256, 4 * d * sizeof(float), s, tok_ptrs(tok), c.clsf, c.qtsel, c.csel, B, L, d,
                                                                                  c.sel_logits, c.intra_raw);

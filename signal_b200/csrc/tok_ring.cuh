@@ -1,0 +1,255 @@
+// One-pass token kernels on the streaming ring (stream_ring.cuh): the selection scores of SIM (useA.py:50-221, four
+// dot products per patch token) and the mean pool of GAM (useB.py:84-86).  Both read the three bf16 patch maps
+// exactly once -- T*s bytes per sample -- and do a handful of FP32 operations per element, so the only thing that
+// matters is bytes in flight: item = 32 consecutive token rows of one (modality, sample) = 48 KB at d = 768, four
+// stages per SM.  Requires row-contiguous patches (stride_l == d), L == 128, d in {512, 768}; other layouts keep the
+// register-staged kernels (sim_scores_tok_kernel, pool_tok_kernel).
+#pragma once
+#include "common.cuh"
+#include "stream_ring.cuh"
+
+namespace sig {
+
+struct TokSrc3 {
+  const void* patch[3];
+  int64_t psb[3];   // elements between samples
+};
+
+template <int D>
+struct TokRing {
+  static constexpr int kRows = 32;                          // token rows per item
+  static constexpr int kItemsPerGroup = kMaxL / kRows;      // a group = one (modality, sample): 128 rows
+  static constexpr int kStageBytes = kRows * D * 2;
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kConsumers = 256;                    // 8 warps x 4 rows
+  static constexpr int kThreads = kConsumers + 32;
+  static constexpr int kChunks = D / 256;                   // 16-byte chunks per lane and row
+  static constexpr int kQBytes = 4 * D * 4;                 // the four query vectors of a group (scores only)
+};
+
+// bf16 pair -> two floats (exact)
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    v[2 * t] = __uint_as_float(w[t] << 16);
+    v[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u);
+  }
+}
+
+// ---- SIM selection scores ---------------------------------------------------------------------------------------
+// sel_logits [B][3 queries][3 modalities][L] = (qt_r . x + c_r) / sqrt(d);  intra_raw [B][3][L] = cls_m . x
+// grid = min(#SMs, items); a CTA owns the items [i0, i1) of the sequence ((b * 3 + m) * 4 + chunk).
+// The producer also stages each group's four query vectors (qtsel rows 3b..3b+2 and cls row 3b+m, fp32) through a
+// two-deep buffer; a lane keeps its 4 x 8 x kChunks query values in registers for the whole group.  The per-lane
+// accumulation order (chunks lane, lane+32, .. ; 8 channels in order; then a butterfly) is that of
+// sim_scores_tok_kernel, so both kernels return the same bits.
+template <int D>
+static __global__ void __launch_bounds__(TokRing<D>::kThreads, 1)
+sim_scores_ring_kernel(TokSrc3 src, const float* __restrict__ clsf, const float* __restrict__ qtsel, const float* __restrict__ csel,
+                       int B, int n_items, float* __restrict__ sel_logits, float* __restrict__ intra_raw) {
+  using R = TokRing<D>;
+  constexpr int L = kMaxL;
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) unsigned char tr_smem[];
+  unsigned char* stages = tr_smem;
+  float* qbuf = reinterpret_cast<float*>(tr_smem + (size_t)R::kStages * R::kStageBytes);   // [2][4][D]
+  auto* bars = reinterpret_cast<ring::Bars<R::kStages>*>(tr_smem + (size_t)R::kStages * R::kStageBytes + 2 * R::kQBytes);
+  uint64_t* qfull = reinterpret_cast<uint64_t*>(bars + 1);   // [2]
+  uint64_t* qempty = qfull + 2;                               // [2]
+  const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x), i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 2; ++q) {
+      ptx::mbar_init(&qfull[q], 1);
+      ptx::mbar_init(&qempty[q], R::kConsumers / 32);
+    }
+  }
+  ring::init(bars, R::kConsumers / 32);
+  if ((int)threadIdx.x >= R::kConsumers) {
+    if ((int)threadIdx.x == R::kConsumers) {
+      pdl_wait();   // the query vectors come from the kernels launched just before
+      int gcount = 0;
+      for (int it = i0, k = 0; it < i1; ++it, ++k) {
+        const int g = it / R::kItemsPerGroup, chunk = it % R::kItemsPerGroup;
+        const int b = g / 3, m = g % 3;
+        if (k == 0 || chunk == 0) {
+          const int qs = gcount & 1;
+          if (gcount >= 2) ptx::mbar_wait(&qempty[qs], (uint32_t)((gcount >> 1) - 1) & 1u);
+          ptx::mbar_expect_tx(&qfull[qs], R::kQBytes);
+          ring::bulk_g2s(qbuf + (size_t)qs * 4 * D, qtsel + (int64_t)b * 3 * D, 3 * D * 4, &qfull[qs]);
+          ring::bulk_g2s(qbuf + (size_t)qs * 4 * D + 3 * D, clsf + ((int64_t)b * 3 + m) * D, D * 4, &qfull[qs]);
+          ++gcount;
+        }
+        const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(src.patch[m]) + b * src.psb[m] + (int64_t)chunk * R::kRows * D;
+        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, x, R::kStageBytes);
+      }
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float inv = rsqrtf((float)D);
+  float q[4][R::kChunks][8];
+  float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f;
+  int gcount = 0;
+  pdl_wait();
+  for (int it = i0, k = 0; it < i1; ++it, ++k) {
+    const int g = it / R::kItemsPerGroup, chunk = it % R::kItemsPerGroup;
+    const int b = g / 3, m = g % 3;
+    if (k == 0 || chunk == 0) {   // new group: its query vectors -> registers
+      const int qs = gcount & 1;
+      ptx::mbar_wait(&qfull[qs], (uint32_t)(gcount >> 1) & 1u);
+      const float* qv = qbuf + (size_t)qs * 4 * D;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int ch = 0; ch < R::kChunks; ++ch) {
+          const float4 lo = *reinterpret_cast<const float4*>(qv + r * D + (lane + 32 * ch) * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(qv + r * D + (lane + 32 * ch) * 8 + 4);
+          q[r][ch][0] = lo.x; q[r][ch][1] = lo.y; q[r][ch][2] = lo.z; q[r][ch][3] = lo.w;
+          q[r][ch][4] = hi.x; q[r][ch][5] = hi.y; q[r][ch][6] = hi.z; q[r][ch][7] = hi.w;
+        }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&qempty[qs]);
+      cs0 = csel[b * 3 + 0]; cs1 = csel[b * 3 + 1]; cs2 = csel[b * 3 + 2];
+      ++gcount;
+    }
+    ring::consumer_wait(bars, k);
+    const unsigned char* st = stages + (size_t)(k % R::kStages) * R::kStageBytes;
+    float a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < R::kChunks; ++ch) {
+      uint4 raw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        raw[i] = *reinterpret_cast<const uint4*>(st + ((size_t)(w * 4 + i) * D + (lane + 32 * ch) * 8) * 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float xv[8];
+        unpack8(raw[i], xv);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) a[i][r] = fmaf(xv[t], q[r][ch][t], a[i][r]);
+      }
+    }
+    ring::consumer_release(bars, k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[i][r] = warp_sum(a[i][r]);
+    if (lane < 4) {
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (lane == i) { v0 = a[i][0]; v1 = a[i][1]; v2 = a[i][2]; v3 = a[i][3]; }
+      const int l = chunk * R::kRows + w * 4 + lane;
+      const int64_t base = (int64_t)b * 3 * 3 * L + (int64_t)m * L + l;
+      sel_logits[base] = (v0 + cs0) * inv;
+      sel_logits[base + 3 * L] = (v1 + cs1) * inv;
+      sel_logits[base + 6 * L] = (v2 + cs2) * inv;
+      intra_raw[((int64_t)b * 3 + m) * L + l] = v3;
+    }
+  }
+}
+
+template <int D>
+static size_t sim_scores_ring_smem() {
+  using R = TokRing<D>;
+  return (size_t)R::kStages * R::kStageBytes + 2 * R::kQBytes + sizeof(ring::Bars<R::kStages>) + 4 * sizeof(uint64_t) + 128;
+}
+
+// ---- GAM mean pool ----------------------------------------------------------------------------------------------
+// mean [3][B][D] (zero-filled by the caller) += sum over the CTA's rows of the group / L.  Item order (m * B + b) * 4 +
+// chunk.  A group that straddles two CTAs receives two atomic adds onto zero: order-independent, so the result is
+// deterministic; within a CTA the eight warps' partial sums are added in a fixed order.
+template <int D>
+static __global__ void __launch_bounds__(TokRing<D>::kThreads, 1)
+pool_ring_kernel(TokSrc3 src, int B, int n_items, float* __restrict__ mean) {
+  using R = TokRing<D>;
+  constexpr int kWarps = R::kConsumers / 32;
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) unsigned char tr_smem[];
+  unsigned char* stages = tr_smem;
+  float* red = reinterpret_cast<float*>(tr_smem + (size_t)R::kStages * R::kStageBytes);   // [8][D]
+  auto* bars = reinterpret_cast<ring::Bars<R::kStages>*>(tr_smem + (size_t)R::kStages * R::kStageBytes + kWarps * D * 4);
+  const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x), i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
+  ring::init(bars, kWarps);
+  if ((int)threadIdx.x >= R::kConsumers) {
+    if ((int)threadIdx.x == R::kConsumers) {
+      // (the tokens are inputs of the call: the ring fills under the previous kernel's tail)
+      for (int it = i0, k = 0; it < i1; ++it, ++k) {
+        const int g = it / R::kItemsPerGroup, chunk = it % R::kItemsPerGroup;
+        const int m = g / B, b = g % B;
+        const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(src.patch[m]) + b * src.psb[m] + (int64_t)chunk * R::kRows * D;
+        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, x, R::kStageBytes);
+      }
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float acc[R::kChunks][8];
+#pragma unroll
+  for (int ch = 0; ch < R::kChunks; ++ch)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[ch][t] = 0.f;
+  pdl_wait();   // `mean` was zero-filled by the memset node in front of this kernel
+  for (int it = i0, k = 0; it < i1; ++it, ++k) {
+    const int g = it / R::kItemsPerGroup, chunk = it % R::kItemsPerGroup;
+    ring::consumer_wait(bars, k);
+    const unsigned char* st = stages + (size_t)(k % R::kStages) * R::kStageBytes;
+#pragma unroll
+    for (int ch = 0; ch < R::kChunks; ++ch) {
+      uint4 raw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        raw[i] = *reinterpret_cast<const uint4*>(st + ((size_t)(w * 4 + i) * D + (lane + 32 * ch) * 8) * 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float xv[8];
+        unpack8(raw[i], xv);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[ch][t] += xv[t];
+      }
+    }
+    ring::consumer_release(bars, k);
+    if (chunk == R::kItemsPerGroup - 1 || it == i1 - 1) {   // end of the group (or of this CTA's part of it)
+#pragma unroll
+      for (int ch = 0; ch < R::kChunks; ++ch) {
+        float* dst = red + w * D + (lane + 32 * ch) * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[ch][4], acc[ch][5], acc[ch][6], acc[ch][7]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[ch][t] = 0.f;
+      }
+      ring::consumer_sync(R::kConsumers);
+      const bool whole = (it - i0) >= R::kItemsPerGroup - 1 && chunk == R::kItemsPerGroup - 1;   // all four items were ours
+      for (int i = threadIdx.x; i < D; i += R::kConsumers) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) t += red[q * D + i];
+        t *= 1.f / kMaxL;
+        if (whole) mean[(int64_t)g * D + i] = t;
+        else atomicAdd(mean + (int64_t)g * D + i, t);
+      }
+      ring::consumer_sync(R::kConsumers);
+    }
+  }
+}
+
+template <int D>
+static size_t pool_ring_smem() {
+  using R = TokRing<D>;
+  return (size_t)R::kStages * R::kStageBytes + (R::kConsumers / 32) * D * 4 + sizeof(ring::Bars<R::kStages>) + 128;
+}
+
+inline bool tok_ring_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SIG_TOK_RING");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+}  // namespace sig
