@@ -163,13 +163,13 @@ def phase_work(B, d, s=2):
     gemm = 3 * 2 * L * d * d * B                                   # folded 1x1 conv, three modalities
     return {
         # phase: (bound, work [bytes for hbm, flops for tensor], kernel)
-        "lam_offsetnet_fwd": ("tensor", gemm, "pipeline_kernel<256,GemmProblem<256,K,K>>  H = X W'^T + b'"),
-        "lam_offsetnet_bwd_dx": ("tensor", gemm, "pipeline_kernel<256,GemmProblem<256,K,MN>>  dX = dH W' (+GAM rows)"),
-        "lam_offsetnet_bwd_dw": ("tensor", gemm, "pipeline_kernel<256,GemmProblem<256,MN,MN>>  dW' = dH^T X (split-K)"),
-        "lam_dwconv_fwd": ("hbm", B * T * s, "lam_dw_fwd_tc_kernel  (read H)"),
-        "lam_dwconv_bwd": ("hbm", 2 * B * T * s, "lam_dw_bwd_tc_kernel  (read H, write dH)"),
-        "sim_scores": ("hbm", B * T * s, "sim_scores_tok_kernel  (one pass over the tokens)"),
-        "gam_pool": ("hbm", B * T * s, "pool_tok_kernel  (one pass over the tokens)"),
+        "lam_offsetnet_fwd": ("tensor", gemm, "pair_gemm_kernel (cta_group::2, 256x256 units, K-major x K-major)  H = X W'^T + b'"),
+        "lam_offsetnet_bwd_dx": ("tensor", gemm, "pair_gemm_kernel (K-major x MN-major)  dX = dH W' (+GAM rows, + SIM's k-blocks under FusionHead)"),
+        "lam_offsetnet_bwd_dw": ("tensor", gemm, "pair_gemm_kernel (MN-major x MN-major)  dW' = dH^T X (split-K)"),
+        "lam_dwconv_fwd": ("hbm", B * T * s, "lam_dw_fwd_ring_kernel  (read H)"),
+        "lam_dwconv_bwd": ("hbm", 2 * B * T * s, "lam_dw_bwd_ring_kernel  (read H, write dH)"),
+        "sim_scores": ("hbm", B * T * s, "sim_scores_ring_kernel  (one pass over the tokens)"),
+        "gam_pool": ("hbm", B * T * s, "pool_ring_kernel  (one pass over the tokens)"),
         "sim_attn_logits_fwd": ("hbm", B * T * s, "pipeline_kernel<32,RowsProblem>  (one pass over the tokens)"),
         "sim_attn_pool_fwd": ("hbm", B * T * s, "pipeline_kernel<32,ColsProblem>  (one pass over the tokens)"),
         "sim_attn_dlogits_bwd": ("hbm", B * T * s, "pipeline_kernel<32,RowsProblem>  (one pass over the tokens)"),
@@ -488,7 +488,7 @@ def run_gpu(args):
             w = work["lam_offsetnet_fwd"][1]
             ach = w / (us * 1e-6) / 1e12
             tr = [g["traffic"] for g in gem if g["traffic"]]
-            roof = {"kernel": "tc::pipeline_kernel<256,1,GemmProblem<256,...>> (LAM offset-net GEMMs: H = X W'^T, dX = dH W', dW' = dH^T X)",
+            roof = {"kernel": "pair_gemm_kernel (tcgen05 cta_group::2, 256x256 units; LAM offset-net GEMMs: H = X W'^T, dX = dH W', dW' = dH^T X)",
                     "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tensor"], "unit": "TFLOP/s", "frac": round(ach / pk["tensor"], 4),
                     "traffic": round(sum(tr) / len(tr)) if tr else None, "peak_source": pk["src"] + " (sustained cuBLAS bf16; burst %.0f)" % pk["tensor_burst"],
                     "launches_per_step": len(gem), "avg_launch_us": round(us, 1),
