@@ -50,6 +50,12 @@ enum sig_ctx_kind { SIG_CTX_SIM = 0, SIG_CTX_ALIGN = 1, SIG_CTX_SELECT = 2, SIG_
 
 /* sig_flags bits (argument `flags` of the fwd/bwd entry points) */
 #define SIG_FLAG_FORCE_SIMT 1u /* bf16 inputs: use the fp32 SIMT kernels instead of tcgen05 (cross-check) */
+/* sig_align_fwd / sig_align_bwd, tensor-core path with LAM: the part of the backward that is linear in the loss weight
+ * and needs nothing from the caller's backward call (d(MSE) -> d(samples) -> d(offset logits) -> depthwise/GELU tail)
+ * already runs inside the FORWARD call with a unit weight; the backward call, given the same flag and the same ctx,
+ * skips it and applies d(loss)/d(lam) where the results are consumed.  Ignored on the fp32 SIMT path.  Only set it
+ * when a backward call will follow (training). */
+#define SIG_FLAG_EAGER_BWD 2u
 
 /* Three modality token maps, order RGB, NI, TI.
  * patch[m] -> element (b=0,l=0,c=0) of the [B,L,d] patch view, cls[m] -> (b=0,c=0)

@@ -341,7 +341,7 @@ static __global__ void __launch_bounds__(256) lam_mse_bwd_kernel(const float* __
                                                                  const float* __restrict__ gptr, float* __restrict__ dS) {
   pdl_enter();
   const int64_t bp = blockIdx.x;
-  const float k = scale * (*gptr);
+  const float k = gptr ? scale * (*gptr) : scale;   // (NULL: unit loss weight)
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     const float r = S[bp * d + c], n = S[mstride + bp * d + c], t = S[2 * mstride + bp * d + c];
     dS[bp * d + c] = k * (2.f * r - n - t);
@@ -648,7 +648,7 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   if (do_lam) SIG_TRY(check_grid(h, w, L));
   if (tc_path_ok(tok, flags)) {
     if (ctx_bytes < align_tc_ctx(nullptr, B, L, d).bytes) return SIG_ERR_WORKSPACE;
-    return align_forward_tc(tok, p, h, w, do_lam, losses, ctx, s);
+    return align_forward_tc(tok, p, h, w, do_lam, losses, ctx, do_lam && (flags & SIG_FLAG_EAGER_BWD), s);
   }
   if (ctx_bytes < align_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
   AlignCtx c = align_ctx(ctx, B, L, d, 3);
@@ -707,7 +707,7 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
       if (dtok->patch_stride_b[m] != dtok->patch_stride_b[0] || dtok->patch_stride_l[m] != dtok->patch_stride_l[0])
         return SIG_ERR_SHAPE;
     if (dtok->fuse_pds && !do_lam) return SIG_ERR_SHAPE;   // the fused operands ride on the LAM dX GEMM
-    return align_backward_tc(tok, p, h, w, do_lam, dlosses, dtok, dp, ctx, s);
+    return align_backward_tc(tok, p, h, w, do_lam, dlosses, dtok, dp, ctx, do_lam && (flags & SIG_FLAG_EAGER_BWD), s);
   }
   if (dtok->fuse_pds) return SIG_ERR_SHAPE;   // only the tensor-core path can take SIM's operands
   if (ctx_bytes < align_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;

@@ -221,7 +221,8 @@ static __global__ void __launch_bounds__(384, 2) lam_dw_bwd_tc_kernel(const __nv
 // deterministic reduction of the partials into the parameter gradients.  grid (ceil(d/64), 19, 3), 256 threads:
 // 64 channels x 4 chunk lanes
 static __global__ void __launch_bounds__(256) lam_dw_param_reduce_kernel(const float* __restrict__ part, int nchunk,
-                                                                         sig_align_param_grads gr, float* __restrict__ dbf, int d) {
+                                                                         sig_align_param_grads gr, float* __restrict__ dbf, int d,
+                                                                         const float* __restrict__ wscale) {
   pdl_enter();
   __shared__ float sm[4][64];
   const int m = blockIdx.z, i = blockIdx.y;
@@ -233,7 +234,7 @@ static __global__ void __launch_bounds__(256) lam_dw_param_reduce_kernel(const f
   sm[r][cl] = acc;
   __syncthreads();
   if (r == 0 && c < d) {
-    const float t = sm[0][cl] + sm[1][cl] + sm[2][cl] + sm[3][cl];
+    const float t = (sm[0][cl] + sm[1][cl] + sm[2][cl] + sm[3][cl]) * (wscale ? *wscale : 1.f);   // (eager chain: unit weight)
     if (i < 16) gr.off2_w[m][c * 16 + i] = t;
     else if (i == 16) gr.off2_b[m][c] = t;
     else if (i == 17) gr.off4_w[m][c] = t;
@@ -298,12 +299,37 @@ static __global__ void __launch_bounds__(128) lam_sample_bwd_tok_kernel(TokPtrs3
   if (threadIdx.x == 0) dO[(int64_t)m * B * g.P + bp] = giy * t.gy + gix * t.gx;
 }
 
+// dst = bf16(scale * src), n a multiple of 4 (d * d elements); scale is a device scalar
+template <typename T>
+static __global__ void __launch_bounds__(256) scale_to_bf16_kernel(const T* __restrict__ src, const float* __restrict__ scale,
+                                                                   __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_enter();
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float k = *scale;
+  float v[4];
+  if constexpr (sizeof(T) == 4) {
+    const float4 x = *reinterpret_cast<const float4*>(src + i);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  } else {
+    const uint2 x = *reinterpret_cast<const uint2*>(src + i);
+    v[0] = bf16lo_to_f32(x.x); v[1] = bf16hi_to_f32(x.x); v[2] = bf16lo_to_f32(x.y); v[3] = bf16hi_to_f32(x.y);
+  }
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0] * k, v[1] * k), b = __floats2bfloat162_rn(v[2] * k, v[3] * k);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dst + i) = o;
+}
+
 // sparse part of d(patches): every bilinear tap adds w * dS[p,:] to the token row it read.
 // grid (B, 3), d/8 threads; taps are applied one after the other, so no two threads touch the same element.
 template <typename T>
 static __global__ void __launch_bounds__(128) lam_sparse_add_kernel(GradPtrs3 gp, const float* __restrict__ o,
-                                                                    const float* __restrict__ dS, Geo g, int B, int d) {
+                                                                    const float* __restrict__ dS, Geo g, int B, int d,
+                                                                    const float* __restrict__ wscale) {
   pdl_enter();
+  const float ws = wscale ? *wscale : 1.f;   // (dS of the eager chain carries a unit loss weight)
   const int m = blockIdx.y, b = blockIdx.x;
   const int c = threadIdx.x * 8;
   if (c >= d) return;
@@ -312,6 +338,8 @@ static __global__ void __launch_bounds__(128) lam_sparse_add_kernel(GradPtrs3 gp
     const Taps t = make_taps(o[((int64_t)m * B + b) * g.P + p], p, g);
     float ds[8];
     load8(dS + (((int64_t)m * B + b) * g.P + p) * d + c, ds);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ds[i] *= ws;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (t.l[k] >= 0 && t.wgt[k] != 0.f) {
@@ -400,7 +428,7 @@ struct AlignTcCtx {
   float *gstat, *lossp, *dtaup;
   __nv_bfloat16 *fb, *fA, *fB, *WW;
   // LAM
-  __nv_bfloat16 *W0b, *Wqb, *Wfb, *dWfb;   // [3][d*d]
+  __nv_bfloat16 *W0b, *Wqb, *Wfb, *dWfb, *Wfs;   // [3][d*d]
   float *bfold, *dWf, *dbf;                // [3][d], [3][d*d], [3][d]
   __nv_bfloat16 *H, *dH;                   // [3][B*L*d]
   float *U, *dwpart, *o, *dO, *S, *dS, *part;
@@ -438,6 +466,7 @@ static AlignTcCtx align_tc_ctx(void* base, int B, int L, int d) {
   c.Wqb = a.take<__nv_bfloat16>(3 * dd);
   c.Wfb = a.take<__nv_bfloat16>(3 * dd);
   c.dWfb = a.take<__nv_bfloat16>(3 * dd);
+  c.Wfs = a.take<__nv_bfloat16>(3 * dd);
   c.bfold = a.take<float>((size_t)3 * d);
   c.dWf = a.take<float>(3 * dd);
   c.dbf = a.take<float>((size_t)3 * d);
@@ -663,8 +692,51 @@ static __global__ void __launch_bounds__(256) gam_final_kernel(const float* __re
   }
 }
 
+// The part of LAM's backward that is LINEAR in the loss weight and needs nothing from the caller's backward call:
+// d(MSE) -> d(samples) -> d(offset logits) -> depthwise/GELU tail (dH and the partial parameter sums).  `gscale` is the
+// device scalar d(loss)/d(lam) or NULL for a unit weight -- with SIG_FLAG_EAGER_BWD the forward call runs this chain with
+// a unit weight right behind the forward kernels (where the GPU is otherwise waiting for SIM's chain of small kernels),
+// and the backward call applies the weight where the results are consumed.
+static int lam_backward_chain_tc(const AlignTcCtx& c, const TokPtrs3& tp, const sig_align_params* p, const Geo& g, int B, int L, int d,
+                                 int h, int w, const float* gscale, cudaStream_t s) {
+  const size_t BL = (size_t)B * L;
+  const unsigned cthreads = (unsigned)ceil_div(d / 8, 32) * 32;
+  const bool dw_ring = dw_ring_ok(L, h, w, d);
+  {
+    SIG_PHASE("lam_sample_bwd");
+    SIG_LAUNCH((lam_mse_bwd_kernel), B * g.P, 256, 0, s, c.S, (int64_t)B * g.P * d, d, 2.f / (3.f * (float)B * g.P * d), gscale, c.dS);
+    SIG_CHECK_LAUNCH();
+    SIG_LAUNCH((lam_sample_bwd_tok_kernel<__nv_bfloat16>), dim3(B * g.P, 3), cthreads, 0, s, tp, c.o, c.dS, g, B, d, c.dO);
+    SIG_CHECK_LAUNCH();
+  }
+  if (dw_ring) {
+    SIG_PHASE("lam_dwconv_bwd");
+    if (d == 768 && w == 8) SIG_TRY((launch_dw_bwd_ring<768, 8>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+    else if (d == 768) SIG_TRY((launch_dw_bwd_ring<768, 16>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+    else if (w == 8) SIG_TRY((launch_dw_bwd_ring<512, 8>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+    else SIG_TRY((launch_dw_bwd_ring<512, 16>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
+  } else {
+    SIG_PHASE("lam_dwconv_bwd");
+    const int pts = dw_pts_per_cta((int64_t)B * g.P, 0);
+    const int nchunk = (int)ceil_div((int64_t)B * g.P, pts);
+    const size_t dw_smem_bytes = (size_t)16 * d * sizeof(float);
+    const unsigned thr = (unsigned)ceil_div(d / 2, 32) * 32;
+#define SIG_DW_BWD(D, W)                                                                                                    \
+  SIG_LAUNCH((lam_dw_bwd_tc_kernel<D, W>), dim3(nchunk, 3), thr, dw_smem_bytes, s, c.H, (int64_t)BL * d, c.U, c.dO, *p, g, B, L, d, \
+             pts, c.dH, c.dwpart)
+    if (d == 768 && w == 8) SIG_DW_BWD(768, 8);
+    else if (d == 768 && w == 16) SIG_DW_BWD(768, 16);
+    else if (d == 512 && w == 8) SIG_DW_BWD(512, 8);
+    else if (d == 512 && w == 16) SIG_DW_BWD(512, 16);
+    else SIG_DW_BWD(0, 0);
+#undef SIG_DW_BWD
+    SIG_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
 static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
-                            cudaStream_t s) {
+                            bool eager, cudaStream_t s) {
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);
@@ -788,12 +860,13 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
     SIG_LAUNCH((sum_kernel), 1, 256, 0, s, c.part, B * g.P, 1.f / (3.f * (float)B * g.P * d), losses + 1);
     SIG_CHECK_LAUNCH();
   }
+  if (eager) SIG_TRY(lam_backward_chain_tc(c, tp, p, g, B, L, d, h, w, nullptr, s));
   if (fk.ok()) fk.join(smain);
   return 0;
 }
 
 static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, const float* dlosses,
-                             const sig_token_grads* dtok, const sig_align_param_grads* dp, void* ctx, cudaStream_t s) {
+                             const sig_token_grads* dtok, const sig_align_param_grads* dp, void* ctx, bool eager, cudaStream_t s) {
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);
@@ -860,35 +933,11 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   }
   const Geo g = make_geo(h, w);
   const unsigned cthreads = (unsigned)ceil_div(d / 8, 32) * 32;
-  {
-    SIG_PHASE("lam_sample_bwd");
-    SIG_LAUNCH((lam_mse_bwd_kernel), B * g.P, 256, 0, s, c.S, (int64_t)B * g.P * d, d, 2.f / (3.f * (float)B * g.P * d), dlosses + 1, c.dS);
-    SIG_CHECK_LAUNCH();
-    SIG_LAUNCH((lam_sample_bwd_tok_kernel<__nv_bfloat16>), dim3(B * g.P, 3), cthreads, 0, s, tp, c.o, c.dS, g, B, d, c.dO);
-    SIG_CHECK_LAUNCH();
-  }
   const bool dw_ring = dw_ring_ok(L, h, w, d);
-  if (dw_ring) {
-    SIG_PHASE("lam_dwconv_bwd");
-    if (d == 768 && w == 8) SIG_TRY((launch_dw_bwd_ring<768, 8>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
-    else if (d == 768) SIG_TRY((launch_dw_bwd_ring<768, 16>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
-    else if (w == 8) SIG_TRY((launch_dw_bwd_ring<512, 8>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
-    else SIG_TRY((launch_dw_bwd_ring<512, 16>(c.H, c.U, c.dO, *p, B, h, c.dH, c.dwpart, s)));
-  } else {
-    SIG_PHASE("lam_dwconv_bwd");
-    const int pts = dw_pts_per_cta((int64_t)B * g.P, 0);
-    const int nchunk = (int)ceil_div((int64_t)B * g.P, pts);
-    const size_t dw_smem_bytes = (size_t)16 * d * sizeof(float);
-    const unsigned thr = (unsigned)ceil_div(d / 2, 32) * 32;
-#define SIG_DW_BWD(D, W)                                                                                                    \
-  SIG_LAUNCH((lam_dw_bwd_tc_kernel<D, W>), dim3(nchunk, 3), thr, dw_smem_bytes, s, c.H, (int64_t)BL * d, c.U, c.dO, *p, g, B, L, d, \
-             pts, c.dH, c.dwpart)
-    if (d == 768 && w == 8) SIG_DW_BWD(768, 8);
-    else if (d == 768 && w == 16) SIG_DW_BWD(768, 16);
-    else if (d == 512 && w == 8) SIG_DW_BWD(512, 8);
-    else if (d == 512 && w == 16) SIG_DW_BWD(512, 16);
-    else SIG_DW_BWD(0, 0);
-#undef SIG_DW_BWD
+  const float* lam_w = eager ? dlosses + 1 : nullptr;   // eager: the chain ran in the forward call with a unit weight
+  if (!eager) SIG_TRY(lam_backward_chain_tc(c, tp, p, g, B, L, d, h, w, dlosses + 1, s));
+  if (eager) {   // Wfs = d(loss)/d(lam) * W'  (B operand of the dX GEMM)
+    SIG_LAUNCH((scale_to_bf16_kernel<__nv_bfloat16>), (unsigned)ceil_div((int64_t)(3 * dd) / 4, 256), 256, 0, s, c.Wfb, lam_w, c.Wfs, (int64_t)(3 * dd));
     SIG_CHECK_LAUNCH();
   }
   // Everything below that is not on the dH -> dX / dW' path runs on a second side stream: the partial-sum
@@ -905,7 +954,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     SIG_PHASE("lam_dwconv_param_grads");
     const int pts = dw_pts_per_cta((int64_t)B * g.P, 0);
     const int nchunk = dw_ring ? dw_ring_ctas_per_mod(B, h) : (int)ceil_div((int64_t)B * g.P, pts);
-    SIG_LAUNCH((lam_dw_param_reduce_kernel), dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s, c.dwpart, nchunk, *dp, c.dbf, d);
+    SIG_LAUNCH((lam_dw_param_reduce_kernel), dim3((unsigned)ceil_div(d, 64), 19, 3), 256, 0, s, c.dwpart, nchunk, *dp, c.dbf, d, lam_w);
     SIG_CHECK_LAUNCH();
     SIG_LAUNCH((lam_unfold_bias_kernel), dim3((unsigned)ceil_div(d, 32), 3), 1024, 0, s, *p, *dp, c.dbf, d);   // db0 = db', dbq = W0^T db'
     SIG_CHECK_LAUNCH();
@@ -935,7 +984,12 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     if (fk2.ok()) fk2.fork(s);   // after the dW' GEMM
     cudaStream_t s = s2;
     SIG_PHASE("lam_unfold_grads");
-    SIG_TRY(cast_f32_to_bf16(c.dWf, c.dWfb, 3 * dd, s));
+    if (eager) {
+      SIG_LAUNCH((scale_to_bf16_kernel<float>), (unsigned)ceil_div((int64_t)(3 * dd) / 4, 256), 256, 0, s, c.dWf, lam_w, c.dWfb, (int64_t)(3 * dd));
+      SIG_CHECK_LAUNCH();
+    } else {
+      SIG_TRY(cast_f32_to_bf16(c.dWf, c.dWfb, 3 * dd, s));
+    }
     {  // dWq[d_mid, d_in] = W0^T dW'  : A[m = d_mid, k = d_out] = W0[k][m] (MN-major), B[n = d_in, k = d_out] = dW'[k][n] (MN-major)
       TcGemmDesc t = tc_desc();
       t.A = batched(tc_mn2d(nullptr, d, d, d), c.W0b, dd);
@@ -974,7 +1028,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     // d(patches) (+)= dH W' + g_gam * dmean  -> in the token dtype, at the token strides
     TcGemmDesc t = tc_desc();
     t.A = batched(tc_k2d(nullptr, (int64_t)BL, d, d), c.dH, BL * d);
-    t.B = batched(tc_mn2d(nullptr, d, d, d), c.Wfb, dd);
+    t.B = batched(tc_mn2d(nullptr, d, d, d), eager ? c.Wfs : c.Wfb, dd);   // eager: dH carries a unit weight, W' the real one
     t.M = (int)BL; t.N = d; t.K = d; t.batch = 3;
     for (int m = 0; m < 3; ++m) {
       t.C[m] = dtok->dpatch[m];
@@ -994,7 +1048,7 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
   }
   {
     SIG_PHASE("lam_sparse_dx");
-    SIG_LAUNCH((lam_sparse_add_kernel<__nv_bfloat16>), dim3(B, 3), cthreads, 0, s, gp, c.o, c.dS, g, B, d);
+    SIG_LAUNCH((lam_sparse_add_kernel<__nv_bfloat16>), dim3(B, 3), cthreads, 0, s, gp, c.o, c.dS, g, B, d, lam_w);
     SIG_CHECK_LAUNCH();
     if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
   }

@@ -457,6 +457,12 @@ class HeadFunction(torch.autograd.Function):
         buf_a = torch.empty(nb_a, dtype=torch.uint8, device=dev)
         main = torch.cuda.current_stream(dev)
         hi = event[2] if len(event) > 2 and event[2] is not None else main    # SIM's (high-priority) stream
+        # Training step: AlignM's forward call also runs the loss-weight-independent part of its backward (unit weight,
+        # SIG_FLAG_EAGER_BWD) -- on the side stream, under SIM's forward chain of small kernels, where the GPU is
+        # otherwise mostly idle; the backward call then starts at the weight-gradient GEMM.
+        flags_a = flags
+        if do_lam and any(ctx.needs_input_grad[9:]) and os.environ.get("SIG_EAGER_BWD", "1") != "0":
+            flags_a = flags | L_.SIG_FLAG_EAGER_BWD
         with torch.cuda.device(dev):
             side.wait_stream(main)
             if hi is not main:
@@ -464,18 +470,18 @@ class HeadFunction(torch.autograd.Function):
             L_.check(lib.sig_sim_fwd(C.byref(tok), C.byref(sprm), k1, k2, max_keep, out.data_ptr(), masks.data_ptr(),
                                      buf_s.data_ptr(), nb_s, flags, dev.index, hi.cuda_stream), "sig_sim_fwd")
             L_.check(lib.sig_align_fwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), losses.data_ptr(), buf_a.data_ptr(), nb_a,
-                                       flags, dev.index, side.cuda_stream), "sig_align_fwd")
+                                       flags_a, dev.index, side.cuda_stream), "sig_align_fwd")
             main.wait_stream(side)
             if hi is not main:
                 main.wait_stream(hi)
         ctx.save_for_backward(*toks, *sp, *ap, buf_s, buf_a)
-        ctx.cfg = (h, w, do_lam, flags, side, event, len(fold))   # event: (torch.cuda.Event, grad_sync or None)
+        ctx.cfg = (h, w, do_lam, flags, side, event, len(fold), flags_a)   # event: (torch.cuda.Event, grad_sync or None, ...)
         ctx.mark_non_differentiable(masks)
         return out, masks, losses[0], losses[1]
 
     @staticmethod
     def backward(ctx, dout, _dmasks, dgam, dlam):
-        h, w, do_lam, flags, side, event, nfold = ctx.cfg
+        h, w, do_lam, flags, side, event, nfold, flags_a = ctx.cfg
         saved = ctx.saved_tensors
         toks, sp, ap, buf_s, buf_a = saved[:3], saved[3:19], saved[19:41], saved[41], saved[42]
         lib = L_.load()
@@ -549,7 +555,7 @@ class HeadFunction(torch.autograd.Function):
                 with torch.cuda.stream(hi):
                     grad_sync(flat_s)
             L_.check(lib.sig_align_bwd(C.byref(tok_a), C.byref(aprm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg_a), C.byref(gs_a),
-                                       buf_a.data_ptr(), buf_a.numel(), flags, dev.index, side.cuda_stream), "sig_align_bwd")
+                                       buf_a.data_ptr(), buf_a.numel(), flags_a, dev.index, side.cuda_stream), "sig_align_bwd")
             if sync is not None:
                 with torch.cuda.stream(comm):
                     comm.wait_event(sync[2])
