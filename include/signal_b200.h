@@ -255,6 +255,28 @@ unsigned long long sig_debug_launch_count(void);
  * this (dtype, L, flags) combination does not run on that path. */
 int sig_sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flags, void** pds, void** dxqt);
 
+/* ---- ID / metric losses behind the head ---------------------------------------------
+ * logits/feat: row-major [B, C] / [B, D] with leading dimension ld (elements), dtype SIG_F32 or SIG_BF16; targets and
+ * labels int64 [B] on the device (no host copy, unlike layers/softmax_loss.py:30); fp32 arithmetic; ws: sig_loss_ws_bytes(B).
+ * CrossEntropyLabelSmooth.forward (layers/softmax_loss.py:23-34): loss = mean_b sum_k -((1-eps) 1[k=y_b] + eps/C) log p_bk;
+ * lse [B] is saved for the backward; dlogits has the dtype of logits. */
+size_t sig_loss_ws_bytes(int B);
+int sig_xent_ls_fwd(const void* logits, int dtype, int64_t ld, const int64_t* targets, int B, int C, float eps, float* loss,
+                    float* lse, void* ws, size_t ws_bytes, int device, void* stream);
+int sig_xent_ls_bwd(const void* logits, int dtype, int64_t ld, const int64_t* targets, int B, int C, float eps, const float* lse,
+                    const float* dloss, void* dlogits, int64_t ldd, int device, void* stream);
+/* TripletLoss.__call__ (layers/triplet_loss.py:121-135): euclidean_dist (:16-31, clamp 1e-12 before the sqrt),
+ * hard_example_mining (:51-104; the anchor itself counts as a positive, ties -> lowest index), dist_ap *= 1 + hard_factor,
+ * dist_an *= 1 - hard_factor, then SoftMarginLoss(an - ap, 1) (soft_margin != 0; margin=None in the reference) or
+ * MarginRankingLoss(margin)(an, ap, 1).  Outputs: loss [1], dist_ap/dist_an [B], p_idx/n_idx int32 [B].
+ * Backward: dloss [1] and optional cotangents of dist_ap / dist_an (may be NULL) -> dfeat (dtype of feat).  B <= 1024. */
+int sig_triplet_fwd(const void* feat, int dtype, int64_t ld, const int64_t* labels, int B, int D, float margin, int soft_margin,
+                    float hard_factor, float* loss, float* dist_ap, float* dist_an, int* p_idx, int* n_idx, void* ws, size_t ws_bytes,
+                    int device, void* stream);
+int sig_triplet_bwd(const void* feat, int dtype, int64_t ld, int B, int D, float margin, int soft_margin, float hard_factor,
+                    const float* dist_ap, const float* dist_an, const int* p_idx, const int* n_idx, const float* dloss,
+                    const float* d_dist_ap, const float* d_dist_an, void* dfeat, int64_t ldd, int device, void* stream);
+
 int sig_profile_enable(int on);
 int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);
 /* Time line of the recorded scopes ("name start_us end_us" lines, relative to the earliest start); with

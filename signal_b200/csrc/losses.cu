@@ -1,0 +1,302 @@
+// ID / metric losses that follow the fusion head in the training step:
+//   CrossEntropyLabelSmooth.forward   layers/softmax_loss.py:23-34
+//   TripletLoss.__call__              layers/triplet_loss.py:106-135 (euclidean_dist :16-31, hard_example_mining :51-104)
+// The reference builds the one-hot targets on the HOST every call (softmax_loss.py:30: `.data.cpu()` + scatter_, a
+// forced synchronisation per loss term) and mines hard examples with boolean-mask reshapes; here both are one forward
+// and one backward kernel, no host synchronisation, deterministic (no atomics), fp32 arithmetic on fp32 or bf16 inputs.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "signal_b200.h"
+
+namespace sig {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p, int64_t i) { return to_f32<T>(p[i]); }
+
+// ---- label-smoothed cross entropy ---------------------------------------------------------------------------------
+// row loss_b = sum_k -t_bk log p_bk,  t = (1 - eps) onehot(y_b) + eps / C
+//            = lse_b - (1 - eps) z_b[y_b] - (eps / C) sum_k z_bk        (sum_k t_bk = 1)
+// grid B, 256 threads.  rowloss [B], lse [B] (saved for the backward).
+template <typename T>
+__global__ void __launch_bounds__(256) xent_ls_fwd_kernel(const T* __restrict__ z, int64_t ld, const int64_t* __restrict__ y, int C,
+                                                          float eps, float* __restrict__ rowloss, float* __restrict__ lse) {
+  pdl_enter();
+  __shared__ float scratch[33];
+  const int b = blockIdx.x;
+  const T* zb = z + (int64_t)b * ld;
+  float mx = -INFINITY;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) mx = fmaxf(mx, ldf(zb, k));
+  mx = block_max(mx, scratch);
+  float se = 0.f, sz = 0.f;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    const float v = ldf(zb, k);
+    se += expf(v - mx);
+    sz += v;
+  }
+  se = block_sum(se, scratch);
+  sz = block_sum(sz, scratch);
+  if (threadIdx.x == 0) {
+    const float l = mx + logf(se);
+    const int64_t t = y[b];
+    const float zy = (t >= 0 && t < C) ? ldf(zb, t) : 0.f;
+    lse[b] = l;
+    rowloss[b] = l - (1.f - eps) * zy - (eps / C) * sz;
+  }
+}
+
+// out = scale * sum_i x[i]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256) sum_scale_kernel(const float* __restrict__ x, int n, float scale, float* __restrict__ out) {
+  pdl_enter();
+  __shared__ float scratch[33];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += x[i];
+  a = block_sum(a, scratch);
+  if (threadIdx.x == 0) *out = a * scale;
+}
+
+// dz_bk = g / B * (softmax_bk - t_bk)
+template <typename T>
+__global__ void __launch_bounds__(256) xent_ls_bwd_kernel(const T* __restrict__ z, int64_t ld, const int64_t* __restrict__ y, int B, int C,
+                                                          float eps, const float* __restrict__ lse, const float* __restrict__ g,
+                                                          T* __restrict__ dz, int64_t ldd) {
+  pdl_enter();
+  const int b = blockIdx.x;
+  const float k0 = *g / B, l = lse[b], off = eps / C;
+  const int64_t t = y[b];
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    const float p = expf(ldf(z + (int64_t)b * ld, k) - l);
+    const float tg = off + (k == t ? 1.f - eps : 0.f);
+    dz[(int64_t)b * ldd + k] = from_f32<T>(k0 * (p - tg));
+  }
+}
+
+// ---- triplet loss with hard example mining ------------------------------------------------------------------------
+// grid B (anchor i), 256 threads.  dist_ij = sqrt(max(|x_i|^2 + |x_j|^2 - 2 x_i.x_j, 1e-12)); hardest positive = max over
+// {j: y_j == y_i} (the anchor itself included, as in the reference), hardest negative = min over {j: y_j != y_i}; ties go
+// to the lowest index.  Per-anchor outputs: dist_ap, dist_an (after the hard_factor scaling), their indices, the raw
+// distances (for the backward) and the loss term.
+template <typename T>
+__global__ void __launch_bounds__(256) triplet_fwd_kernel(const T* __restrict__ x, int64_t ld, const int64_t* __restrict__ y, int B, int D,
+                                                          float margin, int soft, float hard_factor, float* __restrict__ dist_ap,
+                                                          float* __restrict__ dist_an, int* __restrict__ p_idx, int* __restrict__ n_idx,
+                                                          float* __restrict__ rowloss) {
+  pdl_enter();
+  extern __shared__ float xi[];   // [D]
+  __shared__ float s_val[2][8];
+  __shared__ int s_idx[2][8];
+  __shared__ float scratch[33];
+  const int i = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float xx = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = ldf(x + (int64_t)i * ld, c);
+    xi[c] = v;
+    xx = fmaf(v, v, xx);
+  }
+  xx = block_sum(xx, scratch);   // (ends with a barrier: xi is complete)
+  const int64_t yi = y[i];
+  float best_p = -INFINITY, best_n = INFINITY;
+  int ip = -1, in_ = -1;
+  for (int j = w; j < B; j += nw) {
+    float dot = 0.f, yy = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float v = ldf(x + (int64_t)j * ld, c);
+      dot = fmaf(v, xi[c], dot);
+      yy = fmaf(v, v, yy);
+    }
+    dot = warp_sum(dot);
+    yy = warp_sum(yy);
+    const float dist = sqrtf(fmaxf(xx + yy - 2.f * dot, 1e-12f));
+    if (y[j] == yi) {
+      if (dist > best_p) { best_p = dist; ip = j; }     // j ascends within a warp: the first maximum is kept
+    } else {
+      if (dist < best_n) { best_n = dist; in_ = j; }
+    }
+  }
+  if (lane == 0) {
+    s_val[0][w] = best_p; s_idx[0][w] = ip;
+    s_val[1][w] = best_n; s_idx[1][w] = in_;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < nw; ++q) {
+      const float vp = s_val[0][q], vn = s_val[1][q];
+      const int jp = s_idx[0][q], jn = s_idx[1][q];
+      if (jp >= 0 && (ip < 0 || vp > best_p || (vp == best_p && jp < ip))) { best_p = vp; ip = jp; }
+      if (jn >= 0 && (in_ < 0 || vn < best_n || (vn == best_n && jn < in_))) { best_n = vn; in_ = jn; }
+    }
+    const float ap = best_p * (1.f + hard_factor), an = (in_ >= 0 ? best_n : 0.f) * (1.f - hard_factor);
+    dist_ap[i] = ap;
+    dist_an[i] = an;
+    p_idx[i] = ip;
+    n_idx[i] = in_;
+    const float s = an - ap;
+    // SoftMarginLoss(s, 1) = log(1 + exp(-s)); MarginRankingLoss(an, ap, 1) = max(0, -(an - ap) + margin)
+    rowloss[i] = soft ? (s > 0.f ? log1pf(expf(-s)) : -s + log1pf(expf(s))) : fmaxf(0.f, margin - s);
+  }
+}
+
+// grid B (row j of dx), 256 threads.  coef_ap[i] = dL/d(dist_ap_i) etc. are recomputed from the saved distances:
+//   dL/ds_i = g/B * (soft ? -1/(1+exp(s_i)) : (margin - s_i > 0 ? -1 : 0)),  s = an - ap,
+//   d/d(an) = dL/ds * (1 - hf) (+ g_an_i),  d/d(ap) = -dL/ds * (1 + hf) (+ g_ap_i)   [w.r.t. the RAW distances]
+// and d dist_ij / d x_i = (x_i - x_j) / dist_ij, d dist_ij / d x_j = (x_j - x_i) / dist_ij (0 where the clamp is active).
+template <typename T>
+__global__ void __launch_bounds__(256) triplet_bwd_kernel(const T* __restrict__ x, int64_t ld, int B, int D, float margin, int soft,
+                                                          float hard_factor, const float* __restrict__ dist_ap,
+                                                          const float* __restrict__ dist_an, const int* __restrict__ p_idx,
+                                                          const int* __restrict__ n_idx, const float* __restrict__ g,
+                                                          const float* __restrict__ g_ap, const float* __restrict__ g_an,
+                                                          T* __restrict__ dx, int64_t ldd) {
+  pdl_enter();
+  extern __shared__ float sm[];   // cp [B], cn [B]  (coefficient / raw distance, 0 where clamped or missing)
+  float* cp = sm;
+  float* cn = sm + B;
+  __shared__ int sp[1024], sn[1024];   // (B <= 1024, checked by the host)
+  const int j = blockIdx.x;
+  const float gl = g ? *g / B : 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float ap = dist_ap[i], an = dist_an[i];
+    const float s = an - ap;
+    const float dls = gl * (soft ? -1.f / (1.f + expf(s)) : (margin - s > 0.f ? -1.f : 0.f));
+    float c_an = dls + (g_an ? g_an[i] : 0.f);
+    float c_ap = -dls + (g_ap ? g_ap[i] : 0.f);
+    c_an *= (1.f - hard_factor);
+    c_ap *= (1.f + hard_factor);
+    const float rap = ap / (1.f + hard_factor), ran = (1.f - hard_factor) != 0.f ? an / (1.f - hard_factor) : 0.f;   // raw distances
+    const int ip = p_idx[i], in_ = n_idx[i];
+    sp[i] = ip; sn[i] = in_;
+    cp[i] = (ip >= 0 && rap > 1.0000001e-6f) ? c_ap / rap : 0.f;     // dist == sqrt(1e-12): the clamp was active, no gradient
+    cn[i] = (in_ >= 0 && ran > 1.0000001e-6f) ? c_an / ran : 0.f;
+  }
+  __syncthreads();
+  // dx_j = sum over the pairs (i, q) in {(i, p_i), (i, n_i)} that contain j of coef * (x_j - x_other)
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float xj = ldf(x + (int64_t)j * ld, c);
+    float acc = 0.f;
+    if (sp[j] >= 0 && cp[j] != 0.f) acc = fmaf(cp[j], xj - ldf(x + (int64_t)sp[j] * ld, c), acc);
+    if (sn[j] >= 0 && cn[j] != 0.f) acc = fmaf(cn[j], xj - ldf(x + (int64_t)sn[j] * ld, c), acc);
+    for (int i = 0; i < B; ++i) {
+      if (sp[i] == j && cp[i] != 0.f) acc = fmaf(cp[i], xj - ldf(x + (int64_t)i * ld, c), acc);
+      if (sn[i] == j && cn[i] != 0.f) acc = fmaf(cn[i], xj - ldf(x + (int64_t)i * ld, c), acc);
+    }
+    dx[(int64_t)j * ldd + c] = from_f32<T>(acc);
+  }
+}
+
+}  // namespace
+}  // namespace sig
+
+namespace {
+struct DevGuard {
+  int prev = -1, rc = 0;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      cudaError_t e = cudaSetDevice(dev);
+      if (e != cudaSuccess) rc = (int)e;
+    }
+  }
+  ~DevGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
+extern "C" {
+
+size_t sig_loss_ws_bytes(int B) { return (size_t)(B > 0 ? B : 0) * 2 * sizeof(float); }
+
+int sig_xent_ls_fwd(const void* logits, int dtype, int64_t ld, const int64_t* targets, int B, int C, float eps, float* loss,
+                    float* lse, void* ws, size_t ws_bytes, int device, void* stream) {
+  DevGuard guard(device);
+  if (guard.rc) return guard.rc;
+  cudaGetLastError();
+  using namespace sig;
+  if (!logits || !targets || !loss || !lse || !ws) return SIG_ERR_NULL;
+  if (B < 1 || C < 1 || ld < C) return SIG_ERR_SHAPE;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  if (ws_bytes < sig_loss_ws_bytes(B)) return SIG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* rowloss = static_cast<float*>(ws);
+  if (dtype == SIG_BF16)
+    SIG_LAUNCH((xent_ls_fwd_kernel<__nv_bfloat16>), B, 256, 0, s, static_cast<const __nv_bfloat16*>(logits), ld, targets, C, eps, rowloss, lse);
+  else
+    SIG_LAUNCH((xent_ls_fwd_kernel<float>), B, 256, 0, s, static_cast<const float*>(logits), ld, targets, C, eps, rowloss, lse);
+  SIG_CHECK_LAUNCH();
+  SIG_LAUNCH((sum_scale_kernel), 1, 256, 0, s, rowloss, B, 1.f / B, loss);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+int sig_xent_ls_bwd(const void* logits, int dtype, int64_t ld, const int64_t* targets, int B, int C, float eps, const float* lse,
+                    const float* dloss, void* dlogits, int64_t ldd, int device, void* stream) {
+  DevGuard guard(device);
+  if (guard.rc) return guard.rc;
+  cudaGetLastError();
+  using namespace sig;
+  if (!logits || !targets || !lse || !dloss || !dlogits) return SIG_ERR_NULL;
+  if (B < 1 || C < 1 || ld < C || ldd < C) return SIG_ERR_SHAPE;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SIG_BF16)
+    SIG_LAUNCH((xent_ls_bwd_kernel<__nv_bfloat16>), B, 256, 0, s, static_cast<const __nv_bfloat16*>(logits), ld, targets, B, C, eps, lse, dloss,
+               static_cast<__nv_bfloat16*>(dlogits), ldd);
+  else
+    SIG_LAUNCH((xent_ls_bwd_kernel<float>), B, 256, 0, s, static_cast<const float*>(logits), ld, targets, B, C, eps, lse, dloss,
+               static_cast<float*>(dlogits), ldd);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+int sig_triplet_fwd(const void* feat, int dtype, int64_t ld, const int64_t* labels, int B, int D, float margin, int soft_margin,
+                    float hard_factor, float* loss, float* dist_ap, float* dist_an, int* p_idx, int* n_idx, void* ws, size_t ws_bytes,
+                    int device, void* stream) {
+  DevGuard guard(device);
+  if (guard.rc) return guard.rc;
+  cudaGetLastError();
+  using namespace sig;
+  if (!feat || !labels || !loss || !dist_ap || !dist_an || !p_idx || !n_idx || !ws) return SIG_ERR_NULL;
+  if (B < 1 || B > 1024 || D < 1 || D > 8192 || ld < D) return SIG_ERR_SHAPE;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  if (ws_bytes < sig_loss_ws_bytes(B)) return SIG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* rowloss = static_cast<float*>(ws);
+  const size_t smem = (size_t)D * sizeof(float);
+  if (dtype == SIG_BF16)
+    SIG_LAUNCH((triplet_fwd_kernel<__nv_bfloat16>), B, 256, smem, s, static_cast<const __nv_bfloat16*>(feat), ld, labels, B, D, margin, soft_margin,
+               hard_factor, dist_ap, dist_an, p_idx, n_idx, rowloss);
+  else
+    SIG_LAUNCH((triplet_fwd_kernel<float>), B, 256, smem, s, static_cast<const float*>(feat), ld, labels, B, D, margin, soft_margin, hard_factor,
+               dist_ap, dist_an, p_idx, n_idx, rowloss);
+  SIG_CHECK_LAUNCH();
+  SIG_LAUNCH((sum_scale_kernel), 1, 256, 0, s, rowloss, B, 1.f / B, loss);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+int sig_triplet_bwd(const void* feat, int dtype, int64_t ld, int B, int D, float margin, int soft_margin, float hard_factor,
+                    const float* dist_ap, const float* dist_an, const int* p_idx, const int* n_idx, const float* dloss,
+                    const float* d_dist_ap, const float* d_dist_an, void* dfeat, int64_t ldd, int device, void* stream) {
+  DevGuard guard(device);
+  if (guard.rc) return guard.rc;
+  cudaGetLastError();
+  using namespace sig;
+  if (!feat || !dist_ap || !dist_an || !p_idx || !n_idx || !dfeat) return SIG_ERR_NULL;
+  if (B < 1 || B > 1024 || D < 1 || ld < D || ldd < D) return SIG_ERR_SHAPE;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = (size_t)2 * B * sizeof(float);
+  if (dtype == SIG_BF16)
+    SIG_LAUNCH((triplet_bwd_kernel<__nv_bfloat16>), B, 256, smem, s, static_cast<const __nv_bfloat16*>(feat), ld, B, D, margin, soft_margin,
+               hard_factor, dist_ap, dist_an, p_idx, n_idx, dloss, d_dist_ap, d_dist_an, static_cast<__nv_bfloat16*>(dfeat), ldd);
+  else
+    SIG_LAUNCH((triplet_bwd_kernel<float>), B, 256, smem, s, static_cast<const float*>(feat), ld, B, D, margin, soft_margin, hard_factor, dist_ap,
+               dist_an, p_idx, n_idx, dloss, d_dist_ap, d_dist_an, static_cast<float*>(dfeat), ldd);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

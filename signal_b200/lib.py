@@ -73,6 +73,7 @@ EXPORTS = [
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
     "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_profile_scope_begin", "sig_profile_scope_end", "sig_sim_dx_operands",
+    "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd",
 ]
 
 
@@ -113,6 +114,13 @@ def load():
     lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
     lib.sig_sim_dx_operands.argtypes = [vp, i, i, i, i, u, P(vp), P(vp)]
     lib.sig_profile_timeline.argtypes = [C.c_char_p, sz]
+    f = C.c_float
+    lib.sig_loss_ws_bytes.restype = sz
+    lib.sig_loss_ws_bytes.argtypes = [i]
+    lib.sig_xent_ls_fwd.argtypes = [vp, i, i64, vp, i, i, f, vp, vp, vp, sz, i, vp]
+    lib.sig_xent_ls_bwd.argtypes = [vp, i, i64, vp, i, i, f, vp, vp, vp, i64, i, vp]
+    lib.sig_triplet_fwd.argtypes = [vp, i, i64, vp, i, i, f, i, f, vp, vp, vp, vp, vp, vp, sz, i, vp]
+    lib.sig_triplet_bwd.argtypes = [vp, i, i64, i, i, f, i, f, vp, vp, vp, vp, vp, vp, vp, vp, i64, i, vp]
     lib.sig_profile_scope_begin.restype = vp
     lib.sig_profile_scope_begin.argtypes = [C.c_char_p, vp]
     lib.sig_profile_scope_end.restype = None
