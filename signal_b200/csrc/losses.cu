@@ -171,16 +171,27 @@ __global__ void __launch_bounds__(256) triplet_bwd_kernel(const T* __restrict__ 
     cn[i] = (in_ >= 0 && ran > 1.0000001e-6f) ? c_an / ran : 0.f;
   }
   __syncthreads();
-  // dx_j = sum over the pairs (i, q) in {(i, p_i), (i, n_i)} that contain j of coef * (x_j - x_other)
+  // the pairs (i, p_i) / (i, n_i) with i != j that contain j, in ascending i (fixed order: deterministic sums)
+  __shared__ int l_other[2 * 1024];
+  __shared__ float l_coef[2 * 1024];
+  __shared__ int l_n;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 0; i < B; ++i) {
+      if (sp[i] == j && cp[i] != 0.f) { l_other[n] = i; l_coef[n] = cp[i]; ++n; }
+      if (sn[i] == j && cn[i] != 0.f) { l_other[n] = i; l_coef[n] = cn[i]; ++n; }
+    }
+    l_n = n;
+  }
+  __syncthreads();
+  const int n = l_n;
+  // dx_j = sum over the pairs that contain j of coef * (x_j - x_other)
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     const float xj = ldf(x + (int64_t)j * ld, c);
     float acc = 0.f;
     if (sp[j] >= 0 && cp[j] != 0.f) acc = fmaf(cp[j], xj - ldf(x + (int64_t)sp[j] * ld, c), acc);
     if (sn[j] >= 0 && cn[j] != 0.f) acc = fmaf(cn[j], xj - ldf(x + (int64_t)sn[j] * ld, c), acc);
-    for (int i = 0; i < B; ++i) {
-      if (sp[i] == j && cp[i] != 0.f) acc = fmaf(cp[i], xj - ldf(x + (int64_t)i * ld, c), acc);
-      if (sn[i] == j && cn[i] != 0.f) acc = fmaf(cn[i], xj - ldf(x + (int64_t)i * ld, c), acc);
-    }
+    for (int q = 0; q < n; ++q) acc = fmaf(l_coef[q], xj - ldf(x + (int64_t)l_other[q] * ld, c), acc);
     dx[(int64_t)j * ldd + c] = from_f32<T>(acc);
   }
 }

@@ -75,6 +75,20 @@ class CrossEntropyLabelSmooth(nn.Module):
         return _XentLS.apply(inputs, targets, self.epsilon)
 
 
+class LabelSmoothingCrossEntropy(nn.Module):
+    """layers/softmax_loss.py:36-55: ``confidence * nll + smoothing * (-mean_k log p)``, averaged over the batch --
+    the same smoothed target ``(1 - s) onehot + s / C`` as CrossEntropyLabelSmooth with C taken from the logits."""
+
+    def __init__(self, smoothing=0.1):
+        super().__init__()
+        assert smoothing < 1.0
+        self.smoothing = smoothing
+        self.confidence = 1. - smoothing
+
+    def forward(self, x, target):
+        return _XentLS.apply(x, target, self.smoothing)
+
+
 class _Triplet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, labels, margin, hard_factor):
