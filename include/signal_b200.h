@@ -277,6 +277,22 @@ int sig_triplet_bwd(const void* feat, int dtype, int64_t ld, int B, int D, float
                     const float* dist_ap, const float* dist_an, const int* p_idx, const int* n_idx, const float* dloss,
                     const float* d_dist_ap, const float* d_dist_an, void* dfeat, int64_t ldd, int device, void* stream);
 
+/* BNNeck + classifier (modeling/make_model.py:128-131,194-195,212-214: nn.BatchNorm1d(D) -> nn.Linear(D, C, bias=False)).
+ * feat [B, D] (ld); bn_out [B, D] and logits [B, C] in the dtype of feat; training != 0: batch statistics, running_mean /
+ * running_var (may be NULL) updated in place with `momentum` (unbiased variance), else the running statistics are used.
+ * save_mean / save_rstd [D] and y32 [B, D] fp32 are kept by the caller for the backward; ws: sig_bnneck_ws_bytes(B, D, C).
+ * Backward: dlogits and/or d_bn_out (either may be NULL) -> dfeat (dtype of feat), d_bn_weight, d_bn_bias [D],
+ * d_cls_weight [C, D] fp32 (overwritten). */
+size_t sig_bnneck_ws_bytes(int B, int D, int C);
+int sig_bnneck_cls_fwd(const void* feat, int dtype, int64_t ld, int B, int D, int C, const float* bn_weight, const float* bn_bias,
+                       float* running_mean, float* running_var, float momentum, float eps, int training, const float* cls_weight,
+                       void* bn_out, int64_t ldo, void* logits, int64_t ldl, float* save_mean, float* save_rstd, float* y32, void* ws,
+                       size_t ws_bytes, int device, void* stream);
+int sig_bnneck_cls_bwd(const void* feat, int dtype, int64_t ld, int B, int D, int C, const float* bn_weight, const float* cls_weight,
+                       const float* save_mean, const float* save_rstd, int training, const float* y32, const void* dlogits, int64_t ldl,
+                       const void* d_bn_out, int64_t lddo, void* dfeat, int64_t ldx, float* d_bn_weight, float* d_bn_bias,
+                       float* d_cls_weight, void* ws, size_t ws_bytes, int device, void* stream);
+
 int sig_profile_enable(int on);
 int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);
 /* Time line of the recorded scopes ("name start_us end_us" lines, relative to the earliest start); with

@@ -64,3 +64,23 @@ def triplet_loss(feat: Tensor, labels: Tensor, margin: Optional[float] = None, h
     else:
         loss = (margin - s).clamp(min=0).mean()               # MarginRankingLoss(margin)(an, ap, y=1)
     return loss, ap, an
+
+
+def bnneck_classifier(x: Tensor, gamma: Tensor, beta: Tensor, W: Tensor, eps: float = 1e-5,
+                      running: Optional[Tuple[Tensor, Tensor]] = None, momentum: float = 0.1, training: bool = True):
+    """modeling/make_model.py:128-131,194-195: BatchNorm1d (batch statistics when training, biased variance for the
+    normalisation, unbiased for the running update) followed by a bias-free Linear.
+    Returns (feat_bn, logits, new_running_mean, new_running_var)."""
+    B = x.shape[0]
+    if training:
+        mean = x.sum(dim=0) / B
+        var = ((x - mean) ** 2).sum(dim=0) / B
+        new_rm = new_rv = None
+        if running is not None:
+            new_rm = (1 - momentum) * running[0] + momentum * mean.detach()
+            new_rv = (1 - momentum) * running[1] + momentum * var.detach() * B / (B - 1)
+    else:
+        mean, var = running
+        new_rm, new_rv = running
+    y = (x - mean) / torch.sqrt(var + eps) * gamma + beta
+    return y, y @ W.t(), new_rm, new_rv

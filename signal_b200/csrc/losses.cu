@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "signal_b200.h"
+#include "simt_ops.cuh"
 
 namespace sig {
 namespace {
@@ -196,6 +197,155 @@ __global__ void __launch_bounds__(256) triplet_bwd_kernel(const T* __restrict__ 
   }
 }
 
+// ---- BNNeck + classifier (make_model.py:128-131,194-195,212-214: nn.BatchNorm1d -> nn.Linear(bias=False)) ------------
+// One CTA = 32 feature columns x 8 row groups.  Training: batch statistics (two passes: mean, then centred variance),
+// running statistics updated like nn.BatchNorm1d (momentum, unbiased variance); eval: running statistics.
+// y32 [B, D] fp32 (operand of the classifier GEMM, saved for the backward), out [B, D] in the input dtype.
+template <typename T>
+__global__ void __launch_bounds__(256) bn1d_fwd_kernel(const T* __restrict__ x, int64_t ld, int B, int D, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float* __restrict__ run_mean,
+                                                       float* __restrict__ run_var, float momentum, float eps, int training,
+                                                       float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                                       float* __restrict__ y32, T* __restrict__ out, int64_t ldo) {
+  pdl_enter();
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool ok = c < D;
+  float mean = 0.f, rstd = 0.f;
+  if (training) {
+    float s = 0.f;
+    if (ok) for (int r = ry; r < B; r += 8) s += ldf(x + (int64_t)r * ld, c);
+    red[ry][cx] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][cx];
+    mean = s / B;
+    __syncthreads();
+    float v = 0.f;
+    if (ok) for (int r = ry; r < B; r += 8) {
+      const float t = ldf(x + (int64_t)r * ld, c) - mean;
+      v = fmaf(t, t, v);
+    }
+    red[ry][cx] = v;
+    __syncthreads();
+    v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += red[q][cx];
+    const float var = v / B;
+    rstd = rsqrtf(var + eps);
+    if (ok && ry == 0) {
+      if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+      if (run_var) run_var[c] = (1.f - momentum) * run_var[c] + momentum * (B > 1 ? var * B / (B - 1) : var);
+    }
+  } else if (ok) {
+    mean = run_mean[c];
+    rstd = rsqrtf(run_var[c] + eps);
+  }
+  if (!ok) return;
+  if (ry == 0) { save_mean[c] = mean; save_rstd[c] = rstd; }
+  const float g = gamma[c], b = beta[c];
+  for (int r = ry; r < B; r += 8) {
+    const float y = (ldf(x + (int64_t)r * ld, c) - mean) * rstd * g + b;
+    y32[(int64_t)r * D + c] = y;
+    out[(int64_t)r * ldo + c] = from_f32<T>(y);
+  }
+}
+
+// dx = gamma * rstd * (dy - mean_b(dy) - xhat * mean_b(dy * xhat))  (training; eval: gamma * rstd * dy),
+// dgamma = sum_b dy * xhat, dbeta = sum_b dy;  dy = dY32 (from the classifier) + optional dout (cotangent of the BN output)
+template <typename T>
+__global__ void __launch_bounds__(256) bn1d_bwd_kernel(const T* __restrict__ x, int64_t ld, int B, int D, const float* __restrict__ gamma,
+                                                       const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                                       int training, const float* __restrict__ dY32, const T* __restrict__ dout,
+                                                       int64_t lddo, T* __restrict__ dx, int64_t ldx, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta) {
+  pdl_enter();
+  __shared__ float red[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool ok = c < D;
+  const float mean = ok ? save_mean[c] : 0.f, rstd = ok ? save_rstd[c] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  if (ok) for (int r = ry; r < B; r += 8) {
+    float dy = dY32 ? dY32[(int64_t)r * D + c] : 0.f;
+    if (dout) dy += ldf(dout + (int64_t)r * lddo, c);
+    const float xh = (ldf(x + (int64_t)r * ld, c) - mean) * rstd;
+    s1 += dy;
+    s2 = fmaf(dy, xh, s2);
+  }
+  red[0][ry][cx] = s1;
+  red[1][ry][cx] = s2;
+  __syncthreads();
+  s1 = s2 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { s1 += red[0][q][cx]; s2 += red[1][q][cx]; }
+  if (!ok) return;
+  if (ry == 0) { dgamma[c] = s2; dbeta[c] = s1; }
+  const float g = gamma[c] * rstd, m1 = training ? s1 / B : 0.f, m2 = training ? s2 / B : 0.f;
+  for (int r = ry; r < B; r += 8) {
+    float dy = dY32 ? dY32[(int64_t)r * D + c] : 0.f;
+    if (dout) dy += ldf(dout + (int64_t)r * lddo, c);
+    const float xh = (ldf(x + (int64_t)r * ld, c) - mean) * rstd;
+    dx[(int64_t)r * ldx + c] = from_f32<T>(g * (dy - m1 - xh * m2));
+  }
+}
+
+// rows of a [R, N] matrix with leading dimension ld: T -> fp32 (dense) or fp32 (dense) -> T
+template <typename T>
+__global__ void __launch_bounds__(256) rows_to_f32_kernel(const T* __restrict__ src, int64_t ld, int R, int N, float* __restrict__ dst) {
+  pdl_enter();
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < (int64_t)R * N) dst[i] = ldf(src + (i / N) * ld, i % N);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) rows_from_f32_kernel(const float* __restrict__ src, int R, int N, T* __restrict__ dst, int64_t ld) {
+  pdl_enter();
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < (int64_t)R * N) dst[(i / N) * ld + i % N] = from_f32<T>(src[i]);
+}
+
+template <typename T>
+int bnneck_fwd(const T* x, int64_t ld, int B, int D, int C, const float* gamma, const float* beta, float* rm, float* rv, float momentum,
+               float eps, int training, const float* W, T* out, int64_t ldo, T* logits, int64_t ldl, float* save_mean, float* save_rstd,
+               float* y32, float* ws, cudaStream_t s) {
+  SIG_LAUNCH((bn1d_fwd_kernel<T>), (unsigned)ceil_div(D, 32), 256, 0, s, x, ld, B, D, gamma, beta, rm, rv, momentum, eps, training, save_mean,
+             save_rstd, y32, out, ldo);
+  SIG_CHECK_LAUNCH();
+  // logits = y W^T  (fp32 SIMT GEMM: 2 B C D = 0.1 GFLOP at the training shape, latency-bound)
+  if (sizeof(T) == 4 && ldl == C) {
+    SIG_TRY(launch_gemm(gemm_nt(y32, D, W, D, reinterpret_cast<float*>(logits), C, nullptr, B, C, D), s));
+  } else {
+    SIG_TRY(launch_gemm(gemm_nt(y32, D, W, D, ws, C, nullptr, B, C, D), s));
+    SIG_LAUNCH((rows_from_f32_kernel<T>), (unsigned)ceil_div((int64_t)B * C, 256), 256, 0, s, ws, B, C, logits, ldl);
+    SIG_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+template <typename T>
+int bnneck_bwd(const T* x, int64_t ld, int B, int D, int C, const float* gamma, const float* W, const float* save_mean,
+               const float* save_rstd, int training, const float* y32, const T* dlogits, int64_t ldl, const T* dout, int64_t lddo, T* dx,
+               int64_t ldx, float* dgamma, float* dbeta, float* dW, float* ws, cudaStream_t s) {
+  float* dl32 = ws;                        // [B, C]
+  float* dY32 = ws + (size_t)B * C;        // [B, D]
+  const float* dy = nullptr;
+  if (dlogits) {
+    SIG_LAUNCH((rows_to_f32_kernel<T>), (unsigned)ceil_div((int64_t)B * C, 256), 256, 0, s, dlogits, ldl, B, C, dl32);
+    SIG_CHECK_LAUNCH();
+    SIG_TRY(launch_gemm(gemm_tn(dl32, C, y32, D, dW, D, C, D, B), s));      // dW = dlogits^T y
+    SIG_TRY(launch_gemm(gemm_nn(dl32, C, W, D, dY32, D, B, D, C), s));      // dy = dlogits W
+    dy = dY32;
+  } else {
+    cudaMemsetAsync(dW, 0, (size_t)C * D * sizeof(float), s);
+  }
+  SIG_LAUNCH((bn1d_bwd_kernel<T>), (unsigned)ceil_div(D, 32), 256, 0, s, x, ld, B, D, gamma, save_mean, save_rstd, training, dy, dout, lddo, dx,
+             ldx, dgamma, dbeta);
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace
 }  // namespace sig
 
@@ -308,6 +458,57 @@ int sig_triplet_bwd(const void* feat, int dtype, int64_t ld, int B, int D, float
                dist_an, p_idx, n_idx, dloss, d_dist_ap, d_dist_an, static_cast<float*>(dfeat), ldd);
   SIG_CHECK_LAUNCH();
   return 0;
+}
+
+size_t sig_bnneck_ws_bytes(int B, int D, int C) {
+  if (B < 1 || D < 1 || C < 1) return 0;
+  return ((size_t)B * C + (size_t)B * D) * sizeof(float);
+}
+
+int sig_bnneck_cls_fwd(const void* feat, int dtype, int64_t ld, int B, int D, int C, const float* bn_weight, const float* bn_bias,
+                       float* running_mean, float* running_var, float momentum, float eps, int training, const float* cls_weight,
+                       void* bn_out, int64_t ldo, void* logits, int64_t ldl, float* save_mean, float* save_rstd, float* y32, void* ws,
+                       size_t ws_bytes, int device, void* stream) {
+  DevGuard guard(device);
+  if (guard.rc) return guard.rc;
+  cudaGetLastError();
+  using namespace sig;
+  if (!feat || !bn_weight || !bn_bias || !cls_weight || !bn_out || !logits || !save_mean || !save_rstd || !y32 || !ws) return SIG_ERR_NULL;
+  if (!training && (!running_mean || !running_var)) return SIG_ERR_NULL;
+  if (B < 1 || D < 1 || C < 1 || ld < D || ldo < D || ldl < C) return SIG_ERR_SHAPE;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  if (ws_bytes < sig_bnneck_ws_bytes(B, D, C)) return SIG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SIG_BF16)
+    return bnneck_fwd<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(feat), ld, B, D, C, bn_weight, bn_bias, running_mean, running_var, momentum,
+                                     eps, training, cls_weight, static_cast<__nv_bfloat16*>(bn_out), ldo, static_cast<__nv_bfloat16*>(logits), ldl,
+                                     save_mean, save_rstd, y32, static_cast<float*>(ws), s);
+  return bnneck_fwd<float>(static_cast<const float*>(feat), ld, B, D, C, bn_weight, bn_bias, running_mean, running_var, momentum, eps, training,
+                           cls_weight, static_cast<float*>(bn_out), ldo, static_cast<float*>(logits), ldl, save_mean, save_rstd, y32,
+                           static_cast<float*>(ws), s);
+}
+
+int sig_bnneck_cls_bwd(const void* feat, int dtype, int64_t ld, int B, int D, int C, const float* bn_weight, const float* cls_weight,
+                       const float* save_mean, const float* save_rstd, int training, const float* y32, const void* dlogits, int64_t ldl,
+                       const void* d_bn_out, int64_t lddo, void* dfeat, int64_t ldx, float* d_bn_weight, float* d_bn_bias,
+                       float* d_cls_weight, void* ws, size_t ws_bytes, int device, void* stream) {
+  DevGuard guard(device);
+  if (guard.rc) return guard.rc;
+  cudaGetLastError();
+  using namespace sig;
+  if (!feat || !bn_weight || !cls_weight || !save_mean || !save_rstd || !y32 || !dfeat || !d_bn_weight || !d_bn_bias || !d_cls_weight || !ws)
+    return SIG_ERR_NULL;
+  if (B < 1 || D < 1 || C < 1 || ld < D || ldx < D || (dlogits && ldl < C) || (d_bn_out && lddo < D)) return SIG_ERR_SHAPE;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  if (ws_bytes < sig_bnneck_ws_bytes(B, D, C)) return SIG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SIG_BF16)
+    return bnneck_bwd<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(feat), ld, B, D, C, bn_weight, cls_weight, save_mean, save_rstd, training,
+                                     y32, static_cast<const __nv_bfloat16*>(dlogits), ldl, static_cast<const __nv_bfloat16*>(d_bn_out), lddo,
+                                     static_cast<__nv_bfloat16*>(dfeat), ldx, d_bn_weight, d_bn_bias, d_cls_weight, static_cast<float*>(ws), s);
+  return bnneck_bwd<float>(static_cast<const float*>(feat), ld, B, D, C, bn_weight, cls_weight, save_mean, save_rstd, training, y32,
+                           static_cast<const float*>(dlogits), ldl, static_cast<const float*>(d_bn_out), lddo, static_cast<float*>(dfeat), ldx,
+                           d_bn_weight, d_bn_bias, d_cls_weight, static_cast<float*>(ws), s);
 }
 
 }  // extern "C"

@@ -73,7 +73,7 @@ EXPORTS = [
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
     "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_profile_scope_begin", "sig_profile_scope_end", "sig_sim_dx_operands",
-    "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd",
+    "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd", "sig_bnneck_ws_bytes", "sig_bnneck_cls_fwd", "sig_bnneck_cls_bwd",
 ]
 
 
@@ -121,6 +121,10 @@ def load():
     lib.sig_xent_ls_bwd.argtypes = [vp, i, i64, vp, i, i, f, vp, vp, vp, i64, i, vp]
     lib.sig_triplet_fwd.argtypes = [vp, i, i64, vp, i, i, f, i, f, vp, vp, vp, vp, vp, vp, sz, i, vp]
     lib.sig_triplet_bwd.argtypes = [vp, i, i64, i, i, f, i, f, vp, vp, vp, vp, vp, vp, vp, vp, i64, i, vp]
+    lib.sig_bnneck_ws_bytes.restype = sz
+    lib.sig_bnneck_ws_bytes.argtypes = [i, i, i]
+    lib.sig_bnneck_cls_fwd.argtypes = [vp, i, i64, i, i, i, vp, vp, vp, vp, f, f, i, vp, vp, i64, vp, i64, vp, vp, vp, vp, sz, i, vp]
+    lib.sig_bnneck_cls_bwd.argtypes = [vp, i, i64, i, i, i, vp, vp, vp, vp, i, vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, sz, i, vp]
     lib.sig_profile_scope_begin.restype = vp
     lib.sig_profile_scope_begin.argtypes = [C.c_char_p, vp]
     lib.sig_profile_scope_end.restype = None

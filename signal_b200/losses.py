@@ -154,3 +154,78 @@ class TripletLoss(object):
         loss, ap, an, idx = _Triplet.apply(global_feat, labels, self.margin, self.hard_factor)
         self.last_indices = idx
         return loss, ap, an
+
+
+class _BNNeckCls(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, bn_w, bn_b, cls_w, run_mean, run_var, momentum, eps, training):
+        lib = L_.load()
+        x = _rows(feat, "feat")
+        B, D = x.shape
+        C_ = cls_w.shape[0]
+        dev = x.device
+        for t in (bn_w, bn_b, cls_w):
+            L_._f32c(t)
+        out = torch.empty(B, D, dtype=x.dtype, device=dev)
+        logits = torch.empty(B, C_, dtype=x.dtype, device=dev)
+        stats = torch.empty(2, D, dtype=torch.float32, device=dev)
+        y32 = torch.empty(B, D, dtype=torch.float32, device=dev)
+        nws = lib.sig_bnneck_ws_bytes(B, D, C_)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_bnneck_cls_fwd(x.data_ptr(), L_.dtype_enum(x), x.stride(0), B, D, C_, bn_w.data_ptr(), bn_b.data_ptr(),
+                                            ptr(run_mean), ptr(run_var), float(momentum), float(eps), int(training), cls_w.data_ptr(),
+                                            out.data_ptr(), D, logits.data_ptr(), C_, stats[0].data_ptr(), stats[1].data_ptr(),
+                                            y32.data_ptr(), ws.data_ptr(), nws, dev.index, L_.stream_ptr(dev)), "sig_bnneck_cls_fwd")
+        ctx.save_for_backward(x, bn_w, cls_w, stats, y32)
+        ctx.cfg = (int(training), feat.dtype)
+        return out, logits
+
+    @staticmethod
+    def backward(ctx, dout, dlogits):
+        lib = L_.load()
+        x, bn_w, cls_w, stats, y32 = ctx.saved_tensors
+        training, in_dtype = ctx.cfg
+        B, D = x.shape
+        C_ = cls_w.shape[0]
+        dev = x.device
+        cast = lambda t: None if t is None else t.to(x.dtype).contiguous()
+        dout, dlogits = cast(dout), cast(dlogits)
+        dx = torch.empty(B, D, dtype=x.dtype, device=dev)
+        dg = torch.empty(D, dtype=torch.float32, device=dev)
+        db = torch.empty(D, dtype=torch.float32, device=dev)
+        dW = torch.empty(C_, D, dtype=torch.float32, device=dev)
+        nws = lib.sig_bnneck_ws_bytes(B, D, C_)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_bnneck_cls_bwd(x.data_ptr(), L_.dtype_enum(x), x.stride(0), B, D, C_, bn_w.data_ptr(), cls_w.data_ptr(),
+                                            stats[0].data_ptr(), stats[1].data_ptr(), training, y32.data_ptr(), ptr(dlogits), C_,
+                                            ptr(dout), D, dx.data_ptr(), D, dg.data_ptr(), db.data_ptr(), dW.data_ptr(), ws.data_ptr(),
+                                            nws, dev.index, L_.stream_ptr(dev)), "sig_bnneck_cls_bwd")
+        return dx.to(in_dtype), dg, db, dW, None, None, None, None, None
+
+
+class BNNeckClassifier:
+    """The BNNeck of the reference as ONE call (modeling/make_model.py:128-131, 194-195, 212-214):
+
+        feat_bn = self.bottleneck(feat); score = self.classifier(feat_bn)      # nn.BatchNorm1d, nn.Linear(bias=False)
+
+    becomes ``feat_bn, score = BNNeckClassifier(model.bottleneck, model.classifier)(feat)``.  Owns no parameters
+    (checkpoints unchanged); honours ``bottleneck.training`` (batch statistics + in-place running-statistics update
+    vs running statistics), ``momentum``, ``eps`` and a frozen ``bias`` (``requires_grad_(False)``)."""
+
+    def __init__(self, bottleneck: nn.BatchNorm1d, classifier: nn.Linear):
+        if classifier.bias is not None:
+            raise RuntimeError("signal_b200: the reference's classifier has no bias (make_model.py:130)")
+        self.bottleneck, self.classifier = bottleneck, classifier
+
+    def __call__(self, feat):
+        bn = self.bottleneck
+        training = bn.training or bn.running_mean is None
+        if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        return _BNNeckCls.apply(feat, bn.weight, bn.bias, self.classifier.weight, bn.running_mean, bn.running_var,
+                                momentum, bn.eps, training)

@@ -93,3 +93,35 @@ def test_losses_no_cpu_path_and_strided_rows():
     c = losses.LabelSmoothingCrossEntropy(0.1)(z, y)
     ref = torch.nn.functional.cross_entropy(z.detach(), y, label_smoothing=0.1)
     assert float((c.detach() - ref).abs()) < 1e-5 * float(ref.abs()) and torch.equal(a, c)
+
+
+@pytest.mark.parametrize("name", ["rgbnt201", "hardfactor"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_bnneck_classifier_matches_torch_modules(name, mode, dtype, tol):
+    """BNNeckClassifier(bottleneck, classifier) vs the fp64 golden run of nn.BatchNorm1d -> nn.Linear(bias=False):
+    both outputs, every gradient, and the in-place running-statistics update."""
+    losses = _mods()
+    from make_loss_golden import CASES
+    c = CASES[name]
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"losses_{name}.npz"))
+    t = lambda k: torch.from_numpy(g[k]).float().cuda()
+    bn = torch.nn.BatchNorm1d(c["D"]).cuda()
+    cls = torch.nn.Linear(c["D"], c["C"], bias=False).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(t("bn_w")); bn.bias.copy_(t("bn_b")); cls.weight.copy_(t("cls_w"))
+        bn.running_mean.copy_(t("bn_rm0")); bn.running_var.copy_(t("bn_rv0"))
+    bn.bias.requires_grad_(False)                       # make_model.py:129
+    bn.train(mode == "train")
+    x = t("feat").to(dtype).requires_grad_(True)
+    if dtype == torch.bfloat16:                         # compare against the golden run only where rounding of x is negligible
+        tol = 3e-2
+    fb, sc = losses.BNNeckClassifier(bn, cls)(x)
+    assert fb.dtype == dtype and sc.dtype == dtype
+    ((sc.float() * t("cot_s")).sum() + (fb.float() * t("cot_f")).sum()).backward()
+    assert rel(fb, g[f"nk_{mode}_feat"]) < tol and rel(sc, g[f"nk_{mode}_score"]) < tol
+    assert rel(x.grad, g[f"nk_{mode}_dx"]) < tol
+    assert rel(bn.weight.grad, g[f"nk_{mode}_dbn_w"]) < tol and rel(cls.weight.grad, g[f"nk_{mode}_dcls_w"]) < tol
+    assert bn.bias.grad is None
+    assert rel(bn.running_mean, g[f"nk_{mode}_rm"]) < tol and rel(bn.running_var, g[f"nk_{mode}_rv"]) < tol
+    assert int(bn.num_batches_tracked) == (1 if mode == "train" else 0)

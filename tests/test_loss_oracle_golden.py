@@ -59,3 +59,18 @@ def test_hard_mining_ties_and_self_positive():
     assert pi.tolist()[0] == 1 and ni.tolist()[0] == 3
     assert abs(float(d[0, 0]) - 1e-6) < 1e-12
     assert pi.tolist()[1] == 0 and pi.tolist()[3] == 4
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_bnneck_oracle_matches_torch_modules(name, mode):
+    """BNNeck + classifier restatement vs nn.BatchNorm1d -> nn.Linear(bias=False) (what make_model.py:128-131 builds)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"losses_{name}.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    x = t("feat").clone().requires_grad_(True)
+    gamma, beta, W = (t(k).clone().requires_grad_(True) for k in ("bn_w", "bn_b", "cls_w"))
+    fb, sc, rm, rv = lo.bnneck_classifier(x, gamma, beta, W, 1e-5, (t("bn_rm0"), t("bn_rv0")), 0.1, mode == "train")
+    ((sc * t("cot_s")).sum() + (fb * t("cot_f")).sum()).backward()
+    for got, key in ((fb, "feat"), (sc, "score"), (x.grad, "dx"), (gamma.grad, "dbn_w"), (beta.grad, "dbn_b"), (W.grad, "dcls_w"),
+                     (rm, "rm"), (rv, "rv")):
+        assert rel(got.detach().numpy(), g[f"nk_{mode}_{key}"]) < 1e-9, key
