@@ -56,7 +56,7 @@ lam_dw_fwd_ring_kernel(const __nv_bfloat16* __restrict__ H, sig_align_params prm
     if ((int)threadIdx.x == R::kConsumers) {
       pdl_wait();   // H is the output of the GEMM launched just before
       for (int it = i0, k = 0; it < i1; ++it, ++k)
-        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, Hm + (int64_t)it * R::kTok * D, R::kStageBytes);
+        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, Hm + (int64_t)it * R::kTok * D, R::kStageBytes, ptx::kPolStream);
     }
     return;
   }
@@ -132,7 +132,7 @@ lam_dw_bwd_ring_kernel(const __nv_bfloat16* __restrict__ H, const float* __restr
     if ((int)threadIdx.x == R::kConsumers) {
       // (H was written by the forward call: the ring starts filling under the previous kernel's tail)
       for (int it = i0, k = 0; it < i1; ++it, ++k)
-        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, Hm + (int64_t)it * R::kTok * D, R::kStageBytes);
+        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, Hm + (int64_t)it * R::kTok * D, R::kStageBytes, ptx::kPolStream);
     }
     return;
   }

@@ -11,9 +11,9 @@ namespace sig {
 namespace ring {
 
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar` (complete_tx)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(bytes), "r"(ptx::smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol = ptx::kPolNormal) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(bytes), "r"(ptx::smem_u32(bar)), "l"(pol)
                : "memory");
 }
 
@@ -42,11 +42,12 @@ __device__ __forceinline__ void init(Bars<STAGES>* b, int consumer_warps) {
 // producer side of item number k (0-based count of this CTA's items): waits until stage k % STAGES is free,
 // then starts the copy
 template <int STAGES>
-__device__ __forceinline__ void produce(Bars<STAGES>* b, int k, void* stage, const void* src, uint32_t bytes) {
+__device__ __forceinline__ void produce(Bars<STAGES>* b, int k, void* stage, const void* src, uint32_t bytes,
+                                        uint64_t pol = ptx::kPolNormal) {
   const int s = k % STAGES;
   if (k >= STAGES) ptx::mbar_wait(&b->empty[s], (uint32_t)((k / STAGES) - 1) & 1u);
   ptx::mbar_expect_tx(&b->full[s], bytes);
-  bulk_g2s(stage, src, bytes, &b->full[s]);
+  bulk_g2s(stage, src, bytes, &b->full[s], pol);
 }
 
 template <int STAGES>

@@ -460,14 +460,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) pair_gemm_kernel(const __grid
             for (int j = 0; j < kExtent / 64; ++j) ptx::tma_load_2d_2sm(dst + j * 64 * BK * 2, &p.tbx, lbar, n0 + 64 * j, b * 64);
           }
         } else
-        if (mode == TC_K2D) ptx::tma_load_2d_2sm(dst, tm, lbar, k0, mn0);
-        else if (mode == TC_KTOK) ptx::tma_load_3d_2sm(dst, tm, lbar, k0, 0, mn0 >> 7);
+        // (L2 hints: token operands are re-read by other kernels of the step -> evict_last; the A operand of the dX / dW'
+        //  GEMMs is dH, read once here and never again -> evict_first; weights: normal)
+        if (mode == TC_K2D) ptx::tma_load_2d_2sm(dst, tm, lbar, k0, mn0, is_a ? ptx::kPolStream : ptx::kPolNormal);
+        else if (mode == TC_KTOK) ptx::tma_load_3d_2sm(dst, tm, lbar, k0, 0, mn0 >> 7, ptx::kPolTokens);
         else if (mode == TC_MN2D) {
 #pragma unroll
-          for (int j = 0; j < kExtent / 64; ++j) ptx::tma_load_2d_2sm(dst + j * 64 * BK * 2, tm, lbar, mn0 + 64 * j, k0);
+          for (int j = 0; j < kExtent / 64; ++j)
+            ptx::tma_load_2d_2sm(dst + j * 64 * BK * 2, tm, lbar, mn0 + 64 * j, k0, is_a ? ptx::kPolStream : ptx::kPolNormal);
         } else {
 #pragma unroll
-          for (int j = 0; j < kExtent / 64; ++j) ptx::tma_load_3d_2sm(dst + j * 64 * BK * 2, tm, lbar, mn0 + 64 * j, k0 & 127, k0 >> 7);
+          for (int j = 0; j < kExtent / 64; ++j)
+            ptx::tma_load_3d_2sm(dst + j * 64 * BK * 2, tm, lbar, mn0 + 64 * j, k0 & 127, k0 >> 7, ptx::kPolTokens);
         }
         if (++stage == (uint32_t)nstages) { stage = 0; ph ^= 1; }
       }

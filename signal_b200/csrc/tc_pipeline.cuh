@@ -54,13 +54,13 @@ __device__ __forceinline__ void load_kmajor_2d(const CUtensorMap* tm, uint8_t* d
   ptx::tma_load_2d(dst, tm, bar, k0, row0);
 }
 __device__ __forceinline__ void load_kmajor_tok(const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int k0, int sample, int nsamples) {
-  for (int j = 0; j < nsamples; ++j) ptx::tma_load_3d(dst + j * 128 * BK * 2, tm, bar, k0, 0, sample + j);
+  for (int j = 0; j < nsamples; ++j) ptx::tma_load_3d(dst + j * 128 * BK * 2, tm, bar, k0, 0, sample + j, ptx::kPolTokens);
 }
 __device__ __forceinline__ void load_mnmajor_2d(const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int mn0, int krow0, int extent) {
   for (int j = 0; j < extent / 64; ++j) ptx::tma_load_2d(dst + j * 64 * BK * 2, tm, bar, mn0 + 64 * j, krow0);
 }
 __device__ __forceinline__ void load_mnmajor_tok(const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int mn0, int l0, int sample, int extent) {
-  for (int j = 0; j < extent / 64; ++j) ptx::tma_load_3d(dst + j * 64 * BK * 2, tm, bar, mn0 + 64 * j, l0, sample);
+  for (int j = 0; j < extent / 64; ++j) ptx::tma_load_3d(dst + j * 64 * BK * 2, tm, bar, mn0 + 64 * j, l0, sample, ptx::kPolTokens);
 }
 
 // Row layout -> tile: lane (= accumulator row) writes its 32 fp32 values.  Call epi_sync() before reading.

@@ -81,7 +81,7 @@ sim_scores_ring_kernel(TokSrc3 src, const float* __restrict__ clsf, const float*
           ++gcount;
         }
         const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(src.patch[m]) + b * src.psb[m] + (int64_t)chunk * R::kRows * D;
-        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, x, R::kStageBytes);
+        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, x, R::kStageBytes, ptx::kPolTokens);
       }
     }
     return;
@@ -183,7 +183,7 @@ pool_ring_kernel(TokSrc3 src, int B, int n_items, float* __restrict__ mean) {
         const int g = it / R::kItemsPerGroup, chunk = it % R::kItemsPerGroup;
         const int m = g / B, b = g % B;
         const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(src.patch[m]) + b * src.psb[m] + (int64_t)chunk * R::kRows * D;
-        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, x, R::kStageBytes);
+        ring::produce(bars, k, stages + (size_t)(k % R::kStages) * R::kStageBytes, x, R::kStageBytes, ptx::kPolTokens);
       }
     }
     return;

@@ -38,19 +38,19 @@ def _arena(shapes, device) -> Tuple[torch.Tensor, List[torch.Tensor]]:
 
 
 def _head_arena(d: int, device):
-    """ONE flat arena for the gradients of both modules, ``[AlignM | SIM late part | SIM early part]``, so that a
-    data-parallel exchange needs two collectives: ``flat[cut:]`` as soon as SIM's early gradients are final and
-    ``flat[:cut]`` (AlignM's arena + W_q/W_k/in_proj_bias) once the token-side backward is through.
-    Returns (flat, SIM grads, AlignM grads, cut)."""
+    """ONE flat arena for the gradients of both modules, ``[SIM late part | SIM early part | AlignM]``, so that a
+    data-parallel exchange needs two collectives: ``flat[cut:]`` (28.5 MB at d = 768) once SIM's early gradients and
+    AlignM's gradients are final -- both happen in the first third of the backward when AlignM's weight-independent
+    chain already ran in the forward call (SIG_FLAG_EAGER_BWD) -- and ``flat[:cut]`` (W_q/W_k/in_proj_bias, 4.7 MB)
+    when SIM's token-side backward is through.  Returns (flat, SIM grads, AlignM grads, cut)."""
     sshapes, ashapes = _SIM_GRAD_SHAPES(d), _align_grad_shapes(d)
     order = [1, 0] + list(range(2, len(sshapes)))
-    flat, views = _arena(ashapes + [sshapes[i] for i in order], device)
-    pg_a, sv = views[:len(ashapes)], views[len(ashapes):]
+    flat, views = _arena([sshapes[i] for i in order] + ashapes, device)
+    sv, pg_a = views[:len(sshapes)], views[len(sshapes):]
     pg_s = [None] * len(sshapes)
     for i, v in zip(order, sv):
         pg_s[i] = v
-    n_a = sum(((int(torch.Size(x).numel()) + 3) // 4 * 4) for x in ashapes)
-    cut = n_a + (3 * d + 3) // 4 * 4 + 2 * d * d
+    cut = (3 * d + 3) // 4 * 4 + 2 * d * d
     return flat, pg_s, pg_a, cut
 
 
@@ -461,7 +461,11 @@ class HeadFunction(torch.autograd.Function):
         # SIG_FLAG_EAGER_BWD) -- on the side stream, under SIM's forward chain of small kernels, where the GPU is
         # otherwise mostly idle; the backward call then starts at the weight-gradient GEMM.
         flags_a = flags
-        if do_lam and any(ctx.needs_input_grad[9:]) and os.environ.get("SIG_EAGER_BWD", "1") != "0":
+        # (single-GPU steps only by default: next to the in-backward gradient exchange it measured 2.5 % slower at N = 2,
+        #  0.7088 vs 0.6908 ms -- the shortened AlignM backward leaves less compute for the collectives to hide under)
+        eager_env = os.environ.get("SIG_EAGER_BWD", "auto")
+        eager_ok = eager_env == "1" or (eager_env == "auto" and (len(event) < 2 or event[1] is None))
+        if do_lam and any(ctx.needs_input_grad[9:]) and eager_ok:
             flags_a = flags | L_.SIG_FLAG_EAGER_BWD
         with torch.cuda.device(dev):
             side.wait_stream(main)
@@ -500,7 +504,7 @@ class HeadFunction(torch.autograd.Function):
         if sync is not None and sync[3] == 2:
             flat_h, pg_s, pg_a, cut_h = _head_arena(d, dev)
             if not do_lam:
-                flat_h[:cut_h].zero_()
+                flat_h[cut_h:].zero_()
         else:
             flat_s, pg_s, split_s = _sim_arena(d, dev)
             flat_a, pg_a = _arena(_align_grad_shapes(d), dev)
@@ -542,15 +546,17 @@ class HeadFunction(torch.autograd.Function):
             # (SIM first: its call records the event AlignM's call waits on)
             L_.check(lib.sig_sim_bwd(C.byref(tok), C.byref(sprm), dout.data_ptr(), C.byref(tg_s), C.byref(gs_s), buf_s.data_ptr(),
                                      buf_s.numel(), flags, dev.index, hi.cuda_stream), "sig_sim_bwd")
-            # Data parallel: the exchange runs on a communication stream in pieces, each started by the event the
+            # Data parallel: the exchange runs on a communication stream in pieces, each started by the event(s) the
             # library records when that piece is final -- SIM's early part (FFN, out_proj, norms, W_v: ready before
-            # the token-side backward), then AlignM's arena (ready before its dX GEMM) and SIM's W_q/W_k part, as one
-            # collective (default: a collective costs ~25 us + 2.2 us/MB at N = 2) or as two (SIG_SYNC_CHUNKS=3)
+            # the token-side backward) together with AlignM's arena (ready before its dX GEMM; in the first third of
+            # the backward with the eager chain) as ONE collective, then SIM's W_q/W_k part (a collective costs
+            # ~25 us + 2.2 us/MB at N = 2); SIG_SYNC_CHUNKS=3: three collectives
             if sync is not None:
                 comm = sync[0]
-                with torch.cuda.stream(comm):
-                    comm.wait_event(sync[1])
-                    grad_sync(flat_h[cut_h:] if sync[3] == 2 else flat_s[split_s:])
+                if sync[3] != 2:
+                    with torch.cuda.stream(comm):
+                        comm.wait_event(sync[1])
+                        grad_sync(flat_s[split_s:])
             elif grad_sync is not None:
                 with torch.cuda.stream(hi):
                     grad_sync(flat_s)
@@ -559,7 +565,9 @@ class HeadFunction(torch.autograd.Function):
             if sync is not None:
                 with torch.cuda.stream(comm):
                     comm.wait_event(sync[2])
-                    if sync[3] == 2:      # AlignM's arena and SIM's late part are adjacent: one collective
+                    if sync[3] == 2:      # SIM's early part and AlignM's arena are adjacent: one collective, then the late part
+                        comm.wait_event(sync[1])
+                        grad_sync(flat_h[cut_h:])
                         comm.wait_stream(hi)
                         grad_sync(flat_h[:cut_h])
                     else:
