@@ -74,3 +74,64 @@ def test_shard_batch_rejects_ragged():
     import pytest
     with pytest.raises(ValueError):
         parallel.shard_batch(130, 0, 4)
+
+
+def test_head_arena_layout():
+    """One arena for both modules, [SIM late | SIM early | AlignM]: the two exchange pieces tile it once, the late piece
+    is exactly in_proj_bias + in_proj_weight rows [0, 2d) (W_q, W_k), every view is 16-byte aligned and the views come
+    back in the C structs' field order."""
+    from signal_b200 import functional as F_
+    d = 64
+    flat, pg_s, pg_a, cut = F_._head_arena(d, "cpu")
+    sshapes, ashapes = F_._SIM_GRAD_SHAPES(d), F_._align_grad_shapes(d)
+    assert [tuple(g.shape) for g in pg_s] == [tuple(s) for s in sshapes]
+    assert [tuple(g.shape) for g in pg_a] == [tuple(s) for s in ashapes]
+    base = flat.data_ptr()
+    off = lambda t: (t.data_ptr() - base) // 4
+    assert all(off(g) % 4 == 0 for g in pg_s + pg_a)
+    in_w, in_b = pg_s[0], pg_s[1]
+    assert off(in_b) == 0 and off(in_w) == (3 * d + 3) // 4 * 4
+    assert cut == off(in_w) + 2 * d * d                       # W_v rows are the first thing of the early piece
+    assert all(off(g) >= cut for g in pg_s[2:]) and all(off(g) >= cut for g in pg_a)
+    assert min(off(g) for g in pg_a) > max(off(g) for g in pg_s)          # AlignM behind SIM
+    used = sum(((g.numel() + 3) // 4 * 4) for g in pg_s + pg_a)
+    assert used == flat.numel()
+    # writes through the views land in the right piece
+    flat.zero_()
+    in_w[: 2 * d].fill_(1.0); in_b.fill_(1.0)
+    assert float(flat[:cut].sum()) == 2 * d * d + 3 * d and float(flat[cut:].sum()) == 0.0
+
+
+def _worker_pieces(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from signal_b200 import functional as F_
+    d = 64
+    flat, pg_s, pg_a, cut = F_._head_arena(d, "cpu")
+    g = torch.Generator().manual_seed(100 + rank)
+    flat.copy_(torch.randn(flat.numel(), generator=g))
+    mine = flat.clone()
+    # the order FusionHead.grad_sync is called in (functional.HeadFunction.backward): early + AlignM piece, then the late piece
+    for piece in (flat[cut:], flat[:cut]):
+        dist.all_reduce(piece)
+        piece.div_(world)
+    other = torch.randn(flat.numel(), generator=torch.Generator().manual_seed(100 + (1 - rank)))
+    ok = torch.allclose(flat, 0.5 * (mine + other), atol=1e-6)
+    ok = ok and torch.allclose(pg_a[1], 0.5 * (mine + other)[(pg_a[1].data_ptr() - flat.data_ptr()) // 4:][: pg_a[1].numel()].view_as(pg_a[1]))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_piece_exchange_world2():
+    """The two-piece in-backward exchange order on the combined arena averages every gradient exactly once."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pieces, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}
