@@ -843,7 +843,19 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
     for (int m = 0; m < 3; ++m) { src.patch[m] = tok->patch[m]; src.psb[m] = tok->patch_stride_b[m]; }
     const int n_items = 3 * B * (kMaxL / 32);
     const int ctas = n_items < tc_num_sms() ? n_items : tc_num_sms();
-    if (d == 768) {
+    if (scores_split_enabled()) {
+      if (d == 768) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(sim_scores_split_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSplit<768>::kSmemBytes); attr = true; }
+        SIG_LAUNCH((sim_scores_split_kernel<768>), ctas, ScoreSplit<768>::kThreads, ScoreSplit<768>::kSmemBytes, s, src, c.clsf, c.qtsel, c.csel, B,
+                   n_items, c.sel_logits, c.intra_raw);
+      } else {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(sim_scores_split_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSplit<512>::kSmemBytes); attr = true; }
+        SIG_LAUNCH((sim_scores_split_kernel<512>), ctas, ScoreSplit<512>::kThreads, ScoreSplit<512>::kSmemBytes, s, src, c.clsf, c.qtsel, c.csel, B,
+                   n_items, c.sel_logits, c.intra_raw);
+      }
+    } else if (d == 768) {
       static bool attr = false;
       if (!attr) { cudaFuncSetAttribute(sim_scores_ring_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_scores_ring_smem<768>()); attr = true; }
       SIG_LAUNCH((sim_scores_ring_kernel<768>), ctas, TokRing<768>::kThreads, sim_scores_ring_smem<768>(), s, src, c.clsf, c.qtsel, c.csel, B, n_items,
