@@ -226,8 +226,8 @@ def run_gpu(args):
     al.load_state_dict(syn.make_params(syn.align_param_shapes(d), 1235))
     sim, al = sim.to(dev), al.to(dev)
     params = [p for p in list(sim.parameters()) + list(al.parameters())]
-    # each backward returns its parameter gradients as views of ONE flat fp32 arena (one for SIM, one
-    # for AlignM); autograd adopts those views as .grad, so data parallel needs two all-reduces per step
+    # each backward returns its parameter gradients as views of a flat fp32 arena (FusionHead: one arena for both
+    # modules, exchanged in two pieces inside the backward; separate module calls: one arena per module)
 
     from signal_b200 import parallel
     ncoll = [0]     # collectives issued by the last step

@@ -4,7 +4,9 @@ The head shards by batch only: SIM and LAM are per-sample, the 
 computed on the local shard exactly like the reference under DDP (useB.py:76-126 has no all-gather).
 The only exchange step is the gradient all-reduce.  Each backward of signal_b200.functional returns
 its parameter gradients as views of ONE flat fp32 arena, which autograd adopts as ``.grad``; so the
-exchange is one all-reduce per arena (two per step: SIM and AlignM) instead of one per parameter.
+exchange is one all-reduce per arena (SIM and AlignM called separately: two per step) instead of one per
+parameter.  ``FusionHead`` goes further: one arena for both modules, exchanged INSIDE the backward in two
+pieces as soon as each is final (``FusionHead.grad_sync``, functional.HeadFunction.backward).
 """
 from __future__ import annotations
 
