@@ -34,7 +34,9 @@ extern "C" {
 
 #define SIG_ABI_VERSION 1
 
-enum sig_dtype { SIG_F32 = 0, SIG_BF16 = 1 };
+/* SIG_F16 is accepted by sig_convert_half only: fp16 callers (the reference's amp.autocast, engine/processor.py:165) are
+ * bridged to the bf16 kernels by one conversion pass per token map at the module boundary. */
+enum sig_dtype { SIG_F32 = 0, SIG_BF16 = 1, SIG_F16 = 2 };
 
 enum sig_error {
   SIG_OK = 0,
@@ -244,6 +246,35 @@ int sig_volume3_fwd(const float* l, const float* v, const float* a, int B1, int 
 int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int B2, int d,
                     const float* dvol, float* dl, float* dv, float* da,
                     void* ws, size_t ws_bytes, int device, void* stream);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory ------------------------------
+ * Replaces the DDP all-reduce of the head's gradients (engine/processor.py:100-105) by ONE kernel that needs no shared
+ * memory, so it runs next to the persistent compute kernels of the backward instead of waiting for their SMs.
+ * Every rank (one process per GPU, same node) owns a SYMMETRIC buffer: `buf[r]` / `flags[r]` are the addresses, mapped
+ * into THIS process, of rank r's gradient arena and of its flag region (sig_xchg_flag_bytes() bytes, zeroed once before
+ * the first call, never touched by the caller afterwards); `multicast` is the NVLS multicast address of the arena or
+ * NULL (plain peer loads/stores then).  The caller obtains them from its IPC mechanism of choice -- the Python side uses
+ * torch.distributed._symmetric_memory (signal_b200.parallel.GradExchange).
+ * sig_xchg_allreduce_f32: arena[off, off+count) <- scale * sum over ranks, in place on every rank; all ranks must
+ * issue the same sequence of calls with the same (off, count, ctas).  off, count: fp32 elements, multiples of 4.
+ * Stream-ordered, CUDA-graph capturable, no host synchronisation. */
+typedef struct sig_xchg_peers {
+  void* buf[8];
+  void* flags[8];
+  void* multicast;
+  int32_t rank, world;
+} sig_xchg_peers;
+size_t sig_xchg_flag_bytes(void);
+int sig_xchg_allreduce_f32(const sig_xchg_peers* peers, size_t off, size_t count, float scale, int ctas, int device, void* stream);
+
+/* ---- fp16 boundary ------------------------------------------------------------ */
+/* dst = convert(src) over a strided [nb, nl, d] map (element strides, unit channel stride, d % 8 == 0, 16-byte aligned
+ * rows): SIG_F16 -> SIG_BF16 (round to nearest even; every fp16 value is in bf16's range) or SIG_BF16 -> SIG_F16
+ * (round to nearest even, saturating at +-65504).  Used by the nn.Module shims for fp16 (autocast) token maps and for
+ * the token gradients on the way back. */
+int sig_convert_half(const void* src, int64_t src_stride_b, int64_t src_stride_l, int src_dtype,
+                     void* dst, int64_t dst_stride_b, int64_t dst_stride_l, int dst_dtype,
+                     int nb, int nl, int d, int device, void* stream);
 
 /* ---- measurement aids (no effect on results) ------------------------------ */
 /* number of kernel launches the library has enqueued since it was loaded */

@@ -223,16 +223,14 @@ def sim_forward(params: Params, patches, cls, k: int, keep_ratio=None):
 # --------------------------------------------------------------------------
 # GAM -- Gram volume + contrastive CE (utils/volume.py:14-62, useB.py:76-126)
 # --------------------------------------------------------------------------
-def volume3(language: Tensor, video: Tensor, audio: Tensor) -> Tensor:
-    """sqrt|det G| for G = Gram(l_i, v_j, a_j), closed form -- volume.py:35-60.
+def _volume3_f64(language: Tensor, video: Tensor, audio: Tensor) -> Tensor:
+    """sqrt|det G| evaluated in fp64 whatever the input precision (inputs are up-cast exactly).
 
-    det = ll(vv*aa - va^2) - lv(lv*aa - va*la) + la(lv*va - vv*la)
-    (cofactor expansion of the symmetric 3x3 the reference stacks at :47-52).
-    Output [B1, B2], fp32 like ``G.float()`` at :57.
-    """
-    l, v, a = language.float() if language.dtype != torch.float64 else language, \
-        video.float() if video.dtype != torch.float64 else video, \
-        audio.float() if audio.dtype != torch.float64 else audio
+    The checker deliberately does NOT reproduce the reference's fp32 determinant (``torch.det(G.float())``, volume.py:57):
+    the determinant cancels when the modalities align, and d(gam)/d(contra_temp) cancels to ~1e-3 of its terms, so an
+    fp32 evaluation carries ~3e-4 of rounding noise on that gradient -- more than the 1e-4 parity tolerance it is used
+    to check.  The algorithm is the reference's; only the arithmetic is wider."""
+    l, v, a = language.double(), video.double(), audio.double()
     ll = (l * l).sum(-1)[:, None]
     vv = (v * v).sum(-1)[None, :]
     aa = (a * a).sum(-1)[None, :]
@@ -241,6 +239,17 @@ def volume3(language: Tensor, video: Tensor, audio: Tensor) -> Tensor:
     la = l @ a.T
     det = ll * (vv * aa - va * va) - lv * (lv * aa - va * la) + la * (lv * va - vv * la)
     return torch.sqrt(torch.abs(det))
+
+
+def volume3(language: Tensor, video: Tensor, audio: Tensor) -> Tensor:
+    """sqrt|det G| for G = Gram(l_i, v_j, a_j), closed form -- volume.py:35-60.
+
+    det = ll(vv*aa - va^2) - lv(lv*aa - va*la) + la(lv*va - vv*la)
+    (cofactor expansion of the symmetric 3x3 the reference stacks at :47-52).
+    Output [B1, B2], fp32 like ``G.float()`` at :57 (fp64 for fp64 inputs); evaluated in fp64 (_volume3_f64).
+    """
+    V = _volume3_f64(language, video, audio)
+    return V if language.dtype == torch.float64 else V.float()
 
 
 def _ce_label_smoothing(logits: Tensor) -> Tensor:
@@ -258,9 +267,10 @@ def gam_loss(patches: Sequence[Tensor], contra_temp: Tensor) -> Tensor:
     for p in patches:
         m = p.mean(dim=1)                                              # :92-94
         feats.append(m / m.norm(dim=-1, keepdim=True).clamp_min(1e-12))  # :98-100
-    V = volume3(*feats)                                                # :106
-    vol = V / contra_temp                                              # :107
-    return 0.5 * (_ce_label_smoothing(-vol) + _ce_label_smoothing(-vol.T))  # :120-124
+    V = _volume3_f64(*feats)                                           # :106 (fp64 arithmetic, see _volume3_f64)
+    vol = V / contra_temp.double()                                     # :107
+    loss = 0.5 * (_ce_label_smoothing(-vol) + _ce_label_smoothing(-vol.T))  # :120-124
+    return loss.to(patches[0].dtype if patches[0].dtype == torch.float64 else torch.float32)
 
 
 # --------------------------------------------------------------------------

@@ -25,23 +25,48 @@ struct GradPtrs3 {
 // GAM
 // =============================================================================================
 // mean over the L tokens: grid (B, 3), thread per channel.  useB.py:92-94
-static __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ Xf, int B, int L, int d, float* __restrict__ mean) {
+static __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ Xf, int B, int L, int d, float* __restrict__ mean,
+                                                          double* __restrict__ meand) {
   pdl_enter();
   const int b = blockIdx.x, m = blockIdx.y;
   const float* x = Xf + ((int64_t)m * B + b) * L * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float a = 0.f;
-    for (int l = 0; l < L; ++l) a += x[(int64_t)l * d + c];
-    mean[((int64_t)m * B + b) * d + c] = a / L;
+    double a = 0.0;      // exact path: the sum of L fp32 values in fp64 is exact to the last bit of the result
+    for (int l = 0; l < L; ++l) a += (double)x[(int64_t)l * d + c];
+    const double mu = a / L;
+    mean[((int64_t)m * B + b) * d + c] = (float)mu;
+    if (meand) meand[((int64_t)m * B + b) * d + c] = mu;
   }
 }
 
 // F.normalize (useB.py:98-100) for the three modalities of sample b, then the per-sample
 // Gram entries ll, vv, aa, va (volume.py:35,42-44).  grid B.
+// block-wide sum in double (the exact path evaluates the Gram volume in fp64: the determinant cancels when the
+// modalities align and d(loss)/d(tau) = sum_ij dZ_ij V_ij / tau^2 cancels to ~1e-3 of its terms on iid tokens)
+__device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = lane < nw ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
 static __global__ void __launch_bounds__(256) gam_norm_kernel(const float* __restrict__ mean, int B, int d, float* __restrict__ f,
-                                                              float* __restrict__ nrm, float* __restrict__ self4) {
+                                                              float* __restrict__ nrm, float* __restrict__ self4,
+                                                              const double* __restrict__ meand, double* __restrict__ fd,
+                                                              double* __restrict__ self4d) {
   pdl_enter();
   __shared__ float scratch[33];
+  __shared__ double scratchd[33];
   const int b = blockIdx.x;
   float inv[3];
   for (int m = 0; m < 3; ++m) {
@@ -68,6 +93,53 @@ static __global__ void __launch_bounds__(256) gam_norm_kernel(const float* __res
   if (threadIdx.x == 0) {
     self4[0 * B + b] = ll; self4[1 * B + b] = vv; self4[2 * B + b] = aa; self4[3 * B + b] = va;
   }
+  if (self4d) {   // exact path: the normalised features and their Gram entries once more in fp64, from the fp64 means
+    double dinv[3];
+    for (int m = 0; m < 3; ++m) {
+      double sq = 0.0;
+      for (int c = threadIdx.x; c < d; c += blockDim.x) { const double x = meand[((int64_t)m * B + b) * d + c]; sq += x * x; }
+      dinv[m] = 1.0 / fmax(sqrt(block_sum_f64(sq, scratchd)), 1e-12);
+    }
+    double dll = 0.0, dvv = 0.0, daa = 0.0, dva = 0.0;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      const double r = meand[((int64_t)0 * B + b) * d + c] * dinv[0], n = meand[((int64_t)1 * B + b) * d + c] * dinv[1],
+                   t = meand[((int64_t)2 * B + b) * d + c] * dinv[2];
+      fd[((int64_t)0 * B + b) * d + c] = r; fd[((int64_t)1 * B + b) * d + c] = n; fd[((int64_t)2 * B + b) * d + c] = t;
+      dll += r * r; dvv += n * n; daa += t * t; dva += n * t;
+    }
+    dll = block_sum_f64(dll, scratchd); dvv = block_sum_f64(dvv, scratchd);
+    daa = block_sum_f64(daa, scratchd); dva = block_sum_f64(dva, scratchd);
+    if (threadIdx.x == 0) {
+      self4d[0 * B + b] = dll; self4d[1 * B + b] = dvv; self4d[2 * B + b] = daa; self4d[3 * B + b] = dva;
+    }
+  }
+}
+
+// lv[i,j] = f_r[i] . f_n[j], la[i,j] = f_r[i] . f_t[j] accumulated in fp64 (exact path).  grid (ceil(B/32), B), 1024 threads:
+// warp w of CTA (jb, i) owns the pair (i, 32 jb + w).
+static __global__ void __launch_bounds__(1024) gam_gram_f64_kernel(const double* __restrict__ f, int B, int d, double* __restrict__ lvd,
+                                                                   double* __restrict__ lad) {
+  pdl_enter();
+  const int i = blockIdx.y, j = blockIdx.x * 32 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= B) return;
+  const double* fr = f + (int64_t)i * d;
+  const double* fn = f + ((int64_t)B + j) * d;
+  const double* ft = f + ((int64_t)2 * B + j) * d;
+  double a = 0.0, b = 0.0;
+  for (int c = lane; c < d; c += 32) {
+    const double r = fr[c];
+    a += r * fn[c];
+    b += r * ft[c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    lvd[(int64_t)i * B + j] = a;
+    lad[(int64_t)i * B + j] = b;
+  }
 }
 
 __device__ __forceinline__ float gram_det(float ll, float vv, float aa, float va, float lv, float la) {
@@ -92,99 +164,119 @@ __device__ __forceinline__ float ddet_of(float dV, float det, float V) {
   return dV * (det > 0.f ? 0.5f : -0.5f) / V;
 }
 
+__device__ __forceinline__ double gram_det_f64(double ll, double vv, double aa, double va, double lv, double la) {
+  return ll * (vv * aa - va * va) - lv * (lv * aa - va * la) + la * (lv * va - vv * la);
+}
+
 // Single CTA (1024 threads): symmetric label-smoothed CE on Z = -V/tau (useB.py:107-124) and
 // d(loss)/d(everything the Gram entries depend on), for unit upstream gradient:
 //   Wlv[i,j] = ddet*c_lv, Wla[i,j] = ddet*c_la, rowA[i] = sum_j ddet*c_ll,
 //   colC[0..2][j] = sum_i ddet*{c_vv, c_va, c_aa},  dtau = sum_ij dZ_ij V_ij / tau^2.
-static __global__ void __launch_bounds__(1024) gam_loss_kernel(const float* __restrict__ self4, const float* __restrict__ lv,
-                                                               const float* __restrict__ la, const float* __restrict__ tau_p, int B,
-                                                               float* __restrict__ V, float* __restrict__ rowstat /*[2][B]*/,
-                                                               float* __restrict__ colstat /*[2][B]*/, float* __restrict__ Wlv,
-                                                               float* __restrict__ Wla, float* __restrict__ rowA,
-                                                               float* __restrict__ colC, float* __restrict__ loss_out,
-                                                               float* __restrict__ dtau_out) {
+// Exact path: the Gram entries arrive in fp64 (gam_norm_kernel, gam_gram_f64_kernel) and the determinant, the volume,
+// the softmax statistics and the sums are evaluated in fp64 (B x B = 16 K pairs: nothing); results are stored in fp32.
+static __global__ void __launch_bounds__(1024) gam_loss_kernel(const double* __restrict__ self4, const double* __restrict__ lv,
+                                                               const double* __restrict__ la, const float* __restrict__ tau_p, int B,
+                                                               double* __restrict__ V, double* __restrict__ rowstat /*[B]*/,
+                                                               double* __restrict__ colstat /*[B]*/, float* __restrict__ Vf,
+                                                               float* __restrict__ Wlv, float* __restrict__ Wla,
+                                                               float* __restrict__ rowA, float* __restrict__ colC,
+                                                               float* __restrict__ loss_out, float* __restrict__ dtau_out) {
   pdl_enter();
-  __shared__ float scratch[33];
-  const float* ll = self4;
-  const float* vv = self4 + B;
-  const float* aa = self4 + 2 * B;
-  const float* va = self4 + 3 * B;
-  const float tau = *tau_p, itau = 1.f / tau;
+  __shared__ double scratch[33];
+  const double* ll = self4;
+  const double* vv = self4 + B;
+  const double* aa = self4 + 2 * B;
+  const double* va = self4 + 3 * B;
+  const double tau = (double)*tau_p, itau = 1.0 / tau;
+  const double ls = (double)kLabelSmooth;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const int64_t n2 = (int64_t)B * B;
   for (int64_t idx = tid; idx < n2; idx += blockDim.x) {
     const int i = (int)(idx / B), j = (int)(idx % B);
-    V[idx] = sqrtf(fabsf(gram_det(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx])));
+    const double v = sqrt(fabs(gram_det_f64(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx])));
+    V[idx] = v;
+    if (Vf) Vf[idx] = (float)v;
   }
   __syncthreads();
+  auto wsum = [](double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  };
+  auto wmax = [](double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+  };
   // log-sum-exp and mean of Z along rows (d2a) and columns (a2d)
-  float lpart = 0.f;
+  double lpart = 0.0;
   for (int r = w; r < 2 * B; r += nw) {
     const bool is_row = r < B;
     const int i = is_row ? r : r - B;
-    float mx = -INFINITY;
-    for (int j = lane; j < B; j += 32) mx = fmaxf(mx, -(is_row ? V[(int64_t)i * B + j] : V[(int64_t)j * B + i]) * itau);
-    mx = warp_max(mx);
-    float se = 0.f, sz = 0.f;
+    double mx = -INFINITY;
+    for (int j = lane; j < B; j += 32) mx = fmax(mx, -(is_row ? V[(int64_t)i * B + j] : V[(int64_t)j * B + i]) * itau);
+    mx = wmax(mx);
+    double se = 0.0, sz = 0.0;
     for (int j = lane; j < B; j += 32) {
-      const float z = -(is_row ? V[(int64_t)i * B + j] : V[(int64_t)j * B + i]) * itau;
-      se += expf(z - mx);
+      const double z = -(is_row ? V[(int64_t)i * B + j] : V[(int64_t)j * B + i]) * itau;
+      se += exp(z - mx);
       sz += z;
     }
-    se = warp_sum(se);
-    sz = warp_sum(sz);
-    const float lse = mx + logf(se);
+    se = wsum(se);
+    sz = wsum(sz);
+    const double lse = mx + log(se);
     if (lane == 0) {
       (is_row ? rowstat : colstat)[i] = lse;
-      const float zii = -V[(int64_t)i * B + i] * itau;
-      lpart += (1.f - kLabelSmooth) * (lse - zii) + kLabelSmooth * (lse - sz / B);
+      const double zii = -V[(int64_t)i * B + i] * itau;
+      lpart += (1.0 - ls) * (lse - zii) + ls * (lse - sz / B);
     }
   }
-  const float loss = block_sum(lpart, scratch) * (0.5f / B);
-  if (tid == 0) *loss_out = loss;
+  const double loss = block_sum_f64(lpart, scratch) * (0.5 / B);
+  if (tid == 0) *loss_out = (float)loss;
   __syncthreads();
   // row sweep: Wlv, Wla, rowA, dtau
-  float tpart = 0.f;
-  const float tgt_off = kLabelSmooth / B, tgt_on = 1.f - kLabelSmooth + kLabelSmooth / B;
+  double tpart = 0.0;
+  const double tgt_off = ls / B, tgt_on = 1.0 - ls + ls / B;
+  auto ddet_of64 = [](double dV, double det, double v) { return v > 0.0 ? dV * (det > 0.0 ? 0.5 : -0.5) / v : 0.0; };
   for (int i = w; i < B; i += nw) {
-    float ra = 0.f;
+    double ra = 0.0;
     for (int j = lane; j < B; j += 32) {
       const int64_t idx = (int64_t)i * B + j;
-      const float v = V[idx], z = -v * itau;
-      const float tg = i == j ? tgt_on : tgt_off;
-      const float dZ = (0.5f / B) * ((expf(z - rowstat[i]) - tg) + (expf(z - colstat[j]) - tg));
-      // sum_j (P_row - T)_ij = 0 and sum_i (P_col - T)_ij = 0, so the diagonal volume can be
-      // subtracted without changing the sum; it removes most of the cancellation in fp32
-      tpart += (0.5f / B) * ((expf(z - rowstat[i]) - tg) * (v - V[(int64_t)i * B + i]) +
-                             (expf(z - colstat[j]) - tg) * (v - V[(int64_t)j * B + j])) * itau * itau;
-      const float det = gram_det(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]);
-      const float dd = ddet_of(-dZ * itau, det, v);
-      Wlv[idx] = dd * (-2.f * (lv[idx] * aa[j] - va[j] * la[idx]));
-      Wla[idx] = dd * (2.f * (lv[idx] * va[j] - vv[j] * la[idx]));
+      const double v = V[idx], z = -v * itau;
+      const double tg = i == j ? tgt_on : tgt_off;
+      const double pr = exp(z - rowstat[i]) - tg, pc = exp(z - colstat[j]) - tg;
+      const double dZ = (0.5 / B) * (pr + pc);
+      // sum_j (P_row - T)_ij = 0 and sum_i (P_col - T)_ij = 0: subtracting the diagonal volume changes nothing in
+      // exact arithmetic and removes most of the cancellation
+      tpart += (0.5 / B) * (pr * (v - V[(int64_t)i * B + i]) + pc * (v - V[(int64_t)j * B + j])) * itau * itau;
+      const double det = gram_det_f64(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]);
+      const double dd = ddet_of64(-dZ * itau, det, v);
+      Wlv[idx] = (float)(dd * (-2.0 * (lv[idx] * aa[j] - va[j] * la[idx])));
+      Wla[idx] = (float)(dd * (2.0 * (lv[idx] * va[j] - vv[j] * la[idx])));
       ra += dd * (vv[j] * aa[j] - va[j] * va[j]);
     }
-    ra = warp_sum(ra);
-    if (lane == 0) rowA[i] = ra;
+    ra = wsum(ra);
+    if (lane == 0) rowA[i] = (float)ra;
   }
-  const float dtau = block_sum(tpart, scratch);
-  if (tid == 0) *dtau_out = dtau;
+  const double dtau = block_sum_f64(tpart, scratch);
+  if (tid == 0) *dtau_out = (float)dtau;
   // column sweep: colC
   for (int j = w; j < B; j += nw) {
-    float cvv = 0.f, cva = 0.f, caa = 0.f;
+    double cvv = 0.0, cva = 0.0, caa = 0.0;
     for (int i = lane; i < B; i += 32) {
       const int64_t idx = (int64_t)i * B + j;
-      const float v = V[idx], z = -v * itau;
-      const float tg = i == j ? tgt_on : tgt_off;
-      const float dZ = (0.5f / B) * ((expf(z - rowstat[i]) - tg) + (expf(z - colstat[j]) - tg));
-      const float det = gram_det(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]);
-      const float dd = ddet_of(-dZ * itau, det, v);
+      const double v = V[idx], z = -v * itau;
+      const double tg = i == j ? tgt_on : tgt_off;
+      const double dZ = (0.5 / B) * ((exp(z - rowstat[i]) - tg) + (exp(z - colstat[j]) - tg));
+      const double det = gram_det_f64(ll[i], vv[j], aa[j], va[j], lv[idx], la[idx]);
+      const double dd = ddet_of64(-dZ * itau, det, v);
       cvv += dd * (ll[i] * aa[j] - la[idx] * la[idx]);
-      cva += dd * (-2.f * (ll[i] * va[j] - lv[idx] * la[idx]));
+      cva += dd * (-2.0 * (ll[i] * va[j] - lv[idx] * la[idx]));
       caa += dd * (ll[i] * vv[j] - lv[idx] * lv[idx]);
     }
-    cvv = warp_sum(cvv); cva = warp_sum(cva); caa = warp_sum(caa);
+    cvv = wsum(cvv); cva = wsum(cva); caa = wsum(caa);
     if (lane == 0) {
-      colC[0 * B + j] = cvv; colC[1 * B + j] = cva; colC[2 * B + j] = caa;
+      colC[0 * B + j] = (float)cvv; colC[1 * B + j] = (float)cva; colC[2 * B + j] = (float)caa;
     }
   }
 }
@@ -514,6 +606,7 @@ struct AlignCtx {
   float* Xf;
   // GAM
   float *mean, *f, *nrm, *self4, *lv, *la, *V, *rowstat, *colstat, *Wlv, *Wla, *rowA, *colC, *dtau, *df, *dmean;
+  double *self4d, *lvd, *lad, *Vd, *statd, *meand, *fd;   // fp64 evaluation of the Gram volume (exact path)
   // LAM
   LamMod mod[3];
   float *S, *dS, *part, *dH, *dQ, *dXf;
@@ -541,6 +634,13 @@ static AlignCtx align_ctx(void* base, int B, int L, int d, int nmod) {
   c.dtau = a.take<float>(4);
   c.df = a.take<float>((size_t)3 * B * d);
   c.dmean = a.take<float>((size_t)3 * B * d);
+  c.self4d = a.take<double>((size_t)4 * B);
+  c.lvd = a.take<double>((size_t)B * B);
+  c.lad = a.take<double>((size_t)B * B);
+  c.Vd = a.take<double>((size_t)B * B);
+  c.statd = a.take<double>((size_t)2 * B);
+  c.meand = a.take<double>((size_t)3 * B * d);
+  c.fd = a.take<double>((size_t)3 * B * d);
   for (int m = 0; m < nmod; ++m) {
     c.mod[m].Q = a.take<float>(BL * d);
     c.mod[m].H = a.take<float>(BL * d);
@@ -566,7 +666,7 @@ size_t das_ctx_bytes(int B, int L, int d) { return align_ctx(nullptr, B, L, d, 1
 #include "align_tc.inl"
 
 size_t align_ctx_bytes_for(int B, int L, int d, int dtype, unsigned flags) {
-  if (dtype == SIG_BF16 && L == 128 && !(flags & SIG_FLAG_FORCE_SIMT)) return align_tc_ctx(nullptr, B, L, d).bytes;
+  if (tc_shape_ok(dtype, L, d, flags)) return align_tc_ctx(nullptr, B, L, d).bytes;
   return align_ctx_bytes(B, L, d);
 }
 
@@ -647,6 +747,7 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   const int B = tok->B, L = tok->L, d = tok->d;
   if (do_lam) SIG_TRY(check_grid(h, w, L));
   if (tc_path_ok(tok, flags)) {
+    if (!tc_strides_ok(tok)) return SIG_ERR_SHAPE;
     if (ctx_bytes < align_tc_ctx(nullptr, B, L, d).bytes) return SIG_ERR_WORKSPACE;
     return align_forward_tc(tok, p, h, w, do_lam, losses, ctx, do_lam && (flags & SIG_FLAG_EAGER_BWD), s);
   }
@@ -658,17 +759,14 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   // ---- GAM
   {
   SIG_PHASE("gam_fwd");
-  SIG_LAUNCH((pool_kernel), dim3(B, 3), 256, 0, s, c.Xf, B, L, d, c.mean);
+  SIG_LAUNCH((pool_kernel), dim3(B, 3), 256, 0, s, c.Xf, B, L, d, c.mean, c.meand);
   SIG_CHECK_LAUNCH();
-  SIG_LAUNCH((gam_norm_kernel), B, 256, 0, s, c.mean, B, d, c.f, c.nrm, c.self4);
+  SIG_LAUNCH((gam_norm_kernel), B, 256, 0, s, c.mean, B, d, c.f, c.nrm, c.self4, c.meand, c.fd, c.self4d);
   SIG_CHECK_LAUNCH();
-  const float* fr = c.f;
-  const float* fn = c.f + (size_t)B * d;
-  const float* ft = c.f + (size_t)2 * B * d;
-  SIG_TRY(launch_gemm(gemm_nt(fr, d, fn, d, c.lv, B, nullptr, B, B, d), s));
-  SIG_TRY(launch_gemm(gemm_nt(fr, d, ft, d, c.la, B, nullptr, B, B, d), s));
-  SIG_LAUNCH((gam_loss_kernel), 1, 1024, 0, s, c.self4, c.lv, c.la, p->contra_temp, B, c.V, c.rowstat, c.colstat, c.Wlv, c.Wla, c.rowA,
-                                     c.colC, losses, c.dtau);
+  SIG_LAUNCH((gam_gram_f64_kernel), dim3((unsigned)ceil_div(B, 32), B), 1024, 0, s, c.fd, B, d, c.lvd, c.lad);
+  SIG_CHECK_LAUNCH();
+  SIG_LAUNCH((gam_loss_kernel), 1, 1024, 0, s, c.self4d, c.lvd, c.lad, p->contra_temp, B, c.Vd, c.statd, c.statd + B, (float*)nullptr,
+                                     c.Wlv, c.Wla, c.rowA, c.colC, losses, c.dtau);
   SIG_CHECK_LAUNCH();
   }
   // ---- LAM
@@ -702,6 +800,7 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
   const int B = tok->B, L = tok->L, d = tok->d;
   if (do_lam) SIG_TRY(check_grid(h, w, L));
   if (tc_path_ok(tok, flags)) {
+    if (!tc_strides_ok(tok)) return SIG_ERR_SHAPE;
     if (ctx_bytes < align_tc_ctx(nullptr, B, L, d).bytes) return SIG_ERR_WORKSPACE;
     for (int m = 1; m < 3; ++m)
       if (dtok->patch_stride_b[m] != dtok->patch_stride_b[0] || dtok->patch_stride_l[m] != dtok->patch_stride_l[0])

@@ -513,10 +513,16 @@ static TcOperand tok_operand(const sig_tokens* t, int mode) {
 }
 static TcOperand batched(TcOperand o, const void* base, size_t stride_elems) { return tc_batched(o, base, stride_elems, 3); }
 
-static bool tc_path_ok(const sig_tokens* t, unsigned flags) {
+// ONE predicate for sizing (sig_ctx_bytes knows dtype, L, d, flags -- not the strides) and for dispatch, so the ctx
+// buffer a caller sized always fits the path that runs.
+static bool tc_shape_ok(int dtype, int L, int d, unsigned flags) {
   if (flags & SIG_FLAG_FORCE_SIMT) return false;
-  if (t->dtype != SIG_BF16 || t->L != 128 || t->d > 768) return false;   // (the LAM depthwise kernels run d/2 <= 384 threads)
-  // one 3-D tensor-map geometry for the three modalities
+  return dtype == SIG_BF16 && L == 128 && d <= 768;   // (the LAM depthwise kernels run d/2 <= 384 threads)
+}
+static bool tc_path_ok(const sig_tokens* t, unsigned flags) { return tc_shape_ok(t->dtype, t->L, t->d, flags); }
+// The tensor-core path reads the three modalities through one 3-D tensor-map geometry: their patch strides must agree
+// (SIG_ERR_SHAPE otherwise -- the Python wrapper then hands over contiguous copies; never a silent change of path).
+static bool tc_strides_ok(const sig_tokens* t) {
   for (int m = 1; m < 3; ++m)
     if (t->patch_stride_b[m] != t->patch_stride_b[0] || t->patch_stride_l[m] != t->patch_stride_l[0]) return false;
   return true;
@@ -758,12 +764,10 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
       const int ctas = n_items < tc_num_sms() ? n_items : tc_num_sms();
       cudaMemsetAsync(c.mean, 0, (size_t)3 * B * d * sizeof(float), s);   // groups split between two CTAs are added atomically
       if (d == 768) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(pool_ring_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_ring_smem<768>()); attr = true; }
+        ensure_dyn_smem(pool_ring_kernel<768>, (int)pool_ring_smem<768>());
         SIG_LAUNCH((pool_ring_kernel<768>), ctas, TokRing<768>::kThreads, pool_ring_smem<768>(), s, src, B, n_items, c.mean);
       } else {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(pool_ring_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_ring_smem<512>()); attr = true; }
+        ensure_dyn_smem(pool_ring_kernel<512>, (int)pool_ring_smem<512>());
         SIG_LAUNCH((pool_ring_kernel<512>), ctas, TokRing<512>::kThreads, pool_ring_smem<512>(), s, src, B, n_items, c.mean);
       }
       SIG_CHECK_LAUNCH();

@@ -192,4 +192,22 @@ int sig_sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flag
 
 int sig_debug_tc_stamps(long long* out16) { return sig::tc_read_stamps(out16); }
 
+size_t sig_xchg_flag_bytes(void) { return sig::xchg_flag_bytes(); }
+
+int sig_xchg_allreduce_f32(const sig_xchg_peers* peers, size_t off, size_t count, float scale, int ctas, int device, void* stream) {
+  SIG_ENTER(device);
+  return sig::xchg_allreduce_f32(peers, off, count, scale, ctas, (cudaStream_t)stream);
+}
+
+int sig_convert_half(const void* src, int64_t src_stride_b, int64_t src_stride_l, int src_dtype, void* dst, int64_t dst_stride_b,
+                     int64_t dst_stride_l, int dst_dtype, int nb, int nl, int d, int device, void* stream) {
+  SIG_ENTER(device);
+  if (!src || !dst) return SIG_ERR_NULL;
+  if (!((src_dtype == SIG_F16 && dst_dtype == SIG_BF16) || (src_dtype == SIG_BF16 && dst_dtype == SIG_F16))) return SIG_ERR_DTYPE;
+  if (nb < 1 || nl < 1 || d < 8 || d % 8) return SIG_ERR_SHAPE;
+  if (((uintptr_t)src | (uintptr_t)dst) & 15 || (src_stride_b | src_stride_l | dst_stride_b | dst_stride_l) % 8) return SIG_ERR_ALIGN;
+  return sig::convert_half(src, src_stride_b, src_stride_l, dst_dtype == SIG_BF16, dst, dst_stride_b, dst_stride_l, nb, nl, d,
+                           (cudaStream_t)stream);
+}
+
 }  // extern "C"

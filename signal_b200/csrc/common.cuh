@@ -41,6 +41,23 @@ __device__ __forceinline__ void pdl_enter() {
 
 bool pdl_enabled();   // prof.cu: SIG_PDL=0 in the environment turns the launch attribute off
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) function attribute: it is set the first
+// time a kernel is launched on EACH device (prof.cu keeps a mutex-guarded set of (function, device) pairs), so a
+// process that touches several GPUs -- tests on cuda:1, multi-device threads -- gets it on every one of them.
+bool first_launch_on_device(const void* fn);
+template <class K>
+inline void ensure_dyn_smem(K kernel, int bytes) {
+  if (first_launch_on_device(reinterpret_cast<const void*>(kernel)))
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+int device_num_sms();   // multiprocessor count of the CURRENT device (cached per device)
+// xchg.cu: in-place all-reduce of a symmetric fp32 arena over NVLink peer memory / NVLS
+size_t xchg_flag_bytes();
+int xchg_allreduce_f32(const sig_xchg_peers* peers, size_t off, size_t count, float scale, int ctas, cudaStream_t s);
+// convert.cu: fp16 <-> bf16 over a strided [nb, nl, d] map (element strides, unit channel stride)
+int convert_half(const void* src, int64_t ssb, int64_t ssl, int to_bf16, void* dst, int64_t dsb, int64_t dsl, int nb, int nl, int d,
+                 cudaStream_t s);
+
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -257,11 +257,7 @@ static int dw_ring_ctas_per_mod(int B, int h) {
 template <int D, int W>
 static int launch_dw_fwd_ring(const __nv_bfloat16* H, const sig_align_params& p, int B, int h, float* U, float* o, cudaStream_t s) {
   using R = DwRing<D, W, 0, kDwFwdGroups>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(lam_dw_fwd_ring_kernel<D, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::kSmemBytes);
-    attr = true;
-  }
+  ensure_dyn_smem(lam_dw_fwd_ring_kernel<D, W>, (int)R::kSmemBytes);
   const int bands = B * (h / 4), cpm = dw_ring_ctas_per_mod(B, h);
   SIG_LAUNCH((lam_dw_fwd_ring_kernel<D, W>), 3 * cpm, R::kThreads, R::kSmemBytes, s, H, p, B, bands, cpm, U, o);
   SIG_CHECK_LAUNCH();
@@ -272,11 +268,7 @@ template <int D, int W>
 static int launch_dw_bwd_ring(const __nv_bfloat16* H, const float* U, const float* dO, const sig_align_params& p, int B, int h,
                               __nv_bfloat16* dH, float* part, cudaStream_t s) {
   using R = DwRing<D, W, kDwBwdTapsSmem, kDwBwdGroups>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(lam_dw_bwd_ring_kernel<D, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::kSmemBytes);
-    attr = true;
-  }
+  ensure_dyn_smem(lam_dw_bwd_ring_kernel<D, W>, (int)R::kSmemBytes);
   const int items = B * (h / 4) * R::kItemsPerBand, cpm = dw_ring_ctas_per_mod(B, h);
   SIG_LAUNCH((lam_dw_bwd_ring_kernel<D, W>), 3 * cpm, R::kThreads, R::kSmemBytes, s, H, U, dO, p, B, items, cpm, dH, part);
   SIG_CHECK_LAUNCH();

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <set>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -54,6 +56,29 @@ Fork get_fork(int slot) {
     f.side = st; f.ev_fork = a; f.ev_join = b;
   }
   return f;
+}
+
+bool first_launch_on_device(const void* fn) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  return seen.insert({fn, dev}).second;
+}
+
+int device_num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
 }
 
 bool pdl_enabled() {

@@ -46,13 +46,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU for ever.  The bound
+// is SIG_MBAR_TRAP_CLOCKS SM clocks -- default 1.2e11, about a minute at 2 GHz: clock64 keeps running while the context
+// is time-sliced with other processes or slowed down by compute-sanitizer / cuda-gdb / ncu replay, so the bound has to
+// sit far above any healthy wait (all of them are microseconds).  -DSIG_MBAR_TRAP_CLOCKS=0 compiles the check out.
+#ifndef SIG_MBAR_TRAP_CLOCKS
+#define SIG_MBAR_TRAP_CLOCKS 120000000000LL
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+#if SIG_MBAR_TRAP_CLOCKS > 0
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+    if (clock64() - t0 > SIG_MBAR_TRAP_CLOCKS) __trap();
   }
+#else
+  while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 
 // ---- TMA -----------------------------------------------------------------------------------

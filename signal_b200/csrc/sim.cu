@@ -845,24 +845,20 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
     const int ctas = n_items < tc_num_sms() ? n_items : tc_num_sms();
     if (scores_split_enabled()) {
       if (d == 768) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(sim_scores_split_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSplit<768>::kSmemBytes); attr = true; }
+        ensure_dyn_smem(sim_scores_split_kernel<768>, (int)ScoreSplit<768>::kSmemBytes);
         SIG_LAUNCH((sim_scores_split_kernel<768>), ctas, ScoreSplit<768>::kThreads, ScoreSplit<768>::kSmemBytes, s, src, c.clsf, c.qtsel, c.csel, B,
                    n_items, c.sel_logits, c.intra_raw);
       } else {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(sim_scores_split_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSplit<512>::kSmemBytes); attr = true; }
+        ensure_dyn_smem(sim_scores_split_kernel<512>, (int)ScoreSplit<512>::kSmemBytes);
         SIG_LAUNCH((sim_scores_split_kernel<512>), ctas, ScoreSplit<512>::kThreads, ScoreSplit<512>::kSmemBytes, s, src, c.clsf, c.qtsel, c.csel, B,
                    n_items, c.sel_logits, c.intra_raw);
       }
     } else if (d == 768) {
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(sim_scores_ring_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_scores_ring_smem<768>()); attr = true; }
+      ensure_dyn_smem(sim_scores_ring_kernel<768>, (int)sim_scores_ring_smem<768>());
       SIG_LAUNCH((sim_scores_ring_kernel<768>), ctas, TokRing<768>::kThreads, sim_scores_ring_smem<768>(), s, src, c.clsf, c.qtsel, c.csel, B, n_items,
                  c.sel_logits, c.intra_raw);
     } else {
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(sim_scores_ring_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_scores_ring_smem<512>()); attr = true; }
+      ensure_dyn_smem(sim_scores_ring_kernel<512>, (int)sim_scores_ring_smem<512>());
       SIG_LAUNCH((sim_scores_ring_kernel<512>), ctas, TokRing<512>::kThreads, sim_scores_ring_smem<512>(), s, src, c.clsf, c.qtsel, c.csel, B, n_items,
                  c.sel_logits, c.intra_raw);
     }
@@ -926,7 +922,7 @@ static int run_attention_fwd(const SimCtx& c, const sig_tokens* tok, const sig_s
     SIG_TRY(sim_tc_tokens_fwd(tok, tc_bufs(c, maskf), s));
   } else {
     const size_t sm = attn_fwd_smem(L, d);
-    cudaFuncSetAttribute(sim_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(sim_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   // (d-dependent size: set per call)
     SIG_LAUNCH((sim_attn_fwd_kernel), dim3(B, 4), 256, sm, s, c.Xf, maskf, c.qtatt, c.catt, B, L, d, c.xbar, c.amax, c.asum);
     SIG_CHECK_LAUNCH();
   }
@@ -1027,7 +1023,7 @@ static int run_attention_bwd(const SimCtx& c, const sig_tokens* tok, const sig_t
     SIG_TRY(sim_tc_tokens_bwd(tok, tc_bufs(c, maskf), dtok, s));
   } else {
     const size_t sm = attn_bwd_smem(L, d);
-    cudaFuncSetAttribute(sim_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(sim_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   // (d-dependent size: set per call)
     SIG_LAUNCH((sim_attn_bwd_kernel), B, 256, sm, s, c.Xf, maskf, c.qtatt, c.catt, c.xbar, c.amax, c.asum, c.dxbar, B, L, d, c.dqt, c.dXf);
     SIG_CHECK_LAUNCH();
   }

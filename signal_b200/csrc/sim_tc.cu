@@ -383,11 +383,7 @@ int sim_tc_tokens_fwd(const sig_tokens* tok, const SimTcBufs& k, cudaStream_t s)
     SIG_TRY((tc::launch<32, RowsProblem>(p, 3 * B, s, d / 64)));
   }
   {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(sim_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_tc_softmax_smem());
-      attr = true;
-    }
+    ensure_dyn_smem(sim_softmax_kernel, (int)sim_tc_softmax_smem());
     SIG_LAUNCH((sim_softmax_kernel), B, 1024, sim_tc_softmax_smem(), s, k.S32, k.maskf, B, L, k.Ptok, k.PT);
     SIG_CHECK_LAUNCH();
   }

@@ -96,16 +96,7 @@ int stage_override() {
   return v;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_num_sms(); }
 
 }  // namespace tc
 
@@ -536,11 +527,7 @@ static int launch_pair(const TcKernelParams& p, int units, int kpu, cudaStream_t
   int stages = (220 * 1024 - tc::kEpiBytes) / kStageBytes;
   if (stages > 8) stages = 8;
   const int max_smem = stages * kStageBytes + 1024 + 256 + tc::kEpiBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    attr_set = true;
-  }
+  ensure_dyn_smem(kernel, max_smem);
   if (units <= 0) return 0;
   const int npairs_max = (tc::num_sms() - tc::sm_reserve()) / 2;
   const int npairs = units < npairs_max ? units : npairs_max;

@@ -233,11 +233,7 @@ int stage_override();   // SIG_TC_STAGES in the environment (tuning aid), 0 = au
 // shared memory to carve out, fewer barriers to initialise) -- it only needs to cover the load latency.
 template <int BN, class Problem, int MT = 1>
 int launch(const typename Problem::Params& p, int units, cudaStream_t s, int kblocks_per_unit = 1 << 20) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(pipeline_kernel<BN, MT, Problem>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::kSmemBytes);
-    attr_set = true;
-  }
+  ensure_dyn_smem(pipeline_kernel<BN, MT, Problem>, Cfg<BN, MT>::kSmemBytes);
   if (units <= 0) return 0;
   // Kernels with at least one unit per SM are persistent and would hold every SM for their whole run; leaving a
   // few SMs free (SIG_TC_RESERVE, default in tc_gemm.cu) lets the short kernels of a concurrent stream -- the other

@@ -31,13 +31,23 @@ def _carve(flat: torch.Tensor, shapes) -> List[torch.Tensor]:
     return out
 
 
-def _arena(shapes, device) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+def _arena(shapes, device, flat: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     total = sum(((int(torch.Size(s).numel()) + 3) // 4 * 4) for s in shapes)
-    flat = torch.empty(total, dtype=torch.float32, device=device)
+    if flat is None:
+        flat = torch.empty(total, dtype=torch.float32, device=device)
+    else:        # caller-owned arena (e.g. symmetric memory of parallel.GradExchange)
+        if flat.numel() < total or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise RuntimeError(f"signal_b200: the gradient arena must be a contiguous fp32 tensor of >= {total} elements")
+        flat = flat[:total]
     return flat, _carve(flat, shapes)
 
 
-def _head_arena(d: int, device):
+def head_grad_numel(d: int) -> int:
+    """fp32 elements of the flat gradient arena of SIM + AlignM at width d (FusionHead.grad_numel)."""
+    return sum(((int(torch.Size(s).numel()) + 3) // 4 * 4) for s in _SIM_GRAD_SHAPES(d) + _align_grad_shapes(d))
+
+
+def _head_arena(d: int, device, flat: Optional[torch.Tensor] = None):
     """ONE flat arena for the gradients of both modules, ``[SIM late part | SIM early part | AlignM]``, so that a
     data-parallel exchange needs two collectives: ``flat[cut:]`` (28.5 MB at d = 768) once SIM's early gradients and
     AlignM's gradients are final -- both happen in the first third of the backward when AlignM's weight-independent
@@ -45,7 +55,7 @@ def _head_arena(d: int, device):
     when SIM's token-side backward is through.  Returns (flat, SIM grads, AlignM grads, cut)."""
     sshapes, ashapes = _SIM_GRAD_SHAPES(d), _align_grad_shapes(d)
     order = [1, 0] + list(range(2, len(sshapes)))
-    flat, views = _arena([sshapes[i] for i in order] + ashapes, device)
+    flat, views = _arena([sshapes[i] for i in order] + ashapes, device, flat)
     sv, pg_a = views[:len(sshapes)], views[len(sshapes):]
     pg_s = [None] * len(sshapes)
     for i, v in zip(order, sv):
@@ -87,6 +97,44 @@ def _alloc_token_grads(packed: bool, toks, need_cls: bool):
     dp = [torch.empty(B, L, d, dtype=toks[0].dtype, device=toks[0].device) for _ in range(3)]
     dc = [torch.empty(B, d, dtype=toks[0].dtype, device=toks[0].device) for _ in range(3)] if need_cls else None
     return dp + (dc if dc else []), dp, dc
+
+
+# ------------------------------------------------------------------------------------------
+# fp16 boundary
+# ------------------------------------------------------------------------------------------
+def _convert_half(src: torch.Tensor, dst_dtype: torch.dtype) -> torch.Tensor:
+    """fp16 <-> bf16 copy of a [.., d] tensor with unit channel stride (2-D [B,d] or 3-D [B,L,d] views are read through
+    their strides, no .contiguous()) -> contiguous tensor of dst_dtype.  One streaming kernel (sig_convert_half)."""
+    lib = L_.load()
+    code = {torch.float16: L_.SIG_F16, torch.bfloat16: L_.SIG_BF16}
+    x = src if src.dim() == 3 else src.unsqueeze(1)
+    if x.dim() != 3 or x.stride(2) != 1 or (x.stride(0) | x.stride(1)) % 8 or x.data_ptr() % 16:
+        x = x.reshape(-1, 1, src.shape[-1]).contiguous() if src.dim() != 3 else x.contiguous()
+    nb, nl, d = x.shape
+    dst = torch.empty(nb, nl, d, dtype=dst_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        L_.check(lib.sig_convert_half(x.data_ptr(), x.stride(0), x.stride(1), code[x.dtype], dst.data_ptr(), dst.stride(0),
+                                      dst.stride(1), code[dst_dtype], nb, nl, d, x.device.index, L_.stream_ptr(x.device)),
+                 "sig_convert_half")
+    return dst.view(src.shape)
+
+
+class HalfBridge(torch.autograd.Function):
+    """y = x converted between fp16 and bf16; the backward converts the gradient the other way.
+
+    The reference trains under fp16 autocast (engine/processor.py:165), so SIM / AlignM receive fp16 token maps; the
+    kernels compute on bf16 operands with fp32 accumulation.  The module shims therefore convert each token map once
+    on the way in (fp16 -> bf16, exact exponent, mantissa rounded to 8 bits) and each result / token gradient once on
+    the way out (bf16 -> fp16)."""
+
+    @staticmethod
+    def forward(ctx, x, dst_dtype):
+        ctx.src_dtype = x.dtype
+        return _convert_half(x, dst_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _convert_half(g, ctx.src_dtype), None
 
 
 # ------------------------------------------------------------------------------------------
@@ -330,6 +378,8 @@ class AlignFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             L_.check(lib.sig_align_bwd(C.byref(tok), C.byref(prm), h, w, int(do_lam), dl.data_ptr(), C.byref(tg), C.byref(gs),
                                        buf.data_ptr(), buf.numel(), flags, dev.index, L_.stream_ptr(dev)), "sig_align_bwd")
+        if not do_lam:      # stage == "CLS": the DAS parameters took no part (useB.py:181-183) -> no gradient, like the reference
+            pg = [pg[0]] + [None] * (len(pg) - 1)
         return (None,) * 5 + tuple(ret) + tuple(pg)
 
 
@@ -502,7 +552,7 @@ class HeadFunction(torch.autograd.Function):
         if event[1] is None:
             sync = None
         if sync is not None and sync[3] == 2:
-            flat_h, pg_s, pg_a, cut_h = _head_arena(d, dev)
+            flat_h, pg_s, pg_a, cut_h = _head_arena(d, dev, event[4] if len(event) > 4 else None)
             if not do_lam:
                 flat_h[cut_h:].zero_()
         else:
@@ -581,4 +631,6 @@ class HeadFunction(torch.autograd.Function):
             main.wait_stream(side)
             if hi is not main:
                 main.wait_stream(hi)
+        if not do_lam:      # stage == "CLS": no gradient for the DAS parameters (useB.py:181-183)
+            pg_a = [pg_a[0]] + [None] * (len(pg_a) - 1)
         return (None,) * 9 + tuple(dtoks) + (None,) * 4 + tuple(pg_s) + tuple(pg_a) + (None,) * nfold

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsignal_b200.so")
 
-SIG_F32, SIG_BF16 = 0, 1
+SIG_F32, SIG_BF16, SIG_F16 = 0, 1, 2
 CTX_SIM, CTX_ALIGN, CTX_SELECT, CTX_DAS = 0, 1, 2, 3
 FLAG_FORCE_SIMT = 1
 SIG_FLAG_EAGER_BWD = 2   # sig_align_fwd also runs the loss-weight-independent part of the backward (include/signal_b200.h)
@@ -64,6 +64,10 @@ class SigAlignParamGrads(C.Structure):
     _fields_ = [("contra_temp", C.c_void_p)] + [(n, _VP3) for n in ALIGN_MOD_FIELDS] + [("done_event", C.c_void_p)]
 
 
+class SigXchgPeers(C.Structure):
+    _fields_ = [("buf", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("multicast", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 _lib = None
 
 # every symbol include/signal_b200.h declares (tests check that the .so exports them all)
@@ -73,6 +77,7 @@ EXPORTS = [
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
     "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_profile_scope_begin", "sig_profile_scope_end", "sig_sim_dx_operands",
+    "sig_convert_half", "sig_xchg_flag_bytes", "sig_xchg_allreduce_f32",
     "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd", "sig_bnneck_ws_bytes", "sig_bnneck_cls_fwd", "sig_bnneck_cls_bwd",
 ]
 
@@ -113,6 +118,10 @@ def load():
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
     lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
     lib.sig_sim_dx_operands.argtypes = [vp, i, i, i, i, u, P(vp), P(vp)]
+    lib.sig_xchg_flag_bytes.restype = sz
+    lib.sig_xchg_flag_bytes.argtypes = []
+    lib.sig_xchg_allreduce_f32.argtypes = [P(SigXchgPeers), sz, sz, C.c_float, i, i, vp]
+    lib.sig_convert_half.argtypes = [vp, i64, i64, i, vp, i64, i64, i, i, i, i, i, vp]
     lib.sig_profile_timeline.argtypes = [C.c_char_p, sz]
     f = C.c_float
     lib.sig_loss_ws_bytes.restype = sz
@@ -135,7 +144,8 @@ def load():
     lib.sig_profile_collect.argtypes = [C.c_char_p, sz, P(C.c_float), P(C.c_int), i]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("sig_error_string", "sig_ctx_bytes", "sig_volume3_ws_bytes", "sig_debug_launch_count"):
+        if name not in ("sig_error_string", "sig_ctx_bytes", "sig_volume3_ws_bytes", "sig_debug_launch_count", "sig_xchg_flag_bytes",
+                        "sig_loss_ws_bytes", "sig_bnneck_ws_bytes", "sig_profile_scope_begin", "sig_profile_scope_end"):
             fn.restype = i
     if lib.sig_version() != 1:
         raise RuntimeError("signal_b200: ABI version mismatch between lib.py and libsignal_b200.so")
@@ -154,7 +164,8 @@ def dtype_enum(t: torch.Tensor) -> int:
         return SIG_F32
     if t.dtype == torch.bfloat16:
         return SIG_BF16
-    raise RuntimeError(f"signal_b200: unsupported token dtype {t.dtype} (fp32 or bf16; fp16 autocast is not supported)")
+    raise RuntimeError(f"signal_b200: unsupported kernel dtype {t.dtype} (fp32 or bf16; the nn.Module shims bridge fp16 "
+                       "token maps through functional.HalfBridge)")
 
 
 def stream_ptr(device: torch.device) -> int:

@@ -55,6 +55,39 @@ def _packed_patch_base(patch: torch.Tensor):
     return base
 
 
+def _half_in(patches, globs=None):
+    """fp16 token maps (the reference's amp.autocast, engine/processor.py:165) -> bf16 for the kernels; one conversion
+    pass per [B,1+L,d] map when (patch, glob) are the two views of one map, else one per view.  Returns
+    (patches, globs, was_half); the caller converts its floating-point outputs back with _half_out."""
+    if patches[0].dtype != torch.float16:
+        return list(patches), (list(globs) if globs is not None else None), False
+    bf = torch.bfloat16
+    new_p, new_g = [], []
+    for m, p in enumerate(patches):
+        g = globs[m] if globs is not None else None
+        base = _packed_base(p, g) if g is not None else _packed_patch_base(p)
+        if base is not None:
+            nb = F_.HalfBridge.apply(base, bf)
+            new_p.append(nb[:, 1:])
+            new_g.append(nb[:, 0])
+        else:
+            new_p.append(F_.HalfBridge.apply(p, bf))
+            new_g.append(F_.HalfBridge.apply(g, bf) if g is not None else None)
+    return new_p, (new_g if globs is not None else None), True
+
+
+def _half_out(t, was_half):
+    return F_.HalfBridge.apply(t, torch.float16) if was_half else t
+
+
+def _same_strides(patches):
+    """The bf16 tensor-core path of AlignM reads the three modalities through one tensor-map geometry (the C entry
+    rejects mixed strides with SIG_ERR_SHAPE): hand it contiguous copies in that (unusual) case."""
+    if patches[0].dtype == torch.bfloat16 and len({(p.stride(0), p.stride(1)) for p in patches}) > 1:
+        return [p.contiguous() for p in patches]
+    return list(patches)
+
+
 class LayerNorm(nn.LayerNorm):
     """fp32 LayerNorm that casts back to the input dtype (useA.py:414-423).  Parameter container
     for norm1/norm2; kept callable for code that uses the class on its own."""
@@ -77,6 +110,18 @@ class TokenSelection(nn.Module):
         self.W_q = nn.Linear(dim, dim)
         self.W_k = nn.Linear(dim, dim)
         self.W_v = nn.Linear(dim, dim)   # unused by the reference forward as well (useA.py:48)
+        self.register_load_state_dict_post_hook(lambda module, _incompatible: module.invalidate_fold())
+
+    def invalidate_fold(self):
+        """Drop the cached fold M = W_k^T W_q of the frozen selection parameters (used by the bf16 path).  The cache
+        is keyed on (data_ptr, _version, device, dtype) of the four tensors and is dropped by load_state_dict and by
+        .to()/.cuda()/.float(); in-place edits through ``p.data`` (EMA updates, manual re-initialisation) do NOT bump
+        ``_version`` -- call this after them."""
+        self.__dict__.pop("_fold_cache", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_fold()
+        return super()._apply(fn, *args, **kwargs)
 
     def _sel_params(self):
         return [self.W_q.weight, self.W_q.bias, self.W_k.weight, self.W_k.bias]
@@ -98,8 +143,11 @@ class TokenSelection(nn.Module):
         return -1 if self.keep_ratio is None else int(L * self.keep_ratio)
 
     def _masks(self, which, patches, cls):
+        dt = patches[0].dtype
+        with torch.no_grad():
+            patches, cls, _ = _half_in(patches, cls)
         m = F_.select_masks(which, patches, cls, self._sel_params(), self.k1, self.k2, -1)
-        return tuple(m[i].to(patches[0].dtype).unsqueeze(-1) for i in range(3))
+        return tuple(m[i].to(dt).unsqueeze(-1) for i in range(3))
 
     def intra_modal_token_selection(self, rgb_patches, nir_patches, tir_patches, rgb_global, nir_global, tir_global):
         return self._masks(1, [rgb_patches, nir_patches, tir_patches], [rgb_global, nir_global, tir_global])
@@ -109,10 +157,12 @@ class TokenSelection(nn.Module):
 
     def forward(self, rgb_patches, nir_patches, tir_patches, rgb_global, nir_global, tir_global):
         L = rgb_patches.size(1)
+        (rgb_patches, nir_patches, tir_patches), (rgb_global, nir_global, tir_global), half = _half_in(
+            [rgb_patches, nir_patches, tir_patches], [rgb_global, nir_global, tir_global])
         r, n, t, masks = F_.SelectFunction.apply(self.k1, self.k2, self._max_keep(L), rgb_patches, nir_patches, tir_patches,
                                                  rgb_global, nir_global, tir_global, *[p.detach() for p in self._sel_params()])
         self.last_masks = {"RGB": masks[0].unsqueeze(-1), "NI": masks[1].unsqueeze(-1), "TI": masks[2].unsqueeze(-1)}
-        return r, n, t
+        return _half_out(r, half), _half_out(n, half), _half_out(t, half)
 
 
 class ModalInteractive(nn.Module):
@@ -138,8 +188,10 @@ class ModalInteractive(nn.Module):
     def forward(self, rgb_selected, nir_selected, tir_selected, rgb_global, nir_global, tir_global):
         p = self._attn_params()
         dummy = [p[0].detach()] * 4   # selection parameters are not read by the attention entry point
-        return F_.AttnFunction.apply(0, rgb_selected, nir_selected, tir_selected, rgb_global, nir_global, tir_global,
-                                     *dummy, *p)
+        (rgb_selected, nir_selected, tir_selected), (rgb_global, nir_global, tir_global), half = _half_in(
+            [rgb_selected, nir_selected, tir_selected], [rgb_global, nir_global, tir_global])
+        return _half_out(F_.AttnFunction.apply(0, rgb_selected, nir_selected, tir_selected, rgb_global, nir_global, tir_global,
+                                               *dummy, *p), half)
 
 
 class Select_Interactive_Module(nn.Module):
@@ -160,6 +212,8 @@ class Select_Interactive_Module(nn.Module):
             sel = ts(rgb_patches, nir_patches, tir_patches, rgb_global, nir_global, tir_global)
             return mi(*sel, rgb_global, nir_global, tir_global)
         L = rgb_patches.size(1)
+        (rgb_patches, nir_patches, tir_patches), (rgb_global, nir_global, tir_global), half = _half_in(
+            [rgb_patches, nir_patches, tir_patches], [rgb_global, nir_global, tir_global])
         params = [p.detach() for p in ts._sel_params()] + mi._attn_params()
         if rgb_patches.dtype == torch.bfloat16 and not (self.flags & 1):
             params = params + list(ts._selection_fold())
@@ -174,7 +228,7 @@ class Select_Interactive_Module(nn.Module):
             out, masks = F_.SimFunction.apply(False, ts.k1, ts.k2, ts._max_keep(L), self.flags, rgb_patches, nir_patches,
                                               tir_patches, rgb_global, nir_global, tir_global, *params)
         ts.last_masks = {"RGB": masks[0].unsqueeze(-1), "NI": masks[1].unsqueeze(-1), "TI": masks[2].unsqueeze(-1)}
-        return out
+        return _half_out(out, half)
 
 
 class DA_sample(nn.Module):
@@ -210,6 +264,8 @@ class DA_sample(nn.Module):
         if xt.stride(3) != 1 or xt.stride(1) != W * xt.stride(2):
             xt = xt.contiguous()
         xt = xt.reshape(B, H * W, Cc)
+        if xt.dtype == torch.float16:
+            xt = F_.HalfBridge.apply(xt, torch.bfloat16)
         s = F_.DasFunction.apply(H, W, self.flags, xt, *self._params())    # [B,P,C] fp32
         return s.to(x.dtype).reshape(B, H // 4, W // 4, Cc).permute(0, 3, 1, 2)
 
@@ -236,6 +292,7 @@ class AlignmentM(nn.Module):
         return [self.contra_temp] + self.DAS_r._params() + self.DAS_n._params() + self.DAS_t._params()
 
     def _run(self, RGB_patch, NI_patch, TI_patch, do_lam):
+        (RGB_patch, NI_patch, TI_patch), _, _ = _half_in([RGB_patch, NI_patch, TI_patch])     # (the two losses are fp32)
         bases = None
         if self.fuse_views:
             bases = [_packed_patch_base(p) for p in (RGB_patch, NI_patch, TI_patch)]
@@ -243,7 +300,8 @@ class AlignmentM(nn.Module):
                 bases = None
         if bases is not None:
             return F_.AlignFunction.apply(True, self.h, self.w, do_lam, self.flags, *bases, *self._params())
-        return F_.AlignFunction.apply(False, self.h, self.w, do_lam, self.flags, RGB_patch, NI_patch, TI_patch, *self._params())
+        return F_.AlignFunction.apply(False, self.h, self.w, do_lam, self.flags, *_same_strides([RGB_patch, NI_patch, TI_patch]),
+                                      *self._params())
 
     def Cls_Align(self, RGB_patch, NI_patch, TI_patch):
         return self._run(RGB_patch, NI_patch, TI_patch, False)[0]
@@ -289,6 +347,12 @@ class FusionHead:
         # that piece is final -- e.g. ``lambda a: dist.all_reduce(a, op=dist.ReduceOp.AVG)``.  The gradients
         # that reach ``.grad`` are then already averaged and the exchange overlaps the rest of the backward.
         self.grad_sync = grad_sync
+        # optional caller-owned flat fp32 arena the backward carves the parameter gradients from (grad_numel() elements;
+        # parallel.GradExchange.arena: symmetric memory, so the exchange kernel can reach the peers' gradients)
+        self.grad_arena = None
+
+    def grad_numel(self) -> int:
+        return F_.head_grad_numel(self.sim.token_selection.dim)
 
     def _stream(self, dev):
         st = self._side.get(dev)
@@ -313,11 +377,13 @@ class FusionHead:
     def __call__(self, rgb_patch, ni_patch, ti_patch, rgb_global, ni_global, ti_global, stage="together_CLS_Patch"):
         sim, al = self.sim, self.align
         ts, mi = sim.token_selection, sim.modal_interactive
+        (rgb_patch, ni_patch, ti_patch), (rgb_global, ni_global, ti_global), half = _half_in(
+            [rgb_patch, ni_patch, ti_patch], [rgb_global, ni_global, ti_global])
         bases = [_packed_base(p, g) for p, g in ((rgb_patch, rgb_global), (ni_patch, ni_global), (ti_patch, ti_global))]
         hooked = ts._forward_hooks or ts._forward_pre_hooks or mi._forward_hooks or mi._forward_pre_hooks
         patched = "Cls_Align" in al.__dict__ or "patch_Align" in al.__dict__
         if any(b is None for b in bases) or hooked or patched or not rgb_patch.is_cuda:
-            out = sim(rgb_patch, ni_patch, ti_patch, rgb_global, ni_global, ti_global)
+            out = _half_out(sim(rgb_patch, ni_patch, ti_patch, rgb_global, ni_global, ti_global), half)
             res = al(rgb_patch, ni_patch, ti_patch, stage=stage)
             return (out, res, None) if stage == "CLS" else (out, res[0], res[1])
         L = rgb_patch.size(1)
@@ -327,6 +393,7 @@ class FusionHead:
         if rgb_patch.dtype == torch.bfloat16 and not (flags & 1):
             params = params + list(ts._selection_fold())
         out, masks, gam, lam = F_.HeadFunction.apply(al.h, al.w, stage != "CLS", ts.k1, ts.k2, ts._max_keep(L), flags, side,
-                                                     (ev, self.grad_sync, hi, sync), *bases, *params)
+                                                     (ev, self.grad_sync, hi, sync, self.grad_arena), *bases, *params)
         ts.last_masks = {"RGB": masks[0].unsqueeze(-1), "NI": masks[1].unsqueeze(-1), "TI": masks[2].unsqueeze(-1)}
+        out = _half_out(out, half)
         return (out, gam, None) if stage == "CLS" else (out, gam, lam)

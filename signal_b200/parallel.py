@@ -16,6 +16,76 @@ import torch
 import torch.distributed as dist
 
 
+class GradExchange:
+    """In-place average of the head's flat fp32 gradient arena over the ranks of one node, as ONE kernel over NVLink
+    peer memory (``sig_xchg_allreduce_f32``, csrc/xchg.cu) -- the DDP all-reduce of engine/processor.py:100-105 without
+    NCCL's SM footprint, so it can run under the persistent kernels of the backward.
+
+    torch is the plumbing: ``torch.distributed._symmetric_memory`` allocates the symmetric buffer
+    ``[arena | flag region]`` and exchanges the peer mappings (and the NVLS multicast mapping when the fabric has one);
+    the kernel is ours.  Usage::
+
+        ex = GradExchange(head.grad_numel(), device)          # once, collectively
+        head.grad_arena, head.grad_sync = ex.arena, ex.allreduce
+
+    ``FusionHead`` then carves its parameter-gradient views out of ``ex.arena`` (so ``.grad`` lives in symmetric memory:
+    overwritten by the next backward, like DDP's ``gradient_as_bucket_view=True``) and calls ``ex.allreduce(piece)``
+    on its communication stream as soon as each piece is final.  Every rank must issue the same calls in the same order.
+    """
+
+    def __init__(self, numel: int, device, group=None, ctas: int = 0, use_multicast: bool = True):
+        import ctypes as C
+        import os
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import lib as L_
+        self.lib = L_.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("signal_b200: GradExchange covers the <= 8 GPUs of one node")
+        device = torch.device(device)
+        self.numel = (int(numel) + 3) // 4 * 4
+        flag_floats = int(self.lib.sig_xchg_flag_bytes()) // 4
+        with torch.cuda.device(device):
+            self.buf = symm_mem.empty(self.numel + flag_floats, dtype=torch.float32, device=device)
+            self.buf.zero_()
+            torch.cuda.synchronize(device)
+            gname = self.group.group_name if hasattr(self.group, "group_name") else self.group
+            try:
+                symm_mem.enable_symm_mem_for_group(gname)      # (older torch needs it; a no-op / deprecated later)
+            except Exception:
+                pass
+            self.handle = symm_mem.rendezvous(self.buf, gname)
+        self.arena = self.buf[:self.numel]
+        peers = L_.SigXchgPeers()
+        ptrs = list(self.handle.buffer_ptrs)
+        for r in range(self.world):
+            peers.buf[r] = ptrs[r]
+            peers.flags[r] = ptrs[r] + 4 * self.numel
+        mc = int(self.handle.multicast_ptr) if use_multicast and os.environ.get("SIG_XCHG_MULTICAST", "1") != "0" else 0
+        peers.multicast = mc if mc else None
+        peers.rank, peers.world = self.rank, self.world
+        self.peers, self.multicast = peers, bool(mc)
+        self.ctas = int(os.environ.get("SIG_XCHG_CTAS", str(ctas)))
+        self.device = device
+        self._C = C
+        dist.barrier(self.group)          # every rank's flag region is zero before anyone signals
+
+    def allreduce(self, piece: torch.Tensor, scale=None):
+        """piece: a contiguous fp32 view inside ``self.arena``; averaged over the ranks in place, on the current stream."""
+        from . import lib as L_
+        off = (piece.data_ptr() - self.arena.data_ptr()) // 4
+        n = piece.numel()
+        if piece.dtype != torch.float32 or not piece.is_contiguous() or off < 0 or off + n > self.numel or (off | n) % 4:
+            raise RuntimeError("signal_b200: GradExchange.allreduce needs a contiguous 16-byte aligned fp32 piece of its own arena")
+        s = 1.0 / self.world if scale is None else float(scale)
+        with torch.cuda.device(self.device):
+            L_.check(self.lib.sig_xchg_allreduce_f32(self._C.byref(self.peers), off, n, s, self.ctas, self.device.index,
+                                                     L_.stream_ptr(self.device)), "sig_xchg_allreduce_f32")
+        return piece
+
+
 def grad_arenas(params: Iterable[torch.nn.Parameter]) -> List[torch.Tensor]:
     """The flat arenas behind the parameters' gradients, in first-seen order, each as ONE 1-D tensor over
     the whole storage.  Grouping is by storage, not by ``._base``: the autograd engine adopts the views a

@@ -18,6 +18,33 @@ CASES = {
 }
 
 
+# Reduced-precision (bf16 token) cases.  LAM's deformable sampling is chaotic on white-noise token maps once the offset
+# logits are large (offset_gain >= 25 in the fp32 golden cases): a 0.01 perturbation of an offset logit -- the size of the
+# bf16 rounding of the 1x1-conv weights -- moves a sample point by ~0.03 pixels across *uncorrelated* neighbouring tokens.
+# Reduced-precision parity is therefore asserted where the problem is well conditioned: default-scale offsets (gain 1) on
+# white noise, and 2x larger offsets on spatially smooth token maps.  For each case tests/golden/bf16dev_<name>.npz holds
+# what the REFERENCE's own bf16-autocast run loses against its fp64 run (tests/golden/make_golden.py::run_bf16_case).
+BF16_CASES = {
+    "rgbnt201_d512": dict(d=512, h=16, w=8, B=8, k=80, keep_ratio=None, gain=1.0, structured=False, seed=101, smooth=False),
+    "rgbnt201_d768": dict(d=768, h=16, w=8, B=8, k=80, keep_ratio=None, gain=1.0, structured=False, seed=313, smooth=False),
+    "vehicle_d512": dict(d=512, h=8, w=16, B=8, k=112, keep_ratio=None, gain=1.0, structured=False, seed=212, smooth=False),
+    "smooth_gain2_d512": dict(d=512, h=16, w=8, B=8, k=80, keep_ratio=None, gain=2.0, structured=False, seed=515, smooth=True),
+    "smooth_gain2_vehicle_d768": dict(d=768, h=8, w=16, B=6, k=64, keep_ratio=0.5, gain=2.0, structured=False, seed=616, smooth=True),
+    # BASELINE.json configs #2 / #3 at their full batch
+    "b128_rgbnt201_d768": dict(d=768, h=16, w=8, B=128, k=80, keep_ratio=None, gain=1.0, structured=False, seed=4242, smooth=False),
+    "b128_rgbnt201_d512": dict(d=512, h=16, w=8, B=128, k=80, keep_ratio=None, gain=1.0, structured=False, seed=4343, smooth=False),
+    "b128_vehicle_d512": dict(d=512, h=8, w=16, B=128, k=112, keep_ratio=0.75, gain=1.0, structured=False, seed=4444, smooth=False),
+}
+
+
+def bf16_case_tokens(c):
+    """bf16-rounded token maps of a BF16_CASES entry (smoothed over the grid where the case says so)."""
+    toks = syn.make_tokens(c["B"], c["d"], seed=c["seed"] + 2, structured=c["structured"])
+    if c.get("smooth"):
+        toks = syn.smooth_patches(toks, c["h"], c["w"])
+    return [t.to(torch.bfloat16) for t in toks]
+
+
 def load(name):
     return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
 
@@ -48,25 +75,12 @@ def project_tokens(grads, d):
     return torch.stack([g.detach().double().cpu() @ proj for g in grads]).numpy()
 
 
-def param_tol(key, objective, tol):
-    """Documented fp32-conditioning exceptions to the flat parity tolerance.
-
-    * d(gam)/d(contra_temp) = sum_ij dZ_ij V_ij / tau^2 with sum_j dZ_ij = 0: on iid
-      tokens V ~ 1 everywhere, so the sum cancels to ~1e-3 of its terms and the
-      reference's own fp32 ``torch.det`` (volume.py:57, fp32 even in the fp64 golden
-      run) shows up as ~3e-4 relative noise; an fp32 evaluation of V (1e-7 relative per
-      entry, times 1/tau^2 = 204, over a result of ~0.05) sits at ~1e-3.  Hence 3e-3.
-    * LAM parameter gradients with the offsets pushed into tanh saturation
-      (offset_gain >= 25) pass through 1 - tanh(o)^2, which loses digits in fp32: the
-      fp32 *reference* deviates from its own fp64 run by ~2e-4 there.
-    """
-    if key.endswith("contra_temp"):
-        return max(tol, 3e-3)
-    if objective == "lam" and tol >= 1e-2:
-        # bf16 runs: the offset-path gradients are sums over channels/positions of terms with random
-        # signs; the bf16 rounding of the folded weights and of the stored pre-activation shows up
-        # amplified (measured 1-4% on these parameters while every per-token gradient is < 2%)
-        return max(tol, 5e-2)
-    if objective == "lam" and tol > 1e-5:
-        return max(tol, 5e-4)
-    return tol
+def derived_tol(dev, key, tol, c=3.0, prefix="dev32/"):
+    """Tolerance for quantity `key`, derived from the golden file: the flat parity tolerance `tol`, or -- where the
+    reference's own reduced-precision run already deviates from its fp64 run by more than tol / c -- c times THAT
+    measured deviation (``dev32/<key>`` from the fp32 run, ``dev/<key>`` of bf16dev_*.npz from the bf16-autocast run).
+    No hand-set exceptions: a quantity gets a wider bound only if the reference itself demonstrably loses it."""
+    k = prefix + key
+    if dev is None or k not in dev:
+        return tol
+    return max(tol, c * float(dev[k]))

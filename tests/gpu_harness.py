@@ -52,6 +52,30 @@ def cuda_record(c, dtype=torch.float32, packed=True, flags=0, sim_p=None, al_p=N
     return rec
 
 
+def oracle_record(c, sim_p, al_p, toks, cot, dtype=torch.float32):
+    """The CPU oracle on the same inputs, with FULL gradient tensors (dtok_full_*, dpar_full_*) next to the
+    fingerprints the golden files hold."""
+    from oracle import signal_oracle as so
+    sim_p = {k: v.clone().to(dtype).requires_grad_(True) for k, v in sim_p.items()}
+    al_p = {k: v.clone().to(dtype).requires_grad_(True) for k, v in al_p.items()}
+    toks = [t.clone().to(dtype).requires_grad_(True) for t in toks]
+    out, gam, lam, masks = so.head_forward(sim_p, al_p, toks, c["k"], c["h"], c["w"], c["keep_ratio"])
+    rec = {"sim_out": out.detach().float().numpy(), "masks": np.stack([m[..., 0].numpy().astype(np.uint8) for m in masks]),
+           "gam": gam.item(), "lam": lam.item()}
+    named = [("SIM." + k, p) for k, p in sim_p.items()] + [("AlignM." + k, p) for k, p in al_p.items()]
+    for oname, J in {"sim": (out * cot.to(dtype)).sum(), "gam": gam, "lam": lam}.items():
+        grads = torch.autograd.grad(J, toks + [p for _, p in named], retain_graph=True, allow_unused=True)
+        gt = [torch.zeros_like(t) if g is None else g for t, g in zip(toks, grads[:3])]
+        rec[f"dtok_{oname}"] = gu.project_tokens(gt, c["d"])
+        rec[f"dtok_full_{oname}"] = [g.detach().float() for g in gt]
+        for (key, _), g in zip(named, grads[3:]):
+            if g is None:
+                continue
+            rec[f"dpar_{oname}/{key}"] = gu.fingerprint_param(key, g)
+            rec[f"dpar_full_{oname}/{key}"] = g.detach().float()
+    return rec
+
+
 def lam_flip_samples(got, ref, tol):
     """(modality, sample) pairs whose LAM token gradient deviates by more than `tol`.
 
@@ -59,57 +83,103 @@ def lam_flip_samples(got, ref, tol):
     slope switches to another pair of neighbouring tokens).  A reduced-precision run moves the
     predicted offsets by ~1e-3 px, so in a batch of B*8*3 sample points an occasional point lands on
     the other side of a boundary and that one sample's offset-path gradient changes by O(1).  Such
-    samples are reported, bounded in number, and excluded from the aggregate comparison.
+    samples are reported, bounded in number BY WHAT THE REFERENCE'S OWN bf16 RUN SHOWS (golden
+    ``lam_flip_samples``), and excluded from the aggregate comparison.
     """
-    a = np.asarray(got["dtok_lam"], dtype=np.float64)
-    b = np.asarray(ref["dtok_lam"], dtype=np.float64)
+    if "dtok_full_lam" in got and "dtok_full_lam" in ref:
+        a = torch.stack(got["dtok_full_lam"]).double().numpy()
+        b = torch.stack(ref["dtok_full_lam"]).double().numpy()
+    else:
+        a = np.asarray(got["dtok_lam"], dtype=np.float64)
+        b = np.asarray(ref["dtok_lam"], dtype=np.float64)
     num = np.linalg.norm((a - b).reshape(a.shape[0], a.shape[1], -1), axis=-1)
     den = np.linalg.norm(b.reshape(b.shape[0], b.shape[1], -1), axis=-1)
     bad = np.argwhere(num > tol * np.maximum(den, 1e-30))
     return [(int(m), int(s)) for m, s in bad]
 
 
-def compare_records(got, ref, tol, check_masks=True, ref_masks_key="masks", label="", lam_flip_robust=False):
-    """Assert got (CUDA) matches ref (golden npz or oracle record) within tol (relative L2).
+def _full_err(a, b):
+    """(relative L2, max-abs error / max-abs reference) of two full tensors"""
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300)), float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
 
-    lam_flip_robust (reduced-precision runs only): tolerate a few pixel-boundary flips of LAM sample
-    points, see lam_flip_samples()."""
+
+MAXABS_FACTOR = 4.0   # max|err| <= MAXABS_FACTOR * tol * max|ref| on full tensors (rel-L2 == tol puts a Gaussian error's
+                      # largest of ~1e6 entries at ~1.1 tol max|ref|)
+
+
+def compare_records(got, ref, tol, check_masks=True, ref_masks_key="masks", label="", dev=None, dev_prefix="dev32/", dev_c=3.0,
+                    lam_flip_budget=0, report=None):
+    """Assert got (CUDA) matches ref (golden npz or oracle record).
+
+    Every quantity is held to `tol` (relative L2; BASELINE.json: 1e-4 fp32, 2e-2 bf16) unless the golden record `dev`
+    shows that the reference's own run at this precision deviates from its fp64 run by more than tol / dev_c -- then to
+    dev_c times that measured deviation (golden_util.derived_tol).  When `ref` carries full tensors (live oracle) the
+    comparison is on the FULL gradient tensors, relative L2 and max-abs; fingerprints are only used against .npz files.
+    lam_flip_budget: how many (modality, sample) LAM outliers (pixel-boundary flips, lam_flip_samples) are tolerated and
+    excluded -- callers derive it from the golden record of the reference's own bf16 run; 0 for fp32.
+    report: optional dict that receives {quantity: (error, bound)} for every comparison made."""
     errs = {}
+    full = "dtok_full_sim" in ref and "dtok_full_sim" in got
+    ratios = []      # err / (the reference's own deviation) for every quantity whose bound was derived from it
+
+    def check(key, e, bound, kind="l2"):
+        errs[key if kind == "l2" else key + "#maxabs"] = e
+        if report is not None:
+            report[key if kind == "l2" else key + "#maxabs"] = (e, bound)
+        assert e < bound, (label, key, kind, "err %.3e >= bound %.3e" % (e, bound))
+        if kind == "l2" and dev is not None and dev_prefix + key in dev and dev_c * float(dev[dev_prefix + key]) > tol:
+            ratios.append(e / float(dev[dev_prefix + key]))
+
     flips = []
-    if lam_flip_robust:
+    if lam_flip_budget:
         flips = lam_flip_samples(got, ref, tol)
-        nsamp = np.asarray(ref["dtok_lam"]).shape[1] * 3
-        assert len(flips) <= max(1, int(0.03 * nsamp)), (label, "too many LAM outlier samples", flips[:10])
-        errs["lam_flip_samples"] = float(len(flips))
+        assert len(flips) <= lam_flip_budget, (label, "too many LAM outlier samples", len(flips), lam_flip_budget, flips[:10])
+    errs["lam_flip_samples"] = float(len(flips))
     if check_masks:
         assert np.array_equal(got["masks"], ref[ref_masks_key]), f"{label}: selected-token masks differ"
-    errs["sim_out"] = gu.rel_err(got["sim_out"], ref["sim_out"])
-    errs["gam"] = abs(got["gam"] - float(ref["gam"])) / abs(float(ref["gam"]))
-    errs["lam"] = abs(got["lam"] - float(ref["lam"])) / abs(float(ref["lam"]))
-    for k in ("sim_out", "gam", "lam"):
-        assert errs[k] < tol, (label, k, errs[k])
+    check("sim_out", gu.rel_err(got["sim_out"], ref["sim_out"]), gu.derived_tol(dev, "sim_out", tol, dev_c, dev_prefix))
+    for k in ("gam", "lam"):
+        check(k, abs(got[k] - float(ref[k])) / abs(float(ref[k])), gu.derived_tol(dev, k, tol, dev_c, dev_prefix))
     for oname in ("sim", "gam", "lam"):
-        ga, ra = np.array(got[f"dtok_{oname}"], dtype=np.float64), np.array(ref[f"dtok_{oname}"], dtype=np.float64)
+        bound = gu.derived_tol(dev, f"dtok_{oname}", tol, dev_c, dev_prefix)
+        if full:
+            ga, ra = torch.stack(got[f"dtok_full_{oname}"]).clone(), torch.stack(ref[f"dtok_full_{oname}"]).clone()
+        else:
+            ga, ra = (torch.from_numpy(np.array(x[f"dtok_{oname}"], dtype=np.float64)) for x in (got, ref))
         if oname == "lam":
             for m, sidx in flips:
                 ga[m, sidx] = 0.0
                 ra[m, sidx] = 0.0
-        e = gu.rel_err(ga, ra)
-        errs[f"dtok_{oname}"] = e
-        assert e < tol, (label, f"dtok_{oname}", e)
+        e2, emax = _full_err(ga, ra)
+        check(f"dtok_{oname}", e2, bound)
+        if full:
+            check(f"dtok_{oname}", emax, MAXABS_FACTOR * bound, "maxabs")
         for key in [k for k in ref if k.startswith(f"dpar_{oname}/")]:
             name = key.split("/", 1)[1]
             if float(np.asarray(ref[key])[0]) < 1e-12:
                 assert key not in got or got[key][0] < 1e-6, (label, key)
                 continue
             assert key in got, (label, key, "gradient missing")
-            e = gu.rel_err(got[key], ref[key])
-            errs[key] = e
-            ptol = gu.param_tol(name, oname, tol)
-            if oname == "lam" and flips:
-                mods = {"DAS_r": 0, "DAS_n": 1, "DAS_t": 2}
-                hit = [mods[k] for k in mods if k in name]
-                if hit and any(m == hit[0] for m, _ in flips):
-                    ptol = max(ptol, 0.25)   # one flipped sample carries O(1/B) of this modality's gradient
-            assert e < ptol, (label, key, e)
+            ptol = gu.derived_tol(dev, key, tol, dev_c, dev_prefix)
+            hit = [m for n_, m in (("DAS_r", 0), ("DAS_n", 1), ("DAS_t", 2)) if n_ in name]
+            if oname == "lam" and hit and any(m == hit[0] for m, _ in flips):
+                # a flipped sample point of this modality is in the sum and cannot be taken out of a parameter gradient:
+                # it carries O(1/B) of it; the bound is what the same event costs the reference's own bf16 run
+                ptol = max(ptol, float(dev[dev_prefix + key])) if dev is not None and dev_prefix + key in dev else ptol
+            fkey = key.replace("dpar_", "dpar_full_")
+            if full and fkey in ref and fkey in got:
+                e2, emax = _full_err(got[fkey], ref[fkey])
+                check(key, e2, ptol)
+                check(key, emax, MAXABS_FACTOR * ptol, "maxabs")
+            else:
+                check(key, gu.rel_err(got[key], ref[key]), ptol)
+    # the per-quantity bound allows dev_c x the reference's own loss (two samples of the same rounding noise rarely differ by
+    # more); on the whole the CUDA path must not be worse than the reference's run at this precision
+    if len(ratios) >= 5:
+        med = float(np.median(ratios))
+        errs["median_err_over_reference_dev"] = med
+        if report is not None:
+            report["median(err/ref_dev)"] = (med, 1.0)
+        assert med <= 1.0, (label, "median err / reference deviation over %d derived-bound quantities" % len(ratios), med)
     return errs

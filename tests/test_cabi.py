@@ -44,3 +44,21 @@ def test_product_path_refuses_cpu_tensors():
     x = torch.randn(2, 129, 64)
     with pytest.raises(RuntimeError):
         sim(x[:, 1:], x[:, 1:], x[:, 1:], x[:, 0], x[:, 0], x[:, 0])
+
+
+def test_ctx_sizing_uses_the_dispatch_predicate():
+    """sig_ctx_bytes must size the ctx for the path the entry point will take (bf16 with d > 768 falls to the
+    SIMT path, which needs the larger buffer)."""
+    import __graft_entry__ as entry
+    entry.build()
+    from signal_b200 import lib
+    L_ = lib.load()
+    B, L = 16, 128
+    for d in (64, 512, 768):
+        tc = L_.sig_ctx_bytes(lib.CTX_ALIGN, B, L, d, lib.SIG_BF16, 0)
+        simt = L_.sig_ctx_bytes(lib.CTX_ALIGN, B, L, d, lib.SIG_BF16, lib.FLAG_FORCE_SIMT)
+        assert 0 < tc and 0 < simt and simt == L_.sig_ctx_bytes(lib.CTX_ALIGN, B, L, d, lib.SIG_F32, 0)
+    for d in (832, 1024):
+        assert L_.sig_ctx_bytes(lib.CTX_ALIGN, B, L, d, lib.SIG_BF16, 0) == L_.sig_ctx_bytes(lib.CTX_ALIGN, B, L, d, lib.SIG_F32, 0)
+    # L != 128 never runs on the tensor-core path either
+    assert L_.sig_ctx_bytes(lib.CTX_ALIGN, B, 64, 512, lib.SIG_BF16, 0) == L_.sig_ctx_bytes(lib.CTX_ALIGN, B, 64, 512, lib.SIG_F32, 0)

@@ -20,108 +20,122 @@ def _harness():
     return gpu_harness
 
 
+# How the exceptions to the flat tolerances are bounded (no hand-set numbers):
+#  * fp32: every golden file stores ``dev32/<quantity>``, the deviation of the reference's own fp32 run from its fp64 run
+#    (make_golden.py); a quantity's bound is max(1e-4, FP32_DEV_C x that) -- gpu_harness.compare_records.  Live-oracle
+#    comparisons (B=128) derive the same record on the spot from an fp32 and an fp64 run of the oracle.
+#  * bf16: ``bf16dev_<case>.npz`` stores what the reference's own bf16-autocast run loses against its fp64 run on the same
+#    bf16-rounded tokens: per-quantity deviations, selection flips, LAM outlier samples.  The CUDA path must stay within
+#    max(2e-2, BF16_DEV_C x the deviation of the reference's own bf16 run) per quantity -- both are samples of the same
+#    rounding noise, so a factor 2 either way is chance -- while the MEDIAN of err / reference-deviation over all those
+#    quantities must be <= 1: on the whole at least as close to the fp64 truth as the reference's reduced-precision run
+#    (gpu_harness.compare_records).  It must flip no more mask entries than the reference does, and show at most BF16_FLIP_FRAC of the reference's count of LAM outlier samples (the reference's bf16 run puts
+#    EVERY sample over 2e-2; see the generator's log lines in tests/golden/make_golden.py).
+FP32_DEV_C = 3.0
+BF16_DEV_C = 2.0
+BF16_FLIP_FRAC = 0.25
+BF16_CASES = gu.BF16_CASES
+SMALL_BF16 = [n for n, c in BF16_CASES.items() if c["B"] <= 8]
+FULL_BF16 = [n for n, c in BF16_CASES.items() if c["B"] == 128]
+
+
+def _report(label, rep):
+    """one line per comparison that used more than half of its bound (visible with pytest -s / in the log on failure)"""
+    tight = sorted(((e / b, k, e, b) for k, (e, b) in rep.items() if b > 0 and e / b > 0.5), reverse=True)[:6]
+    if tight:
+        print(f"[{label}] closest to their bounds:", [(k, "%.2e/%.2e" % (e, b)) for _, k, e, b in tight])
+
+
 @pytest.mark.parametrize("packed", [True, False])
 @pytest.mark.parametrize("name", list(gu.CASES))
 def test_fp32_matches_reference_golden(name, packed):
     h = _harness()
     c = gu.CASES[name]
     got = h.cuda_record(c, torch.float32, packed=packed)
-    h.compare_records(got, gu.load(name), FP32_TOL, ref_masks_key="masks32", label=name)
+    ref = gu.load(name)
+    rep = {}
+    h.compare_records(got, ref, FP32_TOL, ref_masks_key="masks32", label=name, dev=ref, dev_prefix="dev32/", dev_c=FP32_DEV_C, report=rep)
+    _report(name, rep)
 
 
-def _oracle_record(c, sim_p, al_p, toks, cot):
-    sim_p = {k: v.clone().requires_grad_(True) for k, v in sim_p.items()}
-    al_p = {k: v.clone().requires_grad_(True) for k, v in al_p.items()}
-    toks = [t.clone().float().requires_grad_(True) for t in toks]
-    out, gam, lam, masks = so.head_forward(sim_p, al_p, toks, c["k"], c["h"], c["w"], c["keep_ratio"])
-    rec = {"sim_out": out.detach().numpy(), "masks": np.stack([m[..., 0].numpy().astype(np.uint8) for m in masks]),
-           "gam": gam.item(), "lam": lam.item()}
-    named = [("SIM." + k, p) for k, p in sim_p.items()] + [("AlignM." + k, p) for k, p in al_p.items()]
-    for oname, J in {"sim": (out * cot).sum(), "gam": gam, "lam": lam}.items():
-        grads = torch.autograd.grad(J, toks + [p for _, p in named], retain_graph=True, allow_unused=True)
-        gt = [torch.zeros_like(t) if g is None else g for t, g in zip(toks, grads[:3])]
-        rec[f"dtok_{oname}"] = gu.project_tokens(gt, c["d"])
-        for (key, _), g in zip(named, grads[3:]):
-            if g is None:
-                continue
-            rec[f"dpar_{oname}/{key}"] = gu.fingerprint_param(key, g)
-    return rec
+def _oracle_record(c, sim_p, al_p, toks, cot, dtype=torch.float32):
+    return _harness().oracle_record(c, sim_p, al_p, toks, cot, dtype)
 
 
-# bf16 cases.  LAM's deformable sampling is chaotic on white-noise token maps once the offset logits
-# are large (offset_gain >= 25 in the fp32 golden cases): a 0.01 perturbation of an offset logit --
-# the size of the bf16 rounding of the folded 1x1-conv weights -- moves a sample point by ~0.03
-# pixels across *uncorrelated* neighbouring tokens and changes d(loss)/d(offset), a cancelling sum
-# over d channels, by tens of percent.  Reduced-precision parity is therefore asserted where the
-# problem is well conditioned: default-scale offsets (gain 1) on white noise, and 2x larger offsets
-# on spatially smooth token maps (gain 6 already gives 3-5% there).  The fp32 tests above keep the
-# saturated white-noise cases at 1e-4.
-BF16_CASES = {
-    "rgbnt201_d512": dict(d=512, h=16, w=8, B=8, k=80, keep_ratio=None, gain=1.0, structured=False, seed=101, smooth=False),
-    "rgbnt201_d768": dict(d=768, h=16, w=8, B=8, k=80, keep_ratio=None, gain=1.0, structured=False, seed=313, smooth=False),
-    "vehicle_d512": dict(d=512, h=8, w=16, B=8, k=112, keep_ratio=None, gain=1.0, structured=False, seed=212, smooth=False),
-    "smooth_gain2_d512": dict(d=512, h=16, w=8, B=8, k=80, keep_ratio=None, gain=2.0, structured=False, seed=515, smooth=True),
-    "smooth_gain2_vehicle_d768": dict(d=768, h=8, w=16, B=6, k=64, keep_ratio=0.5, gain=2.0, structured=False, seed=616, smooth=True),
-}
+def _live_dev32(lo, hi):
+    """dev32 record derived on the spot: the oracle's fp32 run against its fp64 run, on the full tensors"""
+    dev = {}
+    for k, v in hi.items():
+        if k in ("sim_out",):
+            dev["dev32/" + k] = gu.rel_err(lo[k], v)
+        elif k in ("gam", "lam"):
+            dev["dev32/" + k] = abs(lo[k] - v) / abs(v)
+        elif k.startswith("dtok_full_"):
+            a, b = torch.stack(lo[k]).double(), torch.stack(v).double()
+            dev["dev32/" + k.replace("_full", "")] = float((a - b).norm() / b.norm().clamp_min(1e-300))
+        elif k.startswith("dpar_full_") and float(v.abs().max()) > 0:
+            dev["dev32/" + k.replace("_full", "")] = float((lo[k].double() - v.double()).norm() / v.double().norm())
+    return dev
 
 
 def _bf16_inputs(c):
-    from signal_b200 import synthetic as syn
-    sim_p, al_p, toks, cot = gu.case_inputs(c)
-    if c.get("smooth"):
-        toks = syn.smooth_patches(toks, c["h"], c["w"])
-    return sim_p, al_p, [t.to(torch.bfloat16) for t in toks], cot
+    sim_p, al_p, _, cot = gu.case_inputs(c)
+    return sim_p, al_p, gu.bf16_case_tokens(c), cot
 
 
-@pytest.mark.parametrize("name", list(BF16_CASES))
+def _bf16_budget(name):
+    dev = gu.load("bf16dev_" + name)
+    return dev, int(dev["mask_flips"]), int(BF16_FLIP_FRAC * int(dev["lam_flip_samples"]))
+
+
+@pytest.mark.parametrize("name", SMALL_BF16 + FULL_BF16)
 def test_bf16_matches_oracle_on_rounded_inputs(name):
-    """bf16 tokens on the GPU vs the fp32 oracle fed the same bf16-rounded values."""
+    """bf16 tokens on the GPU vs the fp32 oracle fed the same bf16-rounded values (full gradient tensors); includes
+    BASELINE.json configs #2 and #3 at B=128 (grid 16x8 TOPK 80 at d=768 and d=512; grid 8x16 TOPK 112 with keep_ratio)."""
     h = _harness()
     c = BF16_CASES[name]
     sim_p, al_p, toks, cot = _bf16_inputs(c)
+    dev, flip_budget, lam_budget = _bf16_budget(name)
     got = h.cuda_record(c, torch.bfloat16, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
     ref = _oracle_record(c, sim_p, al_p, [t.float() for t in toks], cot)
     flips = int((got["masks"] != ref["masks"]).sum())
-    assert flips <= 2, f"{flips} mask flips vs the oracle on identical (bf16-rounded) inputs"
-    h.compare_records(got, ref, BF16_TOL, check_masks=False, label=name, lam_flip_robust=True)
+    assert flips <= flip_budget, f"{flips} mask flips vs the oracle on identical (bf16-rounded) inputs; the reference's own bf16 run flips {flip_budget}"
+    rep = {}
+    h.compare_records(got, ref, BF16_TOL, check_masks=False, label=name, dev=dev, dev_prefix="dev/", dev_c=BF16_DEV_C,
+                      lam_flip_budget=lam_budget, report=rep)
+    _report(name, rep)
 
 
-@pytest.mark.parametrize("d,hw,k", [(512, (16, 8), 80), (768, (16, 8), 80)])
-def test_full_batch_b128_matches_oracle(d, hw, k):
-    """BASELINE.json config #2 size (B=128) in fp32 against the oracle."""
+@pytest.mark.parametrize("d,hw,k,keep", [(512, (16, 8), 80, None), (768, (16, 8), 80, None), (512, (8, 16), 112, 0.75)])
+def test_full_batch_b128_matches_oracle(d, hw, k, keep):
+    """BASELINE.json config #2 / #3 sizes (B=128) in fp32 against the oracle, full gradient tensors; the per-quantity
+    bound is derived from the oracle's own fp32-vs-fp64 deviation on these inputs."""
     h = _harness()
-    c = dict(d=d, h=hw[0], w=hw[1], B=128, k=k, keep_ratio=None, gain=30.0, structured=False, seed=900 + d)
+    c = dict(d=d, h=hw[0], w=hw[1], B=128, k=k, keep_ratio=keep, gain=30.0, structured=False, seed=900 + d + hw[0])
     sim_p, al_p, toks, cot = gu.case_inputs(c)
     got = h.cuda_record(c, torch.float32, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
-    ref = _oracle_record(c, sim_p, al_p, toks, cot)
+    ref32 = _oracle_record(c, sim_p, al_p, toks, cot)
+    ref = _oracle_record(c, sim_p, al_p, toks, cot, torch.float64)
     flips = int((got["masks"] != ref["masks"]).sum())
     assert flips == 0, f"{flips} mask flips at B=128"
-    h.compare_records(got, ref, FP32_TOL, check_masks=False, label=f"B128 d{d}")
+    rep = {}
+    h.compare_records(got, ref, FP32_TOL, check_masks=False, label=f"B128 d{d}", dev=_live_dev32(ref32, ref), dev_prefix="dev32/",
+                      dev_c=FP32_DEV_C, report=rep)
+    _report(f"B128 d{d} {hw}", rep)
 
 
-@pytest.mark.parametrize("name", list(BF16_CASES))
+@pytest.mark.parametrize("name", SMALL_BF16)
 def test_bf16_tensor_core_path_vs_simt_path(name):
     """Same bf16 inputs through the tcgen05 path and through the fp32 SIMT kernels (FORCE_SIMT)."""
     from signal_b200 import lib
     h = _harness()
     c = BF16_CASES[name]
     sim_p, al_p, toks, cot = _bf16_inputs(c)
+    dev, _, lam_budget = _bf16_budget(name)
     fast = h.cuda_record(c, torch.bfloat16, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
     slow = h.cuda_record(c, torch.bfloat16, flags=lib.FLAG_FORCE_SIMT, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
-    h.compare_records(fast, slow, BF16_TOL, check_masks=True, label=name + " tc-vs-simt", lam_flip_robust=True)
-
-
-def test_bf16_full_batch_b128_matches_oracle():
-    """BASELINE.json config #2 (B=128, bf16, d=768) against the fp32 oracle on the rounded inputs."""
-    h = _harness()
-    c = dict(d=768, h=16, w=8, B=128, k=80, keep_ratio=None, gain=1.0, structured=False, seed=4242)
-    sim_p, al_p, toks, cot = gu.case_inputs(c)
-    toks = [t.to(torch.bfloat16) for t in toks]
-    got = h.cuda_record(c, torch.bfloat16, sim_p=sim_p, al_p=al_p, toks=toks, cot=cot)
-    ref = _oracle_record(c, sim_p, al_p, [t.float() for t in toks], cot)
-    flips = int((got["masks"] != ref["masks"]).sum())
-    assert flips <= 4, f"{flips} mask flips at B=128 bf16"
-    h.compare_records(got, ref, BF16_TOL, check_masks=False, label="B128 d768 bf16", lam_flip_robust=True)
+    h.compare_records(fast, slow, BF16_TOL, check_masks=True, label=name + " tc-vs-simt", dev=dev, dev_prefix="dev/", dev_c=BF16_DEV_C,
+                      lam_flip_budget=lam_budget)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])

@@ -9,8 +9,10 @@ from oracle import signal_oracle as so
 
 # fp64: the restatement must agree with the fp64 run of the reference code to rounding
 # (the reference keeps fp32 islands even when run in fp64 -- the offset range tensor,
-# DAS.py:144, its LayerNorm, useA.py:420-423, and ``torch.det(G.float())``, volume.py:57 --
-# hence 5e-6, not 1e-12).  fp32: 1e-4, the parity tolerance.
+# DAS.py:144, and its LayerNorm, useA.py:420-423 -- hence 5e-6, not 1e-12; the third island,
+# ``torch.det(G.float())`` at volume.py:57, is lifted by the golden generator for its fp64 run).
+# fp32: 1e-4, the parity tolerance, or 3x what the reference's OWN fp32 run loses against its
+# fp64 run on that quantity where that is more (``dev32/<key>`` in the golden file).
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 5e-6), (torch.float32, 1e-4)])
 @pytest.mark.parametrize("name", list(gu.CASES))
 def test_oracle_matches_reference_golden(name, dtype, tol):
@@ -38,7 +40,8 @@ def test_oracle_matches_reference_golden(name, dtype, tol):
     for oname, J in objs.items():
         grads = torch.autograd.grad(J, toks + [p for _, p in named], retain_graph=True, allow_unused=True)
         gt = [torch.zeros_like(t) if g is None else g for t, g in zip(toks, grads[:3])]
-        assert gu.rel_err(gu.project_tokens(gt, c["d"]), rec[f"dtok_{oname}"]) < max(tol, 2e-7), oname
+        bound = max(tol, 2e-7) if dtype == torch.float64 else gu.derived_tol(rec, f"dtok_{oname}", tol)
+        assert gu.rel_err(gu.project_tokens(gt, c["d"]), rec[f"dtok_{oname}"]) < bound, oname
         for (key, _), g in zip(named, grads[3:]):
             rkey = f"dpar_{oname}/{key}"
             if g is None or float(g.abs().max()) == 0.0:
@@ -46,7 +49,8 @@ def test_oracle_matches_reference_golden(name, dtype, tol):
                 assert rkey not in rec or rec[rkey][0] < 1e-12, key
                 continue
             assert rkey in rec, key
-            assert gu.rel_err(gu.fingerprint_param(key, g), rec[rkey]) < gu.param_tol(key, oname, tol), (oname, key)
+            bound = tol if dtype == torch.float64 else gu.derived_tol(rec, rkey, tol)
+            assert gu.rel_err(gu.fingerprint_param(key, g), rec[rkey]) < bound, (oname, key)
 
 
 def test_topk_ties_pick_lowest_index():
