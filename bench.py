@@ -1,20 +1,21 @@
 #!/usr/bin/env python
 """Fusion-head fwd+bwd throughput on B200 (BASELINE.json metric) -- one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--dim 768] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config rgbnt201|rgbnt100|msvr310] [--dim 768|512]
+                    [--batch B] [--impl reference] [--exchange nvlink|nccl] [--check]
 
-One "step" = Select_Interactive_Module fwd + AlignmentM fwd (GAM + LAM) + backward to the three
-[B,129,d] token maps and all head parameters, on one synthetic RGBNT201 batch (B=128 per GPU,
-bf16 tokens, fp32 master parameters).  N>1 (launched by torchrun, one rank per GPU): the batch
-is sharded (weak scaling, B=128 per rank) and the head gradients are all-reduced with NCCL.
+One "step" = Select_Interactive_Module fwd + AlignmentM fwd (GAM + LAM) + backward to the three [B,129,d] token maps and
+all head parameters, on one synthetic batch (B per GPU, bf16 tokens, fp32 master parameters).  --config picks the
+reference configuration whose shape is run (configs/<NAME>/Signal.yml: grid, TOPK, loss weights); the default is the
+one BASELINE.json's metric is quoted on (RGBNT201, B=128, d=768).  N>1 (torchrun, one rank per GPU): the batch is sharded
+(weak scaling, B per rank; --strong: global batch 1024 split over the ranks) and the head gradients are averaged over
+the ranks inside the backward -- by the library's own NVLink kernel (sig_xchg_allreduce_f32) or by NCCL.
 
-value   : samples/s, tokens already resident in HBM, CUDA-event timed, max over ranks
-e2e     : same step through the nn.Module API starting from pinned HOST token maps (H2D copy of
-          the tokens and D2H read of out + losses inside the timed region)
-roofline: dominant phase of the step (CUDA events recorded by the library around each phase in a
-          profiled pass right after the timed region) against MEASURED_PEAKS.json
-cpu_baseline / --impl reference: the CPU oracle port (oracle/signal_oracle.py, torch CPU ops, all
-          host threads) on a bounded sample of the same workload.
+value   : samples/s, tokens already resident in HBM, CUDA-graph replay of the FusionHead step, CUDA events, max over ranks
+variants: the same step eager through FusionHead, and eager through the reference's call sequence SIM(...); AlignM(...)
+e2e     : the step from pinned HOST token maps (H2D of the tokens, D2H of out + losses inside the timed region)
+roofline: dominant kernel (CUDA events around each launch in a profiled pass) against MEASURED_PEAKS.json
+cpu_baseline / --impl reference: the CPU oracle port (oracle/signal_oracle.py, torch CPU ops) on the host cores.
 """
 import argparse
 import json
@@ -29,51 +30,60 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fusion_head_fwd_bwd_samples_per_s"
 UNIT = "samples/s"
-B_PER_GPU = 128
 L = 128
-GRID = (16, 8)
-TOPK = 80
 NSETS = 4            # token sets rotated through the timed region (4 x 76 MB > 126 MB L2)
-W_GAM, W_LAM = 0.2, 0.2   # configs/RGBNT201/Signal.yml:9-10
+
+# configs/<NAME>/Signal.yml of the reference: INPUT.SIZE_TRAIN / 16 -> grid, MODEL.TOPK, Gram_Loss_weight, PAT_Loss_weight,
+# SOLVER.IMS_PER_BATCH; "batch" is what BASELINE.json's configs quote (B=128 on one B200; MSVR310: the YAML's 64)
+CONFIGS = {
+    "rgbnt201": dict(name="RGBNT201", grid=(16, 8), topk=80, w_gam=0.2, w_lam=0.2, batch=128, ref="configs/RGBNT201/Signal.yml:9-12,17"),
+    "rgbnt100": dict(name="RGBNT100", grid=(8, 16), topk=112, w_gam=0.1, w_lam=0.1, batch=128, ref="configs/RGBNT100/Signal.yml:9-12,17"),
+    "msvr310": dict(name="MSVR310", grid=(8, 16), topk=64, w_gam=0.2, w_lam=0.01, batch=64, ref="configs/MSVR310/Signal.yml:9-12,17,38"),
+}
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return {"hbm": j["hbm_gbs"], "tensor_burst": j["bf16_tflops"], "tensor": j["bf16_tflops_sustained"], "src": "measured"}
-    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+        return {"hbm": j["hbm_gbs"], "tensor_burst": j["bf16_tflops"], "tensor": j["bf16_tflops_sustained"], "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
-def workload_name(d):
-    return f"RGBNT201 fusion head (SIM+GAM+LAM) fwd+bwd, B={B_PER_GPU}/GPU, 3x129 tokens, d={d}, grid 16x8, TOPK={TOPK}, bf16"
+def workload_name(cfg, d, B):
+    return (f"{cfg['name']} fusion head (SIM+GAM+LAM) fwd+bwd, B={B}/GPU, 3x129 tokens, d={d}, grid {cfg['grid'][0]}x{cfg['grid'][1]}, "
+            f"TOPK={cfg['topk']}, bf16")
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port)
 # ---------------------------------------------------------------------------------------------
-def cpu_step_fn(d, B, seed=1234):
+def cpu_step_fn(cfg, d, B, seed=1234, fwd_only=False):
     import torch
     from oracle import signal_oracle as so
     from signal_b200 import synthetic as syn
-    sim_p = {k: v.requires_grad_(True) for k, v in syn.make_params(syn.sim_param_shapes(d), seed).items()}
-    al_p = {k: v.requires_grad_(True) for k, v in syn.make_params(syn.align_param_shapes(d), seed + 1).items()}
-    toks = [t.to(torch.bfloat16).float().requires_grad_(True) for t in syn.make_tokens(B, d, seed=seed + 2)]
+    sim_p = {k: v.requires_grad_(not fwd_only) for k, v in syn.make_params(syn.sim_param_shapes(d), seed).items()}
+    al_p = {k: v.requires_grad_(not fwd_only) for k, v in syn.make_params(syn.align_param_shapes(d), seed + 1).items()}
+    toks = [t.to(torch.bfloat16).float().requires_grad_(not fwd_only) for t in syn.make_tokens(B, d, seed=seed + 2)]
     cot = syn.make_cotangent(B, d, seed=seed + 3)
     leaves = toks + [p for p in sim_p.values()] + [p for p in al_p.values()]
 
     def step():
-        out, gam, lam, _ = so.head_forward(sim_p, al_p, toks, TOPK, GRID[0], GRID[1])
-        loss = (out * cot).sum() + W_GAM * gam + W_LAM * lam
+        if fwd_only:
+            with torch.no_grad():
+                so.head_forward(sim_p, al_p, toks, cfg["topk"], cfg["grid"][0], cfg["grid"][1])
+            return
+        out, gam, lam, _ = so.head_forward(sim_p, al_p, toks, cfg["topk"], cfg["grid"][0], cfg["grid"][1])
+        loss = (out * cot).sum() + cfg["w_gam"] * gam + cfg["w_lam"] * lam
         torch.autograd.grad(loss, leaves, allow_unused=True)
     return step
 
 
-def time_cpu(d, B, steps, warmup):
+def time_cpu(cfg, d, B, steps, warmup, threads=None, fwd_only=False):
     import torch
-    cores = os.cpu_count() or 1
+    cores = threads or (os.cpu_count() or 1)
     torch.set_num_threads(cores)
-    step = cpu_step_fn(d, B)
+    step = cpu_step_fn(cfg, d, B, fwd_only=fwd_only)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -83,73 +93,138 @@ def time_cpu(d, B, steps, warmup):
     return B * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
-def run_reference(args):
+def run_reference(args, cfg):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference is pure Python and
+    /root/reference does not travel).  Honours --steps / --warmup; the batch per step is the arm's B when the whole run
+    fits the time budget, else the largest power-of-two slice that does (stated in `sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Bs = 32
-    steps = max(1, min(args.steps, 6))
-    warmup = max(1, min(args.warmup, 2))
-    val, ms, cores = time_cpu(args.dim, Bs, steps, warmup)
-    sample = f"B={Bs} slice of the workload per step, {warmup} warm-up + {steps} timed fwd+bwd steps, fp32, torch CPU ops"
+    import torch
+    d = args.dim
+    B = args.batch or cfg["batch"]
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget = float(os.environ.get("SIG_REF_BUDGET_S", "150"))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # probe: one step at B=8 -> seconds per sample (the oracle is linear in B apart from the B x B GAM grid)
+    probe = cpu_step_fn(cfg, d, 8)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    per_sample = (time.perf_counter() - t0) / 8
+    Bs = B
+    while Bs > 8 and per_sample * Bs * (steps + warmup) > budget:
+        Bs //= 2
+    val, ms, cores = time_cpu(cfg, d, Bs, steps, warmup)
+    one = time_cpu(cfg, d, min(Bs, 16), 2, 1, threads=1)
+    c1 = time_cpu(CONFIGS["rgbnt201"], 768, 8, 5, 2, fwd_only=True)
+    sample = (f"B={Bs} per step ({'the full batch' if Bs == B else 'a slice of the B=%d batch: the full one exceeds the %.0f s budget' % (B, budget)}), "
+              f"{warmup} warm-up + {steps} timed fwd+bwd steps, fp32, torch CPU ops, {cores} threads")
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.dim), "note": "CPU oracle port of the reference modules (the reference is "
-                   "pure Python and /root/reference does not travel to the GPU box)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(cfg, d, B), "global_batch": B, "parallelism": "cpu",
+                   "note": "CPU oracle port of the reference modules, one host process whatever --gpus says"},
+        "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "one_thread": {"value": round(one[0], 2), "unit": UNIT, "cores": 1, "sample": f"B={min(Bs, 16)}, 1 warm-up + 2 timed fwd+bwd steps"},
+                         "config1_cpu_fwd_b8": {"value": round(c1[0], 2), "unit": UNIT, "ms_per_step": round(c1[1], 2), "cores": c1[2],
+                                                "sample": "BASELINE.json configs[0]: forward only, fp32, B=8, d=768, grid 16x8, TOPK=80, torch.no_grad(), 2 warm-up + 5 timed"}},
+        "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
-# clocks sampler
+# clocks sampler: NVML in-process (brackets warm-up + timed region), nvidia-smi as a fall-back
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.mx, self.power = [], set(), None, []
+        self.stop_flag = False
+        self.src = "nvml"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._loop_nvml, daemon=True)
         except Exception:
-            self.proc = None
+            self.nv = None
+            self.src = "nvidia-smi"
+            self.index = index
+            self.th = threading.Thread(target=self._loop_smi, daemon=True)
+        self.mark = None
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
+
+    def _loop_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                c = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                p = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.sm.append((time.perf_counter(), c))
+                self.power.append(p)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def _loop_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in proc.stdout:
+            if self.stop_flag:
+                break
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.sm.append((time.perf_counter(), float(f[0])))
+                self.mx = float(f[1])
+                self.power.append(float(f[6]))
+            except Exception:
                 continue
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(n)
+        proc.terminate()
+
+    def mark_timed(self):
+        self.mark = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag = True
+        self.th.join(timeout=2)
+        allc = sorted(c for _, c in self.sm)
+        timed = sorted(c for t, c in self.sm if self.mark is not None and t >= self.mark)
+        med = lambda v: v[len(v) // 2] if v else None
+        return {"sm_mhz": med(timed) if timed else med(allc), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(allc), "samples_in_timed_region": len(timed), "sm_mhz_warmup_and_timed": med(allc),
+                "power_w_max": round(max(self.power), 1) if self.power else None, "source": self.src}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -162,7 +237,6 @@ def phase_work(B, d, s=2):
     T = 3 * L * d            # token elements per sample
     gemm = 3 * 2 * L * d * d * B                                   # folded 1x1 conv, three modalities
     return {
-        # phase: (bound, work [bytes for hbm, flops for tensor], kernel)
         "lam_offsetnet_fwd": ("tensor", gemm, "pair_gemm_kernel (cta_group::2, 256x256 units, K-major x K-major)  H = X W'^T + b'"),
         "lam_offsetnet_bwd_dx": ("tensor", gemm, "pair_gemm_kernel (K-major x MN-major)  dX = dH W' (+GAM rows, + SIM's k-blocks under FusionHead)"),
         "lam_offsetnet_bwd_dw": ("tensor", gemm, "pair_gemm_kernel (MN-major x MN-major)  dW' = dH^T X (split-K)"),
@@ -192,7 +266,7 @@ def ncu_traffic():
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-def run_gpu(args):
+def run_gpu(args, cfg):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as entry
@@ -207,8 +281,6 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         opts = None
         if os.environ.get("SIG_NCCL_PRIO", "1") != "0":
-            # the gradient exchange runs next to GPU-filling kernels: NCCL's CTAs must be dispatched as soon as an
-            # SM has room, not after the compute kernels launched before them have drained
             opts = dist.ProcessGroupNCCL.Options()
             opts.is_high_priority_stream = True
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
@@ -216,21 +288,36 @@ def run_gpu(args):
         entry.build()
     if world > 1:
         dist.barrier()
-    from signal_b200 import lib, modules as M, synthetic as syn
+    from signal_b200 import lib, modules as M, parallel, synthetic as syn
     lib.load()
 
-    d, B = args.dim, B_PER_GPU
+    if args.check:
+        if world < 2:
+            raise SystemExit("bench.py --check needs --gpus >= 2 under torchrun")
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import dp_worker
+        dp_worker.check_exchange(dev, rank, world)
+        dp_worker.check_head(dev, rank, world)
+        if rank == 0:
+            print(json.dumps({"check": "ok", "n_gpus": world, "what": "NVLink exchange kernel == ncclAllReduce; exchanged head gradients == mean of the "
+                              "shard-local gradients (tests/dp_worker.py)"}), flush=True)
+        torch.cuda.synchronize()
+        os._exit(0)
+
+    d = args.dim
+    B = args.batch or cfg["batch"]
+    if args.strong and world > 1:
+        B = max(1, 1024 // world)
+    GRID, TOPK, W_GAM, W_LAM = cfg["grid"], cfg["topk"], cfg["w_gam"], cfg["w_lam"]
+    sampler = ClockSampler(local) if rank == 0 else None      # brackets warm-up + timed region
+
     sim = M.Select_Interactive_Module(d, k=TOPK)
     al = M.AlignmentM(d, GRID[0], GRID[1])
     sim.load_state_dict(syn.make_params(syn.sim_param_shapes(d), 1234))
     al.load_state_dict(syn.make_params(syn.align_param_shapes(d), 1235))
     sim, al = sim.to(dev), al.to(dev)
     params = [p for p in list(sim.parameters()) + list(al.parameters())]
-    # each backward returns its parameter gradients as views of a flat fp32 arena (FusionHead: one arena for both
-    # modules, exchanged in two pieces inside the backward; separate module calls: one arena per module)
-
-    from signal_b200 import parallel
-    ncoll = [0]     # collectives issued by the last step
+    ncoll = [0]     # exchange calls issued by the last step
 
     def allreduce_grads():
         if args.allreduce and not overlap:
@@ -247,18 +334,23 @@ def run_gpu(args):
 
     head = M.FusionHead(sim, al) if args.fused else None
     overlap = head is not None and world > 1 and args.allreduce and args.overlap
-    if overlap:   # pieces of the gradient arenas are all-reduced inside the backward as soon as they are final
-        nsync = [0]
+    exchange = None
+    nsync = [0]
+    if overlap:   # pieces of the gradient arena are averaged over the ranks inside the backward as soon as they are final
+        if args.exchange == "nvlink":
+            exchange = parallel.GradExchange(head.grad_numel(), dev)
+            head.grad_arena = exchange.arena
 
-        skip = int(os.environ.get("SIG_SYNC_SKIP", "0"))   # (diagnostic bit mask: leave out piece 0/1/2 of the exchange)
-
-        def _sync(flat):
-            nsync[0] += 1
-            if not (skip >> (nsync[0] - 1)) & 1:
+            def _sync(flat):
+                nsync[0] += 1
+                exchange.allreduce(flat)
+        else:
+            def _sync(flat):
+                nsync[0] += 1
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         head.grad_sync = _sync
 
-    def fwd_bwd(toks):
+    def fwd_bwd(toks, use_head=True):
         patches = [t[:, 1:] for t in toks]
         cls = [t[:, 0] for t in toks]
         if args.only == "sim":   # (diagnostic) one module only
@@ -269,9 +361,9 @@ def run_gpu(args):
             gam, lam = al(*patches, stage="together_CLS_Patch")
             torch.autograd.backward([gam, lam], [wg, wl])
             return cot, gam, lam
-        if head is not None:     # one call: AlignM on a side stream next to SIM, one token-gradient writer
+        if head is not None and use_head:     # one call: AlignM on a side stream next to SIM, one token-gradient writer
             out, gam, lam = head(*patches, *cls, stage="together_CLS_Patch")
-        else:                    # the reference's two consecutive module calls (make_model.py:191,205)
+        else:                                 # the reference's two consecutive module calls (make_model.py:191,205)
             out = sim(*patches, *cls)
             gam, lam = al(*patches, stage="together_CLS_Patch")
         if overlap:
@@ -281,13 +373,16 @@ def run_gpu(args):
             ncoll[0] = nsync[0]
         return out, gam, lam
 
-    def step(i):
-        toks = dev_sets[i % NSETS]
+    def clear_grads(toks):
         for t in toks:
             t.grad = None
         for p in params:
             p.grad = None
-        res = fwd_bwd(toks)
+
+    def eager_step(i, use_head=True):
+        toks = dev_sets[i % NSETS]
+        clear_grads(toks)
+        res = fwd_bwd(toks, use_head)
         if world > 1:
             allreduce_grads()
         return res
@@ -297,27 +392,43 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    sync_all()
-    graph_launches = None
-    if args.graph:
-        # capture one CUDA graph per token set (static inputs); replay = the same module calls,
-        # without per-launch host work.  The library is capturable: no syncs, no allocations.
-        graphs = []
+    def capture_graphs():
+        graphs, nl = [], None
         for k in range(NSETS):
-            for t in dev_sets[k]:
-                t.grad = None
-            for p in params:
-                p.grad = None
+            clear_grads(dev_sets[k])
             g = torch.cuda.CUDAGraph()
             lb = lib.launch_count()
             with torch.cuda.graph(g):
                 fwd_bwd(dev_sets[k])
                 if world > 1 and args.allreduce_in_graph:
                     allreduce_grads()
-            graph_launches = lib.launch_count() - lb
+            nl = lib.launch_count() - lb
             graphs.append((g, parallel.grad_arenas(params)))
+        return graphs, nl
+
+    def timed(step_fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for i in range(n):
+            step_fn(i)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        eager_step(i)
+    sync_all()
+    graph_launches = None
+    step = eager_step
+    if args.graph:
+        # one CUDA graph per token set (static inputs); replay = the same module calls without per-launch host work.
+        # The library is capturable: no syncs, no allocations; the exchange kernel / NCCL calls are captured too.
+        graphs, graph_launches = capture_graphs()
 
         def step(i):
             g, arenas = graphs[i % NSETS]
@@ -325,27 +436,52 @@ def run_gpu(args):
             if world > 1 and not args.allreduce_in_graph and args.allreduce and not overlap:
                 ncoll[0] = parallel.allreduce_arenas(arenas, world)
 
-        for i in range(max(args.warmup, 3)):
+        for i in range(W):
             step(i)
         sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
+    if sampler:
+        sampler.mark_timed()
+    ms_total = timed(step, args.steps)
     launches = lib.launch_count() - l0 if graph_launches is None else graph_launches * args.steps
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- N > 1: the same step without any gradient exchange -> what the exchange costs on top of the compute
+    exposed_us = None
+    if world > 1 and overlap and args.graph:
+        hook, arena = head.grad_sync, head.grad_arena
+        head.grad_sync, head.grad_arena = None, None
+        overlap_saved, overlap = overlap, False
+        args_allreduce, args.allreduce = args.allreduce, False
+        g2, _ = capture_graphs()
+
+        def step_nox(i):
+            g2[i % NSETS][0].replay()
+        for i in range(W):
+            step_nox(i)
+        ms_nox = timed(step_nox, args.steps) / args.steps
+        exposed_us = round((ms_step - ms_nox) * 1e3, 1)
+        head.grad_sync, head.grad_arena, overlap, args.allreduce = hook, arena, overlap_saved, args_allreduce
+        del g2
+
+    # ---- variants (N = 1): the same step without graph replay -- through FusionHead, and through the reference's own
+    # call sequence SIM(...); AlignM(...) (make_model.py:191,205)
+    variants = None
+    if world == 1 and not args.no_variants and not args.only:
+        nv = max(3, min(args.steps, 50))
+        variants = {}
+        for name, use_head in (("eager_fusion_head", True), ("eager_two_module_calls", False)):
+            if use_head and head is None:
+                continue
+            fn = lambda i, u=use_head: eager_step(i, u)
+            for i in range(3):
+                fn(i)
+            ms = timed(fn, nv) / nv
+            variants[name] = {"value": round(B / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 4), "steps": nv,
+                              "api": "FusionHead(SIM, AlignM)(...)" if use_head else "SIM(...); AlignM(...)  (reference call sequence)",
+                              "launch": "eager (host-bound: ctypes calls + torch allocations per step)"}
 
     # ---- e2e: pinned HOST token maps -> device -> the same module calls -> results back on the host, every step.
     # Double buffered: the H2D copy of step i+1 runs on a copy stream while step i computes; each step ends
@@ -364,10 +500,7 @@ def run_gpu(args):
         ev.record(main_stream)
 
     def run_stage(k):
-        for t in stage[k]:
-            t.grad = None
-        for p_ in params:
-            p_.grad = None
+        clear_grads(stage[k])
         res = fwd_bwd(stage[k])
         if world > 1:
             allreduce_grads()
@@ -382,10 +515,7 @@ def run_gpu(args):
     runners = []
     for k in range(2):
         if args.graph:
-            for t in stage[k]:
-                t.grad = None
-            for p_ in params:
-                p_.grad = None
+            clear_grads(stage[k])
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 res = fwd_bwd(stage[k])
@@ -426,6 +556,7 @@ def run_gpu(args):
             done[k].synchronize()                       # this step's results are on the host
 
     e2e_run(4)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
     e2e_run(e2e_steps)
@@ -443,6 +574,7 @@ def run_gpu(args):
         prof_steps = 10
         if head is not None:
             head.grad_sync = None            # rank-local pass: no collectives
+            head.grad_arena = None
 
         def seq_step(toks):
             patches = [t[:, 1:] for t in toks]
@@ -457,10 +589,7 @@ def run_gpu(args):
         lib.profile_enable(True)
         for i in range(prof_steps):          # local work only: the other ranks are not in this pass
             toks = dev_sets[i % NSETS]
-            for t in toks:
-                t.grad = None
-            for p_ in params:
-                p_.grad = None
+            clear_grads(toks)
             seq_step(toks)
         torch.cuda.synchronize()
         lib.profile_enable(False)
@@ -474,12 +603,16 @@ def run_gpu(args):
             if k not in phases or phases[k] <= 0:
                 continue
             sec = phases[k] * 1e-6
+            # single launches timed on their own (eager pass, GPU otherwise idle, clocks at their maximum): the BURST
+            # tensor peak is the denominator; the fraction of the sustained peak is given beside it
             if bound == "hbm":
                 ach, peak, unit = w / sec / 1e9, pk["hbm"], "GB/s"
+                extra = {}
             else:
-                ach, peak, unit = w / sec / 1e12, pk["tensor"], "TFLOP/s"
-            kernels[k] = {"kernel": kname, "bound": bound, "us": phases[k], "achieved": round(ach, 1), "peak": peak, "unit": unit,
-                          "frac": round(ach / peak, 4), "traffic": traffic.get(k)}
+                ach, peak, unit = w / sec / 1e12, pk["tensor_burst"], "TFLOP/s"
+                extra = {"frac_of_sustained_peak": round(ach / pk["tensor"], 4)}
+            kernels[k] = dict({"kernel": kname, "bound": bound, "us": phases[k], "achieved": round(ach, 1), "peak": peak, "unit": unit,
+                               "frac": round(ach / peak, 4), "traffic": traffic.get(k)}, **extra)
         # dominant kernel of the step: the tcgen05 GEMM of the LAM offset net (three launches per step: H = X W'^T,
         # dX = dH W', dW' = dH^T X -- one template, one algorithmic work figure)
         gem = [kernels[k] for k in ("lam_offsetnet_fwd", "lam_offsetnet_bwd_dx", "lam_offsetnet_bwd_dw") if k in kernels]
@@ -489,8 +622,10 @@ def run_gpu(args):
             ach = w / (us * 1e-6) / 1e12
             tr = [g["traffic"] for g in gem if g["traffic"]]
             roof = {"kernel": "pair_gemm_kernel (tcgen05 cta_group::2, 256x256 units; LAM offset-net GEMMs: H = X W'^T, dX = dH W', dW' = dH^T X)",
-                    "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tensor"], "unit": "TFLOP/s", "frac": round(ach / pk["tensor"], 4),
-                    "traffic": round(sum(tr) / len(tr)) if tr else None, "peak_source": pk["src"] + " (sustained cuBLAS bf16; burst %.0f)" % pk["tensor_burst"],
+                    "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tensor_burst"], 4),
+                    "frac_of_sustained_peak": round(ach / pk["tensor"], 4),
+                    "traffic": round(sum(tr) / len(tr)) if tr else None,
+                    "peak_source": pk["src"] + ": burst cuBLAS bf16 %.0f TFLOP/s (kernel timed alone at full clocks); sustained %.0f" % (pk["tensor_burst"], pk["tensor"]),
                     "launches_per_step": len(gem), "avg_launch_us": round(us, 1),
                     "algorithmic_flops_per_launch": w, "share_of_step": round(sum(g["us"] for g in gem) / (ms_step * 1e3), 3),
                     "how": "CUDA events around each launch on its stream, modules run back to back (eager), mean of %d steps; "
@@ -501,26 +636,47 @@ def run_gpu(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            Bs = 32
-            v, ms, cores = time_cpu(d, Bs, 3, 1)
+            Bs = min(B, 128)
+            v, ms, cores = time_cpu(cfg, d, Bs, 3, 1)
+            one = time_cpu(cfg, d, 16, 2, 1, threads=1)
+            c1 = time_cpu(CONFIGS["rgbnt201"], 768, 8, 5, 2, fwd_only=True)
             cpu = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"B={Bs} slice of the workload, 1 warm-up + 3 timed fwd+bwd steps of the CPU oracle port, fp32"}
+                   "sample": f"B={Bs} per step, 1 warm-up + 3 timed fwd+bwd steps of the CPU oracle port (torch CPU ops, fp32, all host threads)",
+                   "one_thread": {"value": round(one[0], 2), "unit": UNIT, "cores": 1, "sample": "B=16, 1 warm-up + 2 timed fwd+bwd steps"},
+                   "config1_cpu_fwd_b8": {"value": round(c1[0], 2), "unit": UNIT, "ms_per_step": round(c1[1], 2), "cores": c1[2],
+                                          "sample": "BASELINE.json configs[0]: forward only, fp32, B=8, d=768, grid 16x8, TOPK=80, torch.no_grad(), 2 warm-up + 5 timed"}}
+        if world > 1:
+            if not args.allreduce:
+                xchg = "none (--no-allreduce)"
+            elif overlap:
+                how = ("sig_xchg_allreduce_f32: the library's own two-shot all-reduce kernel over NVLink symmetric memory"
+                       + (" with NVLS multimem.ld_reduce / multimem.st" if exchange is not None and exchange.multicast else " (peer loads/stores)")) \
+                    if exchange is not None else "ncclAllReduce(avg)"
+                xchg = (f"{how}, {ncoll[0]} calls per step on a communication stream inside the backward, each as soon as its piece of the flat "
+                        f"gradient arena is final (FusionHead.grad_sync)" + (", captured in the step graph" if args.graph else ""))
+            else:
+                xchg = f"ncclAllReduce(avg) of the flat gradient arenas after the backward, {ncoll[0]} per step"
+        else:
+            xchg = "n/a"
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(d), "global_batch": B * world, "parallelism": f"dp{world}",
-                       "launch": "cuda_graph_replay" if args.graph else "eager", "api": "FusionHead(SIM, AlignM)" if args.fused else "SIM(...); AlignM(...)", "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
-                       "grad_allreduce": (f"NCCL all-reduce (avg) of the flat head-gradient arenas, {ncoll[0]} collectives per step, "
-                                          + ("issued inside the backward on a communication stream as each piece becomes final (FusionHead.grad_sync), " if overlap else "after the backward, ")
-                                          + ("captured in the step graph" if args.graph and (args.allreduce_in_graph or overlap) else "eager")) if world > 1 else "n/a"},
+            "config": {"workload": workload_name(cfg, d, B), "global_batch": B * world, "parallelism": f"dp{world}", "reference_config": cfg["ref"],
+                       "loss_weights": {"gam": W_GAM, "lam": W_LAM},
+                       "launch": "cuda_graph_replay" if args.graph else "eager", "api": "FusionHead(SIM, AlignM)" if args.fused else "SIM(...); AlignM(...)",
+                       "l2": f"inputs rotate over {NSETS} token sets ({NSETS * 3 * B * (L + 1) * d * 2 / 1e6:.0f} MB > 126 MB L2)",
+                       "grad_exchange": xchg},
             "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "how": "pinned host tokens, H2D of step i+1 on a copy stream under step i's compute (2 staging buffers), "
                            + ("graph replay of the module calls" if args.graph else "eager module calls")
-                           + ", D2H of out + losses and a host wait every step"},
+                           + ", D2H of out + losses and a host wait every step"
+                           + ("; every rank feeds its own tokens over the host's shared PCIe / memory paths, which bounds this number at N > 1" if world > 1 else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "variants": variants,
+            "exposed_exchange_us_per_step": exposed_us,
             "kernels": kernels,
             "phases_us": phases,
             "cpu_baseline": cpu,
@@ -539,23 +695,31 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="rgbnt201", choices=sorted(CONFIGS), help="reference configuration whose head shape is run")
     ap.add_argument("--dim", type=int, default=768, choices=[512, 768])
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the configuration's, 128 / 64)")
+    ap.add_argument("--strong", action="store_true", help="N>1: global batch 1024 split over the ranks (BASELINE.json configs[4])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exchange", default=os.environ.get("SIG_EXCHANGE", "nvlink"), choices=["nvlink", "nccl"],
+                    help="N>1: gradient exchange inside the backward: the library's NVLink kernel or ncclAllReduce")
+    ap.add_argument("--check", action="store_true", help="N>1: numerical check of the data-parallel path (no timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the eager variants")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager module calls instead of CUDA-graph replays")
     ap.add_argument("--allreduce-eager", dest="allreduce_in_graph", action="store_false",
                     help="(diagnostic) issue the NCCL all-reduce after each graph replay instead of capturing it in the step graph")
     ap.add_argument("--only", default="", choices=["", "sim", "align"], help="(diagnostic) time one module's fwd+bwd only")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="(diagnostic) all-reduce after the backward instead of inside it (FusionHead.grad_sync)")
-    ap.add_argument("--no-allreduce", dest="allreduce", action="store_false", help="(diagnostic) skip the gradient all-reduce at N>1")
+    ap.add_argument("--no-allreduce", dest="allreduce", action="store_false", help="(diagnostic) skip the gradient exchange at N>1")
     ap.add_argument("--no-fused", dest="fused", action="store_false",
                     help="call SIM and AlignM one after the other instead of through signal_b200.FusionHead")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
     else:
-        run_gpu(args)
+        run_gpu(args, cfg)
 
 
 if __name__ == "__main__":
