@@ -380,7 +380,7 @@ struct GemmProblem {
 // release the accumulator with a remote arrive on the leader's tmem_empty barrier.
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool AMN, bool BMN>
-__global__ void __launch_bounds__(tc::kThreads, 1) pair_gemm_kernel(const __grid_constant__ TcKernelParams p, const int nstages) {
+__global__ void __maxnreg__(SIG_TC_MAXNREG) pair_gemm_kernel(const __grid_constant__ TcKernelParams p, const int nstages) {
   using P1 = GemmProblem<BN, AMN, BMN, 1>;
   using P2 = GemmProblem<BN, AMN, BMN, 2>;   // unit decode with 256-row M tiles
   constexpr int kABytes = tc::kATileBytes, kBBytes = (BN / 2) * BK * 2, kStageBytes = kABytes + kBBytes;

@@ -80,8 +80,15 @@ __device__ __forceinline__ float4 epi_get(const float* scratch, int lane, int i)
 long long* stamps_ptr();   // nullptr unless SIG_TC_STAMPS=1 (then a 16-slot device buffer, allocated once)
 #define SIG_STAMP(i) do { if (stamps && blockIdx.x == 0) stamps[i] = clock64(); } while (0)
 
+// Register budget: kThreads (384) x 160 registers = 61 440 of the SM's 65 536, which leaves exactly one 128-thread,
+// 32-register CTA of the gradient-exchange kernel (xchg.cu) room on the same SM -- that kernel must run NEXT TO these
+// persistent kernels, not between them.  (The compiler's free choice was 161-162: a 384-thread CTA then owns the whole
+// register file and nothing can be co-resident.)
+#ifndef SIG_TC_MAXNREG
+#define SIG_TC_MAXNREG 160
+#endif
 template <int BN, int MT, class Problem>
-__global__ void __launch_bounds__(kThreads, 1) pipeline_kernel(const __grid_constant__ typename Problem::Params p, const int nstages,
+__global__ void __maxnreg__(SIG_TC_MAXNREG) pipeline_kernel(const __grid_constant__ typename Problem::Params p, const int nstages,
                                                                long long* __restrict__ stamps) {
   if (threadIdx.x == 0) SIG_STAMP(0);
   using C = Cfg<BN, MT>;

@@ -17,15 +17,21 @@
 // Per rank and direction this moves count*4*(N-1)/N bytes over NVLink (P2P) or count*4/N through the switch (NVLS).
 // Each CTA synchronises only with the CTA of the same index on the peers (own flag slots, monotonically increasing
 // epochs kept in device memory, so CUDA-graph replays need no host state and the flags are never reset).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sig {
 namespace {
 
 constexpr int kXchgMaxRanks = 8;
-constexpr int kXchgMaxCtas = 64;
-constexpr int kXchgThreads = 512;
-constexpr int kXchgUnroll = 4;
+constexpr int kXchgMaxCtas = 1024;
+// 128 threads x 32 registers = 4096 registers per CTA: exactly what a 384-thread, 160-register tcgen05 GEMM CTA
+// (tc_pipeline.cuh: SIG_TC_MAXNREG) leaves free on its SM, and no shared memory -- so one CTA of this kernel runs NEXT TO
+// every persistent compute CTA of the backward (more per SM next to the lighter kernels).
+constexpr int kXchgThreads = 128;
+constexpr int kXchgUnroll = 4;      // multimem path: 4 x 16 B per thread in flight
+constexpr int kXchgUnrollP2P = 2;   // peer-load path (accumulator + incoming value per slot): 2 x 16 B
 // flag region of one rank (uint32): [cta][src rank] arrival flags, then [cta] the rank-private epoch counters
 constexpr int kXchgFlagWords = kXchgMaxCtas * kXchgMaxRanks + kXchgMaxCtas;
 #ifndef SIG_XCHG_SPIN_CLOCKS
@@ -82,7 +88,7 @@ __device__ __forceinline__ void xchg_barrier(const XchgArgs& a, int cta, uint32_
 }
 
 template <bool kMultimem>
-__global__ void __launch_bounds__(kXchgThreads) xchg_allreduce_kernel(const XchgArgs a, size_t off, size_t n4, float scale) {
+__global__ void __launch_bounds__(kXchgThreads, 16) xchg_allreduce_kernel(const XchgArgs a, size_t off, size_t n4, float scale) {
   const int cta = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
   __shared__ uint32_t epoch_s;
   uint32_t* epoch_p = a.flags[a.rank] + kXchgMaxCtas * kXchgMaxRanks + cta;
@@ -93,17 +99,18 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_allreduce_kernel(const Xchg
 
   const size_t per = (n4 + a.world - 1) / a.world;
   const size_t lo = min(n4, (size_t)a.rank * per), hi = min(n4, lo + per);
-  const size_t chunk = (size_t)kXchgThreads * kXchgUnroll;
+  constexpr int U = kMultimem ? kXchgUnroll : kXchgUnrollP2P;
+  const size_t chunk = (size_t)kXchgThreads * U;
   for (size_t base = lo + (size_t)cta * chunk; base < hi; base += (size_t)G * chunk) {
-    float4 acc[kXchgUnroll];
+    float4 acc[U];
     if (kMultimem) {
 #pragma unroll
-      for (int u = 0; u < kXchgUnroll; ++u) {
+      for (int u = 0; u < U; ++u) {
         const size_t i = base + (size_t)u * kXchgThreads + tid;
         if (i < hi) acc[u] = multimem_ld_reduce(a.mc + off + 4 * i);
       }
 #pragma unroll
-      for (int u = 0; u < kXchgUnroll; ++u) {
+      for (int u = 0; u < U; ++u) {
         const size_t i = base + (size_t)u * kXchgThreads + tid;
         if (i < hi) {
           acc[u].x *= scale; acc[u].y *= scale; acc[u].z *= scale; acc[u].w *= scale;
@@ -112,23 +119,23 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_allreduce_kernel(const Xchg
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < kXchgUnroll; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       // fixed summation order (rank 0, 1, ...) on every owner: the result does not depend on who reduces
       for (int p = 0; p < a.world; ++p) {
-        float4 v[kXchgUnroll];
+        float4 v[U];
 #pragma unroll
-        for (int u = 0; u < kXchgUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
           const size_t i = base + (size_t)u * kXchgThreads + tid;
           if (i < hi) v[u] = ld_peer(a.buf[p] + off + 4 * i);
         }
 #pragma unroll
-        for (int u = 0; u < kXchgUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
           const size_t i = base + (size_t)u * kXchgThreads + tid;
           if (i < hi) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
         }
       }
 #pragma unroll
-      for (int u = 0; u < kXchgUnroll; ++u) {
+      for (int u = 0; u < U; ++u) {
         const size_t i = base + (size_t)u * kXchgThreads + tid;
         if (i < hi) {
           acc[u].x *= scale; acc[u].y *= scale; acc[u].z *= scale; acc[u].w *= scale;
@@ -160,9 +167,23 @@ int xchg_allreduce_f32(const sig_xchg_peers* pr, size_t off, size_t count, float
   a.rank = pr->rank;
   a.world = pr->world;
   if (count == 0) return 0;
-  if (ctas <= 0) ctas = 32;
+  if (ctas <= 0) ctas = device_num_sms();   // ONE CTA per SM: that is what fits next to a persistent GEMM CTA (a second wave
+                                            // would wait for room and then delay the next compute kernel -- measured)
   if (ctas > kXchgMaxCtas) ctas = kXchgMaxCtas;
   const size_t n4 = count / 4;
+  // Co-residency with the compute kernels: an SM runs CTAs of two kernels at the same time only if both accept its
+  // current L1 / shared-memory split.  The persistent GEMM and ring kernels carve out (nearly) all of it as shared
+  // memory, so this kernel -- which uses none -- must ask for the same carve-out or it waits for whole SMs to drain.
+  static const int carve = [] {
+    const char* e = getenv("SIG_XCHG_CARVEOUT");
+    return e ? atoi(e) : (int)cudaSharedmemCarveoutMaxShared;
+  }();
+  if (carve >= 0) {
+    if (first_launch_on_device(reinterpret_cast<const void*>(xchg_allreduce_kernel<true>))) {
+      cudaFuncSetAttribute(xchg_allreduce_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(xchg_allreduce_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+  }
   // (no programmatic dependent launch: the kernel is ordered behind the gradient producers by events on other streams)
   if (a.mc) xchg_allreduce_kernel<true><<<ctas, kXchgThreads, 0, s>>>(a, off, n4, scale);
   else      xchg_allreduce_kernel<false><<<ctas, kXchgThreads, 0, s>>>(a, off, n4, scale);

@@ -61,7 +61,7 @@ def _head_arena(d: int, device, flat: Optional[torch.Tensor] = None):
     for i, v in zip(order, sv):
         pg_s[i] = v
     cut = (3 * d + 3) // 4 * 4 + 2 * d * d
-    return flat, pg_s, pg_a, cut
+    return flat, pg_s, pg_a, cut, sum(((int(torch.Size(s).numel()) + 3) // 4 * 4) for s in sshapes)
 
 
 def _sim_arena(d: int, device):
@@ -551,10 +551,12 @@ class HeadFunction(torch.autograd.Function):
         sync = event[3] if len(event) > 3 else None     # (comm stream, early event, AlignM event, pieces) of FusionHead
         if event[1] is None:
             sync = None
-        if sync is not None and sync[3] == 2:
-            flat_h, pg_s, pg_a, cut_h = _head_arena(d, dev, event[4] if len(event) > 4 else None)
+        if sync is not None and sync[3] in (2, 3):
+            # ONE arena [SIM late | SIM early | AlignM]; exchanged as 2 pieces ([early + AlignM], [late]: few calls, NCCL) or
+            # 3 pieces (early, AlignM, late: each as soon as it is final -- the NVLink kernel's calls are cheap)
+            flat_h, pg_s, pg_a, cut_h, cut2_h = _head_arena(d, dev, event[4] if len(event) > 4 else None)
             if not do_lam:
-                flat_h[cut_h:].zero_()
+                flat_h[cut2_h:].zero_()
         else:
             flat_s, pg_s, split_s = _sim_arena(d, dev)
             flat_a, pg_a = _arena(_align_grad_shapes(d), dev)
@@ -603,7 +605,11 @@ class HeadFunction(torch.autograd.Function):
             # ~25 us + 2.2 us/MB at N = 2); SIG_SYNC_CHUNKS=3: three collectives
             if sync is not None:
                 comm = sync[0]
-                if sync[3] != 2:
+                if sync[3] == 3:
+                    with torch.cuda.stream(comm):
+                        comm.wait_event(sync[1])          # (recorded on SIM's stream, which is ordered behind `main`)
+                        grad_sync(flat_h[cut_h:cut2_h])
+                elif sync[3] != 2:
                     with torch.cuda.stream(comm):
                         comm.wait_event(sync[1])
                         grad_sync(flat_s[split_s:])
@@ -618,6 +624,10 @@ class HeadFunction(torch.autograd.Function):
                     if sync[3] == 2:      # SIM's early part and AlignM's arena are adjacent: one collective, then the late part
                         comm.wait_event(sync[1])
                         grad_sync(flat_h[cut_h:])
+                        comm.wait_stream(hi)
+                        grad_sync(flat_h[:cut_h])
+                    elif sync[3] == 3:
+                        grad_sync(flat_h[cut2_h:])
                         comm.wait_stream(hi)
                         grad_sync(flat_h[:cut_h])
                     else:

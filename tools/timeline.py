@@ -26,15 +26,22 @@ head = M.FusionHead(sim, al)
 if world > 1:
     marks, t0 = [], [None]
 
+    ex = None
+    if os.environ.get("SIG_EXCHANGE", "nvlink") == "nvlink":
+        from signal_b200 import parallel
+        ex = parallel.GradExchange(head.grad_numel(), dev)
+        head.grad_arena = ex.arena
+    xch = (lambda f: ex.allreduce(f)) if ex is not None else (lambda f: dist.all_reduce(f, op=dist.ReduceOp.AVG))
+
     def _sync(flat):      # torch-side external events: laid on the library's time line through the step-start mark
         if not torch.cuda.is_current_stream_capturing():
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            xch(flat)
             return
         a, b = torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)
         a.record()
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        xch(flat)
         b.record()
-        marks.append((f"allreduce_{flat.numel() * 4 / 1e6:.1f}MB", a, b))
+        marks.append((f"{'xchg' if ex is not None else 'allreduce'}_{flat.numel() * 4 / 1e6:.1f}MB", a, b))
     head.grad_sync = _sync
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 def fwd_bwd():
