@@ -247,6 +247,25 @@ int sig_volume3_bwd(const float* l, const float* v, const float* a, int B1, int 
                     const float* dvol, float* dl, float* dv, float* da,
                     void* ws, size_t ws_bytes, int device, void* stream);
 
+/* ---- inference tail -------------------------------------------------------------------
+ * sig_infer_features: make_model.py:284-290 -- feat[b] = [RGB_global | NI_global | TI_global | vars_total[b]] as fp32
+ *   [B, 6d]; normalize != 0: rows are L2-normalised (F.normalize, eps 1e-12; utils/metrics.py:266-268).  cls[m]: [B,d] views
+ *   (stride in elements), sim_out [B,3d] with leading dimension ld_sim, both of `dtype` (SIG_F32 | SIG_BF16).
+ * sig_euclidean_distmat: utils/metrics.py:494-501 -- dist[i,j] = |q_i|^2 + |g_j|^2 - 2 q_i.g_j (squared, fp32; the operations in
+ *   the reference's order: addmm_(beta=1, alpha=-2)); qf [nq,D], gf [ng,D], dist [nq,ng] contiguous fp32; ws: (nq+ng) floats.
+ * sig_rank_eval: utils/metrics.py:111-170 eval_func (market1501 protocol: gallery entries with the query's pid AND camid are
+ *   discarded; queries whose identity is absent from the valid gallery are skipped) -> cmc float32 [max_rank] (caller clips
+ *   max_rank to ng as the reference does), map_out double [2] = {mAP, number of valid queries}; ranking = stable ascending
+ *   order (ties -> lowest gallery index).  pids / camids int64 on the device.  stats: 3*nq doubles scratch; overflow: one
+ *   int, set to 1 if a query had more than 2048 matches (results then cover the first 2048). */
+int sig_infer_features(const void* const cls[3], const int64_t cls_stride_b[3], const void* sim_out, int64_t ld_sim, int dtype,
+                       int B, int d, int normalize, float* out, int device, void* stream);
+int sig_euclidean_distmat(const float* qf, const float* gf, int nq, int ng, int D, float* dist, void* ws, size_t ws_bytes,
+                          int device, void* stream);
+int sig_rank_eval(const float* dist, int64_t ld, const int64_t* q_pids, const int64_t* g_pids, const int64_t* q_camids,
+                  const int64_t* g_camids, int nq, int ng, int max_rank, float* cmc, double* map_out, double* stats, int* overflow,
+                  int device, void* stream);
+
 /* ---- data-parallel gradient exchange over NVLink peer memory ------------------------------
  * Replaces the DDP all-reduce of the head's gradients (engine/processor.py:100-105) by ONE kernel that needs no shared
  * memory, so it runs next to the persistent compute kernels of the backward instead of waiting for their SMs.

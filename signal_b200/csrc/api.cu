@@ -192,6 +192,34 @@ int sig_sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flag
 
 int sig_debug_tc_stamps(long long* out16) { return sig::tc_read_stamps(out16); }
 
+int sig_infer_features(const void* const cls[3], const int64_t cls_stride_b[3], const void* sim_out, int64_t ld_sim, int dtype, int B,
+                       int d, int normalize, float* out, int device, void* stream) {
+  SIG_ENTER(device);
+  if (!cls || !cls[0] || !cls[1] || !cls[2] || !cls_stride_b || !sim_out || !out) return SIG_ERR_NULL;
+  if (dtype != SIG_F32 && dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  if (B < 1 || d < 1) return SIG_ERR_SHAPE;
+  return sig::infer_features(cls, cls_stride_b, sim_out, ld_sim, dtype, B, d, normalize, out, (cudaStream_t)stream);
+}
+
+int sig_euclidean_distmat(const float* qf, const float* gf, int nq, int ng, int D, float* dist, void* ws, size_t ws_bytes, int device,
+                          void* stream) {
+  SIG_ENTER(device);
+  if (!qf || !gf || !dist || !ws) return SIG_ERR_NULL;
+  if (nq < 1 || ng < 1 || D < 1) return SIG_ERR_SHAPE;
+  if (ws_bytes < (size_t)(nq + ng) * sizeof(float)) return SIG_ERR_WORKSPACE;
+  return sig::euclidean_distmat(qf, gf, nq, ng, D, dist, static_cast<float*>(ws), (cudaStream_t)stream);
+}
+
+int sig_rank_eval(const float* dist, int64_t ld, const int64_t* q_pids, const int64_t* g_pids, const int64_t* q_camids,
+                  const int64_t* g_camids, int nq, int ng, int max_rank, float* cmc, double* map_out, double* stats, int* overflow,
+                  int device, void* stream) {
+  SIG_ENTER(device);
+  if (!dist || !q_pids || !g_pids || !q_camids || !g_camids || !cmc || !map_out || !stats || !overflow) return SIG_ERR_NULL;
+  if (nq < 1 || ng < 1 || max_rank < 1 || max_rank > ng || ld < ng) return SIG_ERR_SHAPE;
+  return sig::rank_eval(dist, ld, q_pids, g_pids, q_camids, g_camids, nq, ng, max_rank, cmc, map_out, stats, overflow,
+                        (cudaStream_t)stream);
+}
+
 size_t sig_xchg_flag_bytes(void) { return sig::xchg_flag_bytes(); }
 
 int sig_xchg_allreduce_f32(const sig_xchg_peers* peers, size_t off, size_t count, float scale, int ctas, int device, void* stream) {

@@ -51,6 +51,12 @@ inline void ensure_dyn_smem(K kernel, int bytes) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 int device_num_sms();   // multiprocessor count of the CURRENT device (cached per device)
+// infer.cu: inference tail (feature concat + L2 norm, euclidean distance matrix, CMC / mAP)
+int infer_features(const void* const cls[3], const int64_t cls_stride_b[3], const void* sim_out, int64_t ld_sim, int dtype, int B, int d,
+                   int normalize, float* out, cudaStream_t s);
+int euclidean_distmat(const float* qf, const float* gf, int nq, int ng, int D, float* dist, float* ws, cudaStream_t s);
+int rank_eval(const float* dist, int64_t ld, const int64_t* q_pids, const int64_t* g_pids, const int64_t* q_cams, const int64_t* g_cams,
+              int nq, int ng, int max_rank, float* cmc, double* map_out, double* stats, int* overflow, cudaStream_t s);
 // xchg.cu: in-place all-reduce of a symmetric fp32 arena over NVLink peer memory / NVLS
 size_t xchg_flag_bytes();
 int xchg_allreduce_f32(const sig_xchg_peers* peers, size_t off, size_t count, float scale, int ctas, cudaStream_t s);

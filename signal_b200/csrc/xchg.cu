@@ -33,7 +33,10 @@ constexpr int kXchgThreads = 128;
 constexpr int kXchgUnroll = 4;      // multimem path: 4 x 16 B per thread in flight
 constexpr int kXchgUnrollP2P = 2;   // peer-load path (accumulator + incoming value per slot): 2 x 16 B
 // flag region of one rank (uint32): [cta][src rank] arrival flags, then [cta] the rank-private epoch counters
-constexpr int kXchgFlagWords = kXchgMaxCtas * kXchgMaxRanks + kXchgMaxCtas;
+// ... then 16 words of phase time stamps of CTA 0's last call (%globaltimer, ns: start, after barrier A, after the data
+// loop, after barrier B) -- a measurement aid, read by tools/bench_xchg.py
+constexpr int kXchgStampWord = kXchgMaxCtas * kXchgMaxRanks + kXchgMaxCtas;
+constexpr int kXchgFlagWords = kXchgStampWord + 16;
 #ifndef SIG_XCHG_SPIN_CLOCKS
 #define SIG_XCHG_SPIN_CLOCKS 60000000000LL   /* ~30 s: a peer that never arrives traps instead of hanging the box */
 #endif
@@ -73,10 +76,10 @@ __device__ __forceinline__ void multimem_st(float* mc, const float4& v) {
 
 // All CTAs of index `cta` on all ranks meet here.  Thread t < world signals peer t and waits for peer t.
 __device__ __forceinline__ void xchg_barrier(const XchgArgs& a, int cta, uint32_t val) {
-  __syncthreads();
+  __syncthreads();   // every thread's data accesses of this CTA happen-before the signalling threads' release below
   if ((int)threadIdx.x < a.world) {
     const int peer = threadIdx.x;
-    __threadfence_system();
+    // (st.release.sys is cumulative over what bar.sync ordered before it: no separate fence.sys -- it measured ~3 us)
     st_release_sys(a.flags[peer] + cta * kXchgMaxRanks + a.rank, val);
     const uint32_t* mine = a.flags[a.rank] + cta * kXchgMaxRanks + peer;
     const long long t0 = clock64();
@@ -95,7 +98,17 @@ __global__ void __launch_bounds__(kXchgThreads, 16) xchg_allreduce_kernel(const 
   if (tid == 0) epoch_s = *epoch_p + 2;          // every call uses two flag values: e - 1 (barrier A) and e (barrier B)
   __syncthreads();
   const uint32_t e = epoch_s;
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.flags[a.rank] + kXchgStampWord);
+  auto stamp = [&](int i) {
+    if (cta == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      stamps[i] = t;
+    }
+  };
+  stamp(0);
   xchg_barrier(a, cta, e - 1);
+  stamp(1);
 
   const size_t per = (n4 + a.world - 1) / a.world;
   const size_t lo = min(n4, (size_t)a.rank * per), hi = min(n4, lo + per);
@@ -144,7 +157,9 @@ __global__ void __launch_bounds__(kXchgThreads, 16) xchg_allreduce_kernel(const 
       }
     }
   }
+  stamp(2);
   xchg_barrier(a, cta, e);
+  stamp(3);
   if (tid == 0) *epoch_p = e;
 }
 

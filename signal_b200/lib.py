@@ -77,7 +77,7 @@ EXPORTS = [
     "sig_sim_attn_fwd", "sig_sim_attn_bwd", "sig_align_fwd", "sig_align_bwd", "sig_das_fwd", "sig_das_bwd",
     "sig_volume3_ws_bytes", "sig_volume3_fwd", "sig_volume3_bwd",
     "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_profile_scope_begin", "sig_profile_scope_end", "sig_sim_dx_operands",
-    "sig_convert_half", "sig_xchg_flag_bytes", "sig_xchg_allreduce_f32",
+    "sig_convert_half", "sig_xchg_flag_bytes", "sig_xchg_allreduce_f32", "sig_infer_features", "sig_euclidean_distmat", "sig_rank_eval",
     "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd", "sig_bnneck_ws_bytes", "sig_bnneck_cls_fwd", "sig_bnneck_cls_bwd",
 ]
 
@@ -118,6 +118,9 @@ def load():
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
     lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
     lib.sig_sim_dx_operands.argtypes = [vp, i, i, i, i, u, P(vp), P(vp)]
+    lib.sig_infer_features.argtypes = [_VP3, _I64x3, vp, i64, i, i, i, i, vp, i, vp]
+    lib.sig_euclidean_distmat.argtypes = [vp, vp, i, i, i, vp, vp, sz, i, vp]
+    lib.sig_rank_eval.argtypes = [vp, i64, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, i, vp]
     lib.sig_xchg_flag_bytes.restype = sz
     lib.sig_xchg_flag_bytes.argtypes = []
     lib.sig_xchg_allreduce_f32.argtypes = [P(SigXchgPeers), sz, sz, C.c_float, i, i, vp]

@@ -72,6 +72,13 @@ class GradExchange:
         self._C = C
         dist.barrier(self.group)          # every rank's flag region is zero before anyone signals
 
+    def last_call_phases_us(self):
+        """(barrier A, data loop, barrier B) of CTA 0 in the last call, microseconds (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        words = int(self.lib.sig_xchg_flag_bytes()) // 4
+        st = self.buf[self.numel + words - 16: self.numel + words].view(torch.int64)[:4].tolist()
+        return tuple((st[i + 1] - st[i]) / 1e3 for i in range(3))
+
     def allreduce(self, piece: torch.Tensor, scale=None):
         """piece: a contiguous fp32 view inside ``self.arena``; averaged over the ranks in place, on the current stream."""
         from . import lib as L_

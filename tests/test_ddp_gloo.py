@@ -82,7 +82,12 @@ def test_head_arena_layout():
     back in the C structs' field order."""
     from signal_b200 import functional as F_
     d = 64
-    flat, pg_s, pg_a, cut = F_._head_arena(d, "cpu")
+    flat, pg_s, pg_a, cut, cut2 = F_._head_arena(d, "cpu")
+    assert cut2 == min((g.data_ptr() - flat.data_ptr()) // 4 for g in pg_a) and flat.numel() == F_.head_grad_numel(d)
+    own = torch.zeros(F_.head_grad_numel(d) + 64)           # a caller-owned arena (parallel.GradExchange) is carved the same way
+    flat2, pg_s2, pg_a2, _, _ = F_._head_arena(d, "cpu", own)
+    assert flat2.data_ptr() == own.data_ptr() and flat2.numel() == flat.numel()
+    assert [(g.data_ptr() - own.data_ptr()) for g in pg_s2 + pg_a2] == [(g.data_ptr() - flat.data_ptr()) for g in pg_s + pg_a]
     sshapes, ashapes = F_._SIM_GRAD_SHAPES(d), F_._align_grad_shapes(d)
     assert [tuple(g.shape) for g in pg_s] == [tuple(s) for s in sshapes]
     assert [tuple(g.shape) for g in pg_a] == [tuple(s) for s in ashapes]
@@ -108,7 +113,7 @@ def _worker_pieces(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from signal_b200 import functional as F_
     d = 64
-    flat, pg_s, pg_a, cut = F_._head_arena(d, "cpu")
+    flat, pg_s, pg_a, cut, _ = F_._head_arena(d, "cpu")
     g = torch.Generator().manual_seed(100 + rank)
     flat.copy_(torch.randn(flat.numel(), generator=g))
     mine = flat.clone()

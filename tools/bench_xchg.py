@@ -43,13 +43,26 @@ def main():
     for mc in (True, False):
         ex = parallel.GradExchange(n, dev, use_multicast=mc)
         ex.arena.normal_()
-        for ctas in (16, 32, 64, 148, 296, 444):
+        for ctas in (32, 148):
             ex.ctas = ctas
             us = timeit(lambda: [ex.allreduce(ex.arena[o:o + c]) for o, c in pieces])
             us1 = timeit(lambda: ex.allreduce(ex.arena[:16]))
+            ph1 = ex.last_call_phases_us()
+            dist.barrier()
+            ex.allreduce(ex.arena[cut:])
+            ph = ex.last_call_phases_us()
             if rank == 0:
                 print(f"  sig_xchg_allreduce_f32 {'multimem' if ex.multicast else 'peer ld/st'} ctas={ctas}: {us:.1f} us "
-                      f"({n * 4 / us / 1e3:.0f} GB/s algorithmic); 64-byte call {us1:.1f} us", flush=True)
+                      f"({n * 4 / us / 1e3:.0f} GB/s algorithmic); 64-byte call {us1:.1f} us; CTA 0 phases (barrier A, data, barrier B): "
+                      f"28.5 MB call {ph[0]:.1f} / {ph[1]:.1f} / {ph[2]:.1f} us, 64-byte call {ph1[0]:.1f} / {ph1[1]:.1f} / {ph1[2]:.1f} us", flush=True)
+        if mc:
+            for mb in (0.25, 1, 4, 16):
+                cnt = int(mb * (1 << 20) / 4) // 4 * 4
+                ex.ctas = 148
+                us = timeit(lambda: ex.allreduce(ex.arena[:cnt]))
+                ph = ex.last_call_phases_us()
+                if rank == 0:
+                    print(f"    size sweep {mb} MB: {us:.1f} us per call; phases {ph[0]:.1f} / {ph[1]:.1f} / {ph[2]:.1f}", flush=True)
     torch.cuda.synchronize()
     os._exit(0)
 
