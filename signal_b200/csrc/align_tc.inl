@@ -743,6 +743,8 @@ static int lam_backward_chain_tc(const AlignTcCtx& c, const TokPtrs3& tp, const 
 
 static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
                             bool eager, cudaStream_t s) {
+  const ScopedSmBudget sm_scope(align_sm_budget());   // (prof.h: leave SMs to SIM's concurrent chain)
+  const ScopedSmWaves wave_scope(align_sm_waves());
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);
@@ -871,6 +873,8 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
 
 static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, const float* dlosses,
                              const sig_token_grads* dtok, const sig_align_param_grads* dp, void* ctx, bool eager, cudaStream_t s) {
+  const ScopedSmBudget sm_scope(align_sm_budget());   // (prof.h: leave SMs to SIM's concurrent chain)
+  const ScopedSmWaves wave_scope(align_sm_waves());
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);
@@ -1048,6 +1052,9 @@ static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, i
     t.bn = (d % 256 == 0) ? 256 : 128;
     t.mt = 1;   // (mt = 2, 256 x 256 units, measured slower: the single TMEM buffer serialises the epilogue)
     t.pair = t.bn == 256 && tc_pair_enabled() && (!t.xa || (B % 2) == 0);   // (a pair covers two samples)
+    // the tail of the step: nothing of SIM's chain is left to make room for -- all SMs, one persistent wave
+    const ScopedSmBudget all_sms(1 << 20);
+    const ScopedSmWaves one_wave(1);
     SIG_TRY(tc_gemm(t, s));
   }
   {

@@ -81,6 +81,36 @@ int device_num_sms() {
   return n;
 }
 
+static thread_local int g_sm_budget = 0;
+int sm_budget() {
+  const int n = device_num_sms();
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+}
+ScopedSmBudget::ScopedSmBudget(int n) : prev(g_sm_budget) { if (n > 0) g_sm_budget = n; }
+ScopedSmBudget::~ScopedSmBudget() { g_sm_budget = prev; }
+static thread_local int g_sm_waves = 1;
+int sm_waves() { return g_sm_waves; }
+ScopedSmWaves::ScopedSmWaves(int k) : prev(g_sm_waves) { if (k > 0) g_sm_waves = k; }
+ScopedSmWaves::~ScopedSmWaves() { g_sm_waves = prev; }
+int align_sm_waves() {
+  static const int v = [] {
+    const char* e = getenv("SIG_ALIGN_WAVES");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+int align_sm_budget() {
+  static const int v = [] {
+    // default: AlignM's persistent kernels leave ~1/5 of the SMs to the short kernels of SIM's chain, which runs next to
+    // them and is the critical path of the fused step (measured at B = 128, d = 768: 148 -> 0.605, 132 -> 0.595,
+    // 116 -> 0.589, 100 -> 0.607, 84 -> 0.642 ms/step); the dX GEMM at the tail of the step always takes all SMs
+    const char* e = getenv("SIG_ALIGN_SMS");
+    return e ? atoi(e) : (device_num_sms() * 116) / 148;
+  }();
+  return v;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("SIG_PDL");

@@ -38,4 +38,28 @@ struct Fork {
   }
 };
 Fork get_fork(int slot);   // returns a disabled Fork (ok() == false) when SIG_FORK=0
+
+int device_num_sms();
+// SM budget of the calling thread's current entry point (prof.cu): persistent kernels size their grids with
+// sm_budget() instead of the device's SM count.  sig_align_fwd / sig_align_bwd run with SIG_ALIGN_SMS (environment,
+// default: all) so that AlignM's long persistent kernels leave SMs to the short kernels of SIM's dependency chain, which
+// runs on another stream and is the critical path of the fused step.
+int sm_budget();
+struct ScopedSmBudget {
+  int prev;
+  explicit ScopedSmBudget(int n);
+  ~ScopedSmBudget();
+};
+int align_sm_budget();   // SIG_ALIGN_SMS or 0 (= all)
+// Waves: a persistent kernel holds its SMs until it is done, so a short high-priority kernel of another stream waits for
+// the whole kernel.  With sm_waves() = k > 1 the calling entry point launches its persistent kernels with k x as many
+// CTAs (each doing 1/k of the work): SMs are handed back k times as often and the hardware scheduler can slot the other
+// stream's CTAs in between (it dispatches pending CTAs of the higher-priority stream first).
+int sm_waves();
+struct ScopedSmWaves {
+  int prev;
+  explicit ScopedSmWaves(int k);
+  ~ScopedSmWaves();
+};
+int align_sm_waves();    // SIG_ALIGN_WAVES or 1
 }  // namespace sig

@@ -96,7 +96,7 @@ int stage_override() {
   return v;
 }
 
-int num_sms() { return device_num_sms(); }
+int num_sms() { return sm_budget(); }
 
 }  // namespace tc
 
@@ -529,7 +529,7 @@ static int launch_pair(const TcKernelParams& p, int units, int kpu, cudaStream_t
   const int max_smem = stages * kStageBytes + 1024 + 256 + tc::kEpiBytes;
   ensure_dyn_smem(kernel, max_smem);
   if (units <= 0) return 0;
-  const int npairs_max = (tc::num_sms() - tc::sm_reserve()) / 2;
+  const int npairs_max = (tc::num_sms() - tc::sm_reserve()) / 2 * sm_waves();
   const int npairs = units < npairs_max ? units : npairs_max;
   const int per_cta = kpu * (int)ceil_div(units, npairs);
   if (per_cta < stages) stages = per_cta < 2 ? 2 : per_cta;

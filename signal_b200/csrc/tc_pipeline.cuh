@@ -245,7 +245,8 @@ int launch(const typename Problem::Params& p, int units, cudaStream_t s, int kbl
   // Kernels with at least one unit per SM are persistent and would hold every SM for their whole run; leaving a
   // few SMs free (SIG_TC_RESERVE, default in tc_gemm.cu) lets the short kernels of a concurrent stream -- the other
   // module's dependency chain -- keep moving.  These kernels are bound by the L2 operand stream, not by SM count.
-  const int grid = units < num_sms() ? units : num_sms() - sm_reserve();
+  const int cap = (num_sms() - sm_reserve()) * sm_waves();
+  const int grid = units < cap ? units : cap;
   int stages = Cfg<BN, MT>::kStages;
   const int per_cta = kblocks_per_unit * (int)ceil_div(units, grid);
   if (per_cta < stages) stages = per_cta < 2 ? 2 : per_cta;
