@@ -137,6 +137,105 @@ def run_reference(args, cfg):
 
 
 # ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: MSVR310 full train step (random-init ViT-B/16 backbone in stock PyTorch + the head)
+# ---------------------------------------------------------------------------------------------
+def _torch_triplet(feat, labels):
+    """soft-margin batch-hard triplet loss (layers/triplet_loss.py:16-31,51-104,121-135) in stock torch ops"""
+    import torch
+    import torch.nn.functional as F
+    d2 = (feat ** 2).sum(1, keepdim=True)
+    dist = (d2 + d2.t() - 2 * feat @ feat.t()).clamp(min=1e-12).sqrt()
+    same = labels[:, None] == labels[None, :]
+    ap = torch.where(same, dist, dist.new_full((), -1e30)).max(1)[0]
+    an = torch.where(same, dist.new_full((), 1e30), dist).min(1)[0]
+    return F.soft_margin_loss(an - ap, torch.ones_like(ap))
+
+
+def _torch_head(step, patches, cls):
+    """Comparison arm: the reference's head arithmetic in stock torch ops on the device (the oracle port, fp32 like the
+    reference's autocast islands) + torch's own cross entropy / the triplet restatement above."""
+    import torch.nn.functional as F
+    from oracle import signal_oracle as so
+    sim_p = dict(step.SIM.state_dict(keep_vars=True))
+    al_p = dict(step.AlignM.state_dict(keep_vars=True))
+    import torch
+    pf, cf = [p.float() for p in patches], [c.float() for c in cls]
+    # fp32 arithmetic (autocast off): under autocast torch would run these matmuls -- including the 1536-wide distance
+    # matrix of the triplet loss -- in half precision, which moves the loss by several percent; the B200 kernels
+    # accumulate in fp32, so the comparison arm does too
+    with torch.autocast("cuda", enabled=False):
+        out, _ = so.sim_forward(sim_p, pf, cf, step.cfg["topk"])
+        gam = so.gam_loss(pf, al_p["contra_temp"])
+        lam = so.lam_loss(al_p, pf, step.h, step.w)
+
+    def head_loss(score, feat, target, c):
+        with torch.autocast("cuda", enabled=False):
+            return c["w_id"] * F.cross_entropy(score.float(), target, label_smoothing=0.1) + c["w_tri"] * _torch_triplet(feat.float(), target)
+    return out.to(patches[0].dtype), gam, lam, head_loss
+
+
+def run_full_step(args, cfg):
+    """One complete training iteration of the reference's MSVR310 configuration (make_model.py:148-255, processor.py:165-261):
+    backbone (stock PyTorch, bf16 autocast) + fusion head + four BNNeck heads + ID/triplet/GAM/LAM losses + Adam; timed
+    with the B200 head and with a stock-PyTorch head (same backbone, same optimizer)."""
+    import torch
+    import __graft_entry__ as entry
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --full-step needs a CUDA device")
+    entry.build()
+    from signal_b200 import fullstep as fs, lib
+    lib.load()
+    dev = torch.device("cuda", 0)
+    B = args.batch or cfg["batch"]
+    H, W = cfg["grid"][0] * 16, cfg["grid"][1] * 16
+    g = torch.Generator().manual_seed(1234)
+    imgs = [torch.randn(B, 3, H, W, generator=g).to(dev) for _ in range(3)]
+    ids = 16                                                    # B / NUM_INSTANCE (4) identities per batch
+    target = (torch.arange(B) // (B // ids)).to(dev)
+    cam = torch.randint(0, 8, (B,), generator=g).to(dev)
+    out = {}
+    for arm, th in (("b200_head", None), ("torch_head", _torch_head)):
+        torch.manual_seed(1234)
+        step = fs.SignalTrainStep(cfg["grid"], cfg["topk"], 155, 8, 512, 0.25, 1.0, cfg["w_gam"], cfg["w_lam"], torch_head=th).to(dev)
+        opt = torch.optim.Adam([p for p in step.parameters() if p.requires_grad], lr=5e-6)
+
+        def it():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = step(imgs, target, cam)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(max(3, args.warmup)):
+            l0 = it()
+        torch.cuda.synchronize()
+        l_before = lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = max(3, min(args.steps, 30))
+        e0.record()
+        for _ in range(n):
+            loss = it()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out[arm] = {"ms_per_step": round(ms, 3), "samples_per_s": round(B / (ms * 1e-3), 1), "loss": round(float(loss), 5),
+                    "library_launches_per_step": (lib.launch_count() - l_before) // n, "steps": n}
+        del step, opt
+        torch.cuda.empty_cache()
+    line = {"metric": "full_train_step_samples_per_s", "value": out["b200_head"]["samples_per_s"], "unit": UNIT, "n_gpus": 1,
+            "ms_per_step": out["b200_head"]["ms_per_step"], "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{cfg['name']} full Signal train step: random-init ViT-B/16 backbone (stock PyTorch, bf16 autocast, one pass over 3x{B} "
+                                   f"{H}x{W} images) + fusion head (TOPK={cfg['topk']}, grid {cfg['grid'][0]}x{cfg['grid'][1]}) + 4 BNNeck heads + "
+                                   f"0.25*ID + 1.0*triplet per head + {cfg['w_gam']}*GAM + {cfg['w_lam']}*LAM + Adam, B={B}",
+                       "reference_config": cfg["ref"], "launch": "eager"},
+            "arms": out,
+            "speedup_of_the_step": round(out["torch_head"]["ms_per_step"] / out["b200_head"]["ms_per_step"], 3),
+            "note": "same backbone, same optimizer in both arms; torch_head = the reference's head algorithm in stock torch ops (oracle port) + "
+                    "torch cross entropy / triplet; the losses of the two arms agree to bf16 rounding (both printed)"}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
 # clocks sampler: NVML in-process (brackets warm-up + timed region), nvidia-smi as a fall-back
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -483,6 +582,23 @@ def run_gpu(args, cfg):
                               "api": "FusionHead(SIM, AlignM)(...)" if use_head else "SIM(...); AlignM(...)  (reference call sequence)",
                               "launch": "eager (host-bound: ctypes calls + torch allocations per step)"}
 
+        if head is not None:
+            # the same step through FusionHead.make_graphed: forward and backward graphs behind the ordinary autograd API
+            # (inputs are copied into the graphs' static buffers every call -- part of the measured time)
+            graphed = head.make_graphed(*dev_sets[0])
+
+            def gstep(i):
+                toks = dev_sets[i % NSETS]
+                clear_grads(toks)
+                out, gam, lam = graphed(*toks)
+                torch.autograd.backward([out, gam, lam], [cot, wg, wl])
+            for i in range(3):
+                gstep(i)
+            ms = timed(gstep, nv) / nv
+            variants["graphed_callable"] = {"value": round(B / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 4), "steps": nv,
+                                            "api": "FusionHead.make_graphed(...)(rgb, ni, ti); autograd.backward(...)",
+                                            "launch": "two CUDA graphs (forward, backward) replayed by autograd; inputs copied into static buffers"}
+
     # ---- e2e: pinned HOST token maps -> device -> the same module calls -> results back on the host, every step.
     # Double buffered: the H2D copy of step i+1 runs on a copy stream while step i computes; each step ends
     # with the D2H read of its fused feature + the two losses and a host-side wait for them.
@@ -703,6 +819,9 @@ def main():
     ap.add_argument("--exchange", default=os.environ.get("SIG_EXCHANGE", "nvlink"), choices=["nvlink", "nccl"],
                     help="N>1: gradient exchange inside the backward: the library's NVLink kernel or ncclAllReduce")
     ap.add_argument("--check", action="store_true", help="N>1: numerical check of the data-parallel path (no timing)")
+    ap.add_argument("--full-step", action="store_true",
+                    help="BASELINE.json configs[3]: time one complete training iteration (backbone + head + losses + Adam) with the B200 "
+                         "head and with a stock-PyTorch head (use with --config msvr310 --dim 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the eager variants")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager module calls instead of CUDA-graph replays")
@@ -718,6 +837,8 @@ def main():
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.full_step:
+        run_full_step(args, cfg)
     else:
         run_gpu(args, cfg)
 

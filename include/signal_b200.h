@@ -58,6 +58,11 @@ enum sig_ctx_kind { SIG_CTX_SIM = 0, SIG_CTX_ALIGN = 1, SIG_CTX_SELECT = 2, SIG_
  * skips it and applies d(loss)/d(lam) where the results are consumed.  Ignored on the fp32 SIMT path.  Only set it
  * when a backward call will follow (training). */
 #define SIG_FLAG_EAGER_BWD 2u
+/* sig_align_fwd / sig_align_bwd, tensor-core path: the caller runs SIM's calls concurrently on another stream
+ * (signal_b200.FusionHead).  AlignM's persistent GEMM / ring kernels then size their grids for SIG_ALIGN_SMS SMs
+ * (environment; default 116 of 148) instead of all of them, so the short kernels of SIM's dependency chain -- the critical
+ * path of the fused step -- find free SMs; the d(patches) GEMM at the tail of the backward always takes all SMs. */
+#define SIG_FLAG_SHARE_SMS 4u
 
 /* Three modality token maps, order RGB, NI, TI.
  * patch[m] -> element (b=0,l=0,c=0) of the [B,L,d] patch view, cls[m] -> (b=0,c=0)

@@ -305,8 +305,8 @@ def das_positions(o: Tensor) -> Tuple[Tensor, Tensor]:
     """
     B, Hk, Wk = o.shape
     t = torch.tanh(o)
-    ref_y = (torch.arange(Hk, dtype=o.dtype) + 0.5) / (Hk - 1.0) * 2.0 - 1.0
-    ref_x = (torch.arange(Wk, dtype=o.dtype) + 0.5) / (Wk - 1.0) * 2.0 - 1.0
+    ref_y = (torch.arange(Hk, dtype=o.dtype, device=o.device) + 0.5) / (Hk - 1.0) * 2.0 - 1.0
+    ref_x = (torch.arange(Wk, dtype=o.dtype, device=o.device) + 0.5) / (Wk - 1.0) * 2.0 - 1.0
     py = (t * (DAS_RANGE_FACTOR / (Hk - 1.0)) + ref_y[None, :, None]).clamp(-1.0, 1.0)
     px = (t * (DAS_RANGE_FACTOR / (Wk - 1.0)) + ref_x[None, None, :]).clamp(-1.0, 1.0)
     return py, px

@@ -749,6 +749,9 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
   if (tc_path_ok(tok, flags)) {
     if (!tc_strides_ok(tok)) return SIG_ERR_SHAPE;
     if (ctx_bytes < align_tc_ctx(nullptr, B, L, d).bytes) return SIG_ERR_WORKSPACE;
+    // SIG_FLAG_SHARE_SMS (FusionHead): SIM's chain runs next to this call on another stream -- leave it SMs (prof.h)
+    const ScopedSmBudget sm_scope((flags & SIG_FLAG_SHARE_SMS) ? align_sm_budget() : 0);
+    const ScopedSmWaves wave_scope((flags & SIG_FLAG_SHARE_SMS) ? align_sm_waves() : 1);
     return align_forward_tc(tok, p, h, w, do_lam, losses, ctx, do_lam && (flags & SIG_FLAG_EAGER_BWD), s);
   }
   if (ctx_bytes < align_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
@@ -806,6 +809,8 @@ int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int 
       if (dtok->patch_stride_b[m] != dtok->patch_stride_b[0] || dtok->patch_stride_l[m] != dtok->patch_stride_l[0])
         return SIG_ERR_SHAPE;
     if (dtok->fuse_pds && !do_lam) return SIG_ERR_SHAPE;   // the fused operands ride on the LAM dX GEMM
+    const ScopedSmBudget sm_scope((flags & SIG_FLAG_SHARE_SMS) ? align_sm_budget() : 0);
+    const ScopedSmWaves wave_scope((flags & SIG_FLAG_SHARE_SMS) ? align_sm_waves() : 1);
     return align_backward_tc(tok, p, h, w, do_lam, dlosses, dtok, dp, ctx, do_lam && (flags & SIG_FLAG_EAGER_BWD), s);
   }
   if (dtok->fuse_pds) return SIG_ERR_SHAPE;   // only the tensor-core path can take SIM's operands

@@ -743,8 +743,6 @@ static int lam_backward_chain_tc(const AlignTcCtx& c, const TokPtrs3& tp, const 
 
 static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
                             bool eager, cudaStream_t s) {
-  const ScopedSmBudget sm_scope(align_sm_budget());   // (prof.h: leave SMs to SIM's concurrent chain)
-  const ScopedSmWaves wave_scope(align_sm_waves());
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);
@@ -873,8 +871,6 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
 
 static int align_backward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, const float* dlosses,
                              const sig_token_grads* dtok, const sig_align_param_grads* dp, void* ctx, bool eager, cudaStream_t s) {
-  const ScopedSmBudget sm_scope(align_sm_budget());   // (prof.h: leave SMs to SIM's concurrent chain)
-  const ScopedSmWaves wave_scope(align_sm_waves());
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);

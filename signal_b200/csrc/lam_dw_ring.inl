@@ -251,7 +251,8 @@ static bool dw_ring_ok(int L, int h, int w, int d) {
 }
 static int dw_ring_ctas_per_mod(int B, int h) {
   const int bands = B * (h / 4);
-  const int cap = (sm_budget() / 3 < kDwRingCtasPerMod ? sm_budget() / 3 : kDwRingCtasPerMod) * sm_waves();
+  // (never more CTAs than kDwRingCtasPerMod: the per-CTA partial-sum buffers of the backward are sized for it)
+  const int cap = sm_budget() / 3 < kDwRingCtasPerMod ? sm_budget() / 3 : kDwRingCtasPerMod;
   return bands < cap ? bands : cap;
 }
 

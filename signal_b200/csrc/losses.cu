@@ -100,16 +100,18 @@ __global__ void __launch_bounds__(256) triplet_fwd_kernel(const T* __restrict__ 
   const int64_t yi = y[i];
   float best_p = -INFINITY, best_n = INFINITY;
   int ip = -1, in_ = -1;
+  (void)xx;
   for (int j = w; j < B; j += nw) {
-    float dot = 0.f, yy = 0.f;
+    // |x_i - x_j|^2 accumulated from the differences: the reference's expansion |x_i|^2 + |x_j|^2 - 2 x_i.x_j
+    // (triplet_loss.py:26-28) cancels when features are close (LayerNorm'd vars_total: |x|^2 = 1536, d^2 ~ 10), which puts
+    // ~1e-5 of noise on the distances -- enough to flip the hard-example choice between near-equidistant samples
+    float d2 = 0.f;
     for (int c = lane; c < D; c += 32) {
-      const float v = ldf(x + (int64_t)j * ld, c);
-      dot = fmaf(v, xi[c], dot);
-      yy = fmaf(v, v, yy);
+      const float df = ldf(x + (int64_t)j * ld, c) - xi[c];
+      d2 = fmaf(df, df, d2);
     }
-    dot = warp_sum(dot);
-    yy = warp_sum(yy);
-    const float dist = sqrtf(fmaxf(xx + yy - 2.f * dot, 1e-12f));
+    d2 = warp_sum(d2);
+    const float dist = sqrtf(fmaxf(d2, 1e-12f));
     if (y[j] == yi) {
       if (dist > best_p) { best_p = dist; ip = j; }     // j ascends within a warp: the first maximum is kept
     } else {

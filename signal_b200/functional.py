@@ -510,13 +510,13 @@ class HeadFunction(torch.autograd.Function):
         # Training step: AlignM's forward call also runs the loss-weight-independent part of its backward (unit weight,
         # SIG_FLAG_EAGER_BWD) -- on the side stream, under SIM's forward chain of small kernels, where the GPU is
         # otherwise mostly idle; the backward call then starts at the weight-gradient GEMM.
-        flags_a = flags
+        flags_a = flags | L_.SIG_FLAG_SHARE_SMS          # SIM's chain runs next to AlignM's kernels
         # (single-GPU steps only by default: next to the in-backward gradient exchange it measured 2.5 % slower at N = 2,
         #  0.7088 vs 0.6908 ms -- the shortened AlignM backward leaves less compute for the collectives to hide under)
         eager_env = os.environ.get("SIG_EAGER_BWD", "auto")
         eager_ok = eager_env == "1" or (eager_env == "auto" and (len(event) < 2 or event[1] is None))
         if do_lam and any(ctx.needs_input_grad[9:]) and eager_ok:
-            flags_a = flags | L_.SIG_FLAG_EAGER_BWD
+            flags_a = flags_a | L_.SIG_FLAG_EAGER_BWD
         with torch.cuda.device(dev):
             side.wait_stream(main)
             if hi is not main:

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libsignal_b200.so")
 SIG_F32, SIG_BF16, SIG_F16 = 0, 1, 2
 CTX_SIM, CTX_ALIGN, CTX_SELECT, CTX_DAS = 0, 1, 2, 3
 FLAG_FORCE_SIMT = 1
+SIG_FLAG_SHARE_SMS = 4   # sig_align_fwd/bwd: SIM runs concurrently on another stream, leave it SMs (include/signal_b200.h)
 SIG_FLAG_EAGER_BWD = 2   # sig_align_fwd also runs the loss-weight-independent part of the backward (include/signal_b200.h)
 
 _VP3 = C.c_void_p * 3

@@ -354,6 +354,47 @@ class FusionHead:
     def grad_numel(self) -> int:
         return F_.head_grad_numel(self.sim.token_selection.dim)
 
+    def make_graphed(self, rgb_tokens, ni_tokens, ti_tokens, stage="together_CLS_Patch"):
+        """CUDA-graph replay speed through the ordinary autograd API.
+
+        The eager step is host-bound (ctypes calls, allocations and ~110 kernel launches cost ~1.5 ms for 0.6 ms of GPU
+        work at B = 128).  ``graphed = head.make_graphed(rgb, ni, ti)`` captures the forward and the backward of the
+        head as two CUDA graphs (``torch.cuda.make_graphed_callables``: static input / output / gradient buffers,
+        three warm-up iterations) and returns a callable
+
+            vars_total, loss_area, patch_loss = graphed(rgb_tokens, ni_tokens, ti_tokens)      # [B,1+L,d] maps
+
+        that takes part in autograd like the module calls it replaces: the losses can be combined with anything else,
+        ``backward()`` replays the backward graph and delivers gradients to the three token maps and to the parameters
+        of SIM / AlignM.  The sample maps fix shape, dtype and device; pass tensors that require grad if the token
+        gradients are needed.  ``sim.token_selection.last_masks`` refers to static tensors that every replay refreshes.
+        Parameters may be updated in place between calls (the graphs read them through their addresses); replacing a
+        parameter tensor, changing ``keep_ratio`` or registering hooks needs a new ``make_graphed``."""
+        head = self
+
+        class _Head(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.SIM, self.AlignM = head.sim, head.align
+
+            def forward(self, rgb, ni, ti):
+                out, gam, lam = head(rgb[:, 1:], ni[:, 1:], ti[:, 1:], rgb[:, 0], ni[:, 0], ti[:, 0], stage=stage)
+                return (out, gam) if lam is None else (out, gam, lam)
+
+        if self.grad_sync is not None:
+            raise RuntimeError("signal_b200: make_graphed captures a rank-local step; capture the data-parallel step (grad_sync "
+                               "set) yourself with torch.cuda.graph as bench.py does")
+        sample = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in (rgb_tokens, ni_tokens, ti_tokens))
+        graphed = torch.cuda.make_graphed_callables(_Head(), sample, allow_unused_input=True)
+        ts = self.sim.token_selection
+        static_masks = dict(ts.last_masks)      # written by the captured forward: the same memory on every replay
+
+        def call(rgb, ni, ti):
+            res = graphed(rgb, ni, ti)
+            ts.last_masks = static_masks
+            return res
+        return call
+
     def _stream(self, dev):
         st = self._side.get(dev)
         if st is None:

@@ -459,3 +459,37 @@ def test_alignment_bf16_wide_dim_and_mixed_strides_run():
         ref = so.gam_loss([t[:, 1:].float().cpu() for t in tk], torch.tensor(0.07))
         assert abs(float(gam) - float(ref)) < BF16_TOL * abs(float(ref))
         assert all(t.grad is not None and bool(torch.isfinite(t.grad).all()) for t in tk)
+
+
+def test_fusion_head_make_graphed_matches_eager():
+    """FusionHead.make_graphed: CUDA-graph replay of forward and backward through the ordinary autograd API -- same
+    outputs and gradients as the eager call, on fresh inputs, repeatedly."""
+    import gpu_harness as gh
+    M = _mods()
+    c = gu.BF16_CASES["rgbnt201_d512"]
+    sim_p, al_p, _, cot = gu.case_inputs(c)
+    sim, al = gh.build_modules(c, sim_p, al_p)
+    head = M.FusionHead(sim, al)
+    sample = [t.cuda().requires_grad_(True) for t in gu.bf16_case_tokens(c)]
+    graphed = head.make_graphed(*sample)
+    params = list(sim.parameters()) + list(al.parameters())
+    w = [cot.to("cuda", torch.bfloat16), torch.tensor(0.2, device="cuda"), torch.tensor(0.2, device="cuda")]
+    for seed in (1, 2):
+        toks = [t.to(torch.bfloat16) for t in syn.make_tokens(c["B"], c["d"], seed=900 + seed)]
+        res = {}
+        for name, fn in (("graphed", lambda a, b, c_: graphed(a, b, c_)),
+                         ("eager", lambda a, b, c_: head(a[:, 1:], b[:, 1:], c_[:, 1:], a[:, 0], b[:, 0], c_[:, 0]))):
+            tk = [t.cuda().requires_grad_(True) for t in toks]
+            for p in params:
+                p.grad = None
+            out, gam, lam = fn(*tk)
+            torch.autograd.backward([out, gam, lam], w)
+            torch.cuda.synchronize()
+            res[name] = ([out.detach().clone(), gam.detach().clone(), lam.detach().clone()] + [t.grad.clone() for t in tk]
+                         + [p.grad.clone() for p in params if p.grad is not None],
+                         {k: v.clone() for k, v in sim.token_selection.last_masks.items()})
+        assert len(res["graphed"][0]) == len(res["eager"][0])
+        for a, b in zip(res["graphed"][0], res["eager"][0]):
+            _close(a.float(), b.float(), 2e-3, "graphed vs eager")       # (split-K atomics: not bit-reproducible)
+        for k in ("RGB", "NI", "TI"):
+            assert torch.equal(res["graphed"][1][k], res["eager"][1][k])

@@ -71,3 +71,46 @@ def test_signatures_match_the_reference():
     finally:
         sys.path.remove(REF)
         _fresh({"layers", "modeling", "utils"})
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the live reference is only present in the build container")
+def test_reference_state_dicts_load_into_the_drop_ins():
+    """Checkpoint compatibility (processor.py:313-321, make_model.py:125-130): a state_dict of the reference's
+    Select_Interactive_Module / AlignmentM loads strictly into the drop-ins -- same keys, same shapes, same dtypes -- and
+    the drop-ins' own state_dict loads back into the reference modules."""
+    import torch
+    _fresh({"layers", "modeling", "utils"})
+    sys.dont_write_bytecode = True
+    for pkg in ("modeling", "utils"):
+        m = types.ModuleType(pkg)
+        m.__path__ = [os.path.join(REF, pkg)]
+        sys.modules[pkg] = m
+    sys.path.insert(0, REF)
+    try:
+        from modeling.AddModule.useA import Select_Interactive_Module as RS
+        from modeling.AddModule.useB import AlignmentM as RA
+        from signal_b200 import modules
+        for k, keep in ((80, None), (112, 0.5)):
+            ref, ours = RS(512, k=k, keep_ratio=keep), modules.Select_Interactive_Module(512, k=k, keep_ratio=keep)
+            sd = ref.state_dict()
+            assert list(sd) == list(ours.state_dict()) and all(sd[n].shape == v.shape and sd[n].dtype == v.dtype for n, v in ours.state_dict().items())
+            ours.load_state_dict(sd, strict=True)
+            ref.load_state_dict(ours.state_dict(), strict=True)
+            assert ours.token_selection.k1 == ref.token_selection.k1 and ours.token_selection.k2 == ref.token_selection.k2
+            assert ours.token_selection.keep_ratio == ref.token_selection.keep_ratio
+        for hw in ((16, 8), (8, 16)):
+            ref, ours = RA(512, *hw), modules.AlignmentM(512, *hw)
+            sd = ref.state_dict()
+            assert list(sd) == list(ours.state_dict()) and all(sd[n].shape == v.shape for n, v in ours.state_dict().items())
+            ours.load_state_dict(sd, strict=True)
+            ref.load_state_dict(ours.state_dict(), strict=True)
+            assert (ours.h, ours.w, ours.feat_dim) == (ref.h, ref.w, ref.feat_dim)
+        # same default initialisation under the same seed (constructor order of the sub-modules is the reference's)
+        torch.manual_seed(1234)
+        a = RS(512, k=80).state_dict()
+        torch.manual_seed(1234)
+        b = modules.Select_Interactive_Module(512, k=80).state_dict()
+        assert all(torch.equal(a[n], b[n]) for n in a)
+    finally:
+        sys.path.remove(REF)
+        _fresh({"layers", "modeling", "utils"})
