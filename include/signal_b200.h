@@ -348,6 +348,28 @@ int sig_bnneck_cls_bwd(const void* feat, int dtype, int64_t ld, int B, int D, in
                        const void* d_bn_out, int64_t lddo, void* dfeat, int64_t ldx, float* d_bn_weight, float* d_bn_bias,
                        float* d_cls_weight, void* ws, size_t ws_bytes, int device, void* stream);
 
+/* ---- Token producer in front of the head ----------------------------------------------------
+ * The tail of the CLIP vision tower: x = ln_post(x); tokens = x @ proj (modeling/clip/model.py:485-487; LayerNorm with
+ * fp32 statistics :154-160), whose rows 0 / 1.. are the CLS and patch views the head consumes (modeling/meta_arch.py:108-110).
+ * x: [B, L1 = 1+L, W] map given by element strides (x_stride_b, x_stride_l; unit channel stride), so the tower's [L1, B, W]
+ * layout (clip/model.py:484) is read in place; dtype SIG_F32 (exact path), SIG_BF16 or SIG_F16 (LayerNorm in fp32, result
+ * rounded to bf16, tcgen05 GEMM with fp32 accumulation: the reference's autocast data flow).  ln_w / ln_b [W], proj [W, D]
+ * fp32 masters.  tokens: contiguous [B, L1, D] in the dtype of x.  patch_mean (optional, may be NULL): fp32 [B, D] mean of
+ * the L patch rows of the rounded tokens -- the GAM mean pool (useB.py:84-86) as a by-product, see sig_align_fwd's
+ * SIG_FLAG_PATCH_MEAN.  saved: sig_tokens_ws_bytes(0, ...) bytes kept by the caller for the backward; scratch:
+ * sig_tokens_ws_bytes(1, ...) (forward) / (2, ...) (backward) bytes, may be NULL when 0.
+ * Backward: dtokens [B, L1, D] (element strides; rows must have one pitch, dt_stride_b == L1 * dt_stride_l, for SIG_F32)
+ * -> dx at (dx_stride_b, dx_stride_l) in the dtype of x, d_ln_w / d_ln_b [W], d_proj [W, D] fp32 (all overwritten;
+ * d_proj is a split-K sum of fp32 atomics: run-to-run differences at the 1e-7 level). */
+size_t sig_tokens_ws_bytes(int which, int B, int L1, int W, int D, int dtype);
+int sig_tokens_fwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_stride_l, int B, int L1, int W, int D, const float* ln_w,
+                   const float* ln_b, float eps, const float* proj, void* tokens, float* patch_mean, void* saved, size_t saved_bytes,
+                   void* scratch, size_t scratch_bytes, int device, void* stream);
+int sig_tokens_bwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_stride_l, int B, int L1, int W, int D, const float* ln_w,
+                   const float* proj, const void* dtokens, int64_t dt_stride_b, int64_t dt_stride_l, const void* saved, size_t saved_bytes,
+                   void* dx, int64_t dx_stride_b, int64_t dx_stride_l, float* d_ln_w, float* d_ln_b, float* d_proj, void* scratch,
+                   size_t scratch_bytes, int device, void* stream);
+
 int sig_profile_enable(int on);
 int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);
 /* Time line of the recorded scopes ("name start_us end_us" lines, relative to the earliest start); with

@@ -80,6 +80,7 @@ EXPORTS = [
     "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_profile_scope_begin", "sig_profile_scope_end", "sig_sim_dx_operands",
     "sig_convert_half", "sig_xchg_flag_bytes", "sig_xchg_allreduce_f32", "sig_infer_features", "sig_euclidean_distmat", "sig_rank_eval",
     "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd", "sig_bnneck_ws_bytes", "sig_bnneck_cls_fwd", "sig_bnneck_cls_bwd",
+    "sig_tokens_ws_bytes", "sig_tokens_fwd", "sig_tokens_bwd",
 ]
 
 
@@ -138,6 +139,10 @@ def load():
     lib.sig_bnneck_ws_bytes.argtypes = [i, i, i]
     lib.sig_bnneck_cls_fwd.argtypes = [vp, i, i64, i, i, i, vp, vp, vp, vp, f, f, i, vp, vp, i64, vp, i64, vp, vp, vp, vp, sz, i, vp]
     lib.sig_bnneck_cls_bwd.argtypes = [vp, i, i64, i, i, i, vp, vp, vp, vp, i, vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, sz, i, vp]
+    lib.sig_tokens_ws_bytes.restype = sz
+    lib.sig_tokens_ws_bytes.argtypes = [i, i, i, i, i, i]
+    lib.sig_tokens_fwd.argtypes = [vp, i, i64, i64, i, i, i, i, vp, vp, f, vp, vp, vp, vp, sz, vp, sz, i, vp]
+    lib.sig_tokens_bwd.argtypes = [vp, i, i64, i64, i, i, i, i, vp, vp, vp, i64, i64, vp, sz, vp, i64, i64, vp, vp, vp, vp, sz, i, vp]
     lib.sig_profile_scope_begin.restype = vp
     lib.sig_profile_scope_begin.argtypes = [C.c_char_p, vp]
     lib.sig_profile_scope_end.restype = None
@@ -149,7 +154,7 @@ def load():
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("sig_error_string", "sig_ctx_bytes", "sig_volume3_ws_bytes", "sig_debug_launch_count", "sig_xchg_flag_bytes",
-                        "sig_loss_ws_bytes", "sig_bnneck_ws_bytes", "sig_profile_scope_begin", "sig_profile_scope_end"):
+                        "sig_loss_ws_bytes", "sig_bnneck_ws_bytes", "sig_tokens_ws_bytes", "sig_profile_scope_begin", "sig_profile_scope_end"):
             fn.restype = i
     if lib.sig_version() != 1:
         raise RuntimeError("signal_b200: ABI version mismatch between lib.py and libsignal_b200.so")
