@@ -63,6 +63,10 @@ enum sig_ctx_kind { SIG_CTX_SIM = 0, SIG_CTX_ALIGN = 1, SIG_CTX_SELECT = 2, SIG_
  * (environment; default 116 of 148) instead of all of them, so the short kernels of SIM's dependency chain -- the critical
  * path of the fused step -- find free SMs; the d(patches) GEMM at the tail of the backward always takes all SMs. */
 #define SIG_FLAG_SHARE_SMS 4u
+/* sig_align_fwd, tensor-core path (bf16 tokens): the caller has already written the mean over the L patch rows of each
+ * modality, fp32 [3][B][d], into the slot sig_align_patch_mean_slot() returns inside `ctx` (e.g. the by-product of
+ * sig_tokens_fwd, which produced the token maps): the GAM pooling pass over the tokens (useB.py:84-86) is skipped. */
+#define SIG_FLAG_PATCH_MEAN 8u
 
 /* Three modality token maps, order RGB, NI, TI.
  * patch[m] -> element (b=0,l=0,c=0) of the [B,L,d] patch view, cls[m] -> (b=0,c=0)
@@ -227,6 +231,9 @@ int sig_sim_attn_bwd(const sig_tokens* tok, const sig_sim_params* p, const float
 int sig_align_fwd(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam,
                   float* losses, void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
 /* dlosses: device fp32 [2] (upstream gradients of the two scalars). */
+/* Where SIG_FLAG_PATCH_MEAN expects the patch means: *slot = fp32 [3][B][d] inside ctx.  SIG_ERR_SHAPE when this
+ * configuration does not run on the tensor-core path (the exact fp32 path pools in fp64 itself). */
+int sig_align_patch_mean_slot(void* ctx, int B, int L, int d, int dtype, unsigned flags, float** slot);
 int sig_align_bwd(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam,
                   const float* dlosses, const sig_token_grads* dtok, const sig_align_param_grads* dp,
                   void* ctx, size_t ctx_bytes, unsigned flags, int device, void* stream);
@@ -354,21 +361,22 @@ int sig_bnneck_cls_bwd(const void* feat, int dtype, int64_t ld, int B, int D, in
  * x: [B, L1 = 1+L, W] map given by element strides (x_stride_b, x_stride_l; unit channel stride), so the tower's [L1, B, W]
  * layout (clip/model.py:484) is read in place; dtype SIG_F32 (exact path), SIG_BF16 or SIG_F16 (LayerNorm in fp32, result
  * rounded to bf16, tcgen05 GEMM with fp32 accumulation: the reference's autocast data flow).  ln_w / ln_b [W], proj [W, D]
- * fp32 masters.  tokens: contiguous [B, L1, D] in the dtype of x.  patch_mean (optional, may be NULL): fp32 [B, D] mean of
+ * fp32 masters.  tokens: contiguous [B, L1, D] of tok_dtype = dtype, or SIG_BF16 / SIG_F16 for fp32 x (an autocast caller
+ * whose residual stream stayed fp32: torch's autocast runs layer_norm in fp32 and the matmul in half).  patch_mean (optional, may be NULL): fp32 [B, D] mean of
  * the L patch rows of the rounded tokens -- the GAM mean pool (useB.py:84-86) as a by-product, see sig_align_fwd's
  * SIG_FLAG_PATCH_MEAN.  saved: sig_tokens_ws_bytes(0, ...) bytes kept by the caller for the backward; scratch:
  * sig_tokens_ws_bytes(1, ...) (forward) / (2, ...) (backward) bytes, may be NULL when 0.
- * Backward: dtokens [B, L1, D] (element strides; rows must have one pitch, dt_stride_b == L1 * dt_stride_l, for SIG_F32)
- * -> dx at (dx_stride_b, dx_stride_l) in the dtype of x, d_ln_w / d_ln_b [W], d_proj [W, D] fp32 (all overwritten;
+ * Backward: dtokens [B, L1, D] of tok_dtype (element strides; rows must have one pitch, dt_stride_b == L1 * dt_stride_l, for
+ * SIG_F32) -> dx at (dx_stride_b, dx_stride_l) in the dtype of x, d_ln_w / d_ln_b [W], d_proj [W, D] fp32 (all overwritten;
  * d_proj is a split-K sum of fp32 atomics: run-to-run differences at the 1e-7 level). */
-size_t sig_tokens_ws_bytes(int which, int B, int L1, int W, int D, int dtype);
+size_t sig_tokens_ws_bytes(int which, int B, int L1, int W, int D, int tok_dtype);
 int sig_tokens_fwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_stride_l, int B, int L1, int W, int D, const float* ln_w,
-                   const float* ln_b, float eps, const float* proj, void* tokens, float* patch_mean, void* saved, size_t saved_bytes,
-                   void* scratch, size_t scratch_bytes, int device, void* stream);
+                   const float* ln_b, float eps, const float* proj, void* tokens, int tok_dtype, float* patch_mean, void* saved,
+                   size_t saved_bytes, void* scratch, size_t scratch_bytes, int device, void* stream);
 int sig_tokens_bwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_stride_l, int B, int L1, int W, int D, const float* ln_w,
-                   const float* proj, const void* dtokens, int64_t dt_stride_b, int64_t dt_stride_l, const void* saved, size_t saved_bytes,
-                   void* dx, int64_t dx_stride_b, int64_t dx_stride_l, float* d_ln_w, float* d_ln_b, float* d_proj, void* scratch,
-                   size_t scratch_bytes, int device, void* stream);
+                   const float* proj, const void* dtokens, int tok_dtype, int64_t dt_stride_b, int64_t dt_stride_l, const void* saved,
+                   size_t saved_bytes, void* dx, int64_t dx_stride_b, int64_t dx_stride_l, float* d_ln_w, float* d_ln_b, float* d_proj,
+                   void* scratch, size_t scratch_bytes, int device, void* stream);
 
 int sig_profile_enable(int on);
 int sig_profile_collect(char* names_buf, size_t names_bytes, float* ms, int* counts, int max);

@@ -665,6 +665,15 @@ size_t das_ctx_bytes(int B, int L, int d) { return align_ctx(nullptr, B, L, d, 1
 
 #include "align_tc.inl"
 
+// SIG_FLAG_PATCH_MEAN: where the caller deposits the [3][B][d] fp32 patch means (tensor-core path only; the exact fp32
+// path pools in fp64)
+int align_patch_mean_slot(void* ctx, int B, int L, int d, int dtype, unsigned flags, float** slot) {
+  if (!ctx || !slot) return SIG_ERR_NULL;
+  if (!tc_shape_ok(dtype, L, d, flags)) return SIG_ERR_SHAPE;
+  *slot = align_tc_ctx(ctx, B, L, d).mean;
+  return 0;
+}
+
 size_t align_ctx_bytes_for(int B, int L, int d, int dtype, unsigned flags) {
   if (tc_shape_ok(dtype, L, d, flags)) return align_tc_ctx(nullptr, B, L, d).bytes;
   return align_ctx_bytes(B, L, d);
@@ -752,7 +761,7 @@ int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w
     // SIG_FLAG_SHARE_SMS (FusionHead): SIM's chain runs next to this call on another stream -- leave it SMs (prof.h)
     const ScopedSmBudget sm_scope((flags & SIG_FLAG_SHARE_SMS) ? align_sm_budget() : 0);
     const ScopedSmWaves wave_scope((flags & SIG_FLAG_SHARE_SMS) ? align_sm_waves() : 1);
-    return align_forward_tc(tok, p, h, w, do_lam, losses, ctx, do_lam && (flags & SIG_FLAG_EAGER_BWD), s);
+    return align_forward_tc(tok, p, h, w, do_lam, losses, ctx, do_lam && (flags & SIG_FLAG_EAGER_BWD), (flags & SIG_FLAG_PATCH_MEAN) != 0, s);
   }
   if (ctx_bytes < align_ctx_bytes(B, L, d)) return SIG_ERR_WORKSPACE;
   AlignCtx c = align_ctx(ctx, B, L, d, 3);

@@ -7,6 +7,7 @@ size_t align_ctx_bytes(int B, int L, int d);
 size_t das_ctx_bytes(int B, int L, int d);
 size_t align_ctx_bytes_for(int B, int L, int d, int dtype, unsigned flags);
 size_t volume_ws_floats(int B1, int B2);
+int align_patch_mean_slot(void* ctx, int B, int L, int d, int dtype, unsigned flags, float** slot);
 int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
                   size_t ctx_bytes, unsigned flags, cudaStream_t s);
 int align_backward(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, const float* dlosses,

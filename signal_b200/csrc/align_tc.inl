@@ -742,7 +742,7 @@ static int lam_backward_chain_tc(const AlignTcCtx& c, const TokPtrs3& tp, const 
 }
 
 static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
-                            bool eager, cudaStream_t s) {
+                            bool eager, bool have_mean, cudaStream_t s) {
   const int B = tok->B, L = tok->L, d = tok->d;
   AlignTcCtx c = align_tc_ctx(ctx, B, L, d);
   const TokPtrs3 tp = tok_ptrs3(tok);
@@ -756,7 +756,10 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   {
     SIG_PHASE("gam_fwd");
     const bool rows_contig = tok->patch_stride_l[0] == d && tok->patch_stride_l[1] == d && tok->patch_stride_l[2] == d;
-    if (tok_ring_enabled() && L == kMaxL && (d == 512 || d == 768) && rows_contig) {
+    if (have_mean) {
+      // SIG_FLAG_PATCH_MEAN: the caller filled c.mean (sig_align_patch_mean_slot) with the mean pool of the patch rows,
+      // e.g. the by-product of sig_tokens_fwd -- one pass over the tokens less
+    } else if (tok_ring_enabled() && L == kMaxL && (d == 512 || d == 768) && rows_contig) {
       SIG_PHASE("gam_pool");   // streaming ring: 4 x 48 KB in flight per SM (tok_ring.cuh)
       TokSrc3 src;
       for (int m = 0; m < 3; ++m) { src.patch[m] = tok->patch[m]; src.psb[m] = tok->patch_stride_b[m]; }

@@ -190,6 +190,10 @@ int sig_sim_dx_operands(void* ctx, int B, int L, int d, int dtype, unsigned flag
   return sig::sim_dx_operands(ctx, B, L, d, dtype, flags, pds, dxqt);
 }
 
+int sig_align_patch_mean_slot(void* ctx, int B, int L, int d, int dtype, unsigned flags, float** slot) {
+  return sig::align_patch_mean_slot(ctx, B, L, d, dtype, flags, slot);
+}
+
 int sig_debug_tc_stamps(long long* out16) { return sig::tc_read_stamps(out16); }
 
 int sig_infer_features(const void* const cls[3], const int64_t cls_stride_b[3], const void* sim_out, int64_t ld_sim, int dtype, int B,

@@ -17,6 +17,8 @@
 // fp32 inputs take the exact path: same kernels with fp32 xn and the fp32 SIMT GEMM (simt_ops.cuh).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "simt_ops.cuh"
 #include "tc_gemm.h"
@@ -256,7 +258,7 @@ int launch_ln_bwd(int ctas, const InT* x, int64_t sb, int64_t sl, int R, int L1,
                   const GT* dxn, InT* dx, int64_t dsb, int64_t dsl, float* part, cudaStream_t s) {
   const size_t red_smem = (size_t)8 * 2 * W * sizeof(float);
   SIG_TOK_NCH_SWITCH(W, {
-    ensure_dyn_smem(ln_rows_bwd_kernel<NCH, InT, GT>, (int)red_smem);
+    ensure_dyn_smem(ln_rows_bwd_kernel<NCH, InT, GT>, 8 * 2 * NCH * 256 * (int)sizeof(float));   // set once per device: the largest W of this NCH
     SIG_LAUNCH((ln_rows_bwd_kernel<NCH, InT, GT>), ctas, 256, red_smem, s, x, sb, sl, R, L1, W, g, mu, rstd, dxn, dx, dsb, dsl, part);
   });
   SIG_CHECK_LAUNCH();
@@ -294,19 +296,22 @@ TokLayout tok_layout(int R, int W, int D, int dtype) {
   return t;
 }
 
-template <typename InT>
-int tokens_fwd_t(const InT* x, int dtype, int64_t sb, int64_t sl, int B, int L1, int W, int D, const float* ln_w, const float* ln_b,
-                 float eps, const float* proj, InT* tokens, float* patch_mean, unsigned char* saved, unsigned char* scratch,
+// XT: dtype of x / dx; TT: dtype of the tokens / their gradient.  TT == float selects the exact fp32 path (XT == float);
+// half tokens select the tensor-core path, with x either in the same half type or fp32 (an autocast caller whose
+// residual stream stayed fp32).  `tdt` = enum of TT (it fixes the buffer layout).
+template <typename XT, typename TT>
+int tokens_fwd_t(const XT* x, int tdt, int64_t sb, int64_t sl, int B, int L1, int W, int D, const float* ln_w, const float* ln_b,
+                 float eps, const float* proj, TT* tokens, float* patch_mean, unsigned char* saved, unsigned char* scratch,
                  cudaStream_t s) {
   const int R = B * L1;
-  const TokLayout t = tok_layout(R, W, D, dtype);
+  const TokLayout t = tok_layout(R, W, D, tdt);
   float* mu = reinterpret_cast<float*>(saved + t.mu);
   float* rstd = reinterpret_cast<float*>(saved + t.rstd);
-  if (dtype == SIG_F32) {
+  if constexpr (std::is_same<TT, float>::value) {
     SIG_PHASE("tokens_ln_fwd");
     float* xn = reinterpret_cast<float*>(saved + t.xn);
     SIG_TRY(launch_ln_fwd(x, sb, sl, R, L1, W, ln_w, ln_b, eps, xn, mu, rstd, s));
-    SIG_TRY(launch_gemm(gemm_nn(xn, W, proj, D, reinterpret_cast<float*>(tokens), D, R, D, W), s));
+    SIG_TRY(launch_gemm(gemm_nn(xn, W, proj, D, tokens, D, R, D, W), s));
   } else {
     __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(saved + t.xn);
     __nv_bfloat16* projb = reinterpret_cast<__nv_bfloat16*>(saved + t.projb);
@@ -322,46 +327,45 @@ int tokens_fwd_t(const InT* x, int dtype, int64_t sb, int64_t sl, int B, int L1,
     g.M = R; g.N = D; g.K = W;
     g.ldc = D;
     g.bn = (D % 256 == 0) ? 256 : 128;
-    if (dtype == SIG_BF16) {
+    if constexpr (std::is_same<TT, __nv_bfloat16>::value) {
       g.C[0] = tokens; g.out_bf16 = 1;
       SIG_TRY(tc_gemm(g, s));
     } else {   // fp16 tokens: fp32 staging, one rounding to fp16
       float* stage = reinterpret_cast<float*>(scratch + t.stage);
       g.C[0] = stage;
       SIG_TRY(tc_gemm(g, s));
-      SIG_LAUNCH((rows_store_kernel<InT>), (unsigned)(device_num_sms() * 4), 256, 0, s, stage, R, L1, D, tokens, (int64_t)L1 * D, (int64_t)D);
+      SIG_LAUNCH((rows_store_kernel<TT>), (unsigned)(device_num_sms() * 4), 256, 0, s, stage, R, L1, D, tokens, (int64_t)L1 * D, (int64_t)D);
       SIG_CHECK_LAUNCH();
     }
   }
   if (patch_mean) {
     SIG_PHASE("tokens_patch_mean");
-    SIG_LAUNCH((patch_mean_kernel<InT>), B, 256, 0, s, tokens, (int64_t)L1 * D, (int64_t)D, L1 - 1, D, patch_mean);
+    SIG_LAUNCH((patch_mean_kernel<TT>), B, 256, 0, s, tokens, (int64_t)L1 * D, (int64_t)D, L1 - 1, D, patch_mean);
     SIG_CHECK_LAUNCH();
   }
   return 0;
 }
 
-template <typename InT>
-int tokens_bwd_t(const InT* x, int dtype, int64_t sb, int64_t sl, int B, int L1, int W, int D, const float* ln_w, const float* proj,
-                 const InT* dtok, int64_t dtsb, int64_t dtsl, const unsigned char* saved, InT* dx, int64_t dxsb, int64_t dxsl,
+template <typename XT, typename TT>
+int tokens_bwd_t(const XT* x, int tdt, int64_t sb, int64_t sl, int B, int L1, int W, int D, const float* ln_w, const float* proj,
+                 const TT* dtok, int64_t dtsb, int64_t dtsl, const unsigned char* saved, XT* dx, int64_t dxsb, int64_t dxsl,
                  float* d_ln_w, float* d_ln_b, float* d_proj, unsigned char* scratch, cudaStream_t s) {
   const int R = B * L1;
-  const TokLayout t = tok_layout(R, W, D, dtype);
+  const TokLayout t = tok_layout(R, W, D, tdt);
   const float* mu = reinterpret_cast<const float*>(saved + t.mu);
   const float* rstd = reinterpret_cast<const float*>(saved + t.rstd);
   float* part = reinterpret_cast<float*>(scratch + t.part);
-  if (dtype == SIG_F32) {
+  if constexpr (std::is_same<TT, float>::value) {
     const float* xn = reinterpret_cast<const float*>(saved + t.xn);
     float* dxn = reinterpret_cast<float*>(scratch + t.dxn);
-    const float* dt = reinterpret_cast<const float*>(dtok);
     if (dtsb != (int64_t)L1 * dtsl) return SIG_ERR_SHAPE;
     {
       SIG_PHASE("tokens_proj_bwd");
       // dxn[R, W] = dtok[R, D] . proj[W, D]^T
-      SIG_TRY(launch_gemm(gemm_nt(dt, dtsl, proj, D, dxn, W, nullptr, R, W, D), s));
+      SIG_TRY(launch_gemm(gemm_nt(dtok, dtsl, proj, D, dxn, W, nullptr, R, W, D), s));
       // dproj[W, D] = xn[R, W]^T dtok[R, D]   (split-K into a zeroed buffer)
       cudaMemsetAsync(d_proj, 0, (size_t)W * D * sizeof(float), s);
-      Gemm g = gemm_tn(xn, W, dt, dtsl, d_proj, D, W, D, R);
+      Gemm g = gemm_tn(xn, W, dtok, dtsl, d_proj, D, W, D, R);
       g.ksplit = R >= 2048 ? 16 : 1;
       SIG_TRY(launch_gemm(g, s));
     }
@@ -373,12 +377,12 @@ int tokens_bwd_t(const InT* x, int dtype, int64_t sb, int64_t sl, int B, int L1,
     __nv_bfloat16* dxn = reinterpret_cast<__nv_bfloat16*>(scratch + t.dxn);
     const __nv_bfloat16* dtb;
     int64_t ldd;
-    if (dtype == SIG_BF16 && dtsb == (int64_t)L1 * dtsl && (dtsl % 8) == 0 && ((uintptr_t)dtok % 16) == 0) {
+    if (std::is_same<TT, __nv_bfloat16>::value && dtsb == (int64_t)L1 * dtsl && (dtsl % 8) == 0 && ((uintptr_t)dtok % 16) == 0) {
       dtb = reinterpret_cast<const __nv_bfloat16*>(dtok);   // uniform row pitch: consumed in place
       ldd = dtsl;
     } else {
       __nv_bfloat16* tmp = reinterpret_cast<__nv_bfloat16*>(scratch + t.dtokb);
-      SIG_LAUNCH((rows_gather_bf16_kernel<InT>), (unsigned)(device_num_sms() * 4), 256, 0, s, dtok, dtsb, dtsl, R, L1, D, tmp);
+      SIG_LAUNCH((rows_gather_bf16_kernel<TT>), (unsigned)(device_num_sms() * 4), 256, 0, s, dtok, dtsb, dtsl, R, L1, D, tmp);
       SIG_CHECK_LAUNCH();
       dtb = tmp;
       ldd = D;
@@ -431,17 +435,48 @@ struct DevGuard {
 bool tok_shape_ok(int B, int L1, int W, int D) {
   return B >= 1 && L1 >= 2 && W >= 8 && D >= 8 && W <= 1024 && D <= 1024 && (W % 8) == 0 && (D % 8) == 0 && (int64_t)B * L1 < (1 << 30);
 }
+// x dtype / token dtype pairs: equal, or fp32 x with half tokens (autocast)
+bool tok_dtypes_ok(int xdt, int tdt) {
+  if (xdt < SIG_F32 || xdt > SIG_F16 || tdt < SIG_F32 || tdt > SIG_F16) return false;
+  return xdt == tdt || xdt == SIG_F32;
+}
 bool a16(const void* p) { return ((uintptr_t)p % 16) == 0; }
+int64_t vec_elems(int dt) { return dt == SIG_F32 ? 4 : 8; }   // elements per 16 bytes
 
 }  // namespace
 }  // namespace sig
 
+#define SIG_TOK_DISPATCH(FN, ...)                                                                    \
+  do {                                                                                               \
+    if (dtype == SIG_F32 && tok_dtype == SIG_F32) return FN<float, float>(__VA_ARGS__);              \
+    if (dtype == SIG_BF16) return FN<__nv_bfloat16, __nv_bfloat16>(__VA_ARGS__);                     \
+    if (dtype == SIG_F16) return FN<__half, __half>(__VA_ARGS__);                                    \
+    if (tok_dtype == SIG_BF16) return FN<float, __nv_bfloat16>(__VA_ARGS__);                         \
+    return FN<float, __half>(__VA_ARGS__);                                                           \
+  } while (0)
+
+template <typename XT, typename TT>
+static int tokens_fwd_entry(const void* x, int tdt, int64_t sb, int64_t sl, int B, int L1, int W, int D, const float* ln_w,
+                            const float* ln_b, float eps, const float* proj, void* tokens, float* patch_mean, void* saved, void* scratch,
+                            cudaStream_t s) {
+  return sig::tokens_fwd_t<XT, TT>(static_cast<const XT*>(x), tdt, sb, sl, B, L1, W, D, ln_w, ln_b, eps, proj, static_cast<TT*>(tokens),
+                                   patch_mean, static_cast<unsigned char*>(saved), static_cast<unsigned char*>(scratch), s);
+}
+template <typename XT, typename TT>
+static int tokens_bwd_entry(const void* x, int tdt, int64_t sb, int64_t sl, int B, int L1, int W, int D, const float* ln_w,
+                            const float* proj, const void* dtok, int64_t dtsb, int64_t dtsl, const void* saved, void* dx, int64_t dxsb,
+                            int64_t dxsl, float* d_ln_w, float* d_ln_b, float* d_proj, void* scratch, cudaStream_t s) {
+  return sig::tokens_bwd_t<XT, TT>(static_cast<const XT*>(x), tdt, sb, sl, B, L1, W, D, ln_w, proj, static_cast<const TT*>(dtok), dtsb,
+                                   dtsl, static_cast<const unsigned char*>(saved), static_cast<XT*>(dx), dxsb, dxsl, d_ln_w, d_ln_b,
+                                   d_proj, static_cast<unsigned char*>(scratch), s);
+}
+
 extern "C" {
 
-size_t sig_tokens_ws_bytes(int which, int B, int L1, int W, int D, int dtype) {
+size_t sig_tokens_ws_bytes(int which, int B, int L1, int W, int D, int tok_dtype) {
   using namespace sig;
-  if (!tok_shape_ok(B, L1, W, D) || dtype < SIG_F32 || dtype > SIG_F16) return 0;
-  const TokLayout t = tok_layout(B * L1, W, D, dtype);
+  if (!tok_shape_ok(B, L1, W, D) || tok_dtype < SIG_F32 || tok_dtype > SIG_F16) return 0;
+  const TokLayout t = tok_layout(B * L1, W, D, tok_dtype);
   if (which == 0) return t.saved_bytes;
   if (which == 1) return t.fwd_scratch_bytes;
   if (which == 2) return t.bwd_scratch_bytes;
@@ -449,65 +484,46 @@ size_t sig_tokens_ws_bytes(int which, int B, int L1, int W, int D, int dtype) {
 }
 
 int sig_tokens_fwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_stride_l, int B, int L1, int W, int D, const float* ln_w,
-                   const float* ln_b, float eps, const float* proj, void* tokens, float* patch_mean, void* saved, size_t saved_bytes,
-                   void* scratch, size_t scratch_bytes, int device, void* stream) {
+                   const float* ln_b, float eps, const float* proj, void* tokens, int tok_dtype, float* patch_mean, void* saved,
+                   size_t saved_bytes, void* scratch, size_t scratch_bytes, int device, void* stream) {
   using namespace sig;
   DevGuard guard(device);
   if (guard.rc) return guard.rc;
   cudaGetLastError();
   if (!x || !ln_w || !ln_b || !proj || !tokens || !saved) return SIG_ERR_NULL;
-  if (dtype < SIG_F32 || dtype > SIG_F16) return SIG_ERR_DTYPE;
+  if (!tok_dtypes_ok(dtype, tok_dtype)) return SIG_ERR_DTYPE;
   if (!tok_shape_ok(B, L1, W, D)) return SIG_ERR_SHAPE;
-  const int64_t ev = dtype == SIG_F32 ? 4 : 8;   // elements per 16 bytes
+  const int64_t ev = vec_elems(dtype);
   if (!a16(x) || !a16(tokens) || !a16(ln_w) || !a16(ln_b) || !a16(proj) || !a16(saved) || (x_stride_b % ev) || (x_stride_l % ev) ||
       (patch_mean && !a16(patch_mean)))
     return SIG_ERR_ALIGN;
-  const TokLayout t = tok_layout(B * L1, W, D, dtype);
+  const TokLayout t = tok_layout(B * L1, W, D, tok_dtype);
   if (saved_bytes < t.saved_bytes || scratch_bytes < t.fwd_scratch_bytes || (t.fwd_scratch_bytes && !scratch)) return SIG_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned char* sv = static_cast<unsigned char*>(saved);
-  unsigned char* sc = static_cast<unsigned char*>(scratch);
-  if (dtype == SIG_F32)
-    return tokens_fwd_t<float>(static_cast<const float*>(x), dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, ln_b, eps, proj,
-                               static_cast<float*>(tokens), patch_mean, sv, sc, s);
-  if (dtype == SIG_BF16)
-    return tokens_fwd_t<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, ln_b, eps, proj,
-                                       static_cast<__nv_bfloat16*>(tokens), patch_mean, sv, sc, s);
-  return tokens_fwd_t<__half>(static_cast<const __half*>(x), dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, ln_b, eps, proj,
-                              static_cast<__half*>(tokens), patch_mean, sv, sc, s);
+  SIG_TOK_DISPATCH(tokens_fwd_entry, x, tok_dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, ln_b, eps, proj, tokens, patch_mean, saved,
+                   scratch, s);
 }
 
 int sig_tokens_bwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_stride_l, int B, int L1, int W, int D, const float* ln_w,
-                   const float* proj, const void* dtokens, int64_t dt_stride_b, int64_t dt_stride_l, const void* saved, size_t saved_bytes,
-                   void* dx, int64_t dx_stride_b, int64_t dx_stride_l, float* d_ln_w, float* d_ln_b, float* d_proj, void* scratch,
-                   size_t scratch_bytes, int device, void* stream) {
+                   const float* proj, const void* dtokens, int tok_dtype, int64_t dt_stride_b, int64_t dt_stride_l, const void* saved,
+                   size_t saved_bytes, void* dx, int64_t dx_stride_b, int64_t dx_stride_l, float* d_ln_w, float* d_ln_b, float* d_proj,
+                   void* scratch, size_t scratch_bytes, int device, void* stream) {
   using namespace sig;
   DevGuard guard(device);
   if (guard.rc) return guard.rc;
   cudaGetLastError();
   if (!x || !ln_w || !proj || !dtokens || !saved || !dx || !d_ln_w || !d_ln_b || !d_proj || !scratch) return SIG_ERR_NULL;
-  if (dtype < SIG_F32 || dtype > SIG_F16) return SIG_ERR_DTYPE;
+  if (!tok_dtypes_ok(dtype, tok_dtype)) return SIG_ERR_DTYPE;
   if (!tok_shape_ok(B, L1, W, D)) return SIG_ERR_SHAPE;
-  const int64_t ev = dtype == SIG_F32 ? 4 : 8;
+  const int64_t ev = vec_elems(dtype), evt = vec_elems(tok_dtype);
   if (!a16(x) || !a16(dtokens) || !a16(dx) || !a16(ln_w) || !a16(proj) || !a16(saved) || !a16(scratch) || !a16(d_proj) || (x_stride_b % ev) ||
-      (x_stride_l % ev) || (dt_stride_b % ev) || (dt_stride_l % ev) || (dx_stride_b % ev) || (dx_stride_l % ev))
+      (x_stride_l % ev) || (dt_stride_b % evt) || (dt_stride_l % evt) || (dx_stride_b % ev) || (dx_stride_l % ev))
     return SIG_ERR_ALIGN;
-  const TokLayout t = tok_layout(B * L1, W, D, dtype);
+  const TokLayout t = tok_layout(B * L1, W, D, tok_dtype);
   if (saved_bytes < t.saved_bytes || scratch_bytes < t.bwd_scratch_bytes) return SIG_ERR_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned char* sv = static_cast<const unsigned char*>(saved);
-  unsigned char* sc = static_cast<unsigned char*>(scratch);
-  if (dtype == SIG_F32)
-    return tokens_bwd_t<float>(static_cast<const float*>(x), dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, proj,
-                               static_cast<const float*>(dtokens), dt_stride_b, dt_stride_l, sv, static_cast<float*>(dx), dx_stride_b,
-                               dx_stride_l, d_ln_w, d_ln_b, d_proj, sc, s);
-  if (dtype == SIG_BF16)
-    return tokens_bwd_t<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, proj,
-                                       static_cast<const __nv_bfloat16*>(dtokens), dt_stride_b, dt_stride_l, sv,
-                                       static_cast<__nv_bfloat16*>(dx), dx_stride_b, dx_stride_l, d_ln_w, d_ln_b, d_proj, sc, s);
-  return tokens_bwd_t<__half>(static_cast<const __half*>(x), dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, proj,
-                              static_cast<const __half*>(dtokens), dt_stride_b, dt_stride_l, sv, static_cast<__half*>(dx), dx_stride_b,
-                              dx_stride_l, d_ln_w, d_ln_b, d_proj, sc, s);
+  SIG_TOK_DISPATCH(tokens_bwd_entry, x, tok_dtype, x_stride_b, x_stride_l, B, L1, W, D, ln_w, proj, dtokens, dt_stride_b, dt_stride_l, saved,
+                   dx, dx_stride_b, dx_stride_l, d_ln_w, d_ln_b, d_proj, scratch, s);
 }
 
 }  // extern "C"

@@ -60,6 +60,7 @@ class ClipViT(nn.Module):
         self.blocks = nn.Sequential(*[_Block(width, heads) for _ in range(layers)])
         self.ln_post = nn.LayerNorm(width)
         self.proj = nn.Parameter(scale * torch.randn(width, out_dim))
+        self.token_producer = None   # signal_b200.tokens.TokenProducer: the tail on the B200 kernels (N3), set by the caller
 
     def forward(self, x, cv_emb=None):
         x = self.conv1(x).flatten(2).transpose(1, 2)
@@ -68,6 +69,8 @@ class ClipViT(nn.Module):
             cls = cls + cv_emb.to(x.dtype)
         x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
         x = self.blocks(self.ln_pre(x))
+        if self.token_producer is not None:
+            return self.token_producer.tokens(x)
         return self.ln_post(x) @ self.proj.to(x.dtype)
 
 
@@ -78,7 +81,7 @@ class SignalTrainStep(nn.Module):
     with stock torch ops -- bench.py's comparison arm."""
 
     def __init__(self, grid=(8, 16), topk=64, num_classes=155, camera_num=8, feat_dim=512, w_id=0.25, w_tri=1.0, w_gam=0.2, w_lam=0.01,
-                 torch_head=None, layers=12, width=768, heads=12):
+                 torch_head=None, layers=12, width=768, heads=12, b200_tokens=True):
         super().__init__()
         self.h, self.w = grid
         self.torch_head = torch_head
@@ -97,6 +100,10 @@ class SignalTrainStep(nn.Module):
         for c in (self.classifier_r, self.classifier_n, self.classifier_t, self.classifier_var):
             nn.init.normal_(c.weight, std=0.001)                # weights_init_classifier
         self.fusion = M.FusionHead(self.SIM, self.AlignM)
+        if torch_head is None and b200_tokens:
+            from .tokens import TokenProducer
+            # object.__setattr__: the producer wraps ln_post / proj of the backbone and must not register them twice
+            object.__setattr__(self.backbone, "token_producer", TokenProducer(self.backbone.ln_post, self.backbone.proj, patch_mean=False))
         self.xent = LS.CrossEntropyLabelSmooth(num_classes)
         self.triplet = LS.TripletLoss()
 

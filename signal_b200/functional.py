@@ -319,16 +319,40 @@ def _align_grad_shapes(d):
     return [()] + one * 3
 
 
+def _deposit_patch_mean(buf, hint, B, L, d, dt, flags, stream=None):
+    """SIG_FLAG_PATCH_MEAN: copy the caller's patch means (three [B,d] fp32 tensors or one [3,B,d], e.g.
+    TokenProducer.last_patch_mean of the three modalities) into the slot of AlignM's ctx buffer.  Returns the flag bit, or 0
+    when this configuration does not run on the tensor-core path (the pool pass then runs as usual)."""
+    if hint is None:
+        return 0
+    slot = C.c_void_p()
+    if L_.load().sig_align_patch_mean_slot(buf.data_ptr(), B, L, d, dt, flags, C.byref(slot)) != 0:
+        return 0
+    off = slot.value - buf.data_ptr()
+    dst = buf[off: off + 3 * B * d * 4].view(torch.float32).view(3, B, d)
+    src = hint if torch.is_tensor(hint) else torch.stack([h.detach() for h in hint])
+    if tuple(src.shape) != (3, B, d) or src.dtype != torch.float32:
+        raise RuntimeError("signal_b200: patch_mean hint must be fp32 [3,B,d] (or three [B,d] tensors)")
+    if stream is None:
+        dst.copy_(src.detach())
+    else:
+        with torch.cuda.stream(stream):
+            dst.copy_(src.detach())
+    return L_.SIG_FLAG_PATCH_MEAN
+
+
 class AlignFunction(torch.autograd.Function):
     """AlignmentM.forward (useB.py:169-190) -> (gam, lam) 0-dim fp32 (lam = 0 when do_lam is False).
 
     tensors: 3 token maps (packed) or 3 patch maps, then contra_temp, then 7 tensors per
-    modality in lib.ALIGN_MOD_FIELDS order (r, n, t).
+    modality in lib.ALIGN_MOD_FIELDS order (r, n, t), then optionally the fp32 [3,B,d] patch means (forward hint,
+    not differentiated: the token gradient of the pool still flows through the token maps).
     """
 
     @staticmethod
     def forward(ctx, packed: bool, h: int, w: int, do_lam: bool, flags: int, *tensors):
-        toks, params = tensors[:3], tensors[3:]
+        toks, params, hint = tensors[:3], tensors[3:25], (tensors[25] if len(tensors) > 25 else None)
+        ctx.has_hint = hint is not None
         lib = L_.load()
         patches = [t[:, 1:] for t in toks] if packed else list(toks)
         B, L, d = patches[0].shape
@@ -343,8 +367,9 @@ class AlignFunction(torch.autograd.Function):
         nbytes = L_.ctx_bytes(L_.CTX_ALIGN, B, L, d, L_.dtype_enum(patches[0]), flags)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
+            fwd_flags = flags | _deposit_patch_mean(buf, hint, B, L, d, L_.dtype_enum(patches[0]), flags)
             L_.check(lib.sig_align_fwd(C.byref(tok), C.byref(prm), h, w, int(do_lam), losses.data_ptr(), buf.data_ptr(), nbytes,
-                                       flags, dev.index, L_.stream_ptr(dev)), "sig_align_fwd")
+                                       fwd_flags, dev.index, L_.stream_ptr(dev)), "sig_align_fwd")
         ctx.save_for_backward(*toks, *params, buf)
         ctx.cfg = (packed, h, w, do_lam, flags)
         return losses[0], losses[1]
@@ -380,7 +405,7 @@ class AlignFunction(torch.autograd.Function):
                                        buf.data_ptr(), buf.numel(), flags, dev.index, L_.stream_ptr(dev)), "sig_align_bwd")
         if not do_lam:      # stage == "CLS": the DAS parameters took no part (useB.py:181-183) -> no gradient, like the reference
             pg = [pg[0]] + [None] * (len(pg) - 1)
-        return (None,) * 5 + tuple(ret) + tuple(pg)
+        return (None,) * 5 + tuple(ret) + tuple(pg) + ((None,) if ctx.has_hint else ())
 
 
 class DasFunction(torch.autograd.Function):

@@ -19,6 +19,7 @@ SIG_F32, SIG_BF16, SIG_F16 = 0, 1, 2
 CTX_SIM, CTX_ALIGN, CTX_SELECT, CTX_DAS = 0, 1, 2, 3
 FLAG_FORCE_SIMT = 1
 SIG_FLAG_SHARE_SMS = 4   # sig_align_fwd/bwd: SIM runs concurrently on another stream, leave it SMs (include/signal_b200.h)
+SIG_FLAG_PATCH_MEAN = 8  # sig_align_fwd: the GAM mean pool was deposited in ctx by the caller (include/signal_b200.h)
 SIG_FLAG_EAGER_BWD = 2   # sig_align_fwd also runs the loss-weight-independent part of the backward (include/signal_b200.h)
 
 _VP3 = C.c_void_p * 3
@@ -80,7 +81,7 @@ EXPORTS = [
     "sig_debug_launch_count", "sig_profile_enable", "sig_profile_collect", "sig_debug_gemm_bf16", "sig_debug_tc_stamps", "sig_profile_timeline", "sig_profile_scope_begin", "sig_profile_scope_end", "sig_sim_dx_operands",
     "sig_convert_half", "sig_xchg_flag_bytes", "sig_xchg_allreduce_f32", "sig_infer_features", "sig_euclidean_distmat", "sig_rank_eval",
     "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd", "sig_bnneck_ws_bytes", "sig_bnneck_cls_fwd", "sig_bnneck_cls_bwd",
-    "sig_tokens_ws_bytes", "sig_tokens_fwd", "sig_tokens_bwd",
+    "sig_tokens_ws_bytes", "sig_tokens_fwd", "sig_tokens_bwd", "sig_align_patch_mean_slot",
 ]
 
 
@@ -120,6 +121,7 @@ def load():
     lib.sig_volume3_bwd.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, sz, i, vp]
     lib.sig_debug_gemm_bf16.argtypes = [vp, i, P(i64), vp, i, P(i64), vp, i64, i, vp, i, i, i, C.c_float, i, i, i, i64, i64, vp, vp, i, i, vp]
     lib.sig_sim_dx_operands.argtypes = [vp, i, i, i, i, u, P(vp), P(vp)]
+    lib.sig_align_patch_mean_slot.argtypes = [vp, i, i, i, i, u, P(vp)]
     lib.sig_infer_features.argtypes = [_VP3, _I64x3, vp, i64, i, i, i, i, vp, i, vp]
     lib.sig_euclidean_distmat.argtypes = [vp, vp, i, i, i, vp, vp, sz, i, vp]
     lib.sig_rank_eval.argtypes = [vp, i64, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, i, vp]
@@ -141,8 +143,8 @@ def load():
     lib.sig_bnneck_cls_bwd.argtypes = [vp, i, i64, i, i, i, vp, vp, vp, vp, i, vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, sz, i, vp]
     lib.sig_tokens_ws_bytes.restype = sz
     lib.sig_tokens_ws_bytes.argtypes = [i, i, i, i, i, i]
-    lib.sig_tokens_fwd.argtypes = [vp, i, i64, i64, i, i, i, i, vp, vp, f, vp, vp, vp, vp, sz, vp, sz, i, vp]
-    lib.sig_tokens_bwd.argtypes = [vp, i, i64, i64, i, i, i, i, vp, vp, vp, i64, i64, vp, sz, vp, i64, i64, vp, vp, vp, vp, sz, i, vp]
+    lib.sig_tokens_fwd.argtypes = [vp, i, i64, i64, i, i, i, i, vp, vp, f, vp, vp, i, vp, vp, sz, vp, sz, i, vp]
+    lib.sig_tokens_bwd.argtypes = [vp, i, i64, i64, i, i, i, i, vp, vp, vp, i, i64, i64, vp, sz, vp, i64, i64, vp, vp, vp, vp, sz, i, vp]
     lib.sig_profile_scope_begin.restype = vp
     lib.sig_profile_scope_begin.argtypes = [C.c_char_p, vp]
     lib.sig_profile_scope_end.restype = None

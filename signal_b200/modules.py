@@ -287,21 +287,33 @@ class AlignmentM(nn.Module):
         self.DAS_t = DA_sample(n_heads, n_head_channels, n_groups, stride, offset_range_factor, ksize)
         self.flags = 0
         self.fuse_views = True
+        # Optional forward hint, consumed by the NEXT call: the fp32 mean over the patch rows of the three modalities
+        # ([3,B,d] or three [B,d] tensors), e.g. TokenProducer.last_patch_mean -- the GAM pool pass over the tokens
+        # (useB.py:84-86) is then skipped on the bf16 path.  It must be the mean of exactly the maps passed in.
+        self.patch_mean_hint = None
 
     def _params(self):
         return [self.contra_temp] + self.DAS_r._params() + self.DAS_n._params() + self.DAS_t._params()
 
     def _run(self, RGB_patch, NI_patch, TI_patch, do_lam):
+        if RGB_patch.dtype != torch.bfloat16:
+            # the hint stands for the pool of the maps the kernels read: fp16 maps are converted to bf16 first and fp32
+            # maps pool in fp64 on the exact path, so only bf16 callers may skip the pass
+            self.patch_mean_hint = None
         (RGB_patch, NI_patch, TI_patch), _, _ = _half_in([RGB_patch, NI_patch, TI_patch])     # (the two losses are fp32)
         bases = None
         if self.fuse_views:
             bases = [_packed_patch_base(p) for p in (RGB_patch, NI_patch, TI_patch)]
             if any(b is None for b in bases):
                 bases = None
+        hint, self.patch_mean_hint = self.patch_mean_hint, None
+        extra = ()
+        if hint is not None:
+            extra = (hint.detach() if torch.is_tensor(hint) else torch.stack([t.detach() for t in hint]),)
         if bases is not None:
-            return F_.AlignFunction.apply(True, self.h, self.w, do_lam, self.flags, *bases, *self._params())
+            return F_.AlignFunction.apply(True, self.h, self.w, do_lam, self.flags, *bases, *self._params(), *extra)
         return F_.AlignFunction.apply(False, self.h, self.w, do_lam, self.flags, *_same_strides([RGB_patch, NI_patch, TI_patch]),
-                                      *self._params())
+                                      *self._params(), *extra)
 
     def Cls_Align(self, RGB_patch, NI_patch, TI_patch):
         return self._run(RGB_patch, NI_patch, TI_patch, False)[0]

@@ -29,10 +29,11 @@ def _u8(n, dev):
 
 
 class TokenProducerFunction(torch.autograd.Function):
-    """(x [B,L1,W] strided, ln_w, ln_b, proj [W,D], eps, want_mean) -> (tokens [B,L1,D], patch_mean [B,D] fp32 or empty)."""
+    """(x [B,L1,W] strided, ln_w, ln_b, proj [W,D], eps, want_mean, tok_dtype) -> (tokens [B,L1,D] of tok_dtype,
+    patch_mean [B,D] fp32 or empty).  tok_dtype = x.dtype, or bf16 / fp16 for fp32 x (autocast)."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, proj, eps: float, want_mean: bool):
+    def forward(ctx, x, ln_w, ln_b, proj, eps: float, want_mean: bool, tok_dtype):
         lib = L_.load()
         if not x.is_cuda:
             raise RuntimeError("signal_b200: TokenProducer input must be a CUDA tensor (there is no CPU path)")
@@ -41,21 +42,26 @@ class TokenProducerFunction(torch.autograd.Function):
         B, L1, W = x.shape
         D = proj.shape[1]
         dev, dt = x.device, _DT[x.dtype]
+        if tok_dtype is None:
+            tok_dtype = x.dtype
+        if tok_dtype not in _DT or (tok_dtype != x.dtype and x.dtype != torch.float32):
+            raise RuntimeError(f"signal_b200: TokenProducer cannot produce {tok_dtype} tokens from {x.dtype} input")
+        tdt = _DT[tok_dtype]
         ln_w, ln_b, proj = L_._f32c(ln_w.detach()), L_._f32c(ln_b.detach()), L_._f32c(proj.detach())
-        nb = [lib.sig_tokens_ws_bytes(k, B, L1, W, D, dt) for k in range(3)]
+        nb = [lib.sig_tokens_ws_bytes(k, B, L1, W, D, tdt) for k in range(3)]
         if nb[0] == 0:
             raise RuntimeError(f"signal_b200: unsupported token producer shape B={B} L1={L1} W={W} D={D} (W, D % 8 == 0, <= 1024)")
-        tokens = torch.empty(B, L1, D, dtype=x.dtype, device=dev)
+        tokens = torch.empty(B, L1, D, dtype=tok_dtype, device=dev)
         mean = torch.empty(B, D, dtype=torch.float32, device=dev) if want_mean else None
         saved = _u8(nb[0], dev)
         scratch = _u8(nb[1], dev) if nb[1] else None
         with torch.cuda.device(dev):
             L_.check(lib.sig_tokens_fwd(x.data_ptr(), dt, x.stride(0), x.stride(1), B, L1, W, D, ln_w.data_ptr(), ln_b.data_ptr(),
-                                        float(eps), proj.data_ptr(), tokens.data_ptr(), None if mean is None else mean.data_ptr(),
+                                        float(eps), proj.data_ptr(), tokens.data_ptr(), tdt, None if mean is None else mean.data_ptr(),
                                         saved.data_ptr(), saved.numel(), None if scratch is None else scratch.data_ptr(),
                                         0 if scratch is None else scratch.numel(), dev.index, L_.stream_ptr(dev)), "sig_tokens_fwd")
         ctx.save_for_backward(x, ln_w, proj, saved)
-        ctx.geom = (B, L1, W, D, dt, nb[2])
+        ctx.geom = (B, L1, W, D, dt, tdt, tok_dtype, nb[2])
         if mean is None:
             mean = torch.empty(0, dtype=torch.float32, device=dev)
         ctx.mark_non_differentiable(mean)
@@ -65,11 +71,11 @@ class TokenProducerFunction(torch.autograd.Function):
     def backward(ctx, dtokens, _dmean):
         lib = L_.load()
         x, ln_w, proj, saved = ctx.saved_tensors
-        B, L1, W, D, dt, nscratch = ctx.geom
+        B, L1, W, D, dt, tdt, tok_dtype, nscratch = ctx.geom
         dev = x.device
-        if dtokens.dtype != x.dtype:
-            dtokens = dtokens.to(x.dtype)
-        if dtokens.stride(2) != 1 or (dt == L_.SIG_F32 and dtokens.stride(0) != L1 * dtokens.stride(1)):
+        if dtokens.dtype != tok_dtype:
+            dtokens = dtokens.to(tok_dtype)
+        if dtokens.stride(2) != 1 or (tdt == L_.SIG_F32 and dtokens.stride(0) != L1 * dtokens.stride(1)):
             dtokens = dtokens.contiguous()
         dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=dev) if _dense(x) else torch.empty_like(x, memory_format=torch.contiguous_format)
         d_ln_w = torch.empty(W, dtype=torch.float32, device=dev)
@@ -78,11 +84,11 @@ class TokenProducerFunction(torch.autograd.Function):
         scratch = _u8(nscratch, dev)
         with torch.cuda.device(dev):
             L_.check(lib.sig_tokens_bwd(x.data_ptr(), dt, x.stride(0), x.stride(1), B, L1, W, D, ln_w.data_ptr(), proj.data_ptr(),
-                                        dtokens.data_ptr(), dtokens.stride(0), dtokens.stride(1), saved.data_ptr(), saved.numel(),
+                                        dtokens.data_ptr(), tdt, dtokens.stride(0), dtokens.stride(1), saved.data_ptr(), saved.numel(),
                                         dx.data_ptr(), dx.stride(0), dx.stride(1), d_ln_w.data_ptr(), d_ln_b.data_ptr(),
                                         d_proj.data_ptr(), scratch.data_ptr(), scratch.numel(), dev.index, L_.stream_ptr(dev)),
                      "sig_tokens_bwd")
-        return dx, d_ln_w, d_ln_b, d_proj, None, None
+        return dx, d_ln_w, d_ln_b, d_proj, None, None, None
 
 
 def _dense(x: torch.Tensor) -> bool:
@@ -114,7 +120,12 @@ class TokenProducer(nn.Module):
 
     def tokens(self, x: torch.Tensor) -> torch.Tensor:
         ln = self._ln
-        tok, mean = TokenProducerFunction.apply(x, ln.weight, ln.bias, self._proj, ln.eps, self.want_patch_mean)
+        # under torch.autocast the reference's tail is layer_norm in fp32 followed by a half matmul: fp32 input (a residual
+        # stream that autocast keeps in fp32) then yields tokens of the autocast dtype, exactly like `ln_post(x) @ proj`
+        tok_dtype = None
+        if x.is_cuda and x.dtype == torch.float32 and torch.is_autocast_enabled("cuda"):
+            tok_dtype = torch.get_autocast_dtype("cuda")
+        tok, mean = TokenProducerFunction.apply(x, ln.weight, ln.bias, self._proj, ln.eps, self.want_patch_mean, tok_dtype)
         self.last_patch_mean = mean if self.want_patch_mean else None
         return tok
 

@@ -80,6 +80,39 @@ def test_tokens_half_training_shape_vs_oracle(dtype, B, grid):
     assert tc.rel(got["patch_mean"], own) < 1e-5
 
 
+@pytest.mark.parametrize("amp_dtype", [torch.bfloat16, torch.float16])
+def test_tokens_fp32_input_under_autocast(amp_dtype):
+    """torch.autocast keeps the tower's residual stream in fp32, runs layer_norm in fp32 and the matmul in half: fp32 x in,
+    half tokens out, fp32 dx back -- compared with stock torch ops under the same autocast and with the oracle."""
+    tokens = _mods()
+    from oracle import tokens_oracle as to
+    c = dict(h=8, w=16, width=768, out=512, B=64, seed=77)
+    inp = tc.gen.synthetic_inputs(c)
+    tp, ln, p = _producer(tokens, inp["ln_w"], inp["ln_b"], inp["proj"])
+    x = inp["x"].cuda().requires_grad_(True)
+    cot = (0.01 * inp["cot"]).to("cuda", amp_dtype)
+    with torch.autocast("cuda", dtype=amp_dtype):
+        tok = tp.tokens(x)
+    assert tok.dtype == amp_dtype
+    tok.backward(cot)
+    got = dict(tokens=tok.float(), dx=x.grad, d_ln_w=ln.weight.grad.clone(), d_ln_b=ln.bias.grad.clone(), d_proj=p.grad.clone())
+    assert x.grad.dtype == torch.float32
+    # stock torch under the same autocast (what fullstep.ClipViT / the reference tower do)
+    x2 = inp["x"].cuda().requires_grad_(True)
+    ln.weight.grad = ln.bias.grad = p.grad = None
+    with torch.autocast("cuda", dtype=amp_dtype):
+        tok2 = ln(x2) @ p
+    assert tok2.dtype == amp_dtype
+    tok2.backward(cot)
+    ref = dict(tokens=tok2.float(), dx=x2.grad, d_ln_w=ln.weight.grad, d_ln_b=ln.bias.grad, d_proj=p.grad)
+    for k in ref:
+        e = tc.rel(got[k], ref[k])
+        assert e < 6e-3, f"autocast {amp_dtype}: {k} vs stock torch {e:.3e}"
+    t32, _, xn = to.tokens_fwd(inp["x"], inp["ln_w"], inp["ln_b"], inp["proj"], 1e-5)
+    dx32 = to.tokens_bwd(inp["x"], inp["ln_w"], inp["proj"], cot.float().cpu(), 1e-5, xn=xn)[0]
+    assert tc.rel(got["tokens"], t32) < 2e-2 and tc.rel(got["dx"], dx32) < 2e-2
+
+
 def test_tokens_feed_the_head_in_place():
     """the produced [B,129,d] maps are consumed by SIM / AlignM as strided views (no copy), fwd + bwd through both"""
     tokens = _mods()
@@ -103,6 +136,47 @@ def test_tokens_feed_the_head_in_place():
     for x in xs:
         assert x.grad is not None and torch.isfinite(x.grad.float()).all() and float(x.grad.float().abs().max()) > 0
     assert p.grad is not None and torch.isfinite(p.grad).all()
+
+
+@pytest.mark.parametrize("stage", ["together_CLS_Patch", "CLS"])
+def test_patch_mean_byproduct_replaces_the_gam_pool_pass(stage):
+    """AlignM with the producer's patch means deposited in its ctx (SIG_FLAG_PATCH_MEAN) == AlignM pooling the tokens
+    itself: same losses and gradients (the two pools add the same 128 bf16 values in a different fp32 order)."""
+    tokens = _mods()
+    from signal_b200 import lib, modules as M, synthetic as syn
+    B, W, D = 32, 768, 512
+    g = torch.Generator().manual_seed(17)
+    tp, _, _ = _producer(tokens, 1.0 + 0.1 * torch.randn(W, generator=g), 0.1 * torch.randn(W, generator=g),
+                         W ** -0.5 * torch.randn(W, D, generator=g))
+    al = M.AlignmentM(D, 16, 8).cuda()
+    al.load_state_dict(syn.make_params(syn.align_param_shapes(D), 12))
+    xs = [torch.randn(B, 129, W, generator=g).to("cuda", torch.bfloat16) for _ in range(3)]
+    res = []
+    for use_hint in (False, True):
+        toks, means = [], []
+        for x in xs:
+            t = tp.tokens(x).detach().requires_grad_(True)
+            toks.append(t)
+            means.append(tp.last_patch_mean)
+        for p in al.parameters():
+            p.grad = None
+        n0 = lib.launch_count()
+        if use_hint:
+            al.patch_mean_hint = means
+        r = al(*[t[:, 1:] for t in toks], stage=stage)
+        launches = lib.launch_count() - n0
+        assert al.patch_mean_hint is None   # consumed
+        loss = r if stage == "CLS" else r[0] + 0.5 * r[1]
+        loss.backward()
+        res.append((launches, [float(v) for v in (r if isinstance(r, tuple) else (r,))], [t.grad.float() for t in toks],
+                    float(al.contra_temp.grad)))
+    (l0, v0, g0, t0), (l1, v1, g1, t1) = res
+    assert l1 == l0 - 1, (l0, l1)          # exactly the pool launch is gone
+    for a, b in zip(v0, v1):
+        assert abs(a - b) <= 2e-5 * max(abs(a), 1e-3), (v0, v1)
+    assert abs(t0 - t1) <= 1e-3 * max(abs(t0), 1e-3)
+    for a, b in zip(g0, g1):
+        assert tc.rel(b, a) < 1e-3
 
 
 def test_tokens_rejects_cpu_and_bad_shapes():
