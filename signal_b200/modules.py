@@ -291,6 +291,9 @@ class AlignmentM(nn.Module):
         # ([3,B,d] or three [B,d] tensors), e.g. TokenProducer.last_patch_mean -- the GAM pool pass over the tokens
         # (useB.py:84-86) is then skipped on the bf16 path.  It must be the mean of exactly the maps passed in.
         self.patch_mean_hint = None
+        # Signal.forward computes AlignM in eval mode too and throws the result away (make_model.py:277-281).  Opt-in:
+        # with skip_in_eval = True an eval-mode call launches nothing and returns fp32 zeros of the reference's shapes.
+        self.skip_in_eval = False
 
     def _params(self):
         return [self.contra_temp] + self.DAS_r._params() + self.DAS_n._params() + self.DAS_t._params()
@@ -322,6 +325,11 @@ class AlignmentM(nn.Module):
         return self._run(RGB_patch, NI_patch, TI_patch, True)[1]
 
     def forward(self, RGB_patch, NI_patch, TI_patch, stage):
+        if self.skip_in_eval and not self.training:
+            if not RGB_patch.is_cuda:
+                raise RuntimeError("signal_b200: patch tokens must be CUDA tensors (there is no CPU path)")
+            z = torch.zeros((), dtype=torch.float32, device=RGB_patch.device)
+            return z if stage == "CLS" else (z, z.clone())
         if stage == "CLS":
             return self.Cls_Align(RGB_patch, NI_patch, TI_patch)
         if "Cls_Align" in self.__dict__ or "patch_Align" in self.__dict__:

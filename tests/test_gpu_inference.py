@@ -78,3 +78,24 @@ def test_r1_map_eval_class_mirrors_the_reference_flow():
     cmc, mAP, distmat, _, _, qf, gf = e.compute()
     assert np.abs(cmc - rec["cmc"]).max() <= 1.0 / c["nq"] + 1e-6 and abs(mAP - float(rec["mAP"])) < 5e-3
     assert distmat.shape == (c["nq"], c["ng"]) and qf.shape[0] == c["nq"]
+
+
+def test_alignm_skip_in_eval_launches_nothing():
+    """make_model.py:277-281 computes AlignM at inference and discards it: the opt-in switch returns zeros without a launch"""
+    import __graft_entry__ as entry
+    entry.build()
+    from signal_b200 import lib, modules as M
+    al = M.AlignmentM(512, 16, 8).cuda()
+    toks = [torch.randn(4, 129, 512, device="cuda").to(torch.bfloat16) for _ in range(3)]
+    patches = [t[:, 1:] for t in toks]
+    al.eval()
+    ref = al(*patches, stage="together_CLS_Patch")
+    assert float(ref[0]) != 0.0 and float(ref[1]) != 0.0        # default: computed like the reference does
+    al.skip_in_eval = True
+    n0 = lib.launch_count()
+    gam, lam = al(*patches, stage="together_CLS_Patch")
+    cls_only = al(*patches, stage="CLS")
+    assert lib.launch_count() == n0
+    assert float(gam) == 0.0 and float(lam) == 0.0 and float(cls_only) == 0.0 and gam.dtype == torch.float32 and gam.dim() == 0
+    al.train()
+    assert float(al(*patches, stage="together_CLS_Patch")[0]) != 0.0   # training mode is never skipped

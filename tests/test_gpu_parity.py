@@ -124,6 +124,44 @@ def test_full_batch_b128_matches_oracle(d, hw, k, keep):
     _report(f"B128 d{d} {hw}", rep)
 
 
+@pytest.mark.parametrize("B", [256, 512])
+def test_large_batch_matches_its_shards_and_the_oracle(B):
+    """BASELINE.json config #5 read as strong scaling: 512 / 256 samples per GPU at 2 / 4 GPUs.  SIM and LAM are per-sample
+    independent, so a B-sample call must reproduce the 128-sample calls on its shards (SIM rows and masks; LAM loss = mean of
+    the shard losses; SIM's token gradient rows); GAM couples the batch through the B x B grid and is checked against the
+    oracle's Cls_Align on the full batch."""
+    _harness()
+    import gpu_harness
+    from oracle import signal_oracle as so
+    from signal_b200 import modules as M
+    c = dict(d=512, h=16, w=8, B=B, k=80, keep_ratio=None, gain=1.0, structured=False, seed=5000 + B)
+    sim_p, al_p, toks, cot = gu.case_inputs(c)
+    sim, al = gpu_harness.build_modules(c, sim_p, al_p)
+    head = M.FusionHead(sim, al)
+    tk = [t.to("cuda", torch.bfloat16).requires_grad_(True) for t in toks]
+    cotd = cot.to("cuda", torch.bfloat16)
+
+    def run(rows):
+        xs = [t.detach()[rows].clone().requires_grad_(True) for t in tk]
+        out, gam, lam = head(*[x[:, 1:] for x in xs], *[x[:, 0] for x in xs])
+        masks = torch.stack([sim.token_selection.last_masks[k] for k in ("RGB", "NI", "TI")]).clone()
+        out.backward(cotd[rows])                      # SIM's part of the token gradient only (per-sample independent)
+        return out.detach().float(), float(gam), float(lam), masks, [x.grad.float() for x in xs]
+
+    out, gam, lam, masks, dt = run(slice(0, B))
+    lams = []
+    for s0 in range(0, B, 128):
+        o, _, l, mk, g = run(slice(s0, s0 + 128))
+        lams.append(l)
+        assert torch.equal(mk, masks[:, s0:s0 + 128]), f"masks of shard {s0 // 128} differ from the B={B} call"
+        assert float((o - out[s0:s0 + 128]).norm() / o.norm()) < 2e-3
+        for m in range(3):
+            assert float((g[m] - dt[m][s0:s0 + 128]).norm() / g[m].norm()) < 5e-3
+    assert abs(lam - sum(lams) / len(lams)) < 2e-3 * abs(lam), (lam, lams)
+    ref_gam = float(so.gam_loss([t.detach().float().cpu()[:, 1:] for t in tk], al_p["contra_temp"].float()))
+    assert abs(gam - ref_gam) < BF16_TOL * abs(ref_gam), (gam, ref_gam)
+
+
 @pytest.mark.parametrize("name", SMALL_BF16)
 def test_bf16_tensor_core_path_vs_simt_path(name):
     """Same bf16 inputs through the tcgen05 path and through the fp32 SIMT kernels (FORCE_SIMT)."""
