@@ -746,14 +746,15 @@ static SimCtx sim_ctx(void* base, int B, int L, int d, bool tc = false) {
   c.asum = a.take<float>(R * 8);
   c.xbar = a.take<float>(R * 8 * d);
   c.o = a.take<float>(R * d);
-  c.attn = a.take<float>(R * d);
   c.r1 = a.take<float>(R * d);
   c.mu1 = a.take<float>(R);
   c.rstd1 = a.take<float>(R);
   c.y1 = a.take<float>(R * d);
+  // [attn | a1 | f] contiguous: the split-K targets of the tensor-core MLP chain are zeroed by ONE memset (sim_mlp_tc.inl)
+  c.attn = a.take<float>(R * d);
   c.a1 = a.take<float>(R * 2 * d);
-  c.h1 = a.take<float>(R * 2 * d);
   c.f = a.take<float>(R * d);
+  c.h1 = a.take<float>(R * 2 * d);
   c.r2 = a.take<float>(R * d);
   c.mu2 = a.take<float>(R);
   c.rstd2 = a.take<float>(R);

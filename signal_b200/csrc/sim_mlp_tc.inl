@@ -37,6 +37,33 @@ static void per_head(TcOperand& o, const __nv_bfloat16* base, int64_t stride) {
   for (int h = 0; h < kHeads; ++h) o.ptr[h] = base + h * stride;
 }
 
+// The dense layers of the chain have M = 3B rows: at B = 128 that is 3 M-tiles x 6..12 N-tiles = 18..36 work units, each
+// pulling its whole K range (393 KB at K = 768) through ONE SM's ~70 GB/s L2 port -- 4-6 us per GEMM while 110+ SMs idle.
+// Split-K spreads the same bytes over ~148 units: fp32 partial tiles are added into a pre-zeroed C (red.global.add.v4,
+// the unit with the first k-blocks also adds the bias).  Only for GEMMs whose consumer is an element-wise kernel reading the
+// fp32 C (LayerNorm, GELU + shadow) or that accumulate onto existing values.
+// MEASURED (B = 128, d = 768, one B200, profiles/r2_splitk_experiment.json): the phases shrink where the GEMM dominated
+// (sim_post 56.4 -> 52.3 us, sim_attn_prep_bwd 28.1 -> 21.3) but sim_post_bwd grows (88.8 -> 93.6) and the fused step does not
+// improve (0.6014 vs 0.5878 ms): next to AlignM's GPU-filling kernels the extra CTAs and 7 MB of atomics per GEMM cost what
+// the shorter K loops save.  Off by default; SIG_SIM_SPLITK=1 turns it on.
+static bool sim_splitk_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SIG_SIM_SPLITK");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+static void split_k(TcGemmDesc& t) {
+  if (!sim_splitk_enabled() || t.out_bf16 || t.act || t.C2[0] || t.pre[0] || t.batch != 1) return;
+  const int tiles = (int)(ceil_div(t.M, 128) * ceil_div(t.N, t.bn));
+  const int kblocks = (int)ceil_div(t.K, 64);
+  int ks = (tc_num_sms() + tiles - 1) / tiles;
+  if (ks > kblocks / 2) ks = kblocks / 2;       // at least two k-blocks per unit
+  if (ks < 2) return;
+  t.ksplit = ks;
+  t.accumulate = 0;                              // atomics add onto what is there: that IS the accumulation
+}
+
 // c[(b,q),h] = scale * q_h . b_k^h   grid R, 256 threads (one warp per head)
 static __global__ void __launch_bounds__(256) catt_kernel(const float* __restrict__ qatt, const float* __restrict__ bk, int d, float scale,
                                                           float* __restrict__ catt) {
@@ -84,6 +111,8 @@ static int attn_prep_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
   const size_t dd = (size_t)d * d;
   const __nv_bfloat16* wqb = c.Wb;
   const __nv_bfloat16* wkb = c.Wb + dd;
+  if (sim_splitk_enabled())   // [attn | a1 | f]: split-K targets of attn_post_tc (one memset, far ahead of their GEMMs)
+    cudaMemsetAsync(c.attn, 0, (size_t)(reinterpret_cast<char*>(c.f) - reinterpret_cast<char*>(c.attn)) + (size_t)R * d * sizeof(float), s);
   SIG_TRY(cast_sim_weights(c, p, d, s));
   {  // q = W_q cls + b_q  (fp32 + bf16 shadow)
     TcGemmDesc t = lin_nt(c.clsb, d, wqb, d, c.qatt, d, p->in_proj_b, R, d, d);
@@ -125,19 +154,29 @@ static int attn_post_tc(const SimCtx& c, const sig_sim_params* p, int B, int d, 
     }
     SIG_TRY(tc_gemm(t, s));
   }
-  SIG_TRY(tc_gemm(lin_nt(c.ob, d, wob, d, c.attn, d, p->out_proj_b, R, d, d), s));
+  {
+    TcGemmDesc t = lin_nt(c.ob, d, wob, d, c.attn, d, p->out_proj_b, R, d, d);
+    split_k(t);
+    SIG_TRY(tc_gemm(t, s));
+  }
   SIG_LAUNCH((layernorm_fwd_kernel<float>), R, 256, 0, s, c.attn, c.clsf, p->ln1_w, p->ln1_b, d, c.r1, c.mu1, c.rstd1, c.y1, c.y1b);
   SIG_CHECK_LAUNCH();
   {
     // a1 = y1 W1^T + b1 (fp32, kept for the backward), then h1 = gelu(a1) as the bf16 operand of the next GEMM.
     // The activation is a separate full-grid elementwise launch: inside the GEMM it would run on the four
     // epilogue warps of 36 CTAs (erf on one warp per scheduler), which measured 3x the GEMM itself.
-    SIG_TRY(tc_gemm(lin_nt(c.y1b, d, w1b, d, c.a1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d), s));
+    TcGemmDesc t = lin_nt(c.y1b, d, w1b, d, c.a1, 2 * (int64_t)d, p->ffn0_b, R, 2 * d, d);
+    split_k(t);
+    SIG_TRY(tc_gemm(t, s));
     const int64_t n = (int64_t)R * 2 * d;
     SIG_LAUNCH((gelu_shadow_kernel), (unsigned)ceil_div(n, 4 * 256), 256, 0, s, c.a1, c.h1b, n);
     SIG_CHECK_LAUNCH();
   }
-  SIG_TRY(tc_gemm(lin_nt(c.h1b, 2 * (int64_t)d, w2b, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d), s));
+  {
+    TcGemmDesc t = lin_nt(c.h1b, 2 * (int64_t)d, w2b, 2 * (int64_t)d, c.f, d, p->ffn2_b, R, d, 2 * d);
+    split_k(t);
+    SIG_TRY(tc_gemm(t, s));
+  }
   SIG_LAUNCH((layernorm_fwd_kernel<OutT>), R, 256, 0, s, c.f, c.y1, p->ln2_w, p->ln2_b, d, c.r2, c.mu2, c.rstd2, out, (__nv_bfloat16*)nullptr);
   SIG_CHECK_LAUNCH();
   return 0;
@@ -170,13 +209,19 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   float* dwv = g->in_proj_w + 2 * dd;
   // the bf16 weight shadows written by the forward call are reused: autograd's version check on the
   // saved parameters rules out an in-place update between forward and backward
+  if (sim_splitk_enabled())   // split-K target of the dh1 GEMM below (ahead of the kernel chain, not inside it)
+    cudaMemsetAsync(c.dh1, 0, (size_t)R * 2 * d * sizeof(float), s);
   SIG_LAUNCH((layernorm_bwd_kernel<InT>), R, 256, 0, s, dout, c.r2, p->ln2_w, c.mu2, c.rstd2, nullptr, d, c.dr2, c.dyx, c.dyf, c.dr2b);
   SIG_CHECK_LAUNCH();
   // (the three column sums read buffers that are rewritten further down this stream -- dyx/dyf by the second
   //  LayerNorm backward, dr2 by the accumulating GEMM -- so they stay on it, as ONE launch)
   SIG_TRY(launch_colsum3(c.dyx, g->ln2_w, c.dyf, g->ln2_b, c.dr2, g->ffn2_b, d, R, d, s));
   SIG_TRY(side_gemm(fk, s, lin_tn(c.dr2b, d, c.h1b, 2 * (int64_t)d, g->ffn2_w, 2 * (int64_t)d, d, 2 * d, R)));   // dW2 = dr2^T h1
-  SIG_TRY(tc_gemm(lin_nn(c.dr2b, d, w2b, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d), s));              // dh1 = dr2 W2
+  {  // dh1 = dr2 W2
+    TcGemmDesc t = lin_nn(c.dr2b, d, w2b, 2 * (int64_t)d, c.dh1, 2 * (int64_t)d, R, 2 * d, d);
+    split_k(t);      // (c.dh1 was zeroed at the top of this function)
+    SIG_TRY(tc_gemm(t, s));
+  }
   {
     const int64_t n = (int64_t)R * 2 * d;
     SIG_LAUNCH((gelu_bwd_shadow_kernel), (unsigned)ceil_div(n, 256), 256, 0, s, c.dh1, c.a1, c.da1b, n);
@@ -187,6 +232,7 @@ static int attn_post_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   {  // dy1 = dr2 + da1 W1
     TcGemmDesc t = lin_nn(c.da1b, 2 * (int64_t)d, w1b, d, c.dr2, d, R, d, 2 * d);
     t.accumulate = 1;
+    split_k(t);
     SIG_TRY(tc_gemm(t, s));
   }
   SIG_LAUNCH((layernorm_bwd_kernel<float>), R, 256, 0, s, c.dr2, c.r1, p->ln1_w, c.mu1, c.rstd1, nullptr, d, c.dr1, c.dyx, c.dyf, c.dr1b);
@@ -262,6 +308,7 @@ static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
   {  // dcls = dr1 (residual) + dq W_q
     TcGemmDesc t = lin_nn(c.dqattb, d, wqb, d, c.dr1, d, R, d, d);
     t.accumulate = 1;
+    split_k(t);
     SIG_TRY(tc_gemm(t, s));
   }
   return 0;

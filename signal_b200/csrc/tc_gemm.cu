@@ -243,8 +243,9 @@ struct GemmProblem {
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
     const int row0 = m0 + q * 32 + sub;              // this lane's row in step i is row0 + 4 i
     const bool red = p.ksplit > 1;
-    const float* bias = red ? nullptr : p.bias[z];
-    const float* rvec = p.rowvec[z] ? p.rowvec[z] + (long long)(m0 >> 7) * p.N : nullptr;   // one sample per 128-row tile
+    // split-K: the partial tiles are added into a pre-zeroed C; the unit that owns the first k-blocks also adds the bias
+    const float* bias = (red && u.kb0 != 0) ? nullptr : p.bias[z];
+    const float* rvec = (p.rowvec[z] && !red) ? p.rowvec[z] + (long long)(m0 >> 7) * p.N : nullptr;   // one sample per 128-row tile
     const float rscale = rvec ? *p.rowvec_scale : 0.f;
     const bool vec_ok = p.c_tok ? ((p.c_stride_b % 8) == 0 && (p.c_stride_l % 8) == 0) : ((p.ldc % 8) == 0);
     const float alpha = p.alpha;
@@ -309,7 +310,8 @@ struct GemmProblem {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 t = tc::epi_get(scratch, lane, i);
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i * step), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i * step), "f"(t.x + cv.x), "f"(t.y + cv.y),
+                         "f"(t.z + cv.z), "f"(t.w + cv.w)
                          : "memory");
           }
         } else {
@@ -344,7 +346,7 @@ struct GemmProblem {
           const long long orow = (long long)(row0 + 4 * i);
           for (int j = 0; j < 4; ++j) {
             if (col + j >= p.N) break;
-            if (red) { atomicAdd(static_cast<float*>(p.C[z]) + o + j, t[j]); continue; }
+            if (red) { atomicAdd(static_cast<float*>(p.C[z]) + o + j, t[j] + bb[j]); continue; }
             float x = t[j] + bb[j];
             if (pre) pre[orow * p.ldc + col + j] = x;
             if (act == 1) x = gelu_f(x);

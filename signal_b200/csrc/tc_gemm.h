@@ -32,7 +32,7 @@ struct TcGemmDesc {
   const float* bias[8];     // optional, per n
   float alpha;
   int act;                  // 0 none, 1 GELU
-  int ksplit;               // > 1: fp32 atomic accumulation into a pre-zeroed C (no bias / act / bf16)
+  int ksplit;               // > 1: fp32 atomic accumulation into a pre-zeroed C (bias allowed: added once; no act / bf16 / C2 / pre)
   int bn;                   // 128 or 256 (N tile)
   int mt;                   // 1 or 2 (with bn == 256): 128-row M tiles per work unit sharing one B tile
   int pair;                 // 1 (with bn == 256, mt == 1): 256 x 256 units on CTA pairs (cta_group::2), see tc_gemm.cu

@@ -35,6 +35,36 @@ def test_bias_gelu_bf16_out():
     _check(out, ref, 6e-3)
 
 
+@pytest.mark.parametrize("M,N,K,ks", [(384, 768, 768, 6), (384, 1536, 768, 4), (200, 776, 1536, 9), (12, 768, 768, 6)])
+def test_split_k_with_bias_and_accumulate(M, N, K, ks):
+    """split-K: partial tiles are added with fp32 atomics; the bias is added exactly once; a non-zero C is accumulated onto
+    (the small M = 3B layers of SIM's MLP chain, csrc/sim_mlp_tc.inl::split_k)."""
+    from signal_b200 import lib
+    A, B = _rand((M, K), 31), _rand((N, K), 32)
+    bias = torch.randn(N, device="cuda")
+    out = lib.debug_gemm_bf16(A, 0, B, 0, M, N, K, bias=bias, alpha=0.25, ksplit=ks)
+    ref = 0.25 * (A.float() @ B.float().T) + bias
+    _check(out, ref)
+    base = torch.randn(M, N, device="cuda")
+    out2 = lib.debug_gemm_bf16(A, 0, B, 0, M, N, K, ksplit=ks)
+    _check(out2, A.float() @ B.float().T)
+    # accumulate semantics: C holds values already
+    C = base.clone()
+    acc = _gemm_into(lib, A, B, C, M, N, K, ks)
+    _check(acc, base + A.float() @ B.float().T)
+
+
+def _gemm_into(lib, A, B, C, M, N, K, ks):
+    """C[M,N] += A B^T through the split-K path (the seam zero-fills only the buffers it allocates itself)."""
+    import ctypes as Ct
+    L = lib.load()
+    ga = (Ct.c_int64 * 5)(A.stride(0), 0, 0, A.shape[0], A.shape[1])
+    gb = (Ct.c_int64 * 5)(B.stride(0), 0, 0, B.shape[0], B.shape[1])
+    lib.check(L.sig_debug_gemm_bf16(A.data_ptr(), 0, ga, B.data_ptr(), 0, gb, C.data_ptr(), N, 0, None, M, N, K, 1.0, 0, ks, 128, 0, 0,
+                                    None, None, 0, C.device.index, lib.stream_ptr(C.device)), "sig_debug_gemm_bf16")
+    return C
+
+
 @pytest.mark.parametrize("bn", [128, 256])
 def test_token_view_as_kmajor_a(bn):
     """A = patch view x[:,1:] of a [B,129,d] token map (3-D tensor map, no copy)."""
