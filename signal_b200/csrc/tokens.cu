@@ -102,43 +102,43 @@ __global__ void __launch_bounds__(256) ln_rows_fwd_kernel(const InT* __restrict_
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dxn * gamma,  xhat = (x - mu) * rstd
-// part [gridDim.x][2][W]: this CTA's sums of dxn * xhat (d gamma) and dxn (d beta) over its rows
+// part [gridDim.x][2][W]: this CTA's sums of dxn * xhat (d gamma) and dxn (d beta) over its rows.
+// Register diet (the first version held xhat, g, gamma and both accumulators as fp32 arrays: 148 registers at W = 768, one
+// 8-warp CTA per SM, 2.0 TB/s): the row is kept as the RAW 16-byte loads and unpacked twice (statistics pass, output pass),
+// gamma is re-read from L1 per chunk, only the two accumulators stay resident -- two to three CTAs per SM.
 template <int NCH, typename InT, typename GT>
-__global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const InT* __restrict__ x, int64_t sb, int64_t sl, int R, int L1, int W,
-                                                         const float* __restrict__ gamma, const float* __restrict__ mu,
-                                                         const float* __restrict__ rstd, const GT* __restrict__ dxn,
-                                                         InT* __restrict__ dx, int64_t dsb, int64_t dsl, float* __restrict__ part) {
+__global__ void __launch_bounds__(256, 2) ln_rows_bwd_kernel(const InT* __restrict__ x, int64_t sb, int64_t sl, int R, int L1, int W,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mu,
+                                                            const float* __restrict__ rstd, const GT* __restrict__ dxn,
+                                                            InT* __restrict__ dx, int64_t dsb, int64_t dsl, float* __restrict__ part) {
   pdl_enter();
   extern __shared__ __align__(16) float red[];   // [8 warps][2][W]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float dg[NCH][8], db[NCH][8], gm[NCH][8];
+  float dg[NCH][8], db[NCH][8];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int e = (c * 32 + lane) * 8;
-    if (e < W) load8(gamma + e, gm[c]);
+  for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int t = 0; t < 8; ++t) dg[c][t] = db[c][t] = 0.f;
-  }
   for (int row = blockIdx.x * 8 + w; row < R; row += gridDim.x * 8) {
     const int b = row / L1, l = row - b * L1;
     const InT* xr = x + b * sb + l * sl;
+    const GT* dr_in = dxn + (int64_t)row * W;
     const float mean = mu[row], rs = rstd[row];
-    float xh[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int e = (c * 32 + lane) * 8;
       if (e < W) {
-        float xv[8], dv[8];
+        float xv[8], dv[8], gm[8];
         load8(xr + e, xv);
-        load8(dxn + (int64_t)row * W + e, dv);
+        load8(dr_in + e, dv);
+        load8(gamma + e, gm);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          xh[c][t] = (xv[t] - mean) * rs;
-          g[c][t] = dv[t] * gm[c][t];
-          s1 += g[c][t];
-          s2 = fmaf(g[c][t], xh[c][t], s2);
-          dg[c][t] = fmaf(dv[t], xh[c][t], dg[c][t]);
+          const float xh = (xv[t] - mean) * rs, g = dv[t] * gm[t];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          dg[c][t] = fmaf(dv[t], xh, dg[c][t]);
           db[c][t] += dv[t];
         }
       }
@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const InT* __restrict_
     for (int c = 0; c < NCH; ++c) {
       const int e = (c * 32 + lane) * 8;
       if (e < W) {
-        float o[8];
+        float xv[8], dv[8], gm[8], o[8];
+        load8(xr + e, xv);        // (second read of the row: L1 hits, 3 KB per warp)
+        load8(dr_in + e, dv);
+        load8(gamma + e, gm);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = rs * (g[c][t] - c1 - xh[c][t] * c2);
+        for (int t = 0; t < 8; ++t) o[t] = rs * (dv[t] * gm[t] - c1 - (xv[t] - mean) * rs * c2);
         store8(dr + e, o);
       }
     }
@@ -287,7 +290,7 @@ TokLayout tok_layout(int R, int W, int D, int dtype) {
   t.saved_bytes = o;
   t.stage = 0;
   t.fwd_scratch_bytes = dtype == SIG_F16 ? al256((size_t)R * D * 4) : 0;
-  t.ctas = 296;   // 2 CTAs of 8 rows per SM on a 148-SM part; any value is correct
+  t.ctas = 296;   // 2 CTAs of 8 warps per SM on a 148-SM part (107 registers at W = 768); any value is correct
   o = 0;
   t.dxn = o; o += al256((size_t)R * W * es);
   t.dtokb = o; o += dtype == SIG_F32 ? 0 : al256((size_t)R * D * 2);
@@ -327,6 +330,7 @@ int tokens_fwd_t(const XT* x, int tdt, int64_t sb, int64_t sl, int B, int L1, in
     g.M = R; g.N = D; g.K = W;
     g.ldc = D;
     g.bn = (D % 256 == 0) ? 256 : 128;
+    // (256 x 256 units, mt = 2, measured slower here: 64.6 vs 51.3 us at R = 49 536 -- 388 units are 2.6 waves of 148 CTAs)
     if constexpr (std::is_same<TT, __nv_bfloat16>::value) {
       g.C[0] = tokens; g.out_bf16 = 1;
       SIG_TRY(tc_gemm(g, s));
