@@ -136,6 +136,12 @@ typedef struct sig_sim_params {
   const float* ln1_w; const float* ln1_b;         /* norm1 [d] */
   const float* ln2_w; const float* ln2_b;         /* norm2 [d] */
   const sig_sel_fold* sel_fold;                   /* optional (NULL: fold on the fly in fp32) */
+  /* Optional by-product of the selection-score pass (bf16 tensor-core path): fp32 [3][B][d] mean over the
+   * L patch rows of each modality = the GAM mean pool (useB.py:84-86), written while the tokens stream through the score
+   * kernel.  Meant for sig_align_fwd's SIG_FLAG_PATCH_MEAN slot when both modules read the same token maps
+   * (make_model.py:191,205); pool_event (cudaEvent_t, may be NULL) is recorded on the stream position where it is complete. */
+  float* pool_out;
+  void* pool_event;
 } sig_sim_params;
 
 /* Gradients of the trainable SIM parameters (token_selection.* never receive
@@ -161,6 +167,9 @@ typedef struct sig_align_params {
   const float* off0_w[3];   const float* off0_b[3];     /* DAS_*.conv_offset.0  [d,d,1,1],[d] */
   const float* off2_w[3];   const float* off2_b[3];     /* DAS_*.conv_offset.2  [d,1,4,4],[d] */
   const float* off4_w[3];                                /* DAS_*.conv_offset.4  [1,d,1,1]     */
+  /* With SIG_FLAG_PATCH_MEAN: optional cudaEvent_t (may be NULL) the GAM chain waits for before it reads the patch means
+   * from the ctx slot (they are being written on another stream, e.g. by sig_sim_fwd's pool_out). */
+  void* patch_mean_event;
 } sig_align_params;
 
 typedef struct sig_align_param_grads {           /* overwritten */

@@ -665,6 +665,13 @@ size_t das_ctx_bytes(int B, int L, int d) { return align_ctx(nullptr, B, L, d, 1
 
 #include "align_tc.inl"
 
+// GAM mean pool for a caller outside this file (SIM's score pass delivers it under FusionHead; this is its fall-back for
+// token layouts the ring kernel does not take)
+int align_pool_tokens(const sig_tokens* tok, float* mean, cudaStream_t s) {
+  if (tok->dtype != SIG_BF16) return SIG_ERR_DTYPE;
+  return pool_tokens_bf16(tok, mean, s);
+}
+
 // SIG_FLAG_PATCH_MEAN: where the caller deposits the [3][B][d] fp32 patch means (tensor-core path only; the exact fp32
 // path pools in fp64)
 int align_patch_mean_slot(void* ctx, int B, int L, int d, int dtype, unsigned flags, float** slot) {

@@ -7,6 +7,8 @@ size_t align_ctx_bytes(int B, int L, int d);
 size_t das_ctx_bytes(int B, int L, int d);
 size_t align_ctx_bytes_for(int B, int L, int d, int dtype, unsigned flags);
 size_t volume_ws_floats(int B1, int B2);
+// mean [3][B][d] fp32 = mean over the L patch rows of each modality (bf16 / fp32 tokens; the pooling kernels of the GAM path)
+int align_pool_tokens(const sig_tokens* tok, float* mean, cudaStream_t s);
 int align_patch_mean_slot(void* ctx, int B, int L, int d, int dtype, unsigned flags, float** slot);
 int align_forward(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
                   size_t ctx_bytes, unsigned flags, cudaStream_t s);

@@ -741,6 +741,33 @@ static int lam_backward_chain_tc(const AlignTcCtx& c, const TokPtrs3& tp, const 
   return 0;
 }
 
+// GAM mean pool of the three bf16 patch maps -> mean [3][B][d] fp32
+static int pool_tokens_bf16(const sig_tokens* tok, float* mean, cudaStream_t s) {
+  const int B = tok->B, L = tok->L, d = tok->d;
+  const bool rows_contig = tok->patch_stride_l[0] == d && tok->patch_stride_l[1] == d && tok->patch_stride_l[2] == d;
+  SIG_PHASE("gam_pool");
+  if (tok_ring_enabled() && L == kMaxL && (d == 512 || d == 768) && rows_contig) {
+    // streaming ring: 4 x 48 KB in flight per SM (tok_ring.cuh)
+    TokSrc3 src;
+    for (int m = 0; m < 3; ++m) { src.patch[m] = tok->patch[m]; src.psb[m] = tok->patch_stride_b[m]; }
+    const int n_items = 3 * B * (kMaxL / 32);
+    const int ctas = n_items < tc_num_sms() ? n_items : tc_num_sms();
+    cudaMemsetAsync(mean, 0, (size_t)3 * B * d * sizeof(float), s);   // groups split between two CTAs are added atomically
+    if (d == 768) {
+      ensure_dyn_smem(pool_ring_kernel<768>, (int)pool_ring_smem<768>());
+      SIG_LAUNCH((pool_ring_kernel<768>), ctas, TokRing<768>::kThreads, pool_ring_smem<768>(), s, src, B, n_items, mean);
+    } else {
+      ensure_dyn_smem(pool_ring_kernel<512>, (int)pool_ring_smem<512>());
+      SIG_LAUNCH((pool_ring_kernel<512>), ctas, TokRing<512>::kThreads, pool_ring_smem<512>(), s, src, B, n_items, mean);
+    }
+  } else {
+    const TokPtrs3 tp = tok_ptrs3(tok);
+    SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), (unsigned)ceil_div(kPoolGroups * (d / 8), 32) * 32, (size_t)kPoolGroups * d * sizeof(float), s, tp, B, L, d, mean);
+  }
+  SIG_CHECK_LAUNCH();
+  return 0;
+}
+
 static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, int h, int w, int do_lam, float* losses, void* ctx,
                             bool eager, bool have_mean, cudaStream_t s) {
   const int B = tok->B, L = tok->L, d = tok->d;
@@ -755,29 +782,13 @@ static int align_forward_tc(const sig_tokens* tok, const sig_align_params* p, in
   }
   {
     SIG_PHASE("gam_fwd");
-    const bool rows_contig = tok->patch_stride_l[0] == d && tok->patch_stride_l[1] == d && tok->patch_stride_l[2] == d;
     if (have_mean) {
-      // SIG_FLAG_PATCH_MEAN: the caller filled c.mean (sig_align_patch_mean_slot) with the mean pool of the patch rows,
-      // e.g. the by-product of sig_tokens_fwd -- one pass over the tokens less
-    } else if (tok_ring_enabled() && L == kMaxL && (d == 512 || d == 768) && rows_contig) {
-      SIG_PHASE("gam_pool");   // streaming ring: 4 x 48 KB in flight per SM (tok_ring.cuh)
-      TokSrc3 src;
-      for (int m = 0; m < 3; ++m) { src.patch[m] = tok->patch[m]; src.psb[m] = tok->patch_stride_b[m]; }
-      const int n_items = 3 * B * (kMaxL / 32);
-      const int ctas = n_items < tc_num_sms() ? n_items : tc_num_sms();
-      cudaMemsetAsync(c.mean, 0, (size_t)3 * B * d * sizeof(float), s);   // groups split between two CTAs are added atomically
-      if (d == 768) {
-        ensure_dyn_smem(pool_ring_kernel<768>, (int)pool_ring_smem<768>());
-        SIG_LAUNCH((pool_ring_kernel<768>), ctas, TokRing<768>::kThreads, pool_ring_smem<768>(), s, src, B, n_items, c.mean);
-      } else {
-        ensure_dyn_smem(pool_ring_kernel<512>, (int)pool_ring_smem<512>());
-        SIG_LAUNCH((pool_ring_kernel<512>), ctas, TokRing<512>::kThreads, pool_ring_smem<512>(), s, src, B, n_items, c.mean);
-      }
-      SIG_CHECK_LAUNCH();
+      // SIG_FLAG_PATCH_MEAN: the caller fills c.mean (sig_align_patch_mean_slot) with the mean pool of the patch rows --
+      // the by-product of sig_tokens_fwd, or of SIM's score pass under FusionHead (sig_sim_params.pool_out), whose event
+      // this stream waits for -- one pass over the tokens less
+      if (p->patch_mean_event) cudaStreamWaitEvent(s, (cudaEvent_t)p->patch_mean_event, 0);
     } else {
-      SIG_PHASE("gam_pool");
-      SIG_LAUNCH((pool_tok_kernel<__nv_bfloat16>), dim3(B, 3), (unsigned)ceil_div(kPoolGroups * (d / 8), 32) * 32, (size_t)kPoolGroups * d * sizeof(float), s, tp, B, L, d, c.mean);
-      SIG_CHECK_LAUNCH();
+      SIG_TRY(pool_tokens_bf16(tok, c.mean, s));
     }
     SIG_LAUNCH((gam_norm_split_kernel), B, 256, 0, s, c.mean, B, d, c.f, c.fb, c.fA, c.fB, c.nrm, c.self4);
     SIG_CHECK_LAUNCH();

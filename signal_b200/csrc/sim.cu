@@ -12,6 +12,7 @@
 // i.e. the K/V projections are applied to 24 effective queries per sample instead of 384 tokens.
 #include "common.cuh"
 #include "sim.h"
+#include "align.h"
 #include "sim_tc.h"
 #include "simt_ops.cuh"
 #include "tc_gemm.h"
@@ -838,6 +839,7 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
   }
   dim3 grid((unsigned)ceil_div(L, 32), 3, (unsigned)B);
   const bool rows_contig = tok->patch_stride_l[0] == d && tok->patch_stride_l[1] == d && tok->patch_stride_l[2] == d;
+  bool pool_done = false;
   if (c.tc && tok_ring_enabled() && L == kMaxL && (d == 512 || d == 768) && rows_contig) {
     SIG_PHASE("sim_scores");   // streaming ring: 4 x 48 KB in flight per SM (tok_ring.cuh)
     TokSrc3 src;
@@ -854,14 +856,22 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
         SIG_LAUNCH((sim_scores_split_kernel<512>), ctas, ScoreSplit<512>::kThreads, ScoreSplit<512>::kSmemBytes, s, src, c.clsf, c.qtsel, c.csel, B,
                    n_items, c.sel_logits, c.intra_raw);
       }
-    } else if (d == 768) {
-      ensure_dyn_smem(sim_scores_ring_kernel<768>, (int)sim_scores_ring_smem<768>());
-      SIG_LAUNCH((sim_scores_ring_kernel<768>), ctas, TokRing<768>::kThreads, sim_scores_ring_smem<768>(), s, src, c.clsf, c.qtsel, c.csel, B, n_items,
-                 c.sel_logits, c.intra_raw);
     } else {
-      ensure_dyn_smem(sim_scores_ring_kernel<512>, (int)sim_scores_ring_smem<512>());
-      SIG_LAUNCH((sim_scores_ring_kernel<512>), ctas, TokRing<512>::kThreads, sim_scores_ring_smem<512>(), s, src, c.clsf, c.qtsel, c.csel, B, n_items,
-                 c.sel_logits, c.intra_raw);
+      // p->pool_out (FusionHead): the pass also delivers GAM's mean pool (tok_ring.cuh, kPool)
+      float* pool = p->pool_out;
+      if (pool) cudaMemsetAsync(pool, 0, (size_t)3 * B * d * sizeof(float), s);   // split groups are added atomically onto zero
+#define SIG_SCORES(DD, PP)                                                                                                      \
+  do {                                                                                                                          \
+    ensure_dyn_smem(sim_scores_ring_kernel<DD, PP>, (int)sim_scores_ring_smem<DD>(PP));                                          \
+    SIG_LAUNCH((sim_scores_ring_kernel<DD, PP>), ctas, TokRing<DD>::kThreads, sim_scores_ring_smem<DD>(PP), s, src, c.clsf, c.qtsel, \
+               c.csel, B, n_items, c.sel_logits, c.intra_raw, pool);                                                            \
+  } while (0)
+      if (d == 768 && pool) SIG_SCORES(768, true);
+      else if (d == 768) SIG_SCORES(768, false);
+      else if (pool) SIG_SCORES(512, true);
+      else SIG_SCORES(512, false);
+#undef SIG_SCORES
+      pool_done = pool != nullptr;
     }
   } else if (c.tc) {
     SIG_PHASE("sim_scores");
@@ -870,6 +880,12 @@ static int run_selection(const SimCtx& c, const sig_tokens* tok, const sig_sim_p
   } else
     SIG_LAUNCH((sim_scores_kernel), grid, 256, 4 * d * sizeof(float), s, c.Xf, c.clsf, c.qtsel, c.csel, B, L, d, c.sel_logits, c.intra_raw);
   SIG_CHECK_LAUNCH();
+  if (p->pool_out) {
+    // the caller (FusionHead) relies on the pool being delivered: layouts the ring kernel does not take get AlignM's own
+    // pooling kernel, on this stream
+    if (!pool_done) SIG_TRY(align_pool_tokens(tok, p->pool_out, s));
+    if (p->pool_event) cudaEventRecord((cudaEvent_t)p->pool_event, s);
+  }
   SIG_LAUNCH((sim_select_kernel), B, 1024, 0, s, c.sel_logits, c.intra_raw, B, L, d, which, k1, k2, max_keep, c.maskf, masks_out);
   SIG_CHECK_LAUNCH();
   return 0;

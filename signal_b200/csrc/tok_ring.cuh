@@ -44,10 +44,15 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
 // two-deep buffer; a lane keeps its 4 x 8 x kChunks query values in registers for the whole group.  The per-lane
 // accumulation order (chunks lane, lane+32, .. ; 8 channels in order; then a butterfly) is that of
 // sim_scores_tok_kernel, so both kernels return the same bits.
-template <int D>
+// kPool (FusionHead): the same pass also delivers GAM's mean pool of the patch rows (useB.py:84-86) --
+// every token value is in a register here anyway, so AlignM's own pass over the 75 MB of tokens (pool_ring_kernel) goes
+// away.  pool_mean [3][B][D] (zero-filled by the caller) receives sum / L per group exactly like pool_ring_kernel: the
+// eight warps' partial sums meet in a [8][256] shared-memory tile in a fixed order, a group that straddles two CTAs gets
+// two atomic adds onto zero (order-independent), so the result is deterministic.
+template <int D, bool kPool>
 static __global__ void __launch_bounds__(TokRing<D>::kThreads, 1)
 sim_scores_ring_kernel(TokSrc3 src, const float* __restrict__ clsf, const float* __restrict__ qtsel, const float* __restrict__ csel,
-                       int B, int n_items, float* __restrict__ sel_logits, float* __restrict__ intra_raw) {
+                       int B, int n_items, float* __restrict__ sel_logits, float* __restrict__ intra_raw, float* __restrict__ pool_mean) {
   using R = TokRing<D>;
   constexpr int L = kMaxL;
   pdl_launch_dependents();
@@ -57,6 +62,7 @@ sim_scores_ring_kernel(TokSrc3 src, const float* __restrict__ clsf, const float*
   auto* bars = reinterpret_cast<ring::Bars<R::kStages>*>(tr_smem + (size_t)R::kStages * R::kStageBytes + 2 * R::kQBytes);
   uint64_t* qfull = reinterpret_cast<uint64_t*>(bars + 1);   // [2]
   uint64_t* qempty = qfull + 2;                               // [2]
+  float* pred = reinterpret_cast<float*>(qempty + 2);         // [8 warps][256] (kPool only)
   const int i0 = (int)((int64_t)blockIdx.x * n_items / gridDim.x), i1 = (int)((int64_t)(blockIdx.x + 1) * n_items / gridDim.x);
   if (threadIdx.x == 0) {
     for (int q = 0; q < 2; ++q) {
@@ -89,6 +95,11 @@ sim_scores_ring_kernel(TokSrc3 src, const float* __restrict__ clsf, const float*
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const float inv = rsqrtf((float)D);
   float q[4][R::kChunks][8];
+  float pacc[kPool ? R::kChunks : 1][8];
+#pragma unroll
+  for (int ch = 0; ch < (kPool ? R::kChunks : 1); ++ch)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) pacc[ch][t] = 0.f;
   float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f;
   int gcount = 0;
   pdl_wait();
@@ -132,9 +143,38 @@ sim_scores_ring_kernel(TokSrc3 src, const float* __restrict__ clsf, const float*
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int t = 0; t < 8; ++t) a[i][r] = fmaf(xv[t], q[r][ch][t], a[i][r]);
+        if constexpr (kPool) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) pacc[ch][t] += xv[t];
+        }
       }
     }
     ring::consumer_release(bars, k);
+    if constexpr (kPool) {
+      if (chunk == R::kItemsPerGroup - 1 || it == i1 - 1) {   // end of the group (or of this CTA's part of it): warp-uniform
+        const bool whole = (it - i0) >= R::kItemsPerGroup - 1 && chunk == R::kItemsPerGroup - 1;   // all four items were ours
+        float* dst = pool_mean + ((int64_t)m * B + b) * D;
+#pragma unroll
+        for (int ch = 0; ch < R::kChunks; ++ch) {
+          float* pw = pred + w * 256 + lane * 8;
+          *reinterpret_cast<float4*>(pw) = make_float4(pacc[ch][0], pacc[ch][1], pacc[ch][2], pacc[ch][3]);
+          *reinterpret_cast<float4*>(pw + 4) = make_float4(pacc[ch][4], pacc[ch][5], pacc[ch][6], pacc[ch][7]);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) pacc[ch][t] = 0.f;
+          ring::consumer_sync(R::kConsumers);
+          {
+            const int i = threadIdx.x;      // 256 consumer threads: channel ch * 256 + i (lane j of a warp holds 8 j .. 8 j + 7)
+            float t = 0.f;
+#pragma unroll
+            for (int qw = 0; qw < R::kConsumers / 32; ++qw) t += pred[qw * 256 + i];
+            t *= 1.f / kMaxL;
+            if (whole) dst[ch * 256 + i] = t;
+            else atomicAdd(dst + ch * 256 + i, t);
+          }
+          ring::consumer_sync(R::kConsumers);
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -312,9 +352,10 @@ sim_scores_split_kernel(TokSrc3 src, const float* __restrict__ clsf, const float
 }
 
 template <int D>
-static size_t sim_scores_ring_smem() {
+static size_t sim_scores_ring_smem(bool pool = false) {
   using R = TokRing<D>;
-  return (size_t)R::kStages * R::kStageBytes + 2 * R::kQBytes + sizeof(ring::Bars<R::kStages>) + 4 * sizeof(uint64_t) + 128;
+  return (size_t)R::kStages * R::kStageBytes + 2 * R::kQBytes + sizeof(ring::Bars<R::kStages>) + 4 * sizeof(uint64_t) + 128 +
+         (pool ? (R::kConsumers / 32) * 256 * sizeof(float) : 0);
 }
 
 // ---- GAM mean pool ----------------------------------------------------------------------------------------------

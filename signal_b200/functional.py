@@ -498,6 +498,19 @@ class VolumeFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------
 # Whole head: SIM and AlignM of one step as ONE autograd node
 # ------------------------------------------------------------------------------------------
+_POOL_EVENTS = {}
+
+
+def _pool_event(dev):
+    """one cudaEvent per device for the SIM -> AlignM hand-over of the mean pool (recorded once so that its handle exists)"""
+    e = _POOL_EVENTS.get(dev)
+    if e is None:
+        e = torch.cuda.Event()
+        e.record(torch.cuda.current_stream(dev))
+        _POOL_EVENTS[dev] = e
+    return e
+
+
 class HeadFunction(torch.autograd.Function):
     """Select_Interactive_Module.forward + AlignmentM.forward on the same three [B,1+L,d] token maps.
 
@@ -536,6 +549,23 @@ class HeadFunction(torch.autograd.Function):
         # SIG_FLAG_EAGER_BWD) -- on the side stream, under SIM's forward chain of small kernels, where the GPU is
         # otherwise mostly idle; the backward call then starts at the weight-gradient GEMM.
         flags_a = flags | L_.SIG_FLAG_SHARE_SMS          # SIM's chain runs next to AlignM's kernels
+        # N2 forward: SIM's selection-score pass has every token value in a register anyway, so it also delivers GAM's mean
+        # pool straight into AlignM's ctx slot (sig_sim_params.pool_out -> SIG_FLAG_PATCH_MEAN); AlignM's own pass over the
+        # tokens goes away and its GAM chain waits for the event SIM records.  (bf16 tensor-core path only.)
+        # Measured on one B200, d = 768 (profiles/r2_fused_pool_experiment.json): 1.788 vs 1.805 ms at B = 512, where the step is
+        # throughput-bound and a 75 MB pass less counts; 0.600 vs 0.592 ms at B = 128, where the score kernel sits on SIM's
+        # latency-bound critical path and the pool ran in its shadow.  Hence: on from 256 samples up (SIG_FUSE_POOL=1 / 0 forces).
+        pool_ev = None
+        fuse_env = os.environ.get("SIG_FUSE_POOL", "auto")
+        if fuse_env == "1" or (fuse_env == "auto" and B >= 256):
+            slot = C.c_void_p()
+            if lib.sig_align_patch_mean_slot(buf_a.data_ptr(), B, L, d, dt, flags, C.byref(slot)) == 0 and dt == L_.SIG_BF16 \
+                    and not (flags & L_.FLAG_FORCE_SIMT):
+                pool_ev = _pool_event(dev)
+                sprm.pool_out = slot.value
+                sprm.pool_event = pool_ev.cuda_event
+                aprm.patch_mean_event = pool_ev.cuda_event
+                flags_a = flags_a | L_.SIG_FLAG_PATCH_MEAN
         # (single-GPU steps only by default: next to the in-backward gradient exchange it measured 2.5 % slower at N = 2,
         #  0.7088 vs 0.6908 ms -- the shortened AlignM backward leaves less compute for the collectives to hide under)
         eager_env = os.environ.get("SIG_EAGER_BWD", "auto")

@@ -48,7 +48,8 @@ class SigSelFold(C.Structure):
 
 
 class SigSimParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in SIM_PARAM_FIELDS] + [("sel_fold", C.POINTER(SigSelFold))]
+    _fields_ = [(n, C.c_void_p) for n in SIM_PARAM_FIELDS] + [("sel_fold", C.POINTER(SigSelFold)), ("pool_out", C.c_void_p),
+                                                                ("pool_event", C.c_void_p)]
 
 
 class SigSimParamGrads(C.Structure):
@@ -59,7 +60,7 @@ ALIGN_MOD_FIELDS = ["proj_q_w", "proj_q_b", "off0_w", "off0_b", "off2_w", "off2_
 
 
 class SigAlignParams(C.Structure):
-    _fields_ = [("contra_temp", C.c_void_p)] + [(n, _VP3) for n in ALIGN_MOD_FIELDS]
+    _fields_ = [("contra_temp", C.c_void_p)] + [(n, _VP3) for n in ALIGN_MOD_FIELDS] + [("patch_mean_event", C.c_void_p)]
 
 
 class SigAlignParamGrads(C.Structure):
