@@ -162,6 +162,39 @@ def test_large_batch_matches_its_shards_and_the_oracle(B):
     assert abs(gam - ref_gam) < BF16_TOL * abs(ref_gam), (gam, ref_gam)
 
 
+@pytest.mark.parametrize("name", ["rgbnt201_d512", "rgbnt201_d768", "vehicle_d512"])
+def test_fused_pool_in_score_pass_matches_own_pool(name):
+    """SIG_FUSE_POOL (N2 forward): GAM's mean pool delivered by SIM's score pass == AlignM pooling the tokens itself -- GAM
+    loss, every gradient and the masks (the score part of the kernel must be unchanged: bit-equal masks and SIM output)."""
+    _harness()
+    import gpu_harness
+    from signal_b200 import lib, modules as M
+    c = BF16_CASES[name]
+    sim_p, al_p, toks, cot = _bf16_inputs(c)
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["SIG_FUSE_POOL"] = mode
+        try:
+            sim, al = gpu_harness.build_modules(c, sim_p, al_p)
+            tk = [t.to("cuda", torch.bfloat16).requires_grad_(True) for t in toks]
+            n0 = lib.launch_count()
+            out, gam, lam = M.FusionHead(sim, al)(*[t[:, 1:] for t in tk], *[t[:, 0] for t in tk])
+            launches = lib.launch_count() - n0
+            torch.autograd.backward([out, gam, lam], [cot.to("cuda", torch.bfloat16), torch.tensor(0.2, device="cuda"), torch.tensor(0.2, device="cuda")])
+            masks = torch.stack([sim.token_selection.last_masks[k] for k in ("RGB", "NI", "TI")]).clone()
+            res[mode] = (launches, out.detach().float(), float(gam), float(lam), masks, [t.grad.float() for t in tk],
+                         float(al.contra_temp.grad))
+        finally:
+            os.environ.pop("SIG_FUSE_POOL", None)
+    a, b = res["0"], res["1"]
+    assert b[0] == a[0] - 1, (a[0], b[0])                       # AlignM's pool launch is gone
+    assert torch.equal(a[4], b[4]) and torch.equal(a[1], b[1])  # selection and SIM output untouched
+    assert abs(a[2] - b[2]) <= 2e-5 * abs(a[2]) and abs(a[3] - b[3]) <= 1e-6 * abs(a[3])
+    assert abs(a[6] - b[6]) <= 1e-3 * max(abs(a[6]), 1e-3)
+    for x, y in zip(a[5], b[5]):
+        assert float((x - y).norm() / x.norm()) < 1e-3
+
+
 @pytest.mark.parametrize("name", SMALL_BF16)
 def test_bf16_tensor_core_path_vs_simt_path(name):
     """Same bf16 inputs through the tcgen05 path and through the fp32 SIMT kernels (FORCE_SIMT)."""
