@@ -397,6 +397,18 @@ int sig_profile_timeline(char* buf, size_t bytes);
 void* sig_profile_scope_begin(const char* name, void* stream);
 void sig_profile_scope_end(void* scope);
 
+/* ---- volume_computation4 / volume_computation5 (utils/volume.py:65-116, :119-182) ----------------------------------
+ * V[i,j] = sqrt|det G(i,j)|, G = Gram matrix of (language_i, video_j, audio_j, subtitles_j [, depth_j]); n = 4 or 5 (3 is
+ * accepted and equals sig_volume3_*).  feats[0] = language [B1,d], feats[1..n-1] = [B2,d], contiguous fp32; vol [B1,B2] fp32.
+ * The reference never calls these two functions; they complete the utils/volume.py surface.  The per-pair determinant and
+ * its cofactors are evaluated in fp64 (the reference: torch.det on G.float()).  Backward: dvol [B1,B2] -> dfeats[k] with the
+ * shapes of feats (overwritten); at det == 0 the gradient is 0 (the reference yields NaN).  ws: sig_volume_n_ws_bytes. */
+size_t sig_volume_n_ws_bytes(int n, int B1, int B2);
+int sig_volume_n_fwd(int n, const float* const* feats, int B1, int B2, int d, float* vol, void* ws, size_t ws_bytes, int device,
+                     void* stream);
+int sig_volume_n_bwd(int n, const float* const* feats, int B1, int B2, int d, const float* dvol, float* const* dfeats, void* ws,
+                     size_t ws_bytes, int device, void* stream);
+
 /* Unit-test seam for the tcgen05 GEMM core: C = alpha * A . B^T (+bias) (GELU if act), bf16 operands.
  * mode: 0 row-major [rows,K]; 1 token view [B,128,d] with rows=(b,l), K=d; 2 row-major [K,cols];
  * 3 token view with K=(b,l), cols=d.  geom = {ld, stride_b, stride_l, rows, cols} (elements).

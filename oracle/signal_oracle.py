@@ -252,6 +252,33 @@ def volume3(language: Tensor, video: Tensor, audio: Tensor) -> Tensor:
     return V if language.dtype == torch.float64 else V.float()
 
 
+def volume_n(language: Tensor, *others: Tensor) -> Tensor:
+    """volume_computation4 / 5 -- volume.py:65-116, :119-182: sqrt|det G| of the n x n Gram matrix of (language_i, o_1_j, ...,
+    o_{n-1}_j), n = 1 + len(others).  Restated without torch.det: Laplace expansion along the first row, recursively, in fp64
+    (like _volume3_f64 the checker keeps the arithmetic wider than the reference's ``G.float()``).  Differentiable."""
+    feats = [language.double()] + [o.double() for o in others]
+    n = len(feats)
+    B1, B2 = feats[0].shape[0], feats[1].shape[0]
+    G = [[None] * n for _ in range(n)]
+    G[0][0] = (feats[0] * feats[0]).sum(-1)[:, None].expand(B1, B2)
+    for k in range(1, n):
+        G[0][k] = G[k][0] = feats[0] @ feats[k].T
+        for l in range(k, n):
+            G[k][l] = G[l][k] = (feats[k] * feats[l]).sum(-1)[None, :].expand(B1, B2)
+
+    def det(rows, cols):
+        if len(rows) == 1:
+            return G[rows[0]][cols[0]]
+        total = 0.0
+        for idx, c in enumerate(cols):
+            minor = det(rows[1:], cols[:idx] + cols[idx + 1:])
+            total = total + (-1.0) ** idx * G[rows[0]][c] * minor
+        return total
+
+    V = torch.sqrt(torch.abs(det(list(range(n)), list(range(n)))))
+    return V if language.dtype == torch.float64 else V.float()
+
+
 def _ce_label_smoothing(logits: Tensor) -> Tensor:
     """F.cross_entropy(logits, arange(B), label_smoothing=0.1), mean reduction."""
     B = logits.shape[0]

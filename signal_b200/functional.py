@@ -495,6 +495,55 @@ class VolumeFunction(torch.autograd.Function):
         return dl.to(ctx.dtypes[0]), dv.to(ctx.dtypes[1]), da.to(ctx.dtypes[2])
 
 
+class VolumeNFunction(torch.autograd.Function):
+    """utils/volume.py:65 volume_computation4 / :119 volume_computation5 -> [B1,B2] fp32 (language first, then the n-1
+    modalities that share the second batch)."""
+
+    @staticmethod
+    def forward(ctx, *feats):
+        lib = L_.load()
+        n = len(feats)
+        fs = [t.float().contiguous() for t in feats]
+        for t in fs:
+            L_._require_cuda(t, "features")
+        B1, d = fs[0].shape
+        B2 = fs[1].shape[0]
+        if any(t.shape != (B2, d) for t in fs[1:]):
+            raise RuntimeError("signal_b200: volume_computation: video / audio / ... must share one [B2, d] shape")
+        dev = fs[0].device
+        vol = torch.empty(B1, B2, dtype=torch.float32, device=dev)
+        nbytes = lib.sig_volume_n_ws_bytes(n, B1, B2)
+        if nbytes == 0:
+            raise RuntimeError(f"signal_b200: volume_computation with {n} modalities is not supported (3, 4 or 5)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in fs])
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_volume_n_fwd(n, ptrs, B1, B2, d, vol.data_ptr(), ws.data_ptr(), nbytes, dev.index, L_.stream_ptr(dev)),
+                     "sig_volume_n_fwd")
+        ctx.save_for_backward(*fs)
+        ctx.dtypes = tuple(t.dtype for t in feats)
+        return vol
+
+    @staticmethod
+    def backward(ctx, dvol):
+        fs = ctx.saved_tensors
+        lib = L_.load()
+        n = len(fs)
+        B1, d = fs[0].shape
+        B2 = fs[1].shape[0]
+        dev = fs[0].device
+        dvol = dvol.float().contiguous()
+        grads = [torch.empty_like(t) for t in fs]
+        nbytes = lib.sig_volume_n_ws_bytes(n, B1, B2)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in fs])
+        gptrs = (C.c_void_p * n)(*[t.data_ptr() for t in grads])
+        with torch.cuda.device(dev):
+            L_.check(lib.sig_volume_n_bwd(n, ptrs, B1, B2, d, dvol.data_ptr(), gptrs, ws.data_ptr(), nbytes, dev.index,
+                                          L_.stream_ptr(dev)), "sig_volume_n_bwd")
+        return tuple(g.to(dt) for g, dt in zip(grads, ctx.dtypes))
+
+
 # ------------------------------------------------------------------------------------------
 # Whole head: SIM and AlignM of one step as ONE autograd node (SURVEY.md 8(f) N2)
 # ------------------------------------------------------------------------------------------

@@ -83,6 +83,7 @@ EXPORTS = [
     "sig_convert_half", "sig_xchg_flag_bytes", "sig_xchg_allreduce_f32", "sig_infer_features", "sig_euclidean_distmat", "sig_rank_eval",
     "sig_loss_ws_bytes", "sig_xent_ls_fwd", "sig_xent_ls_bwd", "sig_triplet_fwd", "sig_triplet_bwd", "sig_bnneck_ws_bytes", "sig_bnneck_cls_fwd", "sig_bnneck_cls_bwd",
     "sig_tokens_ws_bytes", "sig_tokens_fwd", "sig_tokens_bwd", "sig_align_patch_mean_slot",
+    "sig_volume_n_ws_bytes", "sig_volume_n_fwd", "sig_volume_n_bwd",
 ]
 
 
@@ -142,6 +143,10 @@ def load():
     lib.sig_bnneck_ws_bytes.argtypes = [i, i, i]
     lib.sig_bnneck_cls_fwd.argtypes = [vp, i, i64, i, i, i, vp, vp, vp, vp, f, f, i, vp, vp, i64, vp, i64, vp, vp, vp, vp, sz, i, vp]
     lib.sig_bnneck_cls_bwd.argtypes = [vp, i, i64, i, i, i, vp, vp, vp, vp, i, vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, sz, i, vp]
+    lib.sig_volume_n_ws_bytes.restype = sz
+    lib.sig_volume_n_ws_bytes.argtypes = [i, i, i]
+    lib.sig_volume_n_fwd.argtypes = [i, P(vp), i, i, i, vp, vp, sz, i, vp]
+    lib.sig_volume_n_bwd.argtypes = [i, P(vp), i, i, i, vp, P(vp), vp, sz, i, vp]
     lib.sig_tokens_ws_bytes.restype = sz
     lib.sig_tokens_ws_bytes.argtypes = [i, i, i, i, i, i]
     lib.sig_tokens_fwd.argtypes = [vp, i, i64, i64, i, i, i, i, vp, vp, f, vp, vp, i, vp, vp, sz, vp, sz, i, vp]
@@ -157,7 +162,7 @@ def load():
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("sig_error_string", "sig_ctx_bytes", "sig_volume3_ws_bytes", "sig_debug_launch_count", "sig_xchg_flag_bytes",
-                        "sig_loss_ws_bytes", "sig_bnneck_ws_bytes", "sig_tokens_ws_bytes", "sig_profile_scope_begin", "sig_profile_scope_end"):
+                        "sig_loss_ws_bytes", "sig_bnneck_ws_bytes", "sig_tokens_ws_bytes", "sig_volume_n_ws_bytes", "sig_profile_scope_begin", "sig_profile_scope_end"):
             fn.restype = i
     if lib.sig_version() != 1:
         raise RuntimeError("signal_b200: ABI version mismatch between lib.py and libsignal_b200.so")

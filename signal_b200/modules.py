@@ -343,6 +343,16 @@ def volume_computation3(language, video, audio):
     return F_.VolumeFunction.apply(language, video, audio)
 
 
+def volume_computation4(language, video, audio, subtitles):
+    """utils/volume.py:65-116 -> [B1,B2] fp32 (never called by the reference; completes the utils/volume.py surface)."""
+    return F_.VolumeNFunction.apply(language, video, audio, subtitles)
+
+
+def volume_computation5(language, video, audio, subtitles, depth):
+    """utils/volume.py:119-182 -> [B1,B2] fp32."""
+    return F_.VolumeNFunction.apply(language, video, audio, subtitles, depth)
+
+
 class FusionHead:
     """SIM + AlignM of one training step as a single call.
 

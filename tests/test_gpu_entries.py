@@ -493,3 +493,48 @@ def test_fusion_head_make_graphed_matches_eager():
             _close(a.float(), b.float(), 2e-3, "graphed vs eager")       # (split-K atomics: not bit-reproducible)
         for k in ("RGB", "NI", "TI"):
             assert torch.equal(res["graphed"][1][k], res["eager"][1][k])
+
+
+# ---- volume_computation4 / volume_computation5 (utils/volume.py:65-182) -----------------------------------------------------
+@pytest.mark.parametrize("name", ["vol4_indep", "vol4_aligned", "vol5_indep", "vol5_aligned"])
+def test_volume_computation_4_5_match_reference_golden(name):
+    import __graft_entry__ as entry
+    entry.build()
+    import volume_cases as vc
+    from signal_b200 import modules as M
+    c = vc.CASES[name]
+    z = vc.load(name)
+    feats, cot = vc.gen.inputs(c)
+    xs = [t.cuda().requires_grad_(True) for t in feats]
+    fn = M.volume_computation4 if c["n"] == 4 else M.volume_computation5
+    V = fn(*xs)
+    assert V.shape == (c["B1"], c["B2"]) and V.dtype == torch.float32
+    V.backward(cot.cuda())
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu(), torch.from_numpy(b).double()
+        return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+    tol = lambda key: max(1e-4, 3.0 * float(z["dev32/" + key]))     # never below what the reference itself loses in fp32
+    assert rel(V, z["ref/vol"]) <= tol("vol"), rel(V, z["ref/vol"])
+    for k, x in enumerate(xs):
+        assert rel(x.grad, z[f"ref/d{k}"]) <= tol(f"d{k}"), (name, k, rel(x.grad, z[f"ref/d{k}"]))
+
+
+def test_volume_n_entry_with_three_modalities_equals_volume3():
+    import __graft_entry__ as entry
+    entry.build()
+    from signal_b200 import functional as F_, modules as M
+    g = torch.Generator().manual_seed(9)
+    l, v, a = [torch.nn.functional.normalize(torch.randn(n, 256, generator=g), dim=-1).cuda().requires_grad_(True) for n in (20, 33, 33)]
+    cot = torch.randn(20, 33, generator=g).cuda()
+    V3 = M.volume_computation3(l, v, a)
+    V3.backward(cot)
+    g3 = [t.grad.clone() for t in (l, v, a)]
+    for t in (l, v, a):
+        t.grad = None
+    Vn = F_.VolumeNFunction.apply(l, v, a)
+    Vn.backward(cot)
+    assert float((Vn - V3).abs().max()) < 1e-5
+    for x, y in zip((l, v, a), g3):
+        assert float((x.grad - y).norm() / y.norm()) < 1e-4
