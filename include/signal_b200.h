@@ -158,6 +158,11 @@ typedef struct sig_sim_param_grads {
    * caller starts the exchange of the early part on another stream while the rest of the backward runs
    * (FusionHead.grad_sync).  On the fp32 SIMT path it is recorded at the end of the call. */
   void* early_event;
+  /* Optional (cudaEvent_t, may be NULL): recorded once the REST -- in_proj_w rows [0, 2d) and in_proj_b -- is final too, i.e.
+   * when the last weight-gradient GEMM of the call has been enqueued (on the library's side stream); the call's own stream
+   * still has the CLS-gradient GEMM and the token-gradient writes in front of it.  Lets the exchange of the late piece start
+   * before the call's last kernels have run. */
+  void* late_event;
 } sig_sim_param_grads;
 
 /* AlignmentM parameters (modeling/AddModule/useB.py:44-74, DAS.py:30-72), index = modality r,n,t */

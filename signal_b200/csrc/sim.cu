@@ -1169,6 +1169,7 @@ int sim_backward(const sig_tokens* tok, const sig_sim_params* p, bool has_masks,
   SIG_TRY(write_token_grads(dtok, tok->dtype, c.dXf, c.dr1, B, L, d, s));
   if (dtok->done_event) cudaEventRecord((cudaEvent_t)dtok->done_event, s);
   if (dp->early_event) cudaEventRecord((cudaEvent_t)dp->early_event, s);   // (SIMT path: no early part)
+  if (dp->late_event) cudaEventRecord((cudaEvent_t)dp->late_event, s);
   return 0;
 }
 

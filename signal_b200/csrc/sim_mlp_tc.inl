@@ -305,6 +305,8 @@ static int attn_prep_bwd_tc(const SimCtx& c, const sig_sim_params* p, int B, int
     SIG_TRY(launch_colsum(c.dqatt, d, R, d, g->in_proj_b, 1.f, s));
   }
   SIG_TRY(side_gemm(fk, s, lin_tn(c.dqattb, d, c.clsb, d, dwq, d, d, d, R)));                                       // dWq = dq^T cls
+  // every parameter gradient of the call is now enqueued (the late ones on the side stream): sig_sim_param_grads.late_event
+  if (g->late_event) cudaEventRecord((cudaEvent_t)g->late_event, fk.ok() ? fk.side : s);
   {  // dcls = dr1 (residual) + dq W_q
     TcGemmDesc t = lin_nn(c.dqattb, d, wqb, d, c.dr1, d, R, d, d);
     t.accumulate = 1;

@@ -675,9 +675,12 @@ class HeadFunction(torch.autograd.Function):
         gs_a = L_.align_params_struct(pg_a[0], [pg_a[1 + 7 * m: 8 + 7 * m] for m in range(3)], cls=L_.SigAlignParamGrads)
         hi = event[2] if len(event) > 2 else None
         event, grad_sync = event[0], event[1]
+        late_ev = sync[4] if sync is not None and len(sync) > 4 and os.environ.get("SIG_LATE_EVENT", "1") != "0" else None
         if sync is not None:
             gs_s.early_event = sync[1].cuda_event
             gs_a.done_event = sync[2].cuda_event
+            if late_ev is not None:
+                gs_s.late_event = late_ev.cuda_event
         evh = event.cuda_event
         # SIM's token-gradient kernel overwrites the shared map (it has no long GEMM in front of it and finishes
         # first); AlignM's dX GEMM, which can run its weight-gradient GEMM while it waits, adds on top
@@ -728,11 +731,13 @@ class HeadFunction(torch.autograd.Function):
                     if sync[3] == 2:      # SIM's early part and AlignM's arena are adjacent: one collective, then the late part
                         comm.wait_event(sync[1])
                         grad_sync(flat_h[cut_h:])
-                        comm.wait_stream(hi)
+                        # the late piece (W_q / W_k / in_proj_bias): as soon as its last weight-gradient GEMM is through, not
+                        # when SIM's stream has also finished the CLS-gradient GEMM and the token-gradient writes
+                        comm.wait_event(late_ev) if late_ev is not None else comm.wait_stream(hi)
                         grad_sync(flat_h[:cut_h])
                     elif sync[3] == 3:
                         grad_sync(flat_h[cut2_h:])
-                        comm.wait_stream(hi)
+                        comm.wait_event(late_ev) if late_ev is not None else comm.wait_stream(hi)
                         grad_sync(flat_h[:cut_h])
                     else:
                         grad_sync(flat_a)

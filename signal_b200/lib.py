@@ -53,7 +53,7 @@ class SigSimParams(C.Structure):
 
 
 class SigSimParamGrads(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in SIM_GRAD_FIELDS] + [("early_event", C.c_void_p)]
+    _fields_ = [(n, C.c_void_p) for n in SIM_GRAD_FIELDS] + [("early_event", C.c_void_p), ("late_event", C.c_void_p)]
 
 
 ALIGN_MOD_FIELDS = ["proj_q_w", "proj_q_b", "off0_w", "off0_b", "off2_w", "off2_b", "off4_w"]

@@ -435,13 +435,14 @@ class FusionHead:
             # data parallel: a communication stream and the two events the library records when a piece of the
             # parameter gradients is final (sig_sim_param_grads.early_event, sig_align_param_grads.done_event)
             sync = [torch.cuda.Stream(dev, priority=-1), torch.cuda.Event(), torch.cuda.Event()]
-            for e in sync[1:]:
+            late = torch.cuda.Event()          # sig_sim_param_grads.late_event: W_q / W_k / in_proj_bias gradients enqueued
+            for e in sync[1:] + [late]:
                 e.record(torch.cuda.current_stream(dev))
             # SIG_SYNC_CHUNKS (diagnostic): 2 = default; 3 = AlignM's arena and SIM's late part as two collectives;
             # 0 = one exchange per module after its backward
             # 4 = separate arenas per module, three collectives (round-1 layout)
             pieces = int(os.environ.get("SIG_SYNC_CHUNKS", "-1"))
-            sync = None if pieces == 0 else sync + [pieces]
+            sync = None if pieces == 0 else sync + [pieces, late]
             st = (torch.cuda.Stream(dev), ev, hi, sync)
             self._side[dev] = st
         return st
@@ -464,7 +465,7 @@ class FusionHead:
             # default: two pieces, [SIM early + AlignM] and [SIM late] (SIG_SYNC_CHUNKS=3: SIM early on its own as soon as
             # it is final -- measured slower at N = 2 and N = 8: every call costs ~25 us of cross-GPU barriers, and the early
             # piece then runs next to SIM's HBM-bound token passes instead of next to the GEMMs)
-            sync = sync[:3] + [2]
+            sync = sync[:3] + [2] + sync[4:]
         params = [p.detach() for p in ts._sel_params()] + mi._attn_params() + al._params()
         flags = sim.flags | al.flags
         if rgb_patch.dtype == torch.bfloat16 and not (flags & 1):
