@@ -436,7 +436,7 @@ def run_gpu(args, cfg):
     exchange = None
     nsync = [0]
     if args.exchange == "auto":
-        args.exchange = "nvlink" if world >= 3 else "nccl"
+        args.exchange = "nvlink"
     if overlap:   # pieces of the gradient arena are averaged over the ranks inside the backward as soon as they are final
         if args.exchange == "nvlink":
             exchange = parallel.GradExchange(head.grad_numel(), dev)
@@ -819,9 +819,9 @@ def main():
     ap.add_argument("--strong", action="store_true", help="N>1: global batch 1024 split over the ranks (BASELINE.json configs[4])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange", default=os.environ.get("SIG_EXCHANGE", "auto"), choices=["auto", "nvlink", "nccl"],
-                    help="N>1: gradient exchange inside the backward: the library's NVLink/NVLS kernel or ncclAllReduce; auto = what "
-                         "measured faster (profiles/r2_exchange_bench_n2_n8.json, r2_exchange_n4.json): the kernel from 4 ranks up "
-                         "(0.669 vs 0.718 ms at N=4, 0.683 vs 0.734 at N=8), NCCL between 2 ranks (0.656 vs 0.686)")
+                    help="N>1: gradient exchange inside the backward: the library's NVLink/NVLS kernel (auto) or ncclAllReduce.  "
+                         "Measured (profiles/r2_exchange_*.json, r2_eager_dp.json): with AlignM's eager backward chain the kernel "
+                         "wins at every N (0.637 vs 0.664 ms at N=2, 0.634 vs 0.718 at N=4, 0.683 vs 0.734 at N=8 without the chain)")
     ap.add_argument("--check", action="store_true", help="N>1: numerical check of the data-parallel path (no timing)")
     ap.add_argument("--full-step", action="store_true",
                     help="BASELINE.json configs[3]: time one complete training iteration (backbone + head + losses + Adam) with the B200 "

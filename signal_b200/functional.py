@@ -615,10 +615,11 @@ class HeadFunction(torch.autograd.Function):
                 sprm.pool_event = pool_ev.cuda_event
                 aprm.patch_mean_event = pool_ev.cuda_event
                 flags_a = flags_a | L_.SIG_FLAG_PATCH_MEAN
-        # (single-GPU steps only by default: next to the in-backward gradient exchange it measured 2.5 % slower at N = 2,
-        #  0.7088 vs 0.6908 ms -- the shortened AlignM backward leaves less compute for the collectives to hide under)
-        eager_env = os.environ.get("SIG_EAGER_BWD", "auto")
-        eager_ok = eager_env == "1" or (eager_env == "auto" and (len(event) < 2 or event[1] is None))
+        # Data parallel too (round 2): with AlignM's gradients final in the first third of the backward the in-backward
+        # exchange starts earlier and hides under more compute -- measured with the NVLink exchange kernel 0.637 vs 0.676 ms
+        # at N = 2 and 0.634 vs 0.675 ms at N = 4 (with ncclAllReduce 0.664 vs 0.676 at N = 2); round 1 had measured the
+        # opposite with NCCL's SM-hungry kernels.  SIG_EAGER_BWD=0 switches it off.
+        eager_ok = os.environ.get("SIG_EAGER_BWD", "auto") != "0"
         if do_lam and any(ctx.needs_input_grad[9:]) and eager_ok:
             flags_a = flags_a | L_.SIG_FLAG_EAGER_BWD
         with torch.cuda.device(dev):

@@ -77,7 +77,6 @@ def head_grads(c, dtype, sim_p, al_p, toks, cot, dev, hook=None, arena=None):
 def check_head(dev, rank, world):
     import golden_util as gu
     from signal_b200 import parallel, synthetic as syn
-    os.environ["SIG_EAGER_BWD"] = "0"     # same code path with and without a hook (functional.HeadFunction)
     for dtype, B, tol in ((torch.float32, 4, 2e-5), (torch.bfloat16, 16, 4e-3)):
         c = dict(d=512, h=16, w=8, B=B, k=80, keep_ratio=None, gain=1.0, structured=False, seed=77)
         sim_p = syn.make_params(syn.sim_param_shapes(c["d"]), c["seed"])

@@ -267,14 +267,9 @@ def test_fusion_head_grad_sync_pieces(dtype):
         pieces.append((flat.data_ptr(), flat.numel()))
         flat.mul_(2.0)
 
-    # (a hook switches the eager backward chain off -- functional.HeadFunction -- so the hook-less base run must not use
-    #  it either, or the two runs would differ by the bf16 rounding of the two code paths)
-    os.environ["SIG_EAGER_BWD"] = "0"
-    try:
-        base, _ = run(None)
-        got, arenas = run(hook)
-    finally:
-        os.environ.pop("SIG_EAGER_BWD", None)
+    # (with or without a hook the step takes the same code path: AlignM's eager backward chain is on in both)
+    base, _ = run(None)
+    got, arenas = run(hook)
     assert len(pieces) == 6 and len(arenas) == 1          # two pieces per step, one arena for both modules
     total = sum(n for _, n in pieces[-2:])
     assert total == sum(a.numel() for a in arenas)
