@@ -435,11 +435,26 @@ def run_gpu(args, cfg):
     overlap = head is not None and world > 1 and args.allreduce and args.overlap
     exchange = None
     nsync = [0]
-    if args.exchange == "auto":
+    auto_exchange = args.exchange == "auto"
+    if auto_exchange:
         args.exchange = "nvlink"
     if overlap:   # pieces of the gradient arena are averaged over the ranks inside the backward as soon as they are final
         if args.exchange == "nvlink":
-            exchange = parallel.GradExchange(head.grad_numel(), dev)
+            # symmetric memory is torch plumbing that a box may not offer (no NVLink peer access, an older driver): with
+            # --exchange auto every rank then agrees to fall back to ncclAllReduce instead of failing the run
+            try:
+                exchange = parallel.GradExchange(head.grad_numel(), dev)
+                ok = torch.ones(1, device=dev)
+            except Exception as e:   # noqa: BLE001
+                if not auto_exchange:
+                    raise
+                print(f"[bench] rank {rank}: NVLink exchange unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
+                exchange, ok = None, torch.zeros(1, device=dev)
+            if auto_exchange:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok) < 1.0:
+                    exchange, args.exchange = None, "nccl"
+        if exchange is not None:
             head.grad_arena = exchange.arena
 
             def _sync(flat):
