@@ -60,7 +60,7 @@ enum sig_ctx_kind { SIG_CTX_SIM = 0, SIG_CTX_ALIGN = 1, SIG_CTX_SELECT = 2, SIG_
 #define SIG_FLAG_EAGER_BWD 2u
 /* sig_align_fwd / sig_align_bwd, tensor-core path: the caller runs SIM's calls concurrently on another stream
  * (signal_b200.FusionHead).  AlignM's persistent GEMM / ring kernels then size their grids for SIG_ALIGN_SMS SMs
- * (environment; default 116 of 148) instead of all of them, so the short kernels of SIM's dependency chain -- the critical
+ * (environment; default 108 of 148) instead of all of them, so the short kernels of SIM's dependency chain -- the critical
  * path of the fused step -- find free SMs; the d(patches) GEMM at the tail of the backward always takes all SMs. */
 #define SIG_FLAG_SHARE_SMS 4u
 /* sig_align_fwd, tensor-core path (bf16 tokens): the caller has already written the mean over the L patch rows of each

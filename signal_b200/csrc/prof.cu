@@ -104,9 +104,11 @@ int align_sm_budget() {
   static const int v = [] {
     // default: AlignM's persistent kernels leave ~1/5 of the SMs to the short kernels of SIM's chain, which runs next to
     // them and is the critical path of the fused step (measured at B = 128, d = 768: 148 -> 0.605, 132 -> 0.595,
-    // 116 -> 0.589, 100 -> 0.607, 84 -> 0.642 ms/step); the dX GEMM at the tail of the step always takes all SMs
+    // 116 -> 0.589, 100 -> 0.607, 84 -> 0.642 ms/step; re-measured at the end of round 2, same box back to back:
+    // 132 -> 0.595, 124 -> 0.589, 116 -> 0.585 / 0.588 / 0.591, 112 -> 0.583 / 0.589, 108 -> 0.574 / 0.581 / 0.582,
+    // 104 -> 0.598 / 0.600, 100 -> 0.593); the dX GEMM at the tail of the step always takes all SMs
     const char* e = getenv("SIG_ALIGN_SMS");
-    return e ? atoi(e) : (device_num_sms() * 116) / 148;
+    return e ? atoi(e) : (device_num_sms() * 108) / 148;
   }();
   return v;
 }
