@@ -4,29 +4,6 @@
 #include "sim.h"
 #include "tc_gemm.h"
 
-namespace {
-struct DeviceGuard {
-  int prev = -1;
-  int rc = 0;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) {
-      cudaError_t e = cudaSetDevice(dev);
-      if (e != cudaSuccess) rc = (int)e;
-    }
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-  }
-};
-}  // namespace
-
-#define SIG_ENTER(device)          \
-  DeviceGuard guard__(device);     \
-  if (guard__.rc) return guard__.rc; \
-  cudaGetLastError();
-
 extern "C" {
 
 int sig_version(void) { return SIG_ABI_VERSION; }

@@ -253,6 +253,29 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
   return scratch[32];
 }
 
+// ---- entry-point prologue --------------------------------------------------------
+// Every extern "C" entry runs on the device ordinal it is given and restores the caller's current device on return;
+// a sticky error left by earlier, unrelated CUDA calls of the process is cleared so that it is not reported as ours.
+struct DeviceGuard {
+  int prev = -1;
+  int rc = 0;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      cudaError_t e = cudaSetDevice(dev);
+      if (e != cudaSuccess) rc = (int)e;
+    }
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+#define SIG_ENTER(device)              \
+  ::sig::DeviceGuard guard__(device);  \
+  if (guard__.rc) return guard__.rc;   \
+  cudaGetLastError();
+
 // ---- host-side argument checks ---------------------------------------------------
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t elem_size(int dtype) { return dtype == SIG_BF16 ? 2 : 4; }

@@ -351,32 +351,13 @@ int bnneck_bwd(const T* x, int64_t ld, int B, int D, int C, const float* gamma, 
 }  // namespace
 }  // namespace sig
 
-namespace {
-struct DevGuard {
-  int prev = -1, rc = 0;
-  explicit DevGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) {
-      cudaError_t e = cudaSetDevice(dev);
-      if (e != cudaSuccess) rc = (int)e;
-    }
-  }
-  ~DevGuard() {
-    int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-  }
-};
-}  // namespace
-
 extern "C" {
 
 size_t sig_loss_ws_bytes(int B) { return (size_t)(B > 0 ? B : 0) * 2 * sizeof(float); }
 
 int sig_xent_ls_fwd(const void* logits, int dtype, int64_t ld, const int64_t* targets, int B, int C, float eps, float* loss,
                     float* lse, void* ws, size_t ws_bytes, int device, void* stream) {
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   using namespace sig;
   if (!logits || !targets || !loss || !lse || !ws) return SIG_ERR_NULL;
   if (B < 1 || C < 1 || ld < C) return SIG_ERR_SHAPE;
@@ -396,9 +377,7 @@ int sig_xent_ls_fwd(const void* logits, int dtype, int64_t ld, const int64_t* ta
 
 int sig_xent_ls_bwd(const void* logits, int dtype, int64_t ld, const int64_t* targets, int B, int C, float eps, const float* lse,
                     const float* dloss, void* dlogits, int64_t ldd, int device, void* stream) {
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   using namespace sig;
   if (!logits || !targets || !lse || !dloss || !dlogits) return SIG_ERR_NULL;
   if (B < 1 || C < 1 || ld < C || ldd < C) return SIG_ERR_SHAPE;
@@ -417,9 +396,7 @@ int sig_xent_ls_bwd(const void* logits, int dtype, int64_t ld, const int64_t* ta
 int sig_triplet_fwd(const void* feat, int dtype, int64_t ld, const int64_t* labels, int B, int D, float margin, int soft_margin,
                     float hard_factor, float* loss, float* dist_ap, float* dist_an, int* p_idx, int* n_idx, void* ws, size_t ws_bytes,
                     int device, void* stream) {
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   using namespace sig;
   if (!feat || !labels || !loss || !dist_ap || !dist_an || !p_idx || !n_idx || !ws) return SIG_ERR_NULL;
   if (B < 1 || B > 1024 || D < 1 || D > 8192 || ld < D) return SIG_ERR_SHAPE;
@@ -443,9 +420,7 @@ int sig_triplet_fwd(const void* feat, int dtype, int64_t ld, const int64_t* labe
 int sig_triplet_bwd(const void* feat, int dtype, int64_t ld, int B, int D, float margin, int soft_margin, float hard_factor,
                     const float* dist_ap, const float* dist_an, const int* p_idx, const int* n_idx, const float* dloss,
                     const float* d_dist_ap, const float* d_dist_an, void* dfeat, int64_t ldd, int device, void* stream) {
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   using namespace sig;
   if (!feat || !dist_ap || !dist_an || !p_idx || !n_idx || !dfeat) return SIG_ERR_NULL;
   if (B < 1 || B > 1024 || D < 1 || ld < D || ldd < D) return SIG_ERR_SHAPE;
@@ -471,9 +446,7 @@ int sig_bnneck_cls_fwd(const void* feat, int dtype, int64_t ld, int B, int D, in
                        float* running_mean, float* running_var, float momentum, float eps, int training, const float* cls_weight,
                        void* bn_out, int64_t ldo, void* logits, int64_t ldl, float* save_mean, float* save_rstd, float* y32, void* ws,
                        size_t ws_bytes, int device, void* stream) {
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   using namespace sig;
   if (!feat || !bn_weight || !bn_bias || !cls_weight || !bn_out || !logits || !save_mean || !save_rstd || !y32 || !ws) return SIG_ERR_NULL;
   if (!training && (!running_mean || !running_var)) return SIG_ERR_NULL;
@@ -494,9 +467,7 @@ int sig_bnneck_cls_bwd(const void* feat, int dtype, int64_t ld, int B, int D, in
                        const float* save_mean, const float* save_rstd, int training, const float* y32, const void* dlogits, int64_t ldl,
                        const void* d_bn_out, int64_t lddo, void* dfeat, int64_t ldx, float* d_bn_weight, float* d_bn_bias,
                        float* d_cls_weight, void* ws, size_t ws_bytes, int device, void* stream) {
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   using namespace sig;
   if (!feat || !bn_weight || !cls_weight || !save_mean || !save_rstd || !y32 || !dfeat || !d_bn_weight || !d_bn_bias || !d_cls_weight || !ws)
     return SIG_ERR_NULL;

@@ -421,20 +421,6 @@ int tokens_bwd_t(const XT* x, int tdt, int64_t sb, int64_t sl, int B, int L1, in
   return 0;
 }
 
-struct DevGuard {
-  int prev = -1, rc = 0;
-  explicit DevGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) {
-      cudaError_t e = cudaSetDevice(dev);
-      if (e != cudaSuccess) rc = (int)e;
-    }
-  }
-  ~DevGuard() {
-    int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-  }
-};
 
 bool tok_shape_ok(int B, int L1, int W, int D) {
   return B >= 1 && L1 >= 2 && W >= 8 && D >= 8 && W <= 1024 && D <= 1024 && (W % 8) == 0 && (D % 8) == 0 && (int64_t)B * L1 < (1 << 30);
@@ -491,9 +477,7 @@ int sig_tokens_fwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_strid
                    const float* ln_b, float eps, const float* proj, void* tokens, int tok_dtype, float* patch_mean, void* saved,
                    size_t saved_bytes, void* scratch, size_t scratch_bytes, int device, void* stream) {
   using namespace sig;
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   if (!x || !ln_w || !ln_b || !proj || !tokens || !saved) return SIG_ERR_NULL;
   if (!tok_dtypes_ok(dtype, tok_dtype)) return SIG_ERR_DTYPE;
   if (!tok_shape_ok(B, L1, W, D)) return SIG_ERR_SHAPE;
@@ -513,9 +497,7 @@ int sig_tokens_bwd(const void* x, int dtype, int64_t x_stride_b, int64_t x_strid
                    size_t saved_bytes, void* dx, int64_t dx_stride_b, int64_t dx_stride_l, float* d_ln_w, float* d_ln_b, float* d_proj,
                    void* scratch, size_t scratch_bytes, int device, void* stream) {
   using namespace sig;
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   if (!x || !ln_w || !proj || !dtokens || !saved || !dx || !d_ln_w || !d_ln_b || !d_proj || !scratch) return SIG_ERR_NULL;
   if (!tok_dtypes_ok(dtype, tok_dtype)) return SIG_ERR_DTYPE;
   if (!tok_shape_ok(B, L1, W, D)) return SIG_ERR_SHAPE;

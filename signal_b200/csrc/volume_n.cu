@@ -250,20 +250,6 @@ int voln_backward(int n, const VolFeats& f, int B1, int B2, int d, const float* 
   return 0;
 }
 
-struct DevGuard {
-  int prev = -1, rc = 0;
-  explicit DevGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) {
-      cudaError_t e = cudaSetDevice(dev);
-      if (e != cudaSuccess) rc = (int)e;
-    }
-  }
-  ~DevGuard() {
-    int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-  }
-};
 
 }  // namespace
 }  // namespace sig
@@ -278,9 +264,7 @@ size_t sig_volume_n_ws_bytes(int n, int B1, int B2) {
 int sig_volume_n_fwd(int n, const float* const* feats, int B1, int B2, int d, float* vol, void* ws, size_t ws_bytes, int device,
                      void* stream) {
   using namespace sig;
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   if (n < 3 || n > kVolMaxN || B1 < 1 || B2 < 1 || d < 1) return SIG_ERR_SHAPE;
   if (!feats || !vol || !ws) return SIG_ERR_NULL;
   VolFeats f{};
@@ -295,9 +279,7 @@ int sig_volume_n_fwd(int n, const float* const* feats, int B1, int B2, int d, fl
 int sig_volume_n_bwd(int n, const float* const* feats, int B1, int B2, int d, const float* dvol, float* const* dfeats, void* ws,
                      size_t ws_bytes, int device, void* stream) {
   using namespace sig;
-  DevGuard guard(device);
-  if (guard.rc) return guard.rc;
-  cudaGetLastError();
+  SIG_ENTER(device);
   if (n < 3 || n > kVolMaxN || B1 < 1 || B2 < 1 || d < 1) return SIG_ERR_SHAPE;
   if (!feats || !dfeats || !dvol || !ws) return SIG_ERR_NULL;
   VolFeats f{};
