@@ -4,7 +4,7 @@
 
 `cuobjdump -sass` of the in-tree library; for every kernel the total instruction count and the counts of the mnemonics
 that prove which hardware path it uses (tcgen05: UTCHMMA / UTCBAR / LDTM; TMA: UTMALDG / UBLKCP; mbarrier: SYNCS;
-multimem / NVLink: the .MULTIMEM / RED variants; plain math: FFMA, HFMA2, MUFU)."""
+NVLS multimem.ld_reduce: LDGMC (the switch adds the replicas); plain math: FFMA, HFMA2, MUFU)."""
 import collections
 import os
 import re
@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "signal_b200", "libsignal_b200.so")
-KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "MULTIMEM", "FFMA", "HFMA2", "MUFU",
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGMC", "FFMA", "HFMA2", "MUFU",
         "LDG", "STG", "LDS", "STS", "ATOM", "RED", "SHFL", "BAR"]
 
 
@@ -56,8 +56,6 @@ def main():
                 h[base] += 1
             if op.startswith("UTCHMMA") and ".2CTA" in op:
                 h["UTCHMMA.2CTA"] += 1
-            if "MULTIMEM" in op or "MMLS" in op:
-                h["MULTIMEM"] += 1
     names = demangle(list(hist))
     cols = [k for k in KEYS if any(h[k] for h in hist.values())]
     tot = collections.Counter()
