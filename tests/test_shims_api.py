@@ -33,6 +33,12 @@ def test_shims_resolve_to_b200_classes():
         assert tl.TripletLoss is losses.TripletLoss
         assert ua.Select_Interactive_Module is modules.Select_Interactive_Module
         assert ub.AlignmentM is modules.AlignmentM
+        uv = importlib.import_module("utils.volume")
+        um = importlib.import_module("utils.metrics")
+        from signal_b200 import evaluation
+        assert uv.volume_computation3 is modules.volume_computation3 and uv.volume_computation4 is modules.volume_computation4
+        assert uv.volume_computation5 is modules.volume_computation5
+        assert um.R1_mAP_eval is evaluation.R1_mAP_eval and um.eval_func is evaluation.eval_func
     finally:
         sys.path.remove(SHIMS)
         _fresh({"layers", "modeling", "utils"})
@@ -114,3 +120,43 @@ def test_reference_state_dicts_load_into_the_drop_ins():
     finally:
         sys.path.remove(REF)
         _fresh({"layers", "modeling", "utils"})
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the live reference is only present in the build container")
+def test_volume_and_tower_tail_signatures_match_the_reference():
+    """utils/volume.py (all three functions) and the pieces TokenProducer wraps (clip/model.py: VisionTransformer.ln_post is
+    the LayerNorm subclass, .proj a [width, output_dim] Parameter; meta_arch.py returns (x[:, 1:], x[:, 0]))."""
+    _fresh({"layers", "modeling", "utils"})
+    sys.dont_write_bytecode = True
+    for pkg, sub in (("utils", "utils"), ("modeling", "modeling"), ("modeling.clip", "modeling/clip"), ("modeling.backbones", "modeling/backbones")):
+        m = types.ModuleType(pkg)
+        m.__path__ = [os.path.join(REF, sub)]
+        sys.modules[pkg] = m
+    sys.path.insert(0, REF)
+    try:
+        import torch
+        from utils import volume as RV
+        from modeling.clip.model import VisionTransformer
+        from signal_b200 import modules
+        from signal_b200.tokens import TokenProducer
+        for name in ("volume_computation3", "volume_computation4", "volume_computation5"):
+            assert _params(getattr(RV, name)) == _params(getattr(modules, name)), name
+        cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(PROMPT=False, ADAPTER=False))
+        vt = VisionTransformer(8, 16, 16, 16, 64, 1, 2, 32, cfg)
+        tp = TokenProducer(vt.ln_post, vt.proj)            # wraps the reference's own sub-module and parameter
+        assert isinstance(vt.ln_post, torch.nn.LayerNorm) and tuple(vt.proj.shape) == (64, 32)
+        assert list(tp.state_dict()) == [] and list(tp.parameters()) == []      # owns nothing: checkpoints unchanged
+        with pytest.raises(RuntimeError):
+            tp(torch.randn(2, 129, 64))                   # CPU tensors raise: no fallback
+    finally:
+        sys.path.remove(REF)
+        _fresh({"layers", "modeling", "utils"})
+
+
+def test_new_drop_ins_refuse_cpu_tensors():
+    import torch
+    from signal_b200 import evaluation, modules
+    with pytest.raises(RuntimeError):
+        modules.volume_computation4(*[torch.randn(4, 16) for _ in range(4)])
+    with pytest.raises(RuntimeError):
+        evaluation.euclidean_distance(torch.randn(3, 8), torch.randn(5, 8))
