@@ -28,3 +28,21 @@ def test_tokens_oracle_bf16_emulation_is_close_to_fp32():
     t32, m32, _ = to.tokens_fwd(x, ln_w, ln_b, proj, float(z["eps"]))
     t16, m16, _ = to.tokens_fwd(x, ln_w, ln_b, proj, float(z["eps"]), operand_dtype=torch.bfloat16)
     assert tc.rel(t16, t32) < 1e-2 and tc.rel(m16, m32) < 1e-2
+
+
+def test_tokens_oracle_explicit_backward_matches_autograd():
+    """the oracle's hand-written backward (what the CUDA kernels are compared with) against torch.autograd on its forward"""
+    g = torch.Generator().manual_seed(5)
+    B, L1, W, D = 3, 9, 48, 24
+    x = (torch.randn(B, L1, W, generator=g, dtype=torch.float64) * 1.7 + 0.3).requires_grad_(True)
+    ln_w = (1.0 + 0.2 * torch.randn(W, generator=g, dtype=torch.float64)).requires_grad_(True)
+    ln_b = (0.1 * torch.randn(W, generator=g, dtype=torch.float64)).requires_grad_(True)
+    proj = (torch.randn(W, D, generator=g, dtype=torch.float64) / W ** 0.5).requires_grad_(True)
+    cot = torch.randn(B, L1, D, generator=g, dtype=torch.float64)
+    tok, mean, xn = to.tokens_fwd(x, ln_w, ln_b, proj, 1e-5)
+    tok.backward(cot)
+    dx, dg, db, dp = to.tokens_bwd(x.detach(), ln_w.detach(), proj.detach(), cot, 1e-5, xn=xn.detach())
+    for got, ref in ((dx, x.grad), (dg, ln_w.grad), (db, ln_b.grad), (dp, proj.grad)):
+        assert tc.rel(got, ref) < 1e-12
+    # the patch mean is the mean over rows 1.. of the tokens (meta_arch.py:108-110: row 0 is the CLS token)
+    assert tc.rel(mean, tok.detach()[:, 1:].mean(dim=1)) < 1e-15

@@ -33,3 +33,19 @@ def test_volume_n_with_three_modalities_is_volume3():
     c = dict(n=3, B1=7, B2=5, d=32, corr=0.5, seed=3)
     feats, _ = vc.gen.inputs(c)
     assert _rel(so.volume_n(*[f.double() for f in feats]), so.volume3(*[f.double() for f in feats])) < 1e-12
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_volume_n_oracle_equals_torch_det(n):
+    """the Laplace-expansion restatement against torch.det of the same Gram stack (fp64), values and gradients"""
+    c = dict(n=n, B1=6, B2=5, d=40, corr=0.6, seed=100 + n)
+    feats, cot = vc.gen.inputs(c)
+    xs = [t.double().requires_grad_(True) for t in feats]
+    V = so.volume_n(*xs)
+    V.backward(cot.double())
+    ys = [t.double().requires_grad_(True) for t in feats]
+    Vd = torch.sqrt(torch.abs(torch.det(vc.gen.gram_stack64(ys))))
+    Vd.backward(cot.double())
+    assert _rel(V.detach(), Vd.detach()) < 1e-10
+    for a, b in zip(xs, ys):
+        assert _rel(a.grad, b.grad) < 1e-8
